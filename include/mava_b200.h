@@ -1,0 +1,198 @@
+/* mava_b200.h - C ABI of libmava_b200.so: the B200 (sm_100a) kernels behind Mava's Anakin PPO path.
+ *
+ * The reference (RuanJohn/Mava v0.2.0) has no FFI of its own: the seam is a set of Python
+ * callables that XLA compiles.  Each entry point below replaces one XLA-compiled region and
+ * cites the reference lines it stands in for.  This is what a jax.ffi / ctypes binding binds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call is asynchronous on the caller-supplied CUDA stream (cudaStream_t passed as
+ *     void*), never synchronises, never allocates on the hot path;
+ *   - return value: 0 ok, <0 invalid argument (MAVA_E_*), >0 a cudaError_t;
+ *   - buffers are caller-owned; the library keeps only immutable per-scenario constants inside
+ *     the opaque env handle.
+ *
+ * Layouts (NE = envs resident on this GPU = update_batch_size * num_envs, A = agents,
+ * FR = raw observation features per agent, T = rollout_length):
+ *   env state      uint8 [NE][state_stride]           packed per-env record, see DESIGN.md
+ *   view           int8  [NE][A][FR]                   raw integer observation (no ids)
+ *   mask           uint8 [NE][A]                       bit k set = action k legal
+ *   action         int8  [NE][A]
+ *   logp, value    f32   [NE][A]
+ *   reward         f32   [NE][A]
+ *   done           uint8 [NE]
+ *   ep_return f32 [NE], ep_length int32 [NE]           RecordEpisodeMetrics outputs
+ * Rollout buffers stack these with a leading time axis.
+ */
+#ifndef MAVA_B200_H_
+#define MAVA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAVA_B200_ABI_VERSION 1
+
+#define MAVA_E_BADARG (-1)
+#define MAVA_E_UNSUPPORTED (-2)
+#define MAVA_E_NULL (-3)
+
+typedef void* mava_stream_t; /* cudaStream_t */
+typedef struct mava_env_s* mava_env_t;
+
+int mava_abi_version(void);
+/* Human readable text for a return code of any function below (static storage). */
+const char* mava_error_string(int code);
+/* Device properties the host sizes grids with.  out[0]=SM count, out[1]=cc major, out[2]=cc minor. */
+int mava_device_info(int* out3_host);
+
+/* ------------------------------------------------------------------------------------------
+ * PRNG - jax.random (threefry2x32) as the reference uses it.
+ * ---------------------------------------------------------------------------------------- */
+/* Sequential chain of n `key, sub = jax.random.split(key)` (ff_mappo.py:81).  subkeys[n][2]
+ * receives the n sub keys, key_io[2] is advanced in place.  One thread; n is small (T). */
+int mava_prng_split_chain(uint32_t* key_io, uint32_t* subkeys, int n, mava_stream_t s);
+/* jax.random.split(key, num) -> out[num][2] (ff_mappo.py:392-394). */
+int mava_prng_split(const uint32_t* key, uint32_t* out, int num, mava_stream_t s);
+/* jax random_bits(key, (n,)) -> out[n] uint32; the sort keys of jax.random.permutation
+ * (ff_mappo.py:273). */
+int mava_prng_random_bits(const uint32_t* key, uint32_t* out, int64_t n, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Environments - replaces jax.vmap(env.step) / jax.vmap(env.reset) through the whole wrapper
+ * stack RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(RwareWrapper|LbfWrapper(env))))
+ * (ff_mappo.py:88,395; mava/utils/make_env.py:69-83; mava/wrappers/*.py).
+ * ---------------------------------------------------------------------------------------- */
+#define MAVA_ENV_RWARE 1
+#define MAVA_ENV_LBF 2
+
+typedef struct mava_rware_config {
+  int32_t column_height, shelf_rows, shelf_columns;
+  int32_t num_agents, sensor_range, request_queue_size;
+  int32_t time_limit;
+} mava_rware_config; /* configs/env/scenario/tiny-4ag.yaml task_config + env/rware.yaml kwargs */
+
+typedef struct mava_lbf_config {
+  int32_t grid_size, fov, num_agents, num_food, max_agent_level, force_coop;
+  int32_t time_limit;
+  int32_t use_individual_rewards; /* configs/env/lbf.yaml */
+} mava_lbf_config;
+
+typedef struct mava_env_dims {
+  int32_t kind;
+  int32_t num_agents;   /* A  */
+  int32_t view_dim;     /* FR */
+  int32_t num_actions;  /* N  */
+  int32_t state_stride; /* bytes per env record, multiple of 16 */
+  int32_t time_limit;
+  int32_t grid_h, grid_w;
+  int32_t aux0, aux1;   /* RWARE: n_shelves, queue size.  LBF: n_food, max level */
+  int32_t algo_bytes_per_step; /* minimal lossless bytes one env-step moves */
+} mava_env_dims;
+
+int mava_env_create(int kind, const void* config_host, size_t config_size, mava_env_t* out);
+int mava_env_destroy(mava_env_t env);
+int mava_env_dims_of(mava_env_t env, mava_env_dims* out_host);
+
+/* vmap(env.reset)(keys): keys[NE][2] -> state, first observation (view, mask). */
+int mava_env_reset(mava_env_t env, const uint32_t* keys, uint8_t* state, int8_t* view,
+                   uint8_t* mask, int num_envs, mava_stream_t s);
+/* vmap(env.step)(state, action).  State is updated in place.  auto_reset != 0 applies
+ * AutoResetWrapper (training env); 0 is the evaluation env (make_env.py:79-81).  reward is the
+ * per-agent reward after the wrapper's aggregation.  ep_return/ep_length are the
+ * `episode_metrics` extras; `is_terminal_step` equals done. */
+int mava_env_step(mava_env_t env, uint8_t* state, const int8_t* action, int8_t* view,
+                  uint8_t* mask, float* reward, uint8_t* done, float* ep_return,
+                  int32_t* ep_length, int num_envs, int auto_reset, mava_stream_t s);
+/* Decode fields of the packed state for inspection/tests: writes int32 per env.
+ * field ids: 0 step_count, 1 env key (2 words), 2 agents (A*4: x,y,dir,carry ...) */
+int mava_env_peek(mava_env_t env, const uint8_t* state, int field, int32_t* out, int num_envs,
+                  mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Networks - FeedForwardActor / FeedForwardValueNet (mava/networks.py:39-58,88-124,172-207).
+ * Parameters are one flat f32 vector per network in flax order and layout:
+ *   [Dense_0.kernel (in,h1) | Dense_0.bias | Dense_1.kernel (h1,h2) | Dense_1.bias |
+ *    head.kernel (h2,out) | head.bias]
+ * ---------------------------------------------------------------------------------------- */
+#define MAVA_IN_AGENT_VIEW 0 /* x = [onehot(agent) if add_agent_id | view[e][a][:]]            */
+#define MAVA_IN_GLOBAL 1     /* x = concat_a view[e][a][:]  (ObservationGlobalState.global_state) */
+
+typedef struct mava_mlp_desc {
+  int32_t input_mode;   /* MAVA_IN_*                                   */
+  int32_t add_agent_id; /* AgentIDWrapper on (observation.py:41-53)     */
+  int32_t num_agents, view_dim;
+  int32_t in_dim;       /* derived: A*FR, or FR (+A)                    */
+  int32_t h1, h2;       /* MLPTorso.layer_sizes (two hidden layers)     */
+  int32_t out_dim;      /* action_dim for the actor, 1 for the critic   */
+} mava_mlp_desc;
+
+/* Number of f32 parameters of a network. */
+int64_t mava_mlp_param_count(const mava_mlp_desc* d_host);
+
+/* One acting step (ff_mappo.py:81-85): logits -> masked categorical sample (Gumbel arg-max on
+ * threefry bits of policy_key, noise laid out (envs_per_replica, A, N)), log_prob, value.
+ * greedy != 0 takes pi.mode() instead (evaluator.py:183).  value may be NULL (evaluator).
+ * If actions_in != NULL the sample is replaced by the given action (replay for parity tests). */
+int mava_ff_act(const mava_mlp_desc* actor_host, const float* actor_params,
+                const mava_mlp_desc* critic_host, const float* critic_params,
+                const int8_t* view, const uint8_t* mask, const uint32_t* policy_key,
+                int envs_per_replica, int num_envs, int greedy, const int8_t* actions_in,
+                int8_t* action, float* logp, float* value, mava_stream_t s);
+/* Critic only (last_val, ff_mappo.py:110). */
+int mava_ff_value(const mava_mlp_desc* critic_host, const float* critic_params, const int8_t* view,
+                  int num_envs, float* value, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * GAE (ff_mappo.py:112-139; rec_mappo.py:177-199).  One thread per env-agent, reverse scan.
+ * reward/value/adv/targets: [T][NE][A] f32; done [T][NE] uint8; last_val [NE][A].
+ * rec != 0: `done` holds the flag entering each step and last_done[NE] seeds the carry.
+ * ---------------------------------------------------------------------------------------- */
+int mava_gae(const float* reward, const float* value, const uint8_t* done, const float* last_val,
+             const uint8_t* last_done, float gamma, float gae_lambda, int T, int num_envs,
+             int num_agents, int rec, float* adv, float* targets, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * PPO minibatch (ff_mappo.py:144-266).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mava_ppo_hyper {
+  float clip_eps, ent_coef, vf_coef;
+} mava_ppo_hyper;
+
+/* Row index list of one minibatch from a permutation (ff_mappo.py:272-280): for replica u and
+ * position j, rows[u*mb + j] = t*NE + u*E + e with (t,e) = divmod(perm[mb_index*mb + j], E). */
+int mava_ppo_minibatch_rows(const int32_t* perm, int mb_index, int mb_size, int num_replicas,
+                            int envs_per_replica, int32_t* rows, mava_stream_t s);
+
+/* Gradients of the actor and critic losses for one minibatch, averaged over the
+ * update_batch_size replicas on this GPU (value_and_grad + pmean("batch"), :205-226,232-234).
+ * rows[num_replicas*mb_size] index env-steps of the rollout buffers (leading [T*NE]).
+ * grad_out: [actor grads | critic grads | total_actor, actor_loss, entropy, total_critic,
+ * value_loss | pad] f32, the buffer that is all-reduced across GPUs.
+ * workspace: at least mava_ppo_workspace_bytes(...) bytes. */
+int64_t mava_ppo_workspace_bytes(const mava_mlp_desc* actor_host, const mava_mlp_desc* critic_host,
+                                 int rows_total);
+int mava_ppo_loss_grad(const mava_mlp_desc* actor_host, const float* actor_params,
+                       const mava_mlp_desc* critic_host, const float* critic_params,
+                       const mava_ppo_hyper* hyper_host, const int8_t* view, const uint8_t* mask,
+                       const int8_t* action, const float* old_logp, const float* old_value,
+                       const float* adv, const float* targets, const int32_t* rows,
+                       int num_replicas, int mb_size, float* grad_out, void* workspace,
+                       mava_stream_t s);
+
+/* optax.chain(clip_by_global_norm(max_norm), adam(lr, eps=1e-5)) + apply_updates for ONE
+ * network (ff_mappo.py:240-250,359-366).  grad is the summed buffer after the cross-GPU
+ * all-reduce; grad_scale = 1/world_size turns the sum into pmean("device").  count[1] (int32,
+ * device) is optax's step count, incremented here.  lr_decay_num_updates > 0 enables the linear
+ * schedule of mava/utils/training.py:39-47 with steps_per_update = ppo_epochs*num_minibatches. */
+int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const float* grad,
+                   int64_t n, float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
+                   int steps_per_update, mava_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAVA_B200_H_ */

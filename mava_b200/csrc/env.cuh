@@ -1,0 +1,58 @@
+// Internal env handle shared by the per-environment translation units.
+#pragma once
+#include "common.cuh"
+
+namespace mava {
+
+constexpr int kMaxCells = 1024;   // H*W
+constexpr int kMaxShelves = 254;  // shelf ids are stored +1 in a uint8 grid
+constexpr int kMaxAgents = 8;
+constexpr int kMaxQueue = 8;
+
+// Immutable RobotWarehouse scenario constants, passed to kernels by value.
+struct RwareConst {
+  int H, W, HW, A, Q, n, R, FR, time_limit;
+  int stride;  // bytes per env record in HBM (multiple of 16)
+  // byte offsets inside a record
+  int off_ax, off_ay, off_dir, off_carry, off_sx, off_sy, off_req, off_queue;
+  int off_step, off_key, off_mkey, off_run_ret, off_run_len, off_ep_ret, off_ep_len;
+  int goal[2];                            // flat cell index, scan order
+  uint32_t highway[kMaxCells / 32];       // bit per cell
+  uint16_t shelf_home[kMaxShelves + 2];   // flat cell index of shelf s at reset
+};
+
+struct LbfConst {
+  int S, fov, A, NF, max_level, force_coop, time_limit, individual_rewards, FR;
+  int stride;
+  int off_ax, off_ay, off_alvl, off_fx, off_fy, off_flvl, off_featen;
+  int off_step, off_key, off_mkey, off_run_ret, off_run_len, off_ep_ret, off_ep_len;
+};
+
+}  // namespace mava
+
+struct mava_env_s {
+  int kind;
+  mava_env_dims dims;
+  mava::RwareConst rw;
+  mava::LbfConst lbf;
+};
+
+namespace mava {
+int rware_create(const mava_rware_config* cfg, mava_env_s* env);
+int rware_reset(const mava_env_s* env, const uint32_t* keys, uint8_t* state, int8_t* view,
+                uint8_t* mask, int num_envs, cudaStream_t s);
+int rware_step(const mava_env_s* env, uint8_t* state, const int8_t* action, int8_t* view,
+               uint8_t* mask, float* reward, uint8_t* done, float* ep_return, int32_t* ep_length,
+               int num_envs, int auto_reset, cudaStream_t s);
+int rware_peek(const mava_env_s* env, const uint8_t* state, int field, int32_t* out, int num_envs,
+               cudaStream_t s);
+
+int lbf_create(const mava_lbf_config* cfg, mava_env_s* env);
+int lbf_reset(const mava_env_s* env, const uint32_t* keys, uint8_t* state, int8_t* view,
+              uint8_t* mask, int num_envs, cudaStream_t s);
+int lbf_step(const mava_env_s* env, uint8_t* state, const int8_t* action, int8_t* view,
+             uint8_t* mask, float* reward, uint8_t* done, float* ep_return, int32_t* ep_length,
+             int num_envs, int auto_reset, cudaStream_t s);
+int lbf_peek(const mava_env_s* env, const uint8_t* state, int field, int32_t* out, int num_envs,
+             cudaStream_t s);
+}  // namespace mava

@@ -1,0 +1,161 @@
+// GAE reverse scan, minibatch row lists and the fused clip-by-global-norm + Adam step.
+#include "common.cuh"
+
+using namespace mava;
+
+namespace {
+
+// One thread per env-agent, walking time backwards (ff_mappo.py:117-137).  Loads of a block of
+// kU steps are issued together so the HBM latency of the sequential scan overlaps.
+template <bool REC>
+__global__ void __launch_bounds__(256)
+gae_kernel(const float* __restrict__ reward, const float* __restrict__ value,
+           const uint8_t* __restrict__ done, const float* __restrict__ last_val,
+           const uint8_t* __restrict__ last_done, float gamma, float gamma_lambda, int T,
+           int num_envs, int A, float* __restrict__ adv, float* __restrict__ targets) {
+  constexpr int kU = 8;
+  const int64_t n = (int64_t)num_envs * A;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = (int)(i / A);
+  float gae = 0.0f;
+  float next_value = last_val[i];
+  float next_nd = REC ? (last_done[e] ? 0.0f : 1.0f) : 1.0f;
+  for (int t1 = T; t1 > 0; t1 -= kU) {
+    float r[kU], v[kU], nd[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int t = t1 - 1 - u;
+      if (t >= 0) {
+        r[u] = __ldg(reward + (int64_t)t * n + i);
+        v[u] = __ldg(value + (int64_t)t * n + i);
+        nd[u] = __ldg(done + (int64_t)t * num_envs + e) ? 0.0f : 1.0f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int t = t1 - 1 - u;
+      if (t >= 0) {
+        const float m = REC ? next_nd : nd[u];
+        const float delta = r[u] + gamma * next_value * m - v[u];
+        gae = delta + gamma_lambda * m * gae;
+        adv[(int64_t)t * n + i] = gae;
+        targets[(int64_t)t * n + i] = gae + v[u];
+        next_value = v[u];
+        if (REC) next_nd = nd[u];
+      }
+    }
+  }
+}
+
+__global__ void minibatch_rows_kernel(const int32_t* __restrict__ perm, int mb_index, int mb_size,
+                                      int num_replicas, int E, int32_t* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_replicas * mb_size) return;
+  const int u = i / mb_size, j = i - u * mb_size;
+  const int p = perm[(int64_t)mb_index * mb_size + j];
+  const int t = p / E, e = p - t * E;
+  rows[i] = t * (num_replicas * E) + u * E + e;
+}
+
+// optax.clip_by_global_norm -> optax.adam(eps=1e-5) -> apply_updates, one CTA (n is ~5e4).
+__global__ void __launch_bounds__(1024)
+clip_adam_kernel(float* __restrict__ params, float* __restrict__ mu, float* __restrict__ nu,
+                 int32_t* __restrict__ count, const float* __restrict__ grad, int64_t n,
+                 float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
+                 int steps_per_update) {
+  __shared__ double red[32];
+  __shared__ float s_norm;
+  double ss = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = grad[i] * grad_scale;
+    ss += (double)g * (double)g;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_norm = (float)sqrt(v);
+  }
+  __syncthreads();
+  const float g_norm = s_norm;
+  const bool keep = g_norm < max_norm;
+  const int c0 = *count;
+  const int c = c0 + 1;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-5f;
+  const float bc1 = 1.0f - powf(b1, (float)c), bc2 = 1.0f - powf(b2, (float)c);
+  float step_lr = lr;
+  if (lr_decay_num_updates > 0)
+    step_lr = lr * (1.0f - (float)(c0 / steps_per_update) / (float)lr_decay_num_updates);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float g = grad[i] * grad_scale;
+    if (!keep) g = (g / g_norm) * max_norm;
+    const float m = (1.0f - b1) * g + b1 * mu[i];
+    const float v = (1.0f - b2) * g * g + b2 * nu[i];
+    mu[i] = m;
+    nu[i] = v;
+    const float upd = (m / bc1) / (sqrtf(v / bc2) + eps);
+    params[i] += -step_lr * upd;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mava_gae(const float* reward, const float* value, const uint8_t* done, const float* last_val,
+             const uint8_t* last_done, float gamma, float gae_lambda, int T, int num_envs,
+             int num_agents, int rec, float* adv, float* targets, mava_stream_t s) {
+  MAVA_CHECK_PTR(reward);
+  MAVA_CHECK_PTR(value);
+  MAVA_CHECK_PTR(done);
+  MAVA_CHECK_PTR(last_val);
+  MAVA_CHECK_PTR(adv);
+  MAVA_CHECK_PTR(targets);
+  MAVA_CHECK_ARG(T > 0 && num_envs > 0 && num_agents > 0);
+  if (rec) MAVA_CHECK_PTR(last_done);
+  const int64_t n = (int64_t)num_envs * num_agents;
+  const int blocks = (int)ceil_div64(n, 256);
+  // gamma * gae_lambda is folded in double like the reference's Python floats (ff_mappo.py:127)
+  const float gl = (float)((double)gamma * (double)gae_lambda);
+  if (rec)
+    gae_kernel<true><<<blocks, 256, 0, as_stream(s)>>>(reward, value, done, last_val, last_done,
+                                                       gamma, gl, T, num_envs, num_agents, adv,
+                                                       targets);
+  else
+    gae_kernel<false><<<blocks, 256, 0, as_stream(s)>>>(reward, value, done, last_val, last_done,
+                                                        gamma, gl, T, num_envs, num_agents, adv,
+                                                        targets);
+  return launch_status();
+}
+
+int mava_ppo_minibatch_rows(const int32_t* perm, int mb_index, int mb_size, int num_replicas,
+                            int envs_per_replica, int32_t* rows, mava_stream_t s) {
+  MAVA_CHECK_PTR(perm);
+  MAVA_CHECK_PTR(rows);
+  MAVA_CHECK_ARG(mb_index >= 0 && mb_size > 0 && num_replicas > 0 && envs_per_replica > 0);
+  const int n = num_replicas * mb_size;
+  minibatch_rows_kernel<<<ceil_div(n, 256), 256, 0, as_stream(s)>>>(
+      perm, mb_index, mb_size, num_replicas, envs_per_replica, rows);
+  return launch_status();
+}
+
+int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const float* grad,
+                   int64_t n, float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
+                   int steps_per_update, mava_stream_t s) {
+  MAVA_CHECK_PTR(params);
+  MAVA_CHECK_PTR(mu);
+  MAVA_CHECK_PTR(nu);
+  MAVA_CHECK_PTR(count);
+  MAVA_CHECK_PTR(grad);
+  MAVA_CHECK_ARG(n > 0 && steps_per_update > 0);
+  clip_adam_kernel<<<1, 1024, 0, as_stream(s)>>>(params, mu, nu, count, grad, n, grad_scale, lr,
+                                                 max_norm, lr_decay_num_updates, steps_per_update);
+  return launch_status();
+}
+
+}  // extern "C"

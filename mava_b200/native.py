@@ -1,0 +1,230 @@
+"""Torch-tensor level calls into libmava_b200.so.
+
+torch is used only as the owner of device memory and of the CUDA stream: every function here
+validates its tensors (device, dtype, contiguity, size) and forwards raw device pointers and the
+current stream to the C ABI in include/mava_b200.h.  Nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EnvDims, LbfConfig, MlpDesc, PpoHyper, RwareConfig, check
+
+ENV_RWARE, ENV_LBF = 1, 2
+IN_AGENT_VIEW, IN_GLOBAL = 0, 1
+OMAX = 16
+
+
+def _p(t: Optional[torch.Tensor], dtype: torch.dtype, numel: Optional[int] = None, name: str = ""):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (mava_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    if numel is not None and t.numel() < numel:
+        raise ValueError(f"{name}: needs {numel} elements, has {t.numel()}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_info():
+    out = (C.c_int * 3)()
+    check(_lib.load().mava_device_info(out), "mava_device_info")
+    return tuple(out)
+
+
+def mlp_desc(input_mode: int, add_agent_id: bool, num_agents: int, view_dim: int, h1: int, h2: int,
+             out_dim: int) -> MlpDesc:
+    in_dim = num_agents * view_dim if input_mode == IN_GLOBAL else view_dim + (
+        num_agents if add_agent_id else 0)
+    return MlpDesc(input_mode, int(add_agent_id), num_agents, view_dim, in_dim, h1, h2, out_dim)
+
+
+def mlp_param_count(d: MlpDesc) -> int:
+    return int(_lib.load().mava_mlp_param_count(C.byref(d)))
+
+
+class Env:
+    """Opaque native env handle + its dimensions."""
+
+    def __init__(self, kind: int, cfg):
+        lib = _lib.load()
+        self._h = C.c_void_p()
+        check(lib.mava_env_create(kind, C.byref(cfg), C.sizeof(cfg), C.byref(self._h)),
+              "mava_env_create")
+        self.dims = EnvDims()
+        check(lib.mava_env_dims_of(self._h, C.byref(self.dims)), "mava_env_dims_of")
+        self.kind = kind
+
+    @classmethod
+    def rware(cls, column_height=8, shelf_rows=1, shelf_columns=3, num_agents=4, sensor_range=1,
+              request_queue_size=4, time_limit=500) -> "Env":
+        return cls(ENV_RWARE, RwareConfig(column_height, shelf_rows, shelf_columns, num_agents,
+                                          sensor_range, request_queue_size, time_limit))
+
+    @classmethod
+    def lbf(cls, grid_size=8, fov=8, num_agents=2, num_food=2, max_agent_level=2, force_coop=True,
+            time_limit=100, use_individual_rewards=False) -> "Env":
+        return cls(ENV_LBF, LbfConfig(grid_size, fov, num_agents, num_food, max_agent_level,
+                                      int(force_coop), time_limit, int(use_individual_rewards)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().mava_env_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- shapes -------------------------------------------------------------------------------
+    @property
+    def num_agents(self) -> int:
+        return self.dims.num_agents
+
+    @property
+    def view_dim(self) -> int:
+        return self.dims.view_dim
+
+    @property
+    def num_actions(self) -> int:
+        return self.dims.num_actions
+
+    @property
+    def state_stride(self) -> int:
+        return self.dims.state_stride
+
+    def alloc_state(self, num_envs: int, device) -> torch.Tensor:
+        return torch.zeros(num_envs, self.state_stride, dtype=torch.uint8, device=device)
+
+    # -- calls --------------------------------------------------------------------------------
+    def reset(self, keys, state, view, mask, num_envs: int) -> None:
+        A, F = self.num_agents, self.view_dim
+        check(_lib.load().mava_env_reset(
+            self._h, _p(keys, torch.uint32, 2 * num_envs, "keys"),
+            _p(state, torch.uint8, num_envs * self.state_stride, "state"),
+            _p(view, torch.int8, num_envs * A * F, "view"),
+            _p(mask, torch.uint8, num_envs * A, "mask"), num_envs, _stream()), "mava_env_reset")
+
+    def step(self, state, action, view, mask, reward, done, ep_return, ep_length, num_envs: int,
+             auto_reset: bool = True) -> None:
+        A, F = self.num_agents, self.view_dim
+        check(_lib.load().mava_env_step(
+            self._h, _p(state, torch.uint8, num_envs * self.state_stride, "state"),
+            _p(action, torch.int8, num_envs * A, "action"),
+            _p(view, torch.int8, num_envs * A * F, "view"),
+            _p(mask, torch.uint8, num_envs * A, "mask"),
+            _p(reward, torch.float32, num_envs * A, "reward"),
+            _p(done, torch.uint8, num_envs, "done"),
+            _p(ep_return, torch.float32, num_envs, "ep_return"),
+            _p(ep_length, torch.int32, num_envs, "ep_length"), num_envs, int(auto_reset),
+            _stream()), "mava_env_step")
+
+    def peek(self, state, field: int, num_envs: int) -> torch.Tensor:
+        A = self.num_agents
+        width = {0: 1, 1: 2, 2: 4 * A, 3: 3 * self.dims.aux0, 4: self.dims.aux1}[field]
+        out = torch.zeros(num_envs, width, dtype=torch.int32, device=state.device)
+        check(_lib.load().mava_env_peek(self._h, _p(state, torch.uint8, None, "state"), field,
+                                        _p(out, torch.int32), num_envs, _stream()), "mava_env_peek")
+        return out
+
+
+def prng_split_chain(key_io: torch.Tensor, subkeys: torch.Tensor, n: int) -> None:
+    check(_lib.load().mava_prng_split_chain(_p(key_io, torch.uint32, 2, "key"),
+                                            _p(subkeys, torch.uint32, 2 * n, "subkeys"), n,
+                                            _stream()), "mava_prng_split_chain")
+
+
+def prng_split(key: torch.Tensor, out: torch.Tensor, num: int) -> None:
+    check(_lib.load().mava_prng_split(_p(key, torch.uint32, 2, "key"),
+                                      _p(out, torch.uint32, 2 * num, "out"), num, _stream()),
+          "mava_prng_split")
+
+
+def prng_random_bits(key: torch.Tensor, out: torch.Tensor, n: int) -> None:
+    check(_lib.load().mava_prng_random_bits(_p(key, torch.uint32, 2, "key"),
+                                            _p(out, torch.uint32, n, "out"), n, _stream()),
+          "mava_prng_random_bits")
+
+
+def ff_act(actor: MlpDesc, actor_params, critic: Optional[MlpDesc], critic_params, view, mask,
+           policy_key, envs_per_replica: int, num_envs: int, action, logp, value=None,
+           greedy: bool = False, actions_in=None) -> None:
+    A = actor.num_agents
+    check(_lib.load().mava_ff_act(
+        C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
+        C.byref(critic) if critic is not None else None,
+        _p(critic_params, torch.float32, mlp_param_count(critic) if critic is not None else None,
+           "critic_params"),
+        _p(view, torch.int8, num_envs * A * actor.view_dim, "view"),
+        _p(mask, torch.uint8, num_envs * A, "mask"), _p(policy_key, torch.uint32, 2, "policy_key"),
+        envs_per_replica, num_envs, int(greedy), _p(actions_in, torch.int8, num_envs * A, "actions_in"),
+        _p(action, torch.int8, num_envs * A, "action"), _p(logp, torch.float32, num_envs * A, "logp"),
+        _p(value, torch.float32, num_envs * A, "value"), _stream()), "mava_ff_act")
+
+
+def ff_value(critic: MlpDesc, critic_params, view, num_envs: int, value) -> None:
+    A = critic.num_agents
+    check(_lib.load().mava_ff_value(
+        C.byref(critic), _p(critic_params, torch.float32, mlp_param_count(critic), "critic_params"),
+        _p(view, torch.int8, num_envs * A * critic.view_dim, "view"), num_envs,
+        _p(value, torch.float32, num_envs * A, "value"), _stream()), "mava_ff_value")
+
+
+def gae(reward, value, done, last_val, gamma: float, gae_lambda: float, T: int, num_envs: int,
+        num_agents: int, adv, targets, last_done=None) -> None:
+    n = T * num_envs * num_agents
+    check(_lib.load().mava_gae(
+        _p(reward, torch.float32, n, "reward"), _p(value, torch.float32, n, "value"),
+        _p(done, torch.uint8, T * num_envs, "done"),
+        _p(last_val, torch.float32, num_envs * num_agents, "last_val"),
+        _p(last_done, torch.uint8, num_envs, "last_done"), gamma, gae_lambda, T, num_envs,
+        num_agents, int(last_done is not None), _p(adv, torch.float32, n, "adv"),
+        _p(targets, torch.float32, n, "targets"), _stream()), "mava_gae")
+
+
+def ppo_minibatch_rows(perm, mb_index: int, mb_size: int, num_replicas: int, envs_per_replica: int,
+                       rows) -> None:
+    check(_lib.load().mava_ppo_minibatch_rows(
+        _p(perm, torch.int32, (mb_index + 1) * mb_size, "perm"), mb_index, mb_size, num_replicas,
+        envs_per_replica, _p(rows, torch.int32, num_replicas * mb_size, "rows"), _stream()),
+        "mava_ppo_minibatch_rows")
+
+
+def ppo_workspace_bytes(actor: MlpDesc, critic: MlpDesc, rows_total: int) -> int:
+    return int(_lib.load().mava_ppo_workspace_bytes(C.byref(actor), C.byref(critic), rows_total))
+
+
+def ppo_loss_grad(actor: MlpDesc, actor_params, critic: MlpDesc, critic_params, hyper: PpoHyper,
+                  view, mask, action, old_logp, old_value, adv, targets, rows, num_replicas: int,
+                  mb_size: int, grad_out, workspace) -> None:
+    na, nc = mlp_param_count(actor), mlp_param_count(critic)
+    need = ppo_workspace_bytes(actor, critic, num_replicas * mb_size)
+    check(_lib.load().mava_ppo_loss_grad(
+        C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"), C.byref(critic),
+        _p(critic_params, torch.float32, nc, "critic_params"), C.byref(hyper),
+        _p(view, torch.int8, None, "view"), _p(mask, torch.uint8, None, "mask"),
+        _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
+        _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
+        _p(targets, torch.float32, None, "targets"),
+        _p(rows, torch.int32, num_replicas * mb_size, "rows"), num_replicas, mb_size,
+        _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
+        _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad")
+
+
+def clip_adam(params, mu, nu, count, grad, n: int, grad_scale: float, lr: float, max_norm: float,
+              lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:
+    check(_lib.load().mava_clip_adam(
+        _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
+        _p(nu, torch.float32, n, "nu"), _p(count, torch.int32, 1, "count"),
+        _p(grad, torch.float32, n, "grad"), n, grad_scale, lr, max_norm, lr_decay_num_updates,
+        steps_per_update, _stream()), "mava_clip_adam")

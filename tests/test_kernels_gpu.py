@@ -1,0 +1,112 @@
+"""GPU parity for PRNG, GAE, minibatch rows and the fused clip+Adam step (via the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo as oppo
+from oracle import threefry as tf
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _u32(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32)).to(DEV)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 110, 257, 4097])
+def test_random_bits_bit_exact(lib_built, n):
+    from mava_b200 import native
+
+    key = tf.prng_key(1234)
+    out = torch.zeros(n, dtype=torch.uint32, device=DEV)
+    native.prng_random_bits(_u32(key), out, n)
+    np.testing.assert_array_equal(out.cpu().numpy(), tf.random_bits(key, (n,)))
+
+
+def test_split_and_chain_bit_exact(lib_built):
+    from mava_b200 import native
+
+    key = tf.prng_key(42)
+    out = torch.zeros(33, 2, dtype=torch.uint32, device=DEV)
+    native.prng_split(_u32(key), out, 33)
+    np.testing.assert_array_equal(out.cpu().numpy(), tf.split(key, 33))
+    kio = _u32(key)
+    subs = torch.zeros(17, 2, dtype=torch.uint32, device=DEV)
+    native.prng_split_chain(kio, subs, 17)
+    k = key
+    for i in range(17):
+        k, s = tf.split(k)
+        np.testing.assert_array_equal(subs[i].cpu().numpy(), s)
+    np.testing.assert_array_equal(kio.cpu().numpy(), k)
+
+
+@pytest.mark.parametrize("rec", [False, True])
+@pytest.mark.parametrize("T,NE,A", [(128, 33, 4), (5, 7, 2), (37, 129, 3)])
+def test_gae_matches_oracle(lib_built, rec, T, NE, A):
+    from mava_b200 import native
+
+    rng = np.random.default_rng(0)
+    reward = rng.normal(size=(T, NE, A)).astype(np.float32)
+    value = rng.normal(size=(T, NE, A)).astype(np.float32)
+    done = (rng.random((T, NE)) < 0.1)
+    last_val = rng.normal(size=(NE, A)).astype(np.float32)
+    last_done = rng.random(NE) < 0.2
+    done_a = np.repeat(done[:, :, None], A, 2)
+    if rec:
+        oadv, otgt = oppo.gae_rec(reward, value, done_a, last_val, np.repeat(last_done[:, None], A, 1),
+                                  0.99, 0.95)
+    else:
+        oadv, otgt = oppo.gae_ff(reward, value, done_a, last_val, 0.99, 0.95)
+    adv = torch.zeros(T, NE, A, device=DEV)
+    tgt = torch.zeros(T, NE, A, device=DEV)
+    native.gae(torch.from_numpy(reward).to(DEV), torch.from_numpy(value).to(DEV),
+               torch.from_numpy(done.astype(np.uint8)).to(DEV), torch.from_numpy(last_val).to(DEV),
+               0.99, 0.95, T, NE, A, adv, tgt,
+               last_done=torch.from_numpy(last_done.astype(np.uint8)).to(DEV) if rec else None)
+    # tolerance: rtol 1e-5 fp32 (BASELINE.json north_star), atol for cancellations near zero
+    np.testing.assert_allclose(adv.cpu().numpy(), oadv, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(tgt.cpu().numpy(), otgt, rtol=1e-5, atol=2e-5)
+
+
+def test_minibatch_rows(lib_built):
+    from mava_b200 import native
+
+    T, E, U, nmb = 8, 6, 2, 2
+    perm = np.random.default_rng(1).permutation(T * E).astype(np.int32)
+    mb = T * E // nmb
+    for m in range(nmb):
+        rows = torch.zeros(U * mb, dtype=torch.int32, device=DEV)
+        native.ppo_minibatch_rows(torch.from_numpy(perm).to(DEV), m, mb, U, E, rows)
+        exp = []
+        for u in range(U):
+            for j in range(mb):
+                t, e = divmod(int(perm[m * mb + j]), E)
+                exp.append(t * U * E + u * E + e)
+        np.testing.assert_array_equal(rows.cpu().numpy(), np.array(exp, np.int32))
+
+
+@pytest.mark.parametrize("gscale,decay", [(1.0, 0), (0.25, 0), (1.0, 10)])
+def test_clip_adam_matches_oracle(lib_built, gscale, decay):
+    from mava_b200 import native
+
+    rng = np.random.default_rng(5)
+    n = 26245
+    p = rng.normal(size=n).astype(np.float32)
+    mu = np.zeros(n, np.float32)
+    nu = np.zeros(n, np.float32)
+    tp, tmu, tnu = (torch.from_numpy(x.copy()).to(DEV) for x in (p, mu, nu))
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for step in range(12):
+        scale = 0.001 if step % 3 == 0 else 1.0  # below and above the clip threshold
+        g = (rng.normal(size=n) * scale).astype(np.float32)
+        lr = 2.5e-4
+        if decay:
+            lr = oppo.linear_lr(2.5e-4, step, 2, 2, decay)
+        p, mu, nu = oppo.clip_adam(p, g * np.float32(gscale), mu, nu, step, lr, 0.5)
+        native.clip_adam(tp, tmu, tnu, cnt, torch.from_numpy(g).to(DEV), n, gscale, 2.5e-4, 0.5,
+                         lr_decay_num_updates=decay, steps_per_update=4)
+    assert int(cnt.item()) == 12
+    np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(tmu.cpu().numpy(), mu, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(tnu.cpu().numpy(), nu, rtol=1e-5, atol=1e-10)
