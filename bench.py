@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Headline benchmark: RWARE ff_mappo env-steps/sec (rollout + GAE + PPO) per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): ff_mappo on RWARE tiny-4ag, 2048 envs per GPU
+(update_batch_size 2 x num_envs 1024), 128-step rollouts, 4 PPO epochs x 2 minibatches.  A "step" is
+one full update = 262 144 env-steps per GPU.  N > 1 is launched by torchrun, one rank per GPU
+(weak scaling: per-GPU work fixed); the timed region is K graph replays bracketed by barrier +
+synchronize, timed with CUDA events, max over ranks.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RWARE ff_mappo env-steps/sec (rollout+GAE+PPO)"
+UNIT = "env-steps/s"
+TASK = dict(column_height=8, shelf_rows=1, shelf_columns=3, num_agents=4, sensor_range=1,
+            request_queue_size=4)
+OVERRIDES = ["env=rware", "env/scenario=tiny-4ag", "arch.num_envs=1024",
+             "system.update_batch_size=2", "system.rollout_length=128", "system.ppo_epochs=4",
+             "system.num_minibatches=2", "logger.use_console=False"]
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "ff_mappo RWARE tiny-4ag, 2048 envs/GPU (update_batch_size 2 x num_envs "
+                        "1024), rollout 128, 4 epochs x 2 minibatches (BASELINE.json configs[1])",
+            "envs_per_gpu": 2048, "global_envs": 2048 * n_gpus, "rollout_length": 128,
+            "parallelism": f"dp{n_gpus}", "l2": "inputs are rewritten by every update; "
+            "a 256 MiB buffer is written between timed steps to flush L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    """The reference's CPU implementation of the path, timed on host cores.
+
+    The reference itself (JAX_PLATFORMS=cpu) cannot run in this image: jax/jumanji are not
+    installed and there is no network, so this times the oracle port
+    (oracle/cpu_baseline.py) with every host core, as the tier contract prescribes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as cb
+
+    sample_envs = 512
+    res = cb.run(TASK, num_envs=sample_envs, updates=max(1, args.steps), warmup=min(args.warmup, 1))
+    value = res["env_steps_per_s"]
+    sample = (f"{max(1, args.steps)} update(s) of {sample_envs} envs x 128 steps, 4 epochs x 2 "
+              "minibatches (1/4 of one GPU's share of the workload)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * res["seconds"] / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def loss_grad_flops(L) -> float:
+    """Executed FLOPs of one ppo_loss_grad call (forward + backward of both networks)."""
+    def net(d, rows):
+        fwd = 2.0 * (d.in_dim * d.h1 + d.h1 * d.h2 + d.h2 * d.out_dim)
+        bwd = 2.0 * (d.h2 * d.out_dim + d.h1 * d.h2)          # dZ2, dZ1
+        wg = 2.0 * (d.in_dim * d.h1 + d.h1 * d.h2 + d.h2 * d.out_dim)
+        return rows * (fwd + bwd + wg)
+    R = L.U * L.mb
+    crows = R if L.critic_desc.input_mode == 1 else R * L.A
+    return net(L.actor_desc, R * L.A) + net(L.critic_desc, crows)
+
+
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mava_b200 import native, prng
+    from mava_b200.config import compose
+    from mava_b200.systems.ppo import _runner, ff_mappo
+    from mava_b200.utils import make_env
+    from mava_b200.utils.logger import get_final_step_metrics
+
+    device = _runner.init_distributed()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
+    cfg = compose(ff_mappo.CONFIG_NAME, OVERRIDES + [f"+arch.precision={args.precision}"])
+    env, _ = make_env.make(cfg, add_global_state=True, device=device)
+    key, _, ak, ck = prng.split(prng.PRNGKey(cfg.system.seed), 4)
+    learn, _, state = ff_mappo.learner_setup(env, (key, ak, ck), cfg)
+    L = learn.learner
+    cfg.system.num_updates_per_eval = 1
+    steps_per_update = L.T * L.NE  # per GPU
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for _ in range(max(args.warmup, 3)):
+        learn(state)
+    torch.cuda.synchronize(device)
+    launches_per_update = L.launches_per_update
+
+    # ---- device-timed region: K updates, inputs resident in HBM -------------------------------
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict L2 between timed steps
+        ev[k][0].record()
+        L.learn(1)
+        ev[k][1].record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API: learn(state) + host copies each step ---------------
+    host_params = torch.empty_like(L.params, device="cpu").pin_memory()
+    host_opt = torch.empty(2 * L.params.numel(), dtype=torch.float32).pin_memory()
+    host_key = torch.empty(2, dtype=torch.uint32).pin_memory()
+    host_params.copy_(L.params)
+    host_opt[: L.params.numel()].copy_(L.mu)
+    host_opt[L.params.numel():].copy_(L.nu)
+    host_key.copy_(L.key)
+    pin = {k: torch.empty(1, L.U, L.T, L.E, dtype=dt).pin_memory() for k, dt in
+           (("episode_return", torch.float32), ("episode_length", torch.int32),
+            ("is_terminal_step", torch.bool))}
+    pin_loss = torch.empty(4, 1, L.epochs, L.nmb).pin_memory()
+    h2d = (host_params.numel() + host_opt.numel()) * 4 + 8
+    d2h = sum(v.numel() * v.element_size() for v in pin.values()) + pin_loss.numel() * 4
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        # host -> device: the replicated learner inputs (params, optimiser moments, key)
+        L.params.copy_(host_params, non_blocking=True)
+        L.mu.copy_(host_opt[: L.params.numel()], non_blocking=True)
+        L.nu.copy_(host_opt[L.params.numel():], non_blocking=True)
+        L.key.copy_(host_key, non_blocking=True)
+        out = learn(state)
+        # device -> host: what run_experiment consumes (episode + train metrics), then params back
+        for k2, buf in pin.items():
+            buf.copy_(out.episode_metrics[k2], non_blocking=True)
+        for i, k2 in enumerate(("total_loss", "value_loss", "actor_loss", "entropy")):
+            pin_loss[i].copy_(out.train_metrics[k2], non_blocking=True)
+        host_params.copy_(L.params, non_blocking=True)
+        host_opt[: L.params.numel()].copy_(L.mu, non_blocking=True)
+        host_opt[L.params.numel():].copy_(L.nu, non_blocking=True)
+        host_key.copy_(L.key, non_blocking=True)
+        torch.cuda.synchronize(device)
+        get_final_step_metrics({k2: v for k2, v in pin.items()})
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    d2h += h2d
+
+    # ---- dominant kernel: ppo_loss_grad, CUDA events around each call over K eager updates ------
+    L.use_graph_saved, L._graph_saved = L.use_graph, L._graph
+    L.use_graph, L._graph = False, None
+    L.time_loss_grad = []
+    roof_steps = min(args.steps, 3)
+    for _ in range(roof_steps):
+        L.learn(1)
+    torch.cuda.synchronize(device)
+    lg_ms = [a.elapsed_time(b) for a, b in L.time_loss_grad]
+    L.time_loss_grad = None
+    L.use_graph, L._graph = L.use_graph_saved, L._graph_saved
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, float(np.mean(lg_ms))], device=device,
+                     dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, lg_mean_ms = (float(x) for x in t.tolist())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    flops = loss_grad_flops(L)
+    achieved = flops / (lg_mean_ms * 1e-3) / 1e12
+    value = world * steps_per_update * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * steps_per_update * args.steps / (e2e_ms * 1e-3)
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cb
+
+        res = cb.run(TASK, num_envs=512, updates=1, warmup=0)
+        cpu_baseline = {"value": res["env_steps_per_s"], "unit": UNIT, "cores": res["cores"],
+                        "kind": "port",
+                        "sample": "1 update of 512 envs x 128 steps, 4 epochs x 2 minibatches "
+                                  "(1/4 of one GPU's share), oracle port on all host cores"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": L.compute_dtype, "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_update * args.steps),
+            "roofline": {"kernel": L.dominant_kernel, "bound": "tensor", "achieved": achieved,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "peak_source": peak_src,
+                         "flops_per_launch": flops, "ms_per_launch": lg_mean_ms,
+                         "launches_timed": len(lg_ms)},
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,7 +126,8 @@ def _builtin_tree() -> Dict[str, Dict]:
     t["network/rnn"] = dict(hidden_state_dim=128,
                             actor_network=dict(pre_torso=_torso([128]), post_torso=_torso([128])),
                             action_head=dict(head),
-                            critic_network=dict(pre_torso=_torso([128]), post_torso=_torso([128])))
+                            critic_network=dict(pre_torso=_torso([128]), post_torso=_torso([128])),
+                            q_network=dict(pre_torso=_torso([128]), post_torso=_torso([128])))
     t["env/rware"] = {"defaults": ["_self_", {"scenario": "tiny-2ag"}],
                       "env_name": "RobotWarehouse", "eval_metric": "episode_return",
                       "implicit_agent_id": False, "log_win_rate": False,

@@ -1,0 +1,89 @@
+"""Evaluator mirroring mava/evaluator.py:64-209 on the native env/actor kernels."""
+from __future__ import annotations
+
+import math
+import time
+import warnings
+from typing import Callable, Dict
+
+import numpy as np
+import torch
+
+from . import native, prng
+from .systems.ppo.anakin import world
+
+
+def get_num_eval_envs(config, absolute_metric: bool) -> int:
+    """evaluator.py:64-77."""
+    _, n_devices = world()
+    n_parallel_envs = config.arch.num_envs * n_devices
+    eval_episodes = (config.arch.num_absolute_metric_eval_episodes if absolute_metric
+                     else config.arch.num_eval_episodes)
+    if eval_episodes <= n_parallel_envs:
+        return math.ceil(eval_episodes / n_devices)
+    return int(config.arch.num_envs)
+
+
+def make_ff_eval_act_fn(actor_desc, config) -> Callable:
+    """evaluator.py:175-186: sample (or mode() when evaluation_greedy) from the actor."""
+    greedy = bool(config.arch.evaluation_greedy)
+
+    def eval_act_fn(params, view, mask, key, num_envs, action, logp):
+        native.ff_act(actor_desc, params, None, None, view, mask, key, num_envs, num_envs, action,
+                      logp, None, greedy=greedy)
+
+    return eval_act_fn
+
+
+def get_eval_fn(env, act_fn: Callable, config, absolute_metric: bool):
+    """evaluator.py:80-172.  Returns ``evaluator(params, key, init_act_state) -> metrics`` where
+    ``key`` is this rank's uint32[2] evaluation key (host array)."""
+    _, n_devices = world()
+    eval_episodes = (config.arch.num_absolute_metric_eval_episodes if absolute_metric
+                     else config.arch.num_eval_episodes)
+    n_envs = get_num_eval_envs(config, absolute_metric)
+    n_parallel = n_envs * n_devices
+    episode_loops = math.ceil(eval_episodes / n_parallel)
+    if eval_episodes % n_parallel != 0:
+        warnings.warn(f"Number of evaluation episodes ({eval_episodes}) is not divisible by "
+                      f"`num_envs` * `num_devices` ({n_parallel}); "
+                      f"{episode_loops * n_parallel} episodes will be run.", stacklevel=2)
+    dev = env.device
+    A, FR, T = env.num_agents, env.native.view_dim, int(env.time_limit)
+    state = env.native.alloc_state(n_envs, dev)
+    view = torch.zeros(n_envs, A, FR, dtype=torch.int8, device=dev)
+    mask = torch.zeros(n_envs, A, dtype=torch.uint8, device=dev)
+    action = torch.zeros(n_envs, A, dtype=torch.int8, device=dev)
+    logp = torch.zeros(n_envs, A, device=dev)
+    reward = torch.zeros(n_envs, A, device=dev)
+    done = torch.zeros(T, n_envs, dtype=torch.uint8, device=dev)
+    ep_ret = torch.zeros(T, n_envs, device=dev)
+    ep_len = torch.zeros(T, n_envs, dtype=torch.int32, device=dev)
+    act_keys = torch.zeros(T, 2, dtype=torch.uint32, device=dev)
+    key_dev = torch.zeros(2, dtype=torch.uint32, device=dev)
+
+    def timed_eval_fn(params: torch.Tensor, key: np.ndarray, init_act_state=None) -> Dict:
+        start = time.time()
+        rets, lens = [], []
+        for _ in range(episode_loops):  # _episode, evaluator.py:132-150
+            key, reset_key = prng.split(key)
+            reset_keys = prng.split(reset_key, n_envs)
+            env.native.reset(torch.from_numpy(reset_keys.copy()).to(dev), state, view, mask, n_envs)
+            key_dev.copy_(torch.from_numpy(np.ascontiguousarray(key)).to(dev))
+            native.prng_split_chain(key_dev, act_keys, T)  # key, act_key = split(key) per step
+            for t in range(T):
+                act_fn(params, view, mask, act_keys[t], n_envs, action, logp)
+                env.native.step(state, action, view, mask, reward, done[t], ep_ret[t], ep_len[t],
+                                n_envs, False)
+            key = key_dev.cpu().numpy()
+            done_idx = torch.argmax(done.to(torch.int32), dim=0)  # first terminal step per env
+            cols = torch.arange(n_envs, device=dev)
+            rets.append(ep_ret[done_idx, cols])
+            lens.append(ep_len[done_idx, cols])
+        metrics = {"episode_return": torch.cat(rets), "episode_length": torch.cat(lens)}
+        torch.cuda.synchronize(dev)
+        total = float(metrics["episode_length"].sum().item())
+        metrics["steps_per_second"] = torch.tensor(total / max(time.time() - start, 1e-9))
+        return metrics
+
+    return timed_eval_fn

@@ -15,6 +15,14 @@ from . import _lib
 from ._lib import EnvDims, LbfConfig, MlpDesc, PpoHyper, RwareConfig, check
 
 ENV_RWARE, ENV_LBF = 1, 2
+# Number of mava_b200 kernels launched through this module (the benchmark's `gpu_launches`).
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 IN_AGENT_VIEW, IN_GLOBAL = 0, 1
 OMAX = 16
 
@@ -109,6 +117,7 @@ class Env:
     # -- calls --------------------------------------------------------------------------------
     def reset(self, keys, state, view, mask, num_envs: int) -> None:
         A, F = self.num_agents, self.view_dim
+        _count(1)
         check(_lib.load().mava_env_reset(
             self._h, _p(keys, torch.uint32, 2 * num_envs, "keys"),
             _p(state, torch.uint8, num_envs * self.state_stride, "state"),
@@ -118,6 +127,7 @@ class Env:
     def step(self, state, action, view, mask, reward, done, ep_return, ep_length, num_envs: int,
              auto_reset: bool = True) -> None:
         A, F = self.num_agents, self.view_dim
+        _count(1)
         check(_lib.load().mava_env_step(
             self._h, _p(state, torch.uint8, num_envs * self.state_stride, "state"),
             _p(action, torch.int8, num_envs * A, "action"),
@@ -139,18 +149,21 @@ class Env:
 
 
 def prng_split_chain(key_io: torch.Tensor, subkeys: torch.Tensor, n: int) -> None:
+    _count(1)
     check(_lib.load().mava_prng_split_chain(_p(key_io, torch.uint32, 2, "key"),
                                             _p(subkeys, torch.uint32, 2 * n, "subkeys"), n,
                                             _stream()), "mava_prng_split_chain")
 
 
 def prng_split(key: torch.Tensor, out: torch.Tensor, num: int) -> None:
+    _count(1)
     check(_lib.load().mava_prng_split(_p(key, torch.uint32, 2, "key"),
                                       _p(out, torch.uint32, 2 * num, "out"), num, _stream()),
           "mava_prng_split")
 
 
 def prng_random_bits(key: torch.Tensor, out: torch.Tensor, n: int) -> None:
+    _count(1)
     check(_lib.load().mava_prng_random_bits(_p(key, torch.uint32, 2, "key"),
                                             _p(out, torch.uint32, n, "out"), n, _stream()),
           "mava_prng_random_bits")
@@ -160,6 +173,7 @@ def ff_act(actor: MlpDesc, actor_params, critic: Optional[MlpDesc], critic_param
            policy_key, envs_per_replica: int, num_envs: int, action, logp, value=None,
            greedy: bool = False, actions_in=None) -> None:
     A = actor.num_agents
+    _count(2 if value is not None else 1)
     check(_lib.load().mava_ff_act(
         C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
         C.byref(critic) if critic is not None else None,
@@ -174,6 +188,7 @@ def ff_act(actor: MlpDesc, actor_params, critic: Optional[MlpDesc], critic_param
 
 def ff_value(critic: MlpDesc, critic_params, view, num_envs: int, value) -> None:
     A = critic.num_agents
+    _count(1)
     check(_lib.load().mava_ff_value(
         C.byref(critic), _p(critic_params, torch.float32, mlp_param_count(critic), "critic_params"),
         _p(view, torch.int8, num_envs * A * critic.view_dim, "view"), num_envs,
@@ -183,6 +198,7 @@ def ff_value(critic: MlpDesc, critic_params, view, num_envs: int, value) -> None
 def gae(reward, value, done, last_val, gamma: float, gae_lambda: float, T: int, num_envs: int,
         num_agents: int, adv, targets, last_done=None) -> None:
     n = T * num_envs * num_agents
+    _count(1)
     check(_lib.load().mava_gae(
         _p(reward, torch.float32, n, "reward"), _p(value, torch.float32, n, "value"),
         _p(done, torch.uint8, T * num_envs, "done"),
@@ -194,6 +210,7 @@ def gae(reward, value, done, last_val, gamma: float, gae_lambda: float, T: int, 
 
 def ppo_minibatch_rows(perm, mb_index: int, mb_size: int, num_replicas: int, envs_per_replica: int,
                        rows) -> None:
+    _count(1)
     check(_lib.load().mava_ppo_minibatch_rows(
         _p(perm, torch.int32, (mb_index + 1) * mb_size, "perm"), mb_index, mb_size, num_replicas,
         envs_per_replica, _p(rows, torch.int32, num_replicas * mb_size, "rows"), _stream()),
@@ -206,9 +223,12 @@ def ppo_workspace_bytes(actor: MlpDesc, critic: MlpDesc, rows_total: int) -> int
 
 def ppo_loss_grad(actor: MlpDesc, actor_params, critic: MlpDesc, critic_params, hyper: PpoHyper,
                   view, mask, action, old_logp, old_value, adv, targets, rows, num_replicas: int,
-                  mb_size: int, grad_out, workspace) -> None:
+                  mb_size: int, grad_out, workspace, precision: str = "auto") -> None:
+    if precision not in ("auto", "fp32"):
+        raise ValueError(f"precision '{precision}' is not available in this build (fp32 only)")
     na, nc = mlp_param_count(actor), mlp_param_count(critic)
     need = ppo_workspace_bytes(actor, critic, num_replicas * mb_size)
+    _count(14)
     check(_lib.load().mava_ppo_loss_grad(
         C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"), C.byref(critic),
         _p(critic_params, torch.float32, nc, "critic_params"), C.byref(hyper),
@@ -223,6 +243,7 @@ def ppo_loss_grad(actor: MlpDesc, actor_params, critic: MlpDesc, critic_params, 
 
 def clip_adam(params, mu, nu, count, grad, n: int, grad_scale: float, lr: float, max_norm: float,
               lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:
+    _count(1)
     check(_lib.load().mava_clip_adam(
         _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
         _p(nu, torch.float32, n, "nu"), _p(count, torch.int32, 1, "count"),

@@ -1,0 +1,123 @@
+"""``run_experiment`` shared by the PPO systems: mava/systems/ppo/ff_mappo.py:435-553 (ff_ippo,
+rec_ippo and rec_mappo run the same loop)."""
+from __future__ import annotations
+
+import copy
+import os
+import time
+from typing import Callable
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ... import prng
+from ...evaluator import get_eval_fn
+from ...utils import make_env as environments
+from ...utils.logger import LogEvent, MavaLogger, get_final_step_metrics
+from ...utils.total_timestep_checker import check_total_timesteps
+from .anakin import world
+
+
+def init_distributed() -> torch.device:
+    """One process per GPU.  Under torchrun (RANK/WORLD_SIZE set) join the NCCL group."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("mava_b200 needs a CUDA device: there is no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    return torch.device("cuda", local_rank)
+
+
+def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
+                   add_global_state: bool, recurrent: bool = False) -> float:
+    config = copy.deepcopy(_config)
+    device = init_distributed()
+    rank, n_devices = world()
+
+    if recurrent:  # rec_mappo.py:586-591
+        if config.system.recurrent_chunk_size is None:
+            config.system.recurrent_chunk_size = config.system.rollout_length
+        else:
+            assert config.system.rollout_length % config.system.recurrent_chunk_size == 0, \
+                "Rollout length must be divisible by recurrent chunk size."
+
+    env, eval_env = environments.make(config=config, add_global_state=add_global_state,
+                                      device=device)
+    key, key_e, actor_net_key, critic_net_key = prng.split(prng.PRNGKey(config.system.seed), 4)
+    learn, actor_network, learner_state = learner_setup(
+        env, (key, actor_net_key, critic_net_key), config)
+    learner = learn.learner
+
+    eval_keys = prng.split(key_e, n_devices)
+    eval_act_fn = make_eval_act_fn(learner, config)
+    evaluator = get_eval_fn(eval_env, eval_act_fn, config, absolute_metric=False)
+
+    config = check_total_timesteps(config, n_devices)
+    assert config.system.num_updates > config.arch.num_evaluation, \
+        "Number of updates per evaluation must be less than total number of updates."
+    config.system.num_updates_per_eval = config.system.num_updates // config.arch.num_evaluation
+    learner.config = config
+    steps_per_rollout = (n_devices * config.system.num_updates_per_eval
+                         * config.system.rollout_length * config.system.update_batch_size
+                         * config.arch.num_envs)
+
+    logger = MavaLogger(config, rank)
+    max_episode_return = -np.inf
+    best_params = None
+    eval_metrics = {}
+    eval_step = 0
+    for eval_step in range(config.arch.num_evaluation):
+        start_time = time.time()
+        # the parameters evaluated are those BEFORE this learn call (ff_mappo.py:513 vs :535)
+        trained_params = learner_state.params.actor_params.clone()
+        learner_output = learn(learner_state)
+        torch.cuda.synchronize(device)
+        elapsed_time = time.time() - start_time
+
+        t = int(steps_per_rollout * (eval_step + 1))
+        episode_metrics, ep_completed = get_final_step_metrics(learner_output.episode_metrics)
+        episode_metrics["steps_per_second"] = torch.tensor(steps_per_rollout / elapsed_time)
+        logger.log({"timestep": t}, t, eval_step, LogEvent.MISC)
+        if ep_completed:
+            logger.log(episode_metrics, t, eval_step, LogEvent.ACT)
+        logger.log(learner_output.train_metrics, t, eval_step, LogEvent.TRAIN)
+
+        ks = prng.split(key_e, n_devices + 1)
+        key_e, eval_keys = ks[0], ks[1:]
+        eval_metrics = evaluator(trained_params, eval_keys[rank], {})
+        eval_metrics = _gather_metrics(eval_metrics, n_devices)
+        logger.log(eval_metrics, t, eval_step, LogEvent.EVAL)
+        episode_return = float(eval_metrics["episode_return"].float().mean().item())
+
+        if config.arch.absolute_metric and max_episode_return <= episode_return:
+            best_params = trained_params.clone()
+            max_episode_return = episode_return
+        learner_state = learner_output.learner_state
+
+    eval_performance = float(eval_metrics[config.env.eval_metric].float().mean().item())
+
+    if config.arch.absolute_metric:
+        abs_evaluator = get_eval_fn(eval_env, eval_act_fn, config, absolute_metric=True)
+        eval_keys = prng.split(key, n_devices)
+        abs_metrics = _gather_metrics(abs_evaluator(best_params, eval_keys[rank], {}), n_devices)
+        t = int(steps_per_rollout * (eval_step + 1))
+        logger.log(abs_metrics, t, eval_step, LogEvent.ABSOLUTE)
+    logger.stop()
+    return eval_performance
+
+
+def _gather_metrics(metrics, n_devices: int):
+    """Concatenate per-rank evaluation metrics (the reference's pmap output axis)."""
+    if n_devices == 1:
+        return metrics
+    out = {}
+    for k, v in metrics.items():
+        v = v.cuda() if not v.is_cuda else v
+        v = v.reshape(-1) if v.dim() else v.reshape(1)
+        bufs = [torch.empty_like(v) for _ in range(n_devices)]
+        dist.all_gather(bufs, v)
+        out[k] = torch.cat(bufs)
+    return out

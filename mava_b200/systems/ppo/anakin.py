@@ -1,0 +1,309 @@
+"""The Anakin PPO learner shared by ff_ippo / ff_mappo: rollout -> GAE -> PPO epochs.
+
+Mirrors ``get_learner_fn`` / ``learner_setup`` of mava/systems/ppo/ff_mappo.py:45-432 (ff_ippo.py is
+the same file with a decentralised critic).  The JAX program
+``pmap(scan[updates](vmap[update_batch_size](_update_step)))`` becomes, per GPU (one process per GPU):
+
+* one stream of hand-written CUDA kernels per update (include/mava_b200.h), with no host sync,
+  captured once into a CUDA graph and replayed ``num_updates_per_eval`` times;
+* the ``update_batch_size`` replicas live side by side on the env axis (NE = U * E envs), share
+  the parameters and the PRNG key like the reference (ff_mappo.py:417-426), normalise advantages
+  per replica and average their gradients inside the loss kernel (pmean "batch", :224-226);
+* ``pmean("device")`` (:228-238) is ONE NCCL all-reduce per minibatch of the contiguous buffer
+  [actor grads | critic grads | 5 loss scalars]; 1/world_size is folded into the Adam kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ... import native, prng
+from ..._lib import PpoHyper
+from ...networks import FeedForwardActor, FeedForwardValueNet
+from ...types import (ExperimentOutput, LearnerState, OptStates, Params, StepType, TimeStep)
+from ...wrappers import EnvState, NativeMarlEnv
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the data-parallel group (1 process per GPU)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _u32(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32)).to(device)
+
+
+class FFLearner:
+    """Device buffers + the kernel schedule of one GPU's share of the Anakin learner."""
+
+    def __init__(self, env: NativeMarlEnv, actor: FeedForwardActor, critic: FeedForwardValueNet,
+                 config, centralised_critic: bool, device: torch.device):
+        s = config.system
+        self.env, self.config, self.device = env, config, device
+        self.rank, self.world = world()
+        self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
+            config.arch.num_envs)
+        self.NE = self.U * self.E
+        self.A, self.FR, self.N = env.num_agents, env.native.view_dim, env.action_dim
+        self.epochs, self.nmb = int(s.ppo_epochs), int(s.num_minibatches)
+        if (self.T * self.E) % self.nmb != 0:
+            raise ValueError("rollout_length * num_envs must be divisible by num_minibatches")
+        self.mb = self.T * self.E // self.nmb
+        add_id = bool(s.add_agent_id)
+        self.actor_desc = actor.desc(self.A, self.FR, add_id, native.IN_AGENT_VIEW)
+        self.critic_desc = critic.desc(
+            self.A, self.FR, add_id, native.IN_GLOBAL if centralised_critic else native.IN_AGENT_VIEW)
+        self.na = native.mlp_param_count(self.actor_desc)
+        self.nc = native.mlp_param_count(self.critic_desc)
+        self.hyper = PpoHyper(float(s.clip_eps), float(s.ent_coef), float(s.vf_coef))
+        self.use_graph = bool(config.arch.get("use_cuda_graph", True))
+        self.precision = str(config.arch.get("precision", "auto"))
+
+        dev, T, NE, A = device, self.T, self.NE, self.A
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
+        # learner state
+        self.params = z(self.na + self.nc)
+        self.mu, self.nu = z(self.na + self.nc), z(self.na + self.nc)
+        self.counts = z(2, dtype=torch.int32)
+        self.key = z(2, dtype=torch.uint32)
+        self.env_buf = env.native.alloc_state(NE, dev)
+        # rollout buffers (slot t holds the observation step t acts on; slot T the bootstrap obs)
+        self.view = z(T + 1, NE, A, self.FR, dtype=torch.int8)
+        self.mask = z(T + 1, NE, A, dtype=torch.uint8)
+        self.action = z(T, NE, A, dtype=torch.int8)
+        self.logp, self.value, self.reward = z(T, NE, A), z(T, NE, A), z(T, NE, A)
+        self.done = z(T, NE, dtype=torch.uint8)
+        self.ep_ret = z(T, NE)
+        self.ep_len = z(T, NE, dtype=torch.int32)
+        self.last_val = z(NE, A)
+        self.adv, self.targets = z(T, NE, A), z(T, NE, A)
+        # scratch
+        self.policy_keys = z(T, 2, dtype=torch.uint32)
+        self.key3 = z(3, 2, dtype=torch.uint32)
+        self.key2 = z(2, 2, dtype=torch.uint32)
+        self.bits = z(T * self.E, dtype=torch.uint32)
+        self.rows = z(self.U * self.mb, dtype=torch.int32)
+        self.grad = z(self.na + self.nc + 8)
+        self.loss_buf = z(self.epochs, self.nmb, 5)
+        self.workspace = z(native.ppo_workspace_bytes(self.actor_desc, self.critic_desc,
+                                                      self.U * self.mb), dtype=torch.uint8)
+        n = T * self.E
+        self.perm_rounds = int(math.ceil(3 * math.log(max(1, n)) / math.log(2 ** 32 - 1)))
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_update = 0  # mava_b200 kernels per update (counted on the first run)
+        self.time_loss_grad = None  # list of (start, end) CUDA events when profiling (bench.py)
+        self.compute_dtype = "f32"
+        self.dominant_kernel = "ppo_loss_grad (fp32 mlp_fwd/mlp_bwd/mlp_wgrad kernels)"
+        lr_decay = bool(s.decay_learning_rates)
+        self.lr_decay_updates = int(s.num_updates) if lr_decay else 0
+
+    # -- views of the state ---------------------------------------------------------------------
+    @property
+    def actor_params(self) -> torch.Tensor:
+        return self.params[: self.na]
+
+    @property
+    def critic_params(self) -> torch.Tensor:
+        return self.params[self.na:]
+
+    def learner_state(self) -> LearnerState:
+        na = self.na
+        params = Params(self.params[:na], self.params[na:])
+        opt = OptStates({"mu": self.mu[:na], "nu": self.nu[:na], "count": self.counts[0:1]},
+                        {"mu": self.mu[na:], "nu": self.nu[na:], "count": self.counts[1:2]})
+        env_state = EnvState(self.env_buf, self.view[0], self.mask[0])
+        steps = self.env.step_count(env_state)
+        obs = self.env.decode_observation(self.view[0], self.mask[0], steps)
+        ts = TimeStep(torch.full((self.NE,), StepType.MID, dtype=torch.int8, device=self.device),
+                      self.reward[-1], torch.ones(self.NE, self.A, device=self.device), obs, {})
+        return LearnerState(params, opt, self.key, env_state, ts)
+
+    # -- kernels --------------------------------------------------------------------------------
+    def _rollout(self) -> None:
+        """ff_mappo.py:76-106: T acting + env steps, then the bootstrap value (:110)."""
+        envn = self.env.native
+        native.prng_split_chain(self.key, self.policy_keys, self.T)
+        for t in range(self.T):
+            native.ff_act(self.actor_desc, self.actor_params, self.critic_desc, self.critic_params,
+                          self.view[t], self.mask[t], self.policy_keys[t], self.E, self.NE,
+                          self.action[t], self.logp[t], self.value[t])
+            envn.step(self.env_buf, self.action[t], self.view[t + 1], self.mask[t + 1],
+                      self.reward[t], self.done[t], self.ep_ret[t], self.ep_len[t], self.NE, True)
+        native.ff_value(self.critic_desc, self.critic_params, self.view[self.T], self.NE,
+                        self.last_val)
+
+    def _permutation(self, shuffle_key: torch.Tensor) -> torch.Tensor:
+        """jax.random.permutation(shuffle_key, T*E) (ff_mappo.py:273): rounds of a stable sort by
+        fresh threefry bits.  The bits come from our kernel; the sort is torch's radix sort."""
+        n = self.T * self.E
+        x = torch.arange(n, dtype=torch.int32, device=self.device)
+        k = shuffle_key
+        for _ in range(self.perm_rounds):
+            native.prng_split(k, self.key2, 2)
+            k = self.key2[0].clone()
+            native.prng_random_bits(self.key2[1], self.bits, n)
+            # unsigned order under a signed sort: flip the top bit
+            order = torch.sort(self.bits.view(torch.int32) ^ (-2 ** 31), stable=True).indices
+            x = x[order]
+        return x
+
+    def _update_epochs(self) -> None:
+        """ff_mappo.py:141-295."""
+        s = self.config.system
+        na, nc = self.na, self.nc
+        scale = 1.0 / self.world
+        steps_per_update = self.epochs * self.nmb
+        for ep in range(self.epochs):
+            native.prng_split(self.key, self.key3, 3)  # key, shuffle_key, entropy_key (:269)
+            self.key.copy_(self.key3[0])
+            perm = self._permutation(self.key3[1])
+            for m in range(self.nmb):
+                native.ppo_minibatch_rows(perm, m, self.mb, self.U, self.E, self.rows)
+                if self.time_loss_grad is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
+                                     self.critic_params, self.hyper, self.view, self.mask,
+                                     self.action, self.logp, self.value, self.adv, self.targets,
+                                     self.rows, self.U, self.mb, self.grad, self.workspace,
+                                     precision=self.precision)
+                if self.time_loss_grad is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.time_loss_grad.append((e0, e1))
+                if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
+                    dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+                native.clip_adam(self.params[:na], self.mu[:na], self.nu[:na], self.counts[0:1],
+                                 self.grad[:na], na, scale, float(s.actor_lr),
+                                 float(s.max_grad_norm), self.lr_decay_updates, steps_per_update)
+                native.clip_adam(self.params[na:], self.mu[na:], self.nu[na:], self.counts[1:2],
+                                 self.grad[na:na + nc], nc, scale, float(s.critic_lr),
+                                 float(s.max_grad_norm), self.lr_decay_updates, steps_per_update)
+                self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
+        if self.world > 1:
+            self.loss_buf.mul_(scale)
+
+    def _update_step(self) -> None:
+        """One ``_update_step`` of the reference (ff_mappo.py:56-300) for all U replicas."""
+        n0 = native.LAUNCHES
+        self._rollout()
+        native.gae(self.reward, self.value, self.done, self.last_val, float(self.config.system.gamma),
+                   float(self.config.system.gae_lambda), self.T, self.NE, self.A, self.adv,
+                   self.targets)
+        self._update_epochs()
+        self.view[0].copy_(self.view[self.T])
+        self.mask[0].copy_(self.mask[self.T])
+        self.launches_per_update = native.LAUNCHES - n0
+
+    # -- CUDA graph -----------------------------------------------------------------------------
+    def _state_tensors(self):
+        return [self.params, self.mu, self.nu, self.counts, self.key, self.env_buf, self.view,
+                self.mask]
+
+    def _capture(self) -> None:
+        snap = [t.clone() for t in self._state_tensors()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up run: lazy initialisation, allocator priming
+            self._update_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for t, c in zip(self._state_tensors(), snap):
+            t.copy_(c)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._update_step()
+        for t, c in zip(self._state_tensors(), snap):  # capture does not execute, but be explicit
+            t.copy_(c)
+        self._graph = g
+
+    # -- public -----------------------------------------------------------------------------------
+    def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+        dev, T, NE = self.device, self.T, self.NE
+        ep_ret = torch.empty(num_updates, T, NE, device=dev)
+        ep_len = torch.empty(num_updates, T, NE, dtype=torch.int32, device=dev)
+        term = torch.empty(num_updates, T, NE, dtype=torch.bool, device=dev)
+        losses = torch.empty(num_updates, self.epochs, self.nmb, 5, device=dev)
+        if self.use_graph and self._graph is None:
+            self._capture()
+        for u in range(num_updates):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._update_step()
+            ep_ret[u].copy_(self.ep_ret)
+            ep_len[u].copy_(self.ep_len)
+            term[u].copy_(self.done)
+            losses[u].copy_(self.loss_buf)
+        shape = lambda x: x.reshape(num_updates, T, self.U, self.E).permute(0, 2, 1, 3)
+        episode_metrics = {"episode_return": shape(ep_ret), "episode_length": shape(ep_len),
+                           "is_terminal_step": shape(term)}
+        train_metrics = {"total_loss": losses[..., 0] + losses[..., 3], "value_loss": losses[..., 4],
+                         "actor_loss": losses[..., 1], "entropy": losses[..., 2]}
+        return episode_metrics, train_metrics
+
+
+def get_learner_fn(learner: FFLearner, config):
+    """The ``learn`` callable of the reference (ff_mappo.py:302-330): LearnerState -> ExperimentOutput.
+    The state's tensors alias the learner's buffers and are advanced in place."""
+
+    def learner_fn(learner_state: LearnerState) -> ExperimentOutput:
+        _adopt(learner, learner_state)
+        n = int(config.system.get("num_updates_per_eval", 1))
+        episode_metrics, train_metrics = learner.learn(n)
+        return ExperimentOutput(learner.learner_state(), episode_metrics, train_metrics)
+
+    return learner_fn
+
+
+def _adopt(learner: FFLearner, st: LearnerState) -> None:
+    """Copy a foreign state (e.g. restored parameters) into the learner's buffers."""
+    pairs = [(learner.params[: learner.na], st.params.actor_params),
+             (learner.params[learner.na:], st.params.critic_params),
+             (learner.key, st.key), (learner.env_buf, st.env_state.buf),
+             (learner.view[0], st.env_state.view), (learner.mask[0], st.env_state.mask)]
+    for dst, src in pairs:
+        if src.data_ptr() != dst.data_ptr():
+            dst.copy_(src)
+
+
+def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
+                  device: Optional[torch.device] = None):
+    """ff_mappo.py:333-432: networks, optimiser state, env reset, replicated learner state."""
+    from ...networks import instantiate
+
+    device = device or env.device
+    rank, n_devices = world()
+    config.system.num_agents = env.num_agents
+    key, actor_net_key, critic_net_key = keys
+
+    actor_torso = instantiate(config.network.actor_network.pre_torso)
+    action_head = instantiate(config.network.action_head, action_dim=env.action_dim)
+    critic_torso = instantiate(config.network.critic_network.pre_torso)
+    actor_network = FeedForwardActor(torso=actor_torso, action_head=action_head)
+    critic_network = FeedForwardValueNet(torso=critic_torso, centralised_critic=centralised_critic)
+
+    learner = FFLearner(env, actor_network, critic_network, config, centralised_critic, device)
+    ap = actor_network.init(actor_net_key, learner.actor_desc.in_dim)
+    cp = critic_network.init(critic_net_key, learner.critic_desc.in_dim)
+    learner.params.copy_(torch.from_numpy(np.concatenate([ap, cp])).to(device))
+
+    # env keys: one per (device, replica, env), this rank takes its block (ff_mappo.py:392-403)
+    per_dev = learner.U * learner.E
+    all_keys = prng.split(key, n_devices * per_dev + 1)
+    key, env_keys = all_keys[0], all_keys[1 + rank * per_dev: 1 + (rank + 1) * per_dev]
+    env.native.reset(_u32(env_keys, device), learner.env_buf, learner.view[0], learner.mask[0],
+                     learner.NE)
+    # the same step key on every replica and device (ff_mappo.py:417-426)
+    key, step_key = prng.split(key)
+    learner.key.copy_(_u32(step_key, device))
+
+    learn = get_learner_fn(learner, config)
+    learn.learner = learner  # type: ignore[attr-defined]
+    return learn, actor_network, learner.learner_state()

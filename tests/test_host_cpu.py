@@ -1,0 +1,155 @@
+"""CPU tests of the host logic: C-ABI symbol table, config composition, network descriptors,
+launcher plumbing under a 2-rank gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    header = open(os.path.join(ROOT, "include", "mava_b200.h")).read()
+    declared = set(re.findall(r"\b(mava_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mava_env_s"}
+    from mava_b200 import _lib
+
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(str(lib_built))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().mava_abi_version() == 1
+    assert b"invalid argument" in _lib.load().mava_error_string(-1)
+
+
+def test_no_compute_without_gpu_is_loud():
+    import torch
+
+    from mava_b200 import native
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        native.prng_random_bits(torch.zeros(2, dtype=torch.uint32),
+                                torch.zeros(4, dtype=torch.uint32), 4)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mava_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), (dirpath, f)
+                assert "oracle/" not in src.replace("``oracle/``", ""), (dirpath, f)
+
+
+def test_env_handle_dims_without_gpu(lib_built):
+    from mava_b200 import native
+
+    env = native.Env.rware(num_agents=4, request_queue_size=4)
+    d = env.dims
+    assert (d.num_agents, d.view_dim, d.num_actions, d.grid_h, d.grid_w, d.aux0) == (4, 66, 5, 11, 10, 32)
+    assert d.state_stride % 16 == 0 and d.algo_bytes_per_step == 586
+    small = native.Env.rware(shelf_rows=2)
+    assert small.dims.aux0 == 80 and small.dims.algo_bytes_per_step == 874
+    tiny2 = native.Env.rware(num_agents=2, request_queue_size=2)
+    assert tiny2.dims.algo_bytes_per_step == 430
+    with pytest.raises(native._lib.MavaNativeError):
+        native.Env.rware(num_agents=40)
+
+
+def test_config_compose_builtin_and_reference_tree():
+    from mava_b200.config import compose
+
+    c = compose("default_ff_mappo.yaml", ["env/scenario=tiny-4ag", "arch.num_envs=2048",
+                                          "system.total_timesteps=~", "+arch.extra=3"])
+    assert c.env.scenario.task_config.num_agents == 4 and c.arch.num_envs == 2048
+    assert c.system.total_timesteps is None and c.arch.extra == 3
+    assert c.logger.system_name == "ff_mappo" and c.logger.checkpointing.save_model is False
+    assert c.network.actor_network.pre_torso._target_ == "mava.networks.MLPTorso"
+    c = compose("default_rec_mappo.yaml", ["env=lbf", "env/scenario=8x8-2p-2f-coop"])
+    assert c.env.scenario.task_config.fov == 8 and c.system.recurrent_chunk_size is None
+    with pytest.raises(KeyError):
+        compose("default_ff_ippo.yaml", ["system.not_a_key=1"])
+    ref = "/root/reference/mava/configs"
+    if os.path.isdir(ref):  # the reference's own YAML tree composes to the same values
+        for name in ("ff_ippo", "ff_mappo", "rec_ippo", "rec_mappo"):
+            for ov in ([], ["env/scenario=small-4ag"], ["env=lbf"]):
+                a = compose(f"default_{name}.yaml", ov).to_container()
+                b = compose(f"default_{name}.yaml", ov, config_dir=ref).to_container()
+                assert a == b, (name, ov)
+
+
+def test_network_descriptors_and_flax_tree():
+    from mava_b200.networks import (DiscreteActionHead, FeedForwardActor, FeedForwardValueNet,
+                                    MLPTorso, instantiate)
+
+    torso = instantiate({"_target_": "mava.networks.MLPTorso", "layer_sizes": [128, 128],
+                         "use_layer_norm": False, "activation": "relu"})
+    assert isinstance(torso, MLPTorso)
+    actor = FeedForwardActor(torso, DiscreteActionHead(5))
+    flat = actor.init(np.array([1, 2], np.uint32), 70)
+    assert flat.size == 70 * 128 + 128 + 128 * 128 + 128 + 128 * 5 + 5 == 26245
+    tree = actor.to_flax_tree(flat, 70)
+    k0 = tree["params"]["torso"]["Dense_0"]["kernel"]
+    np.testing.assert_allclose(k0.T @ k0, 2.0 * np.eye(128) * (70 / 70) if False else k0.T @ k0)
+    # orthogonal(sqrt 2): rows of the (70,128) kernel are orthogonal with squared norm 2
+    np.testing.assert_allclose(k0 @ k0.T, 2.0 * np.eye(70), atol=1e-4)
+    np.testing.assert_array_equal(actor.from_flax_tree(tree), flat)
+    critic = FeedForwardValueNet(torso, centralised_critic=True)
+    assert critic.init(np.array([3, 4], np.uint32), 264).size == 50561
+    with pytest.raises(NotImplementedError):
+        MLPTorso([128, 128], activation="tanh")
+
+
+def test_total_timestep_checker():
+    from mava_b200.config import compose
+    from mava_b200.utils.total_timestep_checker import check_total_timesteps
+
+    c = compose("default_ff_ippo.yaml")
+    check_total_timesteps(c, 8)
+    assert c.system.total_timesteps == 8 * 1000 * 128 * 2 * 16
+    c = compose("default_ff_ippo.yaml", ["system.total_timesteps=1000000"])
+    check_total_timesteps(c, 2)
+    assert c.system.num_updates == 1000000 // 128 // 2 // 16 // 2
+
+
+GLOO_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, os.environ["MAVA_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+from mava_b200 import prng
+from mava_b200.systems.ppo.anakin import world
+from mava_b200.systems.ppo._runner import _gather_metrics
+rank, n = world()
+assert n == 2
+# env-key partition of learner_setup (ff_mappo.py:392-403): disjoint, rank-ordered blocks
+per_dev = 6
+allk = prng.split(prng.PRNGKey(42), n * per_dev + 1)
+mine = torch.from_numpy(allk[1 + rank * per_dev: 1 + (rank + 1) * per_dev].astype(np.int64))
+bufs = [torch.empty_like(mine) for _ in range(n)]
+dist.all_gather(bufs, mine)
+np.testing.assert_array_equal(torch.cat(bufs).numpy().astype(np.uint32), allk[1:])
+# gradient mean: sum all-reduce then 1/world (pmean "device", ff_mappo.py:228-238)
+g = torch.full((5,), float(rank + 1))
+dist.all_reduce(g)
+assert torch.allclose(g / n, torch.full((5,), 1.5))
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK")
+"""
+
+
+def test_two_rank_gloo_partitioning(tmp_path):
+    script = tmp_path / "gloo_check.py"
+    script.write_text(GLOO_SCRIPT)
+    env = dict(os.environ, MAVA_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29611", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
