@@ -192,6 +192,29 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
                    int64_t n, float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
                    int steps_per_update, mava_stream_t s);
 
+/* ------------------------------------------------------------------------------------------
+ * bf16 tensor-core path (tcgen05 + TMEM).  Same regions as mava_ff_act / mava_ppo_loss_grad with
+ * bf16 operands and fp32 accumulation (tolerance 2e-2, BASELINE.json).  Requires h1 == h2 == 128.
+ * The fp32 parameters are first packed into a bf16 image in the shared-memory operand format;
+ * re-pack whenever the parameters change.
+ * ---------------------------------------------------------------------------------------- */
+int64_t mava_mlp_pack_bytes(const mava_mlp_desc* d_host);
+int mava_mlp_pack_bf16(const mava_mlp_desc* d_host, const float* params, void* image,
+                       mava_stream_t s);
+int mava_ff_act_bf16(const mava_mlp_desc* actor_host, const float* actor_params,
+                     const void* actor_image, const mava_mlp_desc* critic_host,
+                     const float* critic_params, const void* critic_image, const int8_t* view,
+                     const uint8_t* mask, const uint32_t* policy_key, int envs_per_replica,
+                     int num_envs, int greedy, const int8_t* actions_in, int8_t* action,
+                     float* logp, float* value, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics.  One 128 x N x K bf16 GEMM on the tcgen05 tensor cores in each operand arrangement
+ * the fused MLP kernels use (0: X W, 1: dZ W^T, 2: H^T dZ); A, B, D are row-major f32.
+ * ---------------------------------------------------------------------------------------- */
+int mava_tc_selftest(int mode, const float* A, const float* B, float* D, int N, int K,
+                     mava_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

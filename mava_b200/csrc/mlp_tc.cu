@@ -1,0 +1,323 @@
+// bf16 tensor-core (tcgen05 + TMEM) actor / critic kernels for sm_100a.
+//
+//   mava_mlp_pack_bf16   fp32 parameters -> bf16 weight image in the shared-memory operand format
+//   mava_ff_act_bf16     acting step: both networks' forward pass + masked categorical sampling
+//
+// One CTA = 128 threads = one 128-row tile; thread t owns tile row t and TMEM lane t.  Weight
+// images are staged into shared memory by bulk (TMA) copies, the int8 observations are expanded to
+// bf16 in shared memory, each layer is a chain of tcgen05.mma (M=128, N=128|16, K=16) issued by one
+// thread into a TMEM accumulator, and the epilogues (bias, relu, softmax, Gumbel arg-max on threefry
+// bits) read the accumulator back with tcgen05.ld.  Actor tiles and critic tiles run as different
+// CTAs of the same launch.
+//
+// Replaces the same reference regions as mlp_f32.cu (mava/networks.py:39-58,88-124,172-207;
+// mava/systems/ppo/ff_mappo.py:81-85) with bf16 operands / fp32 accumulation (tolerance 2e-2).
+#include "mlp_tc.cuh"
+
+namespace mava {
+namespace tcmlp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ params, int in_dim, int k1p, int out,
+                            unsigned char* __restrict__ image) {
+  // W1 [k1p][HID]
+  const float* w1 = params;
+  const float* w2 = w1 + (size_t)in_dim * HID + HID;
+  const float* w3 = w2 + (size_t)HID * HID + HID;
+  const int n1 = k1p * (HID / 8), n2 = HID * (HID / 8), n3 = HID * (NHEAD / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3;
+       i += gridDim.x * blockDim.x) {
+    const float* src;
+    int rows, r, cg, ld, rows_valid, cols_valid;
+    size_t base;
+    if (i < n1) {
+      rows = k1p; r = i % rows; cg = i / rows; src = w1; ld = HID; rows_valid = in_dim;
+      cols_valid = HID; base = 0;
+    } else if (i < n1 + n2) {
+      const int j = i - n1;
+      rows = HID; r = j % rows; cg = j / rows; src = w2; ld = HID; rows_valid = HID;
+      cols_valid = HID; base = (size_t)k1p * HID * 2;
+    } else {
+      const int j = i - n1 - n2;
+      rows = HID; r = j % rows; cg = j / rows; src = w3; ld = out; rows_valid = HID;
+      cols_valid = out; base = (size_t)k1p * HID * 2 + (size_t)HID * HID * 2;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float v[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = cg * 8 + h * 2 + q;
+        v[q] = (r < rows_valid && c < cols_valid) ? src[(size_t)r * ld + c] : 0.0f;
+      }
+      w[h] = pack_bf16(v[0], v[1]);
+    }
+    const size_t off = base + (size_t)(r >> 3) * 128 + (size_t)cg * (rows / 8) * 128 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(image + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// acting kernel
+// ------------------------------------------------------------------------------------------------
+struct ActArgs {
+  NetDesc actor, critic;
+  const unsigned char *actor_img, *critic_img;
+  const int8_t* view;
+  const uint8_t* mask;
+  const uint32_t* policy_key;
+  const int8_t* actions_in;
+  int8_t* action;
+  float *logp, *value;
+  int num_envs, envs_per_replica, greedy;
+  int actor_ctas, critic_ctas;
+};
+
+struct Ctrl {
+  uint64_t wbar;   // weights landed
+  uint64_t mbar;   // MMA chain done
+  uint32_t tmem;
+};
+
+// shared memory: [weights image][X tile][H tile]
+__global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Ctrl ctrl;
+  const int t = threadIdx.x, warp = t >> 5;
+  const bool is_actor = (int)blockIdx.x < p.actor_ctas;
+  const NetDesc& d = is_actor ? p.actor : p.critic;
+  const unsigned char* img = is_actor ? p.actor_img : p.critic_img;
+  const int tile = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
+  const int64_t M = (int64_t)p.num_envs * (d.mode == MAVA_IN_GLOBAL ? 1 : d.A);
+  const int64_t row0 = (int64_t)tile * TM;
+
+  const WImage wi{d.k1p};
+  const uint32_t s_w = smem_u32(smem);
+  const Tile xt{s_w + wi.total(), 128u, (uint32_t)(TM / 8) * 128u};
+  const Tile ht{xt.base + tile_bytes(TM, d.k1p), 128u, (uint32_t)(TM / 8) * 128u};
+
+  if (warp == 0) tmem_alloc<256>(&ctrl.tmem);
+  if (t == 0) {
+    mbar_init(&ctrl.wbar, 1);
+    mbar_init(&ctrl.mbar, 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctrl.tmem;
+  if (t == 0) load_weights(s_w, img, wi.total(), &ctrl.wbar);
+
+  // while acting, rows are (env, agent) for AGENT_VIEW and env for GLOBAL, in buffer order
+  build_x_tile(d, p.view, xt, row0, M,
+               [&](int64_t r) { return d.mode == MAVA_IN_GLOBAL ? r : r / d.A; });
+  fence_proxy_async();
+  mbar_wait(&ctrl.wbar, 0);
+  fence_before_sync();
+  __syncthreads();
+  uint32_t phase = 0;
+  // ---- layer 1
+  if (t == 0) {
+    fence_after_sync();
+    issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
+  }
+  mbar_wait(&ctrl.mbar, phase);
+  phase ^= 1;
+  fence_after_sync();
+  hidden_epilogue(tmem, d.b1, ht);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  // ---- layer 2 (accumulator reused: every thread has drained its lane)
+  if (t == 0) {
+    fence_after_sync();
+    issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HID, false, &ctrl.mbar);
+  }
+  mbar_wait(&ctrl.mbar, phase);
+  phase ^= 1;
+  fence_after_sync();
+  hidden_epilogue(tmem, d.b2, ht);  // layer-2 MMAs have completed: H1 may be overwritten
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  // ---- head
+  if (t == 0) {
+    fence_after_sync();
+    issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HID, false, &ctrl.mbar);
+  }
+  mbar_wait(&ctrl.mbar, phase);
+  fence_after_sync();
+  float out[NHEAD];
+  ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)HID, out);
+
+  const int64_t row = row0 + t;
+  if (row < M) {
+    if (!is_actor) {
+      const float v = out[0] + __ldg(d.b3);
+      if (d.mode == MAVA_IN_GLOBAL) {
+        for (int a = 0; a < d.A; ++a) p.value[row * d.A + a] = v;
+      } else {
+        p.value[row] = v;
+      }
+    } else {
+      const uint8_t mk = p.mask[row];
+      float mx = kF32Min;
+#pragma unroll
+      for (int j = 0; j < NHEAD; ++j) {
+        if (j < d.out) {
+          out[j] = ((mk >> j) & 1) ? out[j] + __ldg(d.b3 + j) : kF32Min;
+          mx = fmaxf(mx, out[j]);
+        }
+      }
+      float se = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NHEAD; ++j)
+        if (j < d.out) se += expf(out[j] - mx);
+      const float lse = mx + logf(se);
+      int a = 0;
+      if (p.actions_in) {
+        a = p.actions_in[row];
+      } else if (p.greedy) {
+        float best = out[0];
+#pragma unroll
+        for (int j = 1; j < NHEAD; ++j)
+          if (j < d.out && out[j] > best) { best = out[j]; a = j; }
+      } else {
+        const Key key{p.policy_key[0], p.policy_key[1]};
+        const int64_t s = row / d.A;
+        const int ag = (int)(row - s * d.A);
+        const int64_t e = s % p.envs_per_replica;
+        const uint32_t size = (uint32_t)p.envs_per_replica * d.A * d.out;
+        const uint32_t base = (uint32_t)((e * d.A + ag) * d.out);
+        float best = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NHEAD; ++j) {
+          if (j < d.out) {
+            const float z = bits_to_gumbel(random_bits_at(key, base + j, size)) + out[j];
+            if (j == 0 || z > best) { best = z; a = j; }
+          }
+        }
+      }
+      float la = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NHEAD; ++j)
+        if (j == a) la = out[j] - lse;
+      p.action[row] = (int8_t)a;
+      p.logp[row] = la;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+
+int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n) {
+  if (!d) return MAVA_E_NULL;
+  if (d->h1 != HID || d->h2 != HID) return MAVA_E_UNSUPPORTED;
+  if (d->out_dim < 1 || d->out_dim > NHEAD) return MAVA_E_UNSUPPORTED;
+  n->mode = d->input_mode;
+  n->add_id = d->add_agent_id;
+  n->A = d->num_agents;
+  n->FR = d->view_dim;
+  n->in_dim = d->in_dim;
+  n->k1p = pad16(d->in_dim + 1);
+  n->out = d->out_dim;
+  if (n->k1p > 304) return MAVA_E_UNSUPPORTED;  // shared-memory budget of the training kernel
+  if (params) {
+    n->b1 = params + (size_t)d->in_dim * HID;
+    n->b2 = n->b1 + HID + (size_t)HID * HID;
+    n->b3 = n->b2 + HID + (size_t)HID * d->out_dim;
+  } else {
+    n->b1 = n->b2 = n->b3 = nullptr;
+  }
+  return 0;
+}
+
+}  // namespace tcmlp
+}  // namespace mava
+
+using namespace mava;
+using namespace mava::tcmlp;
+
+extern "C" {
+
+int64_t mava_mlp_pack_bytes(const mava_mlp_desc* d) {
+  NetDesc n;
+  if (make_net(d, nullptr, &n)) return -1;
+  return (int64_t)WImage{n.k1p}.total();
+}
+
+int mava_mlp_pack_bf16(const mava_mlp_desc* d, const float* params, void* image,
+                       mava_stream_t s) {
+  NetDesc n;
+  int rc = make_net(d, params, &n);
+  if (rc) return rc;
+  MAVA_CHECK_PTR(params);
+  MAVA_CHECK_PTR(image);
+  pack_kernel<<<32, 256, 0, as_stream(s)>>>(params, n.in_dim, n.k1p, n.out,
+                                            static_cast<unsigned char*>(image));
+  return launch_status();
+}
+
+int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, const void* actor_image,
+                     const mava_mlp_desc* critic, const float* critic_params,
+                     const void* critic_image, const int8_t* view, const uint8_t* mask,
+                     const uint32_t* policy_key, int envs_per_replica, int num_envs, int greedy,
+                     const int8_t* actions_in, int8_t* action, float* logp, float* value,
+                     mava_stream_t s) {
+  ActArgs a{};
+  int rc = make_net(actor, actor_params, &a.actor);
+  if (rc) return rc;
+  MAVA_CHECK_PTR(actor_params);
+  MAVA_CHECK_PTR(actor_image);
+  MAVA_CHECK_PTR(view);
+  MAVA_CHECK_PTR(mask);
+  MAVA_CHECK_PTR(action);
+  MAVA_CHECK_PTR(logp);
+  MAVA_CHECK_ARG(num_envs > 0 && envs_per_replica > 0);
+  MAVA_CHECK_ARG(actor->input_mode == MAVA_IN_AGENT_VIEW);
+  if (!greedy && !actions_in) MAVA_CHECK_PTR(policy_key);
+  a.actor_img = static_cast<const unsigned char*>(actor_image);
+  a.actor_ctas = (int)ceil_div64((int64_t)num_envs * actor->num_agents, TM);
+  int k1p_max = a.actor.k1p;
+  if (value) {
+    rc = make_net(critic, critic_params, &a.critic);
+    if (rc) return rc;
+    MAVA_CHECK_PTR(critic_params);
+    MAVA_CHECK_PTR(critic_image);
+    MAVA_CHECK_ARG(critic->out_dim == 1);
+    a.critic_img = static_cast<const unsigned char*>(critic_image);
+    const int64_t rows = (int64_t)num_envs * (critic->input_mode == MAVA_IN_GLOBAL ? 1 : critic->num_agents);
+    a.critic_ctas = (int)ceil_div64(rows, TM);
+    if (a.critic.k1p > k1p_max) k1p_max = a.critic.k1p;
+  }
+  a.view = view;
+  a.mask = mask;
+  a.policy_key = policy_key;
+  a.actions_in = actions_in;
+  a.action = action;
+  a.logp = logp;
+  a.value = value;
+  a.num_envs = num_envs;
+  a.envs_per_replica = envs_per_replica;
+  a.greedy = greedy;
+  const size_t smem = (size_t)WImage{k1p_max}.total() + tile_bytes(TM, k1p_max) +
+                      tile_bytes(TM, HCOLS) + 128;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  act_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem, as_stream(s)>>>(a);
+  return launch_status();
+}
+
+}  // extern "C"

@@ -249,3 +249,46 @@ def clip_adam(params, mu, nu, count, grad, n: int, grad_scale: float, lr: float,
         _p(nu, torch.float32, n, "nu"), _p(count, torch.int32, 1, "count"),
         _p(grad, torch.float32, n, "grad"), n, grad_scale, lr, max_norm, lr_decay_num_updates,
         steps_per_update, _stream()), "mava_clip_adam")
+
+
+def tc_selftest(mode: int, A, B, D, N: int, K: int) -> None:
+    _count(1)
+    check(_lib.load().mava_tc_selftest(mode, _p(A, torch.float32, None, "A"),
+                                       _p(B, torch.float32, None, "B"),
+                                       _p(D, torch.float32, 128 * N, "D"), N, K, _stream()),
+          "mava_tc_selftest")
+
+
+def mlp_pack_bytes(d: MlpDesc) -> int:
+    n = int(_lib.load().mava_mlp_pack_bytes(C.byref(d)))
+    if n < 0:
+        raise _lib.MavaNativeError("mava_mlp_pack_bytes: network not supported by the bf16 path "
+                                   "(needs two hidden layers of width 128)")
+    return n
+
+
+def mlp_pack_bf16(d: MlpDesc, params, image) -> None:
+    _count(1)
+    check(_lib.load().mava_mlp_pack_bf16(
+        C.byref(d), _p(params, torch.float32, mlp_param_count(d), "params"),
+        _p(image, torch.uint8, mlp_pack_bytes(d), "image"), _stream()), "mava_mlp_pack_bf16")
+
+
+def ff_act_bf16(actor: MlpDesc, actor_params, actor_image, critic: Optional[MlpDesc], critic_params,
+                critic_image, view, mask, policy_key, envs_per_replica: int, num_envs: int, action,
+                logp, value=None, greedy: bool = False, actions_in=None) -> None:
+    A = actor.num_agents
+    _count(1)
+    check(_lib.load().mava_ff_act_bf16(
+        C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"),
+        C.byref(critic) if critic is not None else None,
+        _p(critic_params, torch.float32, mlp_param_count(critic) if critic is not None else None,
+           "critic_params"),
+        _p(critic_image, torch.uint8, mlp_pack_bytes(critic) if critic is not None else None,
+           "critic_image"),
+        _p(view, torch.int8, num_envs * A * actor.view_dim, "view"),
+        _p(mask, torch.uint8, num_envs * A, "mask"), _p(policy_key, torch.uint32, 2, "policy_key"),
+        envs_per_replica, num_envs, int(greedy), _p(actions_in, torch.int8, num_envs * A, "actions_in"),
+        _p(action, torch.int8, num_envs * A, "action"), _p(logp, torch.float32, num_envs * A, "logp"),
+        _p(value, torch.float32, num_envs * A, "value"), _stream()), "mava_ff_act_bf16")
