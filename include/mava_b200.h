@@ -208,6 +208,19 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor_host, const float* actor_params,
                      int num_envs, int greedy, const int8_t* actions_in, int8_t* action,
                      float* logp, float* value, mava_stream_t s);
 
+/* Fused forward + loss + backward of one minibatch on the tensor cores; same contract and
+ * grad_out layout as mava_ppo_loss_grad.  workspace >= mava_ppo_workspace_bytes_bf16(...). */
+int64_t mava_ppo_workspace_bytes_bf16(const mava_mlp_desc* actor_host,
+                                      const mava_mlp_desc* critic_host, int rows_total);
+int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor_host, const float* actor_params,
+                            const void* actor_image, const mava_mlp_desc* critic_host,
+                            const float* critic_params, const void* critic_image,
+                            const mava_ppo_hyper* hyper_host, const int8_t* view,
+                            const uint8_t* mask, const int8_t* action, const float* old_logp,
+                            const float* old_value, const float* adv, const float* targets,
+                            const int32_t* rows, int num_replicas, int mb_size, float* grad_out,
+                            void* workspace, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Diagnostics.  One 128 x N x K bf16 GEMM on the tcgen05 tensor cores in each operand arrangement
  * the fused MLP kernels use (0: X W, 1: dZ W^T, 2: H^T dZ); A, B, D are row-major f32.

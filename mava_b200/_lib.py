@@ -71,6 +71,10 @@ SIGNATURES = {
     "mava_ff_act_bf16": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void, c_void,
                                  c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void,
                                  c_void, c_void]),
+    "mava_ppo_workspace_bytes_bf16": (c_i64, [P(MlpDesc), P(MlpDesc), c_int]),
+    "mava_ppo_loss_grad_bf16": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void,
+                                        P(PpoHyper)] + [c_void] * 8 +
+                                [c_int, c_int, c_void, c_void, c_void]),
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
     "mava_clip_adam": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32,
                                c_int, c_int, c_void]),

@@ -609,6 +609,22 @@ int launch_fwd(const FwdArgs& a, cudaStream_t s) {
 }
 
 }  // namespace
+
+// shared with the bf16 path (ppo_tc.cu)
+int launch_adv_stats(const float* adv, const int32_t* rows, int mb_size, int A, int num_replicas,
+                     double* stats, cudaStream_t s) {
+  dim3 grid((unsigned)min((int64_t)sm_count() * 2, ceil_div64((int64_t)mb_size * A, 256)),
+            (unsigned)num_replicas);
+  adv_stats_kernel<<<grid, 256, 0, s>>>(adv, rows, mb_size, A, stats);
+  return launch_status();
+}
+
+int launch_finalize_loss(const double* acc, double denom, float ent_coef, float vf_coef, float* out5,
+                         cudaStream_t s) {
+  finalize_loss_kernel<<<1, 32, 0, s>>>(acc, denom, ent_coef, vf_coef, out5);
+  return launch_status();
+}
+
 }  // namespace mava
 
 using namespace mava;

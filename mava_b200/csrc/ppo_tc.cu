@@ -1,0 +1,575 @@
+// Fused PPO minibatch kernel on the tcgen05 tensor cores (bf16 operands, fp32 TMEM accumulators).
+//
+// Replaces value_and_grad(_actor_loss_fn) + value_and_grad(_critic_loss_fn) + pmean("batch")
+// (mava/systems/ppo/ff_mappo.py:150-234) for one minibatch:
+//
+//   ppo_fused_kernel   persistent CTAs, actor tiles and critic tiles as different CTAs of one launch.
+//     per 128-row tile:   gather int8 obs rows through the shuffle index (no shuffled copy is ever
+//                         materialised) -> X tile
+//                         H1 = relu(X W1 + b1), H2 = relu(H1 W2 + b2), out = H2 W3 + b3
+//                         loss epilogue in registers (softmax / clip / entropy | clipped value loss)
+//                         dZ3 -> dH2 = dZ3 W3^T ; dW3 += H2^T dZ3          (accumulated in TMEM)
+//                         dZ2 = dH2 * relu' -> dH1 = dZ2 W2^T ; dW2^T,db2 += dZ2^T [H1 | 1]  (TMEM)
+//                         dZ1 = dH1 * relu' -> bf16 tile image in HBM
+//     at the end:         TMEM weight-gradient accumulators -> fp32 atomics into the gradient buffer
+//   ppo_wgrad1_kernel  first-layer gradient: dW1^T,db1 += dZ1^T [X | 1] over all tiles (TMEM), with the
+//                      dZ1 tile images brought in by bulk (TMA) copies and X rebuilt from the int8 obs.
+//
+// Every activation / gradient tile is stored once in shared memory and consumed by up to three GEMMs
+// (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.
+#include <cstdlib>
+
+#include "mlp_tc.cuh"
+
+namespace mava {
+// from mlp_f32.cu
+int launch_adv_stats(const float* adv, const int32_t* rows, int mb_size, int A, int num_replicas,
+                     double* stats, cudaStream_t s);
+int launch_finalize_loss(const double* acc, double denom, float ent_coef, float vf_coef, float* out5,
+                         cudaStream_t s);
+
+namespace tcmlp {
+int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n);
+
+namespace {
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t COL_ACC = 0, COL_HEAD = 128, COL_DW3 = 144, COL_DW2 = 160;  // dW2: 144 columns
+constexpr uint32_t kRegionMin = tile_bytes(TM, HCOLS) + tile_bytes(TM, HID);   // H2 + dZ2
+
+struct TrainArgs {
+  NetDesc actor, critic;
+  const unsigned char *actor_img, *critic_img;
+  const int8_t* view;
+  const uint8_t* mask;
+  const int8_t* action;
+  const float *old_logp, *old_value, *adv, *targets;
+  const int32_t* rows;
+  const double* adv_stats;
+  int R, mb_size, num_replicas;
+  float clip_eps, ent_coef, vf_coef;
+  int actor_ctas, critic_ctas;
+  float *grad_actor, *grad_critic;
+  double* loss_acc;
+  unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
+  int debug_stop;  // MAVA_TC_DEBUG: leave the tile loop after this stage (0 = off)
+};
+
+struct Ctrl {
+  uint64_t wbar, mbar;
+  uint32_t tmem;
+  float db3[NHEAD];
+};
+
+__host__ __device__ inline uint32_t region_bytes(int k1p) {
+  const uint32_t x = tile_bytes(TM, k1p);
+  return x > kRegionMin ? x : kRegionMin;
+}
+
+// dH (TMEM accumulator row) * relu mask -> bf16 row, written either into a shared-memory tile
+// (TO_GLOBAL = false) or into a tile image in global memory.
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void grad_epilogue(uint32_t tmem_acc, const RowMask& m, const Tile& dst,
+                                              unsigned char* gdst) {
+  const int t = threadIdx.x, warp = t >> 5;
+#pragma unroll
+  for (int q = 0; q < HID / 32; ++q) {
+    float v[32];
+    ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((m.w[q] >> j) & 1u) ? v[j] : 0.0f;
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      const uint32_t a = pack_bf16(v[cg * 8], v[cg * 8 + 1]), b = pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]),
+                     c = pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]), d = pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]);
+      const uint32_t off = chunk_off(dst, t, q * 4 + cg);
+      if (TO_GLOBAL) *reinterpret_cast<uint4*>(gdst + off) = make_uint4(a, b, c, d);
+      else st_shared_v4(dst.base + off, a, b, c, d);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Ctrl ctrl;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool is_actor = (int)blockIdx.x < p.actor_ctas;
+  const NetDesc& d = is_actor ? p.actor : p.critic;
+  const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
+  const int n_ctas = is_actor ? p.actor_ctas : p.critic_ctas;
+  const int rows_per_step = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
+  const int64_t M = (int64_t)p.R * rows_per_step;
+  const int n_tiles = (int)ceil_div64(M, TM);
+
+  // shared memory: [weights][region: X, later H2 + dZ2][H1][dZ3]
+  const WImage wi{d.k1p};
+  const uint32_t s_w = smem_u32(smem);
+  const uint32_t s_region = s_w + wi.total();
+  const Tile xt{s_region, 128u, 2048u};
+  const Tile h2t{s_region, 128u, 2048u};
+  const Tile dz2t{s_region + tile_bytes(TM, HCOLS), 128u, 2048u};
+  const Tile h1t{s_region + region_bytes(d.k1p), 128u, 2048u};
+  const Tile dz3t{h1t.base + tile_bytes(TM, HCOLS), 128u, 2048u};
+  const Tile w1 = w1_tile(s_w, d.k1p), w2 = w2_tile(s_w, d.k1p), w3 = w3_tile(s_w, d.k1p);
+
+  if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
+  if (t == 0) {
+    mbar_init(&ctrl.wbar, 1);
+    mbar_init(&ctrl.mbar, 1);
+    fence_mbar_init();
+  }
+  if (t < NHEAD) ctrl.db3[t] = 0.0f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctrl.tmem;
+  if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
+  mbar_wait(&ctrl.wbar, 0);
+
+  uint32_t phase = 0;
+  double l0 = 0.0, l1 = 0.0;
+  const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
+  bool first = true;
+  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
+    const int64_t row0 = (int64_t)tile * TM;
+    const int64_t row = row0 + t;
+    const bool valid = row < M;
+    const int64_t j = valid ? row / rows_per_step : 0;  // position in the minibatch
+    const int ag = (int)(row - j * rows_per_step);
+    const int64_t s = valid ? p.rows[j] : 0;            // env-step index in the rollout buffers
+    const int64_t flat = s * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
+
+    build_x_tile(d, p.view, xt, row0, M, [&](int64_t r) { return (int64_t)p.rows[r / rows_per_step]; });
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    // ---- forward
+    if (t == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    const RowMask m1 = hidden_epilogue(tmem + COL_ACC, d.b1, h1t);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (p.debug_stop == 1) break;
+    if (t == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HID, false, &ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    const RowMask m2 = hidden_epilogue(tmem + COL_ACC, d.b2, h2t);  // X is dead: H2 takes its place
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (p.debug_stop == 2) break;
+    if (t == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HID, false, &ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---- loss epilogue: d(total loss)/d(head output) for this row
+    float out[NHEAD], dz[NHEAD];
+    ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_HEAD, out);
+#pragma unroll
+    for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
+    if (valid) {
+      if (!is_actor) {
+        // _critic_loss_fn, ff_mappo.py:190-201
+        const float v = out[0] + __ldg(d.b3);
+        const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
+        float dv = 0.0f;
+        for (int a = 0; a < reps; ++a) {
+          const float vo = p.old_value[flat + a], tg = p.targets[flat + a];
+          const float diff = v - vo;
+          const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
+          const float e1 = v - tg, e2 = vc - tg;
+          const float a1 = e1 * e1, a2 = e2 * e2;
+          const bool inside = diff > -p.clip_eps && diff < p.clip_eps;
+          float g;
+          if (a1 > a2) g = e1;
+          else if (a2 > a1) g = inside ? e2 : 0.0f;
+          else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
+          dv += g;
+          l0 += 0.5 * (double)fmaxf(a1, a2);
+        }
+        dz[0] = dv * wrow * p.vf_coef;
+      } else {
+        // _actor_loss_fn, ff_mappo.py:159-180
+        const uint8_t mk = p.mask[flat];
+        float mx = kF32Min;
+#pragma unroll
+        for (int q = 0; q < NHEAD; ++q) {
+          if (q < d.out) {
+            out[q] = ((mk >> q) & 1) ? out[q] + __ldg(d.b3 + q) : kF32Min;
+            mx = fmaxf(mx, out[q]);
+          }
+        }
+        float se = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NHEAD; ++q)
+          if (q < d.out) se += expf(out[q] - mx);
+        const float lse = mx + logf(se);
+        const int a = p.action[flat];
+        const int u = (int)(j / p.mb_size);
+        const double cnt = (double)p.mb_size * d.A;
+        const double mean_d = p.adv_stats[2 * u] / cnt;
+        const double var_d = fmax(p.adv_stats[2 * u + 1] / cnt - mean_d * mean_d, 0.0);
+        const float mean = (float)mean_d, sd = (float)sqrt(var_d);
+        float logp[NHEAD], pr[NHEAD];
+        float la = 0.0f, ent = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NHEAD; ++q) {
+          logp[q] = 0.0f;
+          pr[q] = 0.0f;
+          if (q < d.out) {
+            logp[q] = out[q] - lse;
+            pr[q] = expf(logp[q]);
+            if (pr[q] != 0.0f) ent -= pr[q] * logp[q];
+            if (q == a) la = logp[q];
+          }
+        }
+        const float ratio = expf(la - p.old_logp[flat]);
+        const float g = (p.adv[flat] - mean) / (sd + 1e-8f);
+        const float lo = 1.0f - p.clip_eps, hi = 1.0f + p.clip_eps;
+        const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
+        const bool inside = ratio > lo && ratio < hi;
+        float dr;
+        if (t1 < t2) dr = -g;
+        else if (t1 > t2) dr = inside ? -g : 0.0f;
+        else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
+        const float dla = dr * ratio;
+#pragma unroll
+        for (int q = 0; q < NHEAD; ++q) {
+          if (q < d.out && ((mk >> q) & 1)) {
+            float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
+            if (pr[q] != 0.0f) dl += p.ent_coef * pr[q] * (logp[q] + ent);
+            dz[q] = dl * wrow;
+          }
+        }
+        l0 += (double)(-fminf(t1, t2));
+        l1 += (double)ent;
+      }
+    }
+    st_shared_v4(dz3t.base + chunk_off(dz3t, t, 0), pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]),
+                 pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
+    st_shared_v4(dz3t.base + chunk_off(dz3t, t, 1), pack_bf16(dz[8], dz[9]), pack_bf16(dz[10], dz[11]),
+                 pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
+    // head bias gradient: column sums of dZ3 over the tile
+#pragma unroll
+    for (int q = 0; q < NHEAD; ++q) {
+      if (q < d.out) {
+        float sum = dz[q];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) atomicAdd(&ctrl.db3[q], sum);
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (p.debug_stop == 3) break;
+    // ---- backward through the head: dH2 = dZ3 W3^T ; dW3 += H2^T dZ3
+    if (t == 0) {
+      fence_after_sync();
+      if (p.debug_stop != 42 && p.debug_stop != 44) issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
+      if (p.debug_stop != 41 && p.debug_stop != 44) issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
+      commit(&ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    if (p.debug_stop == 43) { fence_before_sync(); __syncthreads(); break; }
+    grad_epilogue<false>(tmem + COL_ACC, m2, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (p.debug_stop == 4 || (p.debug_stop >= 41 && p.debug_stop <= 49)) break;
+    // ---- dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1]
+    if (t == 0) {
+      fence_after_sync();
+      issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, nullptr);
+      issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, &ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    unsigned char* gdst = (is_actor ? p.dz1_actor : p.dz1_critic) + (size_t)tile * tile_bytes(TM, HID);
+    const Tile gimg{0u, 128u, 2048u};
+    grad_epilogue<true>(tmem + COL_ACC, m1, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
+    fence_before_sync();
+    __syncthreads();
+  }
+
+  // ---- flush: TMEM weight-gradient accumulators -> global fp32 gradient (atomics)
+  float* g = is_actor ? p.grad_actor : p.grad_critic;
+  float* gw2 = g + (size_t)d.in_dim * HID + HID;
+  float* gb2 = gw2 + (size_t)HID * HID;
+  float* gw3 = gb2 + HID;
+  float* gb3 = gw3 + (size_t)HID * d.out;
+  if (!first && (p.debug_stop == 0 || (p.debug_stop >= 6 && p.debug_stop < 40))) {
+    fence_after_sync();
+    {  // dW3: lane = hidden unit k, columns = outputs
+      float v[NHEAD];
+      ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW3, v);
+#pragma unroll
+      for (int q = 0; q < NHEAD; ++q)
+        if (q < d.out) atomicAdd(gw3 + (size_t)t * d.out + q, v[q]);
+    }
+    // dW2^T: lane = output unit n, columns = input unit k (column HID = bias gradient)
+#pragma unroll
+    for (int q = 0; q < HID / 32; ++q) {
+      float v[32];
+      ld32(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW2 + (uint32_t)(q * 32), v);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(gw2 + (size_t)(q * 32 + c) * HID + t, v[c]);
+    }
+    {
+      float v[16];
+      ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW2 + HID, v);
+      atomicAdd(gb2 + t, v[0]);
+    }
+    if (t < d.out) atomicAdd(gb3 + t, ctrl.db3[t]);
+  }
+  // loss sums
+  for (int o = 16; o > 0; o >>= 1) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+  }
+  if (lane == 0) {
+    if (is_actor) {
+      atomicAdd(p.loss_acc + 0, l0);
+      atomicAdd(p.loss_acc + 1, l1);
+    } else {
+      atomicAdd(p.loss_acc + 2, l0);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// first-layer weight gradient: [dW1^T | db1] += dZ1^T [X | 1]
+// ------------------------------------------------------------------------------------------------
+struct Wg1Ctrl {
+  uint64_t lbar, mbar;
+  uint32_t tmem;
+};
+
+__global__ void __launch_bounds__(TM, 1) ppo_wgrad1_kernel(const TrainArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Wg1Ctrl ctrl;
+  const int t = threadIdx.x, warp = t >> 5;
+  const bool is_actor = (int)blockIdx.x < p.actor_ctas;
+  const NetDesc& d = is_actor ? p.actor : p.critic;
+  const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
+  const int n_ctas = is_actor ? p.actor_ctas : p.critic_ctas;
+  const int rows_per_step = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
+  const int64_t M = (int64_t)p.R * rows_per_step;
+  const int n_tiles = (int)ceil_div64(M, TM);
+  const unsigned char* dz1 = is_actor ? p.dz1_actor : p.dz1_critic;
+
+  const uint32_t s0 = smem_u32(smem);
+  const Tile dzt{s0, 128u, 2048u};
+  const Tile xt{s0 + tile_bytes(TM, HID), 128u, 2048u};
+  if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
+  if (t == 0) {
+    mbar_init(&ctrl.lbar, 1);
+    mbar_init(&ctrl.mbar, 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctrl.tmem;
+  const int n_lo = d.k1p > 256 ? 256 : d.k1p, n_hi = d.k1p - n_lo;
+  uint32_t phase = 0;
+  bool first = true;
+  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
+    const int64_t row0 = (int64_t)tile * TM;
+    if (t == 0) {
+      mbar_expect_tx(&ctrl.lbar, tile_bytes(TM, HID));
+      bulk_g2s(dzt.base, dz1 + (size_t)tile * tile_bytes(TM, HID), tile_bytes(TM, HID), &ctrl.lbar);
+    }
+    build_x_tile(d, p.view, xt, row0, M, [&](int64_t r) { return (int64_t)p.rows[r / rows_per_step]; });
+    fence_proxy_async();
+    mbar_wait(&ctrl.lbar, phase);
+    fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+      fence_after_sync();
+      // D[n][k] += sum_rows dZ1[row][n] * X[row][k]: A = dZ1 (MN-major), B = X (MN-major)
+      const uint32_t idesc_lo = instr_desc(TM, n_lo, true, true);
+      for (int k = 0; k < TM / 16; ++k)
+        mma(tmem, desc_mnmajor(dzt, k), desc_mnmajor(xt, k), idesc_lo, !first || k > 0);
+      if (n_hi > 0) {
+        const uint32_t idesc_hi = instr_desc(TM, n_hi, true, true);
+        for (int k = 0; k < TM / 16; ++k)
+          mma(tmem + 256, desc_mnmajor(dzt, k), desc_mnmajor(xt, k, 256), idesc_hi, !first || k > 0);
+      }
+      commit(&ctrl.mbar);
+    }
+    mbar_wait(&ctrl.mbar, phase);  // operands are free again once the MMAs have completed
+    phase ^= 1;
+    fence_after_sync();
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (!first) {
+    float* g = is_actor ? p.grad_actor : p.grad_critic;
+    float* gb1 = g + (size_t)d.in_dim * HID;
+    fence_after_sync();
+    for (int c0 = 0; c0 < d.k1p; c0 += 16) {
+      float v[16];
+      ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int k = c0 + c;
+        if (k < d.in_dim) atomicAdd(g + (size_t)k * HID + t, v[c]);
+        else if (k == d.in_dim) atomicAdd(gb1 + t, v[c]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+}
+
+int64_t tile_count(const mava_mlp_desc* d, int rows_total) {
+  const int64_t m = (int64_t)rows_total * (d->input_mode == MAVA_IN_GLOBAL ? 1 : d->num_agents);
+  return ceil_div64(m, TM);
+}
+
+}  // namespace
+}  // namespace tcmlp
+}  // namespace mava
+
+using namespace mava;
+using namespace mava::tcmlp;
+
+extern "C" {
+
+int64_t mava_ppo_workspace_bytes_bf16(const mava_mlp_desc* actor, const mava_mlp_desc* critic,
+                                      int rows_total) {
+  if (!actor || !critic || rows_total <= 0) return -1;
+  return 256 + (tile_count(actor, rows_total) + tile_count(critic, rows_total)) *
+                   (int64_t)tile_bytes(TM, HID);
+}
+
+int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_params,
+                            const void* actor_image, const mava_mlp_desc* critic,
+                            const float* critic_params, const void* critic_image,
+                            const mava_ppo_hyper* hyper, const int8_t* view, const uint8_t* mask,
+                            const int8_t* action, const float* old_logp, const float* old_value,
+                            const float* adv, const float* targets, const int32_t* rows,
+                            int num_replicas, int mb_size, float* grad_out, void* workspace,
+                            mava_stream_t stream) {
+  TrainArgs a{};
+  int rc = make_net(actor, actor_params, &a.actor);
+  if (rc) return rc;
+  rc = make_net(critic, critic_params, &a.critic);
+  if (rc) return rc;
+  MAVA_CHECK_PTR(hyper);
+  MAVA_CHECK_PTR(actor_params);
+  MAVA_CHECK_PTR(critic_params);
+  MAVA_CHECK_PTR(actor_image);
+  MAVA_CHECK_PTR(critic_image);
+  MAVA_CHECK_PTR(view);
+  MAVA_CHECK_PTR(mask);
+  MAVA_CHECK_PTR(action);
+  MAVA_CHECK_PTR(old_logp);
+  MAVA_CHECK_PTR(old_value);
+  MAVA_CHECK_PTR(adv);
+  MAVA_CHECK_PTR(targets);
+  MAVA_CHECK_PTR(rows);
+  MAVA_CHECK_PTR(grad_out);
+  MAVA_CHECK_PTR(workspace);
+  MAVA_CHECK_ARG(num_replicas > 0 && num_replicas <= 8 && mb_size > 0 && critic->out_dim == 1);
+  MAVA_CHECK_ARG(actor->input_mode == MAVA_IN_AGENT_VIEW);
+  cudaStream_t s = as_stream(stream);
+  const int R = num_replicas * mb_size;
+  const int64_t na = mava_mlp_param_count(actor), nc = mava_mlp_param_count(critic);
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  double* stats = reinterpret_cast<double*>(w);
+  double* loss_acc = reinterpret_cast<double*>(w + 128);
+  a.dz1_actor = w + 256;
+  a.dz1_critic = a.dz1_actor + tile_count(actor, R) * (int64_t)tile_bytes(TM, HID);
+  a.actor_img = static_cast<const unsigned char*>(actor_image);
+  a.critic_img = static_cast<const unsigned char*>(critic_image);
+  a.view = view;
+  a.mask = mask;
+  a.action = action;
+  a.old_logp = old_logp;
+  a.old_value = old_value;
+  a.adv = adv;
+  a.targets = targets;
+  a.rows = rows;
+  a.adv_stats = stats;
+  a.R = R;
+  a.mb_size = mb_size;
+  a.num_replicas = num_replicas;
+  a.clip_eps = hyper->clip_eps;
+  a.ent_coef = hyper->ent_coef;
+  a.vf_coef = hyper->vf_coef;
+  a.grad_actor = grad_out;
+  a.grad_critic = grad_out + na;
+  a.loss_acc = loss_acc;
+  {
+    const char* dbg = getenv("MAVA_TC_DEBUG");
+    a.debug_stop = dbg ? atoi(dbg) : 0;
+  }
+
+  // split the SMs between actor and critic tiles in proportion to their estimated cost
+  const int64_t ta = tile_count(actor, R), tcn = tile_count(critic, R);
+  const double ca = (double)ta * ((a.actor.k1p / 16 + 27) * 64.0 + 4500.0);
+  const double cc = (double)tcn * ((a.critic.k1p / 16 + 27) * 64.0 + 4500.0 + 4.0 * a.critic.k1p);
+  const int sms = sm_count();
+  int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
+  n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
+  a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
+  a.critic_ctas = (int)(tcn < sms - n_actor ? tcn : sms - n_actor);
+
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(grad_out, 0, (size_t)(na + nc + 8) * sizeof(float), s);
+  if (e != cudaSuccess) return (int)e;
+  rc = launch_adv_stats(adv, rows, mb_size, actor->num_agents, num_replicas, stats, s);
+  if (rc) return rc;
+
+  const int k1p_max = a.actor.k1p > a.critic.k1p ? a.actor.k1p : a.critic.k1p;
+  const size_t smem_fused = (size_t)WImage{k1p_max}.total() + region_bytes(k1p_max) +
+                            tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
+  const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) + 128;
+  static size_t conf_fused = 0, conf_wg1 = 0;
+  if (smem_fused > conf_fused) {
+    e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_fused);
+    if (e != cudaSuccess) return (int)e;
+    conf_fused = smem_fused;
+  }
+  if (smem_wg1 > conf_wg1) {
+    e = cudaFuncSetAttribute(ppo_wgrad1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_wg1);
+    if (e != cudaSuccess) return (int)e;
+    conf_wg1 = smem_wg1;
+  }
+  ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem_fused, s>>>(a);
+  rc = launch_status();
+  if (rc) return rc;
+  if (a.debug_stop == 0 || (a.debug_stop >= 7 && a.debug_stop < 40)) {
+    ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem_wg1, s>>>(a);
+    rc = launch_status();
+    if (rc) return rc;
+  }
+  return launch_finalize_loss(loss_acc, (double)R * actor->num_agents, hyper->ent_coef,
+                              hyper->vf_coef, grad_out + na + nc, s);
+}
+
+}  // extern "C"

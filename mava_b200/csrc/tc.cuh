@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 
 namespace mava {
 namespace tc {
@@ -163,7 +164,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (spins > (1u << 24)) __trap();
+    if (spins > (1u << 24)) {
+      printf("mava_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, parity);
+      __trap();
+    }
   }
 }
 

@@ -1,6 +1,8 @@
 // Self-test of the tcgen05 operand conventions in tc.cuh: one 128 x N x K GEMM per launch in each
 // of the three operand arrangements the MLP kernels use.  Exposed through the C ABI so the GPU
 // tests can pin descriptor semantics on real hardware before trusting the fused kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -31,7 +33,7 @@ __device__ void fill_tile_f32(const Tile& t, const float* __restrict__ src, int 
 // mode 2: D = A[K][128]^T * B[K][N]        A MN-major, B MN-major  (wgrad     H^T dZ)
 __global__ void __launch_bounds__(128)
 tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B,
-                   float* __restrict__ D, int N, int K) {
+                   float* __restrict__ D, int N, int K, int dcol) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -43,7 +45,7 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
   Tile ta{smem_u32(smem), 128u, (uint32_t)(a_rows / 8) * 128u};
   Tile tb{ta.base + tile_bytes(a_rows, a_cols), 128u, (uint32_t)(b_rows / 8) * 128u};
 
-  if (warp == 0) tmem_alloc<128>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -54,7 +56,8 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_alloc_base = tmem_base_s;
+  const uint32_t tmem = tmem_alloc_base + (uint32_t)dcol;
 
   if (threadIdx.x == 0) {
     const uint32_t idesc = instr_desc(128, N, mode == 2, mode != 1);
@@ -76,7 +79,7 @@ tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restric
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem_alloc_base);
 }
 
 }  // namespace
@@ -94,6 +97,7 @@ extern "C" int mava_tc_selftest(int mode, const float* A, const float* B, float*
   cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  tc_selftest_kernel<<<1, 128, smem, as_stream(s)>>>(mode, A, B, D, N, K);
+  const char* dc = getenv("MAVA_TC_DCOL");
+  tc_selftest_kernel<<<1, 128, smem, as_stream(s)>>>(mode, A, B, D, N, K, dc ? atoi(dc) : 0);
   return launch_status();
 }

@@ -292,3 +292,28 @@ def ff_act_bf16(actor: MlpDesc, actor_params, actor_image, critic: Optional[MlpD
         envs_per_replica, num_envs, int(greedy), _p(actions_in, torch.int8, num_envs * A, "actions_in"),
         _p(action, torch.int8, num_envs * A, "action"), _p(logp, torch.float32, num_envs * A, "logp"),
         _p(value, torch.float32, num_envs * A, "value"), _stream()), "mava_ff_act_bf16")
+
+
+def ppo_workspace_bytes_bf16(actor: MlpDesc, critic: MlpDesc, rows_total: int) -> int:
+    return int(_lib.load().mava_ppo_workspace_bytes_bf16(C.byref(actor), C.byref(critic),
+                                                         rows_total))
+
+
+def ppo_loss_grad_bf16(actor: MlpDesc, actor_params, actor_image, critic: MlpDesc, critic_params,
+                       critic_image, hyper: PpoHyper, view, mask, action, old_logp, old_value, adv,
+                       targets, rows, num_replicas: int, mb_size: int, grad_out, workspace) -> None:
+    na, nc = mlp_param_count(actor), mlp_param_count(critic)
+    need = ppo_workspace_bytes_bf16(actor, critic, num_replicas * mb_size)
+    _count(4)  # adv stats, fused fwd+bwd, first-layer wgrad, loss finalize
+    check(_lib.load().mava_ppo_loss_grad_bf16(
+        C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"), C.byref(critic),
+        _p(critic_params, torch.float32, nc, "critic_params"),
+        _p(critic_image, torch.uint8, mlp_pack_bytes(critic), "critic_image"), C.byref(hyper),
+        _p(view, torch.int8, None, "view"), _p(mask, torch.uint8, None, "mask"),
+        _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
+        _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
+        _p(targets, torch.float32, None, "targets"),
+        _p(rows, torch.int32, num_replicas * mb_size, "rows"), num_replicas, mb_size,
+        _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
+        _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16")

