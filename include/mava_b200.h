@@ -201,6 +201,7 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
 int64_t mava_mlp_pack_bytes(const mava_mlp_desc* d_host);
 int mava_mlp_pack_bf16(const mava_mlp_desc* d_host, const float* params, void* image,
                        mava_stream_t s);
+/* actor_host == NULL evaluates the critic only (bootstrap value). */
 int mava_ff_act_bf16(const mava_mlp_desc* actor_host, const float* actor_params,
                      const void* actor_image, const mava_mlp_desc* critic_host,
                      const float* critic_params, const void* critic_image, const int8_t* view,

@@ -272,20 +272,24 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, cons
                      const int8_t* actions_in, int8_t* action, float* logp, float* value,
                      mava_stream_t s) {
   ActArgs a{};
-  int rc = make_net(actor, actor_params, &a.actor);
-  if (rc) return rc;
-  MAVA_CHECK_PTR(actor_params);
-  MAVA_CHECK_PTR(actor_image);
+  int rc = 0;
   MAVA_CHECK_PTR(view);
-  MAVA_CHECK_PTR(mask);
-  MAVA_CHECK_PTR(action);
-  MAVA_CHECK_PTR(logp);
   MAVA_CHECK_ARG(num_envs > 0 && envs_per_replica > 0);
-  MAVA_CHECK_ARG(actor->input_mode == MAVA_IN_AGENT_VIEW);
-  if (!greedy && !actions_in) MAVA_CHECK_PTR(policy_key);
-  a.actor_img = static_cast<const unsigned char*>(actor_image);
-  a.actor_ctas = (int)ceil_div64((int64_t)num_envs * actor->num_agents, TM);
-  int k1p_max = a.actor.k1p;
+  MAVA_CHECK_ARG(actor != nullptr || value != nullptr);
+  if (actor) {  // actor == NULL: critic only (bootstrap value, ff_mappo.py:110)
+    rc = make_net(actor, actor_params, &a.actor);
+    if (rc) return rc;
+    MAVA_CHECK_PTR(actor_params);
+    MAVA_CHECK_PTR(actor_image);
+    MAVA_CHECK_PTR(mask);
+    MAVA_CHECK_PTR(action);
+    MAVA_CHECK_PTR(logp);
+    MAVA_CHECK_ARG(actor->input_mode == MAVA_IN_AGENT_VIEW);
+    if (!greedy && !actions_in) MAVA_CHECK_PTR(policy_key);
+    a.actor_img = static_cast<const unsigned char*>(actor_image);
+    a.actor_ctas = (int)ceil_div64((int64_t)num_envs * actor->num_agents, TM);
+  }
+  int k1p_max = actor ? a.actor.k1p : 16;
   if (value) {
     rc = make_net(critic, critic_params, &a.critic);
     if (rc) return rc;

@@ -274,20 +274,26 @@ def mlp_pack_bf16(d: MlpDesc, params, image) -> None:
         _p(image, torch.uint8, mlp_pack_bytes(d), "image"), _stream()), "mava_mlp_pack_bf16")
 
 
-def ff_act_bf16(actor: MlpDesc, actor_params, actor_image, critic: Optional[MlpDesc], critic_params,
-                critic_image, view, mask, policy_key, envs_per_replica: int, num_envs: int, action,
-                logp, value=None, greedy: bool = False, actions_in=None) -> None:
-    A = actor.num_agents
+def ff_act_bf16(actor: Optional[MlpDesc], actor_params, actor_image, critic: Optional[MlpDesc],
+                critic_params, critic_image, view, mask, policy_key, envs_per_replica: int,
+                num_envs: int, action, logp, value=None, greedy: bool = False,
+                actions_in=None) -> None:
+    """actor=None evaluates the critic only (the bootstrap value)."""
+    ref = actor if actor is not None else critic
+    A = ref.num_agents
     _count(1)
     check(_lib.load().mava_ff_act_bf16(
-        C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
-        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"),
+        C.byref(actor) if actor is not None else None,
+        _p(actor_params, torch.float32, mlp_param_count(actor) if actor is not None else None,
+           "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor) if actor is not None else None,
+           "actor_image"),
         C.byref(critic) if critic is not None else None,
         _p(critic_params, torch.float32, mlp_param_count(critic) if critic is not None else None,
            "critic_params"),
         _p(critic_image, torch.uint8, mlp_pack_bytes(critic) if critic is not None else None,
            "critic_image"),
-        _p(view, torch.int8, num_envs * A * actor.view_dim, "view"),
+        _p(view, torch.int8, num_envs * A * ref.view_dim, "view"),
         _p(mask, torch.uint8, num_envs * A, "mask"), _p(policy_key, torch.uint32, 2, "policy_key"),
         envs_per_replica, num_envs, int(greedy), _p(actions_in, torch.int8, num_envs * A, "actions_in"),
         _p(action, torch.int8, num_envs * A, "action"), _p(logp, torch.float32, num_envs * A, "logp"),

@@ -91,15 +91,31 @@ class FFLearner:
         self.rows = z(self.U * self.mb, dtype=torch.int32)
         self.grad = z(self.na + self.nc + 8)
         self.loss_buf = z(self.epochs, self.nmb, 5)
-        self.workspace = z(native.ppo_workspace_bytes(self.actor_desc, self.critic_desc,
-                                                      self.U * self.mb), dtype=torch.uint8)
+        # precision: the bf16 tensor-core kernels need two hidden layers of width 128
+        tc_ok = all(d.h1 == 128 and d.h2 == 128 and d.out_dim <= 16
+                    for d in (self.actor_desc, self.critic_desc))
+        if self.precision not in ("auto", "fp32", "bf16"):
+            raise ValueError(f"arch.precision must be auto, fp32 or bf16, got {self.precision}")
+        if self.precision == "bf16" and not tc_ok:
+            raise ValueError("arch.precision=bf16 needs MLP torsos with layer_sizes [128, 128]")
+        self.bf16 = tc_ok and self.precision != "fp32"
+        if self.bf16:
+            self.actor_img = z(native.mlp_pack_bytes(self.actor_desc), dtype=torch.uint8)
+            self.critic_img = z(native.mlp_pack_bytes(self.critic_desc), dtype=torch.uint8)
+            ws_bytes = native.ppo_workspace_bytes_bf16(self.actor_desc, self.critic_desc,
+                                                       self.U * self.mb)
+        else:
+            ws_bytes = native.ppo_workspace_bytes(self.actor_desc, self.critic_desc,
+                                                  self.U * self.mb)
+        self.workspace = z(ws_bytes, dtype=torch.uint8)
         n = T * self.E
         self.perm_rounds = int(math.ceil(3 * math.log(max(1, n)) / math.log(2 ** 32 - 1)))
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0  # mava_b200 kernels per update (counted on the first run)
         self.time_loss_grad = None  # list of (start, end) CUDA events when profiling (bench.py)
-        self.compute_dtype = "f32"
-        self.dominant_kernel = "ppo_loss_grad (fp32 mlp_fwd/mlp_bwd/mlp_wgrad kernels)"
+        self.compute_dtype = "bf16" if self.bf16 else "f32"
+        self.dominant_kernel = ("ppo_fused_kernel + ppo_wgrad1_kernel (tcgen05, bf16)" if self.bf16
+                                else "ppo_loss_grad (fp32 mlp_fwd/mlp_bwd/mlp_wgrad kernels)")
         lr_decay = bool(s.decay_learning_rates)
         self.lr_decay_updates = int(s.num_updates) if lr_decay else 0
 
@@ -129,14 +145,32 @@ class FFLearner:
         """ff_mappo.py:76-106: T acting + env steps, then the bootstrap value (:110)."""
         envn = self.env.native
         native.prng_split_chain(self.key, self.policy_keys, self.T)
+        if self.bf16:
+            self._pack()
         for t in range(self.T):
-            native.ff_act(self.actor_desc, self.actor_params, self.critic_desc, self.critic_params,
-                          self.view[t], self.mask[t], self.policy_keys[t], self.E, self.NE,
-                          self.action[t], self.logp[t], self.value[t])
+            if self.bf16:
+                native.ff_act_bf16(self.actor_desc, self.actor_params, self.actor_img,
+                                   self.critic_desc, self.critic_params, self.critic_img,
+                                   self.view[t], self.mask[t], self.policy_keys[t], self.E, self.NE,
+                                   self.action[t], self.logp[t], self.value[t])
+            else:
+                native.ff_act(self.actor_desc, self.actor_params, self.critic_desc,
+                              self.critic_params, self.view[t], self.mask[t], self.policy_keys[t],
+                              self.E, self.NE, self.action[t], self.logp[t], self.value[t])
             envn.step(self.env_buf, self.action[t], self.view[t + 1], self.mask[t + 1],
                       self.reward[t], self.done[t], self.ep_ret[t], self.ep_len[t], self.NE, True)
-        native.ff_value(self.critic_desc, self.critic_params, self.view[self.T], self.NE,
-                        self.last_val)
+        if self.bf16:
+            native.ff_act_bf16(None, None, None, self.critic_desc, self.critic_params,
+                               self.critic_img, self.view[self.T], None, None, self.E, self.NE,
+                               None, None, self.last_val)
+        else:
+            native.ff_value(self.critic_desc, self.critic_params, self.view[self.T], self.NE,
+                            self.last_val)
+
+    def _pack(self) -> None:
+        """fp32 parameters -> bf16 operand images (after every optimiser step)."""
+        native.mlp_pack_bf16(self.actor_desc, self.actor_params, self.actor_img)
+        native.mlp_pack_bf16(self.critic_desc, self.critic_params, self.critic_img)
 
     def _permutation(self, shuffle_key: torch.Tensor) -> torch.Tensor:
         """jax.random.permutation(shuffle_key, T*E) (ff_mappo.py:273): rounds of a stable sort by
@@ -168,11 +202,17 @@ class FFLearner:
                 if self.time_loss_grad is not None:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
-                                     self.critic_params, self.hyper, self.view, self.mask,
-                                     self.action, self.logp, self.value, self.adv, self.targets,
-                                     self.rows, self.U, self.mb, self.grad, self.workspace,
-                                     precision=self.precision)
+                if self.bf16:
+                    native.ppo_loss_grad_bf16(self.actor_desc, self.actor_params, self.actor_img,
+                                              self.critic_desc, self.critic_params, self.critic_img,
+                                              self.hyper, self.view, self.mask, self.action,
+                                              self.logp, self.value, self.adv, self.targets,
+                                              self.rows, self.U, self.mb, self.grad, self.workspace)
+                else:
+                    native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
+                                         self.critic_params, self.hyper, self.view, self.mask,
+                                         self.action, self.logp, self.value, self.adv, self.targets,
+                                         self.rows, self.U, self.mb, self.grad, self.workspace)
                 if self.time_loss_grad is not None:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
@@ -186,6 +226,8 @@ class FFLearner:
                                  self.grad[na:na + nc], nc, scale, float(s.critic_lr),
                                  float(s.max_grad_norm), self.lr_decay_updates, steps_per_update)
                 self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
+                if self.bf16:
+                    self._pack()
         if self.world > 1:
             self.loss_buf.mul_(scale)
 

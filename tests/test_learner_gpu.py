@@ -24,9 +24,10 @@ def _layers(flat, shapes, dtype=torch.float64):
     return ts, [(ts[0], ts[1]), (ts[2], ts[3]), (ts[4], ts[5])]
 
 
-@pytest.mark.parametrize("system,use_graph", [("ff_mappo", False), ("ff_ippo", False),
-                                              ("ff_mappo", True)])
-def test_one_update_matches_oracle(lib_built, system, use_graph):
+@pytest.mark.parametrize("system,use_graph,precision", [
+    ("ff_mappo", False, "fp32"), ("ff_ippo", False, "fp32"), ("ff_mappo", True, "fp32"),
+    ("ff_mappo", True, "bf16"), ("ff_ippo", False, "bf16")])
+def test_one_update_matches_oracle(lib_built, system, use_graph, precision):
     import importlib
 
     from mava_b200 import prng
@@ -38,7 +39,11 @@ def test_one_update_matches_oracle(lib_built, system, use_graph):
     cfg = compose(f"default_{system}.yaml", [
         "env/scenario=tiny-2ag", "arch.num_envs=8", "system.rollout_length=16",
         "system.ppo_epochs=2", "system.num_minibatches=2", "system.update_batch_size=2",
-        "env.kwargs.time_limit=10", f"+arch.use_cuda_graph={use_graph}"])
+        "env.kwargs.time_limit=10", f"+arch.use_cuda_graph={use_graph}",
+        f"+arch.precision={precision}"])
+    bf16 = precision == "bf16"
+    # fp32 kernels: rtol 1e-5; bf16 tensor-core kernels: 2e-2 of the output scale (BASELINE.json)
+    tol = dict(rtol=2e-2, atol=2e-2) if bf16 else dict(rtol=1e-5, atol=2e-5)
     central = system == "ff_mappo"
     env, _ = make_env.make(cfg, add_global_state=central)
     key, _, ak, ck = prng.split(prng.PRNGKey(3), 4)
@@ -114,10 +119,10 @@ def test_one_update_matches_oracle(lib_built, system, use_graph):
     logits = oppo.actor_logits(al, actor_in(obs_views), mask_bool(obs_masks))
     lp = oppo.categorical_log_prob(logits, torch.tensor(act.astype(np.int64))).detach().numpy()
     val = oppo.critic_value(cl, critic_in(obs_views)).detach().numpy()
-    np.testing.assert_allclose(L.logp.cpu().numpy(), lp, rtol=1e-5, atol=2e-5)
-    np.testing.assert_allclose(L.value.cpu().numpy(), val, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(L.logp.cpu().numpy(), lp, **tol)
+    np.testing.assert_allclose(L.value.cpu().numpy(), val, **tol)
     last_val = oppo.critic_value(cl, critic_in(o_views[T])).detach().numpy()
-    np.testing.assert_allclose(L.last_val.cpu().numpy(), last_val, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(L.last_val.cpu().numpy(), last_val, **tol)
 
     # sampled actions follow the reference key schedule: key, policy_key = split(key) per step
     k = key0
@@ -127,10 +132,10 @@ def test_one_update_matches_oracle(lib_built, system, use_graph):
         g = tf.gumbel(pk, (E, A, N))
         z = np.concatenate([g] * U, 0) + logits[t].detach().numpy().astype(np.float32)
         srt = np.sort(z, -1)
-        safe = (srt[..., -1] - srt[..., -2]) > 1e-4
+        safe = (srt[..., -1] - srt[..., -2]) > (5e-2 if bf16 else 1e-4)
         agree += (np.argmax(z, -1)[safe] == act[t][safe]).sum()
         total += safe.sum()
-    assert agree == total and total > 0.95 * T * NE * A
+    assert agree == total and total > (0.8 if bf16 else 0.95) * T * NE * A
 
     # ---- GAE
     gval = L.value.cpu().numpy()
@@ -138,6 +143,21 @@ def test_one_update_matches_oracle(lib_built, system, use_graph):
                            cfg.system.gamma, cfg.system.gae_lambda)
     np.testing.assert_allclose(L.adv.cpu().numpy(), adv, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(L.targets.cpu().numpy(), tgt, rtol=1e-5, atol=2e-5)
+
+    if bf16:
+        # the bf16 update is checked kernel by kernel against the fp32 kernels (test_tc_gpu.py);
+        # here: the key schedule is the reference's, the parameters moved, the losses are sane
+        kk = k
+        for _ in range(2):
+            kk = tf.split(kk, 3)[0]
+        np.testing.assert_array_equal(L.key.cpu().numpy(), kk)
+        moved = np.abs(L.params.cpu().numpy() - p0).max()
+        assert 1e-4 < moved < 1e-2
+        for name in ("total_loss", "value_loss", "actor_loss", "entropy"):
+            assert torch.isfinite(out.train_metrics[name]).all()
+        ent = out.train_metrics["entropy"][0].cpu().numpy()
+        assert (ent > 0.5).all() and (ent < np.log(5) + 1e-3).all()
+        return
 
     # ---- PPO epochs with the reference's key schedule and permutation
     params = p0.copy()
