@@ -84,10 +84,11 @@ struct Ctrl {
 };
 
 // shared memory: [weights image][X tile][H tile]
-__global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
+__global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Ctrl ctrl;
-  const int t = threadIdx.x, warp = t >> 5;
+  const Lane L;
+  const int t = L.t, warp = L.warp;
   const bool is_actor = (int)blockIdx.x < p.actor_ctas;
   const NetDesc& d = is_actor ? p.actor : p.critic;
   const unsigned char* img = is_actor ? p.actor_img : p.critic_img;
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
   if (t == 0) load_weights(s_w, img, wi.total(), &ctrl.wbar);
 
   // while acting, rows are (env, agent) for AGENT_VIEW and env for GLOBAL, in buffer order
-  build_x_tile(d, p.view, xt, row0, M,
-               [&](int64_t r) { return d.mode == MAVA_IN_GLOBAL ? r : r / d.A; });
+  // (the H tile doubles as the staging area: it is not live before layer 1)
+  build_x_tile(d, p.view, xt, smem + (ht.base - s_w), row0, M, [](int64_t j) { return j; });
   fence_proxy_async();
   mbar_wait(&ctrl.wbar, 0);
   fence_before_sync();
@@ -128,11 +129,11 @@ __global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
   mbar_wait(&ctrl.mbar, phase);
   phase ^= 1;
   fence_after_sync();
-  hidden_epilogue(tmem, d.b1, ht);
+  hidden_epilogue(L, tmem, d.b1, ht);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
-  // ---- layer 2 (accumulator reused: every thread has drained its lane)
+  // ---- layer 2 (accumulator reused: every thread has drained its columns)
   if (t == 0) {
     fence_after_sync();
     issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HID, false, &ctrl.mbar);
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
   mbar_wait(&ctrl.mbar, phase);
   phase ^= 1;
   fence_after_sync();
-  hidden_epilogue(tmem, d.b2, ht);  // layer-2 MMAs have completed: H1 may be overwritten
+  hidden_epilogue(L, tmem, d.b2, ht);  // layer-2 MMAs have completed: H1 may be overwritten
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -151,63 +152,64 @@ __global__ void __launch_bounds__(TM, 1) act_kernel(const ActArgs p) {
   }
   mbar_wait(&ctrl.mbar, phase);
   fence_after_sync();
-  float out[NHEAD];
-  ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)HID, out);
-
-  const int64_t row = row0 + t;
-  if (row < M) {
-    if (!is_actor) {
-      const float v = out[0] + __ldg(d.b3);
-      if (d.mode == MAVA_IN_GLOBAL) {
-        for (int a = 0; a < d.A; ++a) p.value[row * d.A + a] = v;
-      } else {
-        p.value[row] = v;
-      }
-    } else {
-      const uint8_t mk = p.mask[row];
-      float mx = kF32Min;
-#pragma unroll
-      for (int j = 0; j < NHEAD; ++j) {
-        if (j < d.out) {
-          out[j] = ((mk >> j) & 1) ? out[j] + __ldg(d.b3 + j) : kF32Min;
-          mx = fmaxf(mx, out[j]);
+  const int64_t row = row0 + L.r;
+  if (L.q == 0) {  // the first four warps finish the rows (one thread per row)
+    float out[NHEAD];
+    ld16(tmem + L.tmem_lane() + (uint32_t)HID, out);
+    if (row < M) {
+      if (!is_actor) {
+        const float v = out[0] + __ldg(d.b3);
+        if (d.mode == MAVA_IN_GLOBAL) {
+          for (int a = 0; a < d.A; ++a) p.value[row * d.A + a] = v;
+        } else {
+          p.value[row] = v;
         }
-      }
-      float se = 0.0f;
-#pragma unroll
-      for (int j = 0; j < NHEAD; ++j)
-        if (j < d.out) se += expf(out[j] - mx);
-      const float lse = mx + logf(se);
-      int a = 0;
-      if (p.actions_in) {
-        a = p.actions_in[row];
-      } else if (p.greedy) {
-        float best = out[0];
-#pragma unroll
-        for (int j = 1; j < NHEAD; ++j)
-          if (j < d.out && out[j] > best) { best = out[j]; a = j; }
       } else {
-        const Key key{p.policy_key[0], p.policy_key[1]};
-        const int64_t s = row / d.A;
-        const int ag = (int)(row - s * d.A);
-        const int64_t e = s % p.envs_per_replica;
-        const uint32_t size = (uint32_t)p.envs_per_replica * d.A * d.out;
-        const uint32_t base = (uint32_t)((e * d.A + ag) * d.out);
-        float best = 0.0f;
+        const uint8_t mk = p.mask[row];
+        float mx = kF32Min;
 #pragma unroll
         for (int j = 0; j < NHEAD; ++j) {
           if (j < d.out) {
-            const float z = bits_to_gumbel(random_bits_at(key, base + j, size)) + out[j];
-            if (j == 0 || z > best) { best = z; a = j; }
+            out[j] = ((mk >> j) & 1) ? out[j] + __ldg(d.b3 + j) : kF32Min;
+            mx = fmaxf(mx, out[j]);
           }
         }
-      }
-      float la = 0.0f;
+        float se = 0.0f;
 #pragma unroll
-      for (int j = 0; j < NHEAD; ++j)
-        if (j == a) la = out[j] - lse;
-      p.action[row] = (int8_t)a;
-      p.logp[row] = la;
+        for (int j = 0; j < NHEAD; ++j)
+          if (j < d.out) se += expf(out[j] - mx);
+        const float lse = mx + logf(se);
+        int a = 0;
+        if (p.actions_in) {
+          a = p.actions_in[row];
+        } else if (p.greedy) {
+          float best = out[0];
+#pragma unroll
+          for (int j = 1; j < NHEAD; ++j)
+            if (j < d.out && out[j] > best) { best = out[j]; a = j; }
+        } else {
+          const Key key{p.policy_key[0], p.policy_key[1]};
+          const int64_t s = row / d.A;
+          const int ag = (int)(row - s * d.A);
+          const int64_t e = s % p.envs_per_replica;
+          const uint32_t size = (uint32_t)p.envs_per_replica * d.A * d.out;
+          const uint32_t base = (uint32_t)((e * d.A + ag) * d.out);
+          float best = 0.0f;
+#pragma unroll
+          for (int j = 0; j < NHEAD; ++j) {
+            if (j < d.out) {
+              const float z = bits_to_gumbel(random_bits_at(key, base + j, size)) + out[j];
+              if (j == 0 || z > best) { best = z; a = j; }
+            }
+          }
+        }
+        float la = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NHEAD; ++j)
+          if (j == a) la = out[j] - lse;
+        p.action[row] = (int8_t)a;
+        p.logp[row] = la;
+      }
     }
   }
   fence_before_sync();
@@ -229,6 +231,8 @@ int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n) {
   n->k1p = pad16(d->in_dim + 1);
   n->out = d->out_dim;
   if (n->k1p > 304) return MAVA_E_UNSUPPORTED;  // shared-memory budget of the training kernel
+  if (stage_bytes(n->A, n->FR, n->mode == MAVA_IN_GLOBAL ? 1 : n->A) > tile_bytes(TM, HCOLS))
+    return MAVA_E_UNSUPPORTED;  // the observation staging area aliases an activation tile
   if (params) {
     n->b1 = params + (size_t)d->in_dim * HID;
     n->b2 = n->b1 + HID + (size_t)HID * HID;
@@ -320,7 +324,7 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, cons
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  act_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem, as_stream(s)>>>(a);
+  act_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem, as_stream(s)>>>(a);
   return launch_status();
 }
 

@@ -1,5 +1,11 @@
 // Shared pieces of the tcgen05 MLP kernels: packed bf16 weight images, input-tile construction from
 // the int8 observations, and the per-layer GEMM/epilogue building blocks.
+//
+// Thread mapping of every kernel built from these pieces: one CTA = 512 threads = 16 warps works on
+// one 128-row tile.  Warp w reads TMEM lanes 32*(w%4) .. +31 (the hardware restriction) and owns the
+// column quarter w/4, so thread (row r = 32*(w%4)+lane, quarter q = w/4) handles 32 accumulator
+// columns of tile row r in each epilogue.  Four warps per scheduler keep the epilogues from being
+// issue-latency bound while a single elected thread feeds the tensor core.
 #pragma once
 #include "common.cuh"
 #include "prng.cuh"
@@ -10,10 +16,12 @@ namespace tcmlp {
 
 using namespace tc;
 
-constexpr int TM = 128;        // rows per tile (= threads per CTA, thread t owns tile row t)
-constexpr int HID = 128;       // hidden width the tensor-core path supports
+constexpr int TM = 128;          // rows per tile
+constexpr int NT = 512;          // threads per CTA
+constexpr int NWARPS = NT / 32;
+constexpr int HID = 128;         // hidden width the tensor-core path supports
 constexpr int HCOLS = HID + 16;  // activation tiles carry a ones column (bias gradients for free)
-constexpr int NHEAD = 16;      // head width padded to one MMA N step
+constexpr int NHEAD = 16;        // head width padded to one MMA N step
 constexpr float kF32Min = -3.402823466e38f;
 
 __host__ __device__ constexpr int pad16(int x) { return (x + 15) / 16 * 16; }
@@ -44,6 +52,21 @@ struct NetDesc {
   const float *b1, *b2, *b3;                  // fp32 biases inside the flat parameter vector
 };
 
+// Position of the calling thread inside the tile.
+struct Lane {
+  int t, warp, lane;
+  int r;  // tile row (= TMEM lane)
+  int q;  // column quarter
+  __device__ __forceinline__ Lane() {
+    t = threadIdx.x;
+    warp = t >> 5;
+    lane = t & 31;
+    r = (warp & 3) * 32 + lane;
+    q = warp >> 2;
+  }
+  __device__ __forceinline__ uint32_t tmem_lane() const { return (uint32_t)((warp & 3) * 32) << 16; }
+};
+
 // bulk (TMA) copy global -> shared, completion on an mbarrier (complete_tx bytes)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
                                          uint64_t* bar) {
@@ -69,24 +92,73 @@ __device__ __forceinline__ void load_weights(uint32_t dst, const unsigned char* 
   }
 }
 
-// Build the bf16 input tile X[TM][k1p] of one CTA from the int8 observations; thread t fills row t.
-//   step_of_row(r) -> env-step index s of tile row r
-// AGENT_VIEW rows are (s, agent = row % A): x = [onehot(agent) | view[s][agent][:] | 1 | 0...]
-// GLOBAL rows are env-steps:                x = [view[s][0..A)[:]             | 1 | 0...]
+// Build the bf16 input tile X[TM][k1p] of one CTA from the int8 observations.
+//   step_at(j) -> env-step index s of minibatch position j (rows of position j are its A agents
+//   for AGENT_VIEW, or the single joint row for GLOBAL)
+// AGENT_VIEW rows: x = [onehot(agent) | view[s][agent][:] | 1 | 0...]
+// GLOBAL rows:     x = [view[s][0..A)[:]                  | 1 | 0...]
 // The trailing 1 at column in_dim makes the bias gradient fall out of the weight-gradient GEMM
 // (the packed W1 image has a zero row there, so the forward pass is unaffected).
-template <class RowFn>
+//
+// Two phases: (1) the env-steps the tile touches are gathered from HBM into the `stage` scratch
+// area (shared memory, >= stage_bytes()) with asynchronous copies, all in flight at once - one
+// env-step (A*FR contiguous bytes) per warp iteration; (2) thread (r, q) expands every fourth
+// 8-column chunk of row r to bf16.  Contains two __syncthreads().
+__host__ __device__ inline uint32_t stage_bytes(int A, int FR, int rows_per_step) {
+  return ((uint32_t)(TM / rows_per_step + 2) * A * FR + 15) / 16 * 16 + TM * 4 + 16;
+}
+
+template <class StepFn>
 __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __restrict__ view,
-                                             const Tile& xt, int64_t row0, int64_t M,
-                                             RowFn step_of_row) {
-  const int t = threadIdx.x;
-  const int64_t row = row0 + t;
+                                             const Tile& xt, unsigned char* stage, int64_t row0,
+                                             int64_t M, StepFn step_at) {
+  const Lane L;
+  const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
+  const int step_bytes = d.A * d.FR;
+  const int64_t last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
+  const int64_t j0 = row0 / rps;
+  const int nsteps = (int)(last / rps - j0) + 1;
+  // the env-step indices first (one coalesced load), so that the copies below are independent
+  int* steps = reinterpret_cast<int*>(stage + ((size_t)(TM / rps + 2) * step_bytes + 15) / 16 * 16);
+  if (L.t < nsteps) steps[L.t] = (int)step_at(j0 + L.t);
+  __syncthreads();
+  if ((step_bytes & 3) == 0) {
+    const int unit = (step_bytes & 7) == 0 ? 8 : 4;
+    const int units = step_bytes / unit;
+    for (int js = L.warp; js < nsteps; js += NWARPS) {
+      const int8_t* src = view + (size_t)steps[js] * step_bytes;
+      const uint32_t dst = smem_u32(stage) + (uint32_t)js * step_bytes;
+      for (int i = L.lane; i < units; i += 32) {
+        if (unit == 8)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 8), "l"(src + i * 8)
+                       : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * 4), "l"(src + i * 4)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int js = L.warp; js < nsteps; js += NWARPS) {
+      const int8_t* src = view + (size_t)steps[js] * step_bytes;
+      unsigned char* dst = stage + (size_t)js * step_bytes;
+      if ((step_bytes & 1) == 0) {
+        for (int i = L.lane; i < (step_bytes >> 1); i += 32)
+          reinterpret_cast<uint16_t*>(dst)[i] = __ldg(reinterpret_cast<const uint16_t*>(src) + i);
+      } else {
+        for (int i = L.lane; i < step_bytes; i += 32) dst[i] = (unsigned char)__ldg(src + i);
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t row = row0 + L.r;
   const bool valid = row < M;
-  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % d.A);
+  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
   const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
-  const int8_t* src = view;
-  if (valid) src = view + ((size_t)step_of_row(row) * d.A + a) * d.FR;
-  for (int cg = 0; cg < d.k1p / 8; ++cg) {
+  const signed char* mine = reinterpret_cast<const signed char*>(stage) +
+                            (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
+  for (int cg = L.q; cg < d.k1p / 8; cg += 4) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -94,17 +166,17 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
       float x = 0.0f;
       if (valid) {
         if (k < id_cols) x = k == a ? 1.0f : 0.0f;
-        else if (k < d.in_dim) x = (float)__ldg(src + (k - id_cols));
+        else if (k < d.in_dim) x = (float)mine[k - id_cols];
         else if (k == d.in_dim) x = 1.0f;
       }
       v[j] = x;
     }
-    st_shared_v4(xt.base + chunk_off(xt, t, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+    st_shared_v4(xt.base + chunk_off(xt, L.r, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                  pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }
 
-// One thread issues the K/16 MMAs of a GEMM whose A is K-major (rows x K) and commits to `bar`.
+// One thread issues the K/16 MMAs of a GEMM (M = 128) and optionally commits to `bar`.
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool a_mn, const Tile& b,
                                            bool b_mn, int N, int K, bool accumulate,
                                            uint64_t* bar) {
@@ -117,37 +189,29 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool 
   if (bar) commit(bar);
 }
 
-// Hidden-layer epilogue: TMEM accumulator row -> (+bias, relu) -> bf16 activation tile row, with a
-// ones column at HID.  Returns the relu mask of the row (bit c set = unit c active).
-struct RowMask {
-  uint32_t w[HID / 32];
-};
-
-__device__ __forceinline__ RowMask hidden_epilogue(uint32_t tmem_acc, const float* __restrict__ bias,
-                                                   const Tile& ht) {
-  const int t = threadIdx.x, warp = t >> 5;
-  RowMask m;
+// Hidden-layer epilogue for thread (r, q): 32 accumulator columns -> (+bias, relu) -> bf16 into the
+// activation tile (quarter 0 also writes the ones column at HID).  Returns the relu mask of the 32
+// columns (bit c set = unit 32q + c active).
+__device__ __forceinline__ uint32_t hidden_epilogue(const Lane& L, uint32_t tmem_acc,
+                                                    const float* __restrict__ bias, const Tile& ht) {
+  float v[32];
+  ld32(tmem_acc + L.tmem_lane() + (uint32_t)(L.q * 32), v);
+  uint32_t bits = 0;
 #pragma unroll
-  for (int q = 0; q < HID / 32; ++q) {
-    float v[32];
-    ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
-    uint32_t bits = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = fmaxf(v[j] + __ldg(bias + q * 32 + j), 0.0f);
-      bits |= (v[j] > 0.0f ? 1u : 0u) << j;
-    }
-    m.w[q] = bits;
-#pragma unroll
-    for (int cg = 0; cg < 4; ++cg)
-      st_shared_v4(ht.base + chunk_off(ht, t, q * 4 + cg), pack_bf16(v[cg * 8], v[cg * 8 + 1]),
-                   pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]), pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]),
-                   pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]));
+  for (int j = 0; j < 32; ++j) {
+    v[j] = fmaxf(v[j] + __ldg(bias + L.q * 32 + j), 0.0f);
+    bits |= (v[j] > 0.0f ? 1u : 0u) << j;
   }
-  // ones column (bias gradient) + zero padding
-  st_shared_v4(ht.base + chunk_off(ht, t, HID / 8), 0x00003F80u, 0u, 0u, 0u);
-  st_shared_v4(ht.base + chunk_off(ht, t, HID / 8 + 1), 0u, 0u, 0u, 0u);
-  return m;
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg)
+    st_shared_v4(ht.base + chunk_off(ht, L.r, L.q * 4 + cg), pack_bf16(v[cg * 8], v[cg * 8 + 1]),
+                 pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]), pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]),
+                 pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]));
+  if (L.q == 0) {  // ones column (bias gradient) + zero padding
+    st_shared_v4(ht.base + chunk_off(ht, L.r, HID / 8), 0x00003F80u, 0u, 0u, 0u);
+    st_shared_v4(ht.base + chunk_off(ht, L.r, HID / 8 + 1), 0u, 0u, 0u, 0u);
+  }
+  return bits;
 }
 
 }  // namespace tcmlp

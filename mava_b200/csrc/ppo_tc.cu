@@ -16,9 +16,8 @@
 //                      dZ1 tile images brought in by bulk (TMA) copies and X rebuilt from the int8 obs.
 //
 // Every activation / gradient tile is stored once in shared memory and consumed by up to three GEMMs
-// (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.
-#include <cstdlib>
-
+// (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.  Thread
+// mapping: 512 threads per CTA, thread (row r, column quarter q) - see mlp_tc.cuh.
 #include "mlp_tc.cuh"
 
 namespace mava {
@@ -52,7 +51,6 @@ struct TrainArgs {
   float *grad_actor, *grad_critic;
   double* loss_acc;
   unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
-  int debug_stop;  // MAVA_TC_DEBUG: leave the tile loop after this stage (0 = off)
 };
 
 struct Ctrl {
@@ -66,33 +64,30 @@ __host__ __device__ inline uint32_t region_bytes(int k1p) {
   return x > kRegionMin ? x : kRegionMin;
 }
 
-// dH (TMEM accumulator row) * relu mask -> bf16 row, written either into a shared-memory tile
-// (TO_GLOBAL = false) or into a tile image in global memory.
+// dH (32 accumulator columns of row r) * relu mask -> bf16, written either into a shared-memory
+// tile or into a tile image in global memory (same core-matrix layout).
 template <bool TO_GLOBAL>
-__device__ __forceinline__ void grad_epilogue(uint32_t tmem_acc, const RowMask& m, const Tile& dst,
-                                              unsigned char* gdst) {
-  const int t = threadIdx.x, warp = t >> 5;
+__device__ __forceinline__ void grad_epilogue(const Lane& L, uint32_t tmem_acc, uint32_t relu_bits,
+                                              const Tile& dst, unsigned char* gdst) {
+  float v[32];
+  ld32(tmem_acc + L.tmem_lane() + (uint32_t)(L.q * 32), v);
 #pragma unroll
-  for (int q = 0; q < HID / 32; ++q) {
-    float v[32];
-    ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
+  for (int j = 0; j < 32; ++j) v[j] = ((relu_bits >> j) & 1u) ? v[j] : 0.0f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ((m.w[q] >> j) & 1u) ? v[j] : 0.0f;
-#pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      const uint32_t a = pack_bf16(v[cg * 8], v[cg * 8 + 1]), b = pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]),
-                     c = pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]), d = pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]);
-      const uint32_t off = chunk_off(dst, t, q * 4 + cg);
-      if (TO_GLOBAL) *reinterpret_cast<uint4*>(gdst + off) = make_uint4(a, b, c, d);
-      else st_shared_v4(dst.base + off, a, b, c, d);
-    }
+  for (int cg = 0; cg < 4; ++cg) {
+    const uint32_t a = pack_bf16(v[cg * 8], v[cg * 8 + 1]), b = pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]),
+                   c = pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]), d = pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]);
+    const uint32_t off = chunk_off(dst, L.r, L.q * 4 + cg);
+    if (TO_GLOBAL) *reinterpret_cast<uint4*>(gdst + off) = make_uint4(a, b, c, d);
+    else st_shared_v4(dst.base + off, a, b, c, d);
   }
 }
 
-__global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
+__global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Ctrl ctrl;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const Lane L;
+  const int t = L.t, warp = L.warp, lane = L.lane;
   const bool is_actor = (int)blockIdx.x < p.actor_ctas;
   const NetDesc& d = is_actor ? p.actor : p.critic;
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
@@ -101,7 +96,7 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
   const int64_t M = (int64_t)p.R * rows_per_step;
   const int n_tiles = (int)ceil_div64(M, TM);
 
-  // shared memory: [weights][region: X, later H2 + dZ2][H1][dZ3]
+  // shared memory: [weights][region: X, later H2 + dZ2][H1 (also the gather staging area)][dZ3]
   const WImage wi{d.k1p};
   const uint32_t s_w = smem_u32(smem);
   const uint32_t s_region = s_w + wi.total();
@@ -132,14 +127,9 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
   bool first = true;
   for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
     const int64_t row0 = (int64_t)tile * TM;
-    const int64_t row = row0 + t;
-    const bool valid = row < M;
-    const int64_t j = valid ? row / rows_per_step : 0;  // position in the minibatch
-    const int ag = (int)(row - j * rows_per_step);
-    const int64_t s = valid ? p.rows[j] : 0;            // env-step index in the rollout buffers
-    const int64_t flat = s * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
 
-    build_x_tile(d, p.view, xt, row0, M, [&](int64_t r) { return (int64_t)p.rows[r / rows_per_step]; });
+    build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M,
+                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -151,11 +141,10 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
     mbar_wait(&ctrl.mbar, phase);
     phase ^= 1;
     fence_after_sync();
-    const RowMask m1 = hidden_epilogue(tmem + COL_ACC, d.b1, h1t);
+    const uint32_t m1 = hidden_epilogue(L, tmem + COL_ACC, d.b1, h1t);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (p.debug_stop == 1) break;
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HID, false, &ctrl.mbar);
@@ -163,11 +152,10 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
     mbar_wait(&ctrl.mbar, phase);
     phase ^= 1;
     fence_after_sync();
-    const RowMask m2 = hidden_epilogue(tmem + COL_ACC, d.b2, h2t);  // X is dead: H2 takes its place
+    const uint32_t m2 = hidden_epilogue(L, tmem + COL_ACC, d.b2, h2t);  // X is dead: H2 replaces it
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (p.debug_stop == 2) break;
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HID, false, &ctrl.mbar);
@@ -175,122 +163,126 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
     mbar_wait(&ctrl.mbar, phase);
     phase ^= 1;
     fence_after_sync();
-    // ---- loss epilogue: d(total loss)/d(head output) for this row
-    float out[NHEAD], dz[NHEAD];
-    ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_HEAD, out);
+    // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output)
+    if (L.q == 0) {
+      const int64_t row = row0 + L.r;
+      const bool valid = row < M;
+      const int64_t j = valid ? row / rows_per_step : 0;  // position in the minibatch
+      const int ag = (int)(row - j * rows_per_step);
+      const int64_t s = valid ? __ldg(p.rows + j) : 0;    // env-step index in the rollout buffers
+      const int64_t flat = s * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
+      float out[NHEAD], dz[NHEAD];
+      ld16(tmem + L.tmem_lane() + COL_HEAD, out);
 #pragma unroll
-    for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
-    if (valid) {
-      if (!is_actor) {
-        // _critic_loss_fn, ff_mappo.py:190-201
-        const float v = out[0] + __ldg(d.b3);
-        const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
-        float dv = 0.0f;
-        for (int a = 0; a < reps; ++a) {
-          const float vo = p.old_value[flat + a], tg = p.targets[flat + a];
-          const float diff = v - vo;
-          const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
-          const float e1 = v - tg, e2 = vc - tg;
-          const float a1 = e1 * e1, a2 = e2 * e2;
-          const bool inside = diff > -p.clip_eps && diff < p.clip_eps;
-          float g;
-          if (a1 > a2) g = e1;
-          else if (a2 > a1) g = inside ? e2 : 0.0f;
-          else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
-          dv += g;
-          l0 += 0.5 * (double)fmaxf(a1, a2);
-        }
-        dz[0] = dv * wrow * p.vf_coef;
-      } else {
-        // _actor_loss_fn, ff_mappo.py:159-180
-        const uint8_t mk = p.mask[flat];
-        float mx = kF32Min;
-#pragma unroll
-        for (int q = 0; q < NHEAD; ++q) {
-          if (q < d.out) {
-            out[q] = ((mk >> q) & 1) ? out[q] + __ldg(d.b3 + q) : kF32Min;
-            mx = fmaxf(mx, out[q]);
+      for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
+      if (valid) {
+        if (!is_actor) {
+          // _critic_loss_fn, ff_mappo.py:190-201
+          const float v = out[0] + __ldg(d.b3);
+          const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
+          float dv = 0.0f;
+          for (int a = 0; a < reps; ++a) {
+            const float vo = p.old_value[flat + a], tg = p.targets[flat + a];
+            const float diff = v - vo;
+            const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
+            const float e1 = v - tg, e2 = vc - tg;
+            const float a1 = e1 * e1, a2 = e2 * e2;
+            const bool inside = diff > -p.clip_eps && diff < p.clip_eps;
+            float g;
+            if (a1 > a2) g = e1;
+            else if (a2 > a1) g = inside ? e2 : 0.0f;
+            else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
+            dv += g;
+            l0 += 0.5 * (double)fmaxf(a1, a2);
           }
-        }
-        float se = 0.0f;
+          dz[0] = dv * wrow * p.vf_coef;
+        } else {
+          // _actor_loss_fn, ff_mappo.py:159-180
+          const uint8_t mk = p.mask[flat];
+          float mx = kF32Min;
 #pragma unroll
-        for (int q = 0; q < NHEAD; ++q)
-          if (q < d.out) se += expf(out[q] - mx);
-        const float lse = mx + logf(se);
-        const int a = p.action[flat];
-        const int u = (int)(j / p.mb_size);
-        const double cnt = (double)p.mb_size * d.A;
-        const double mean_d = p.adv_stats[2 * u] / cnt;
-        const double var_d = fmax(p.adv_stats[2 * u + 1] / cnt - mean_d * mean_d, 0.0);
-        const float mean = (float)mean_d, sd = (float)sqrt(var_d);
-        float logp[NHEAD], pr[NHEAD];
-        float la = 0.0f, ent = 0.0f;
-#pragma unroll
-        for (int q = 0; q < NHEAD; ++q) {
-          logp[q] = 0.0f;
-          pr[q] = 0.0f;
-          if (q < d.out) {
-            logp[q] = out[q] - lse;
-            pr[q] = expf(logp[q]);
-            if (pr[q] != 0.0f) ent -= pr[q] * logp[q];
-            if (q == a) la = logp[q];
+          for (int q = 0; q < NHEAD; ++q) {
+            if (q < d.out) {
+              out[q] = ((mk >> q) & 1) ? out[q] + __ldg(d.b3 + q) : kF32Min;
+              mx = fmaxf(mx, out[q]);
+            }
           }
-        }
-        const float ratio = expf(la - p.old_logp[flat]);
-        const float g = (p.adv[flat] - mean) / (sd + 1e-8f);
-        const float lo = 1.0f - p.clip_eps, hi = 1.0f + p.clip_eps;
-        const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
-        const bool inside = ratio > lo && ratio < hi;
-        float dr;
-        if (t1 < t2) dr = -g;
-        else if (t1 > t2) dr = inside ? -g : 0.0f;
-        else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
-        const float dla = dr * ratio;
+          float se = 0.0f;
 #pragma unroll
-        for (int q = 0; q < NHEAD; ++q) {
-          if (q < d.out && ((mk >> q) & 1)) {
-            float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
-            if (pr[q] != 0.0f) dl += p.ent_coef * pr[q] * (logp[q] + ent);
-            dz[q] = dl * wrow;
+          for (int q = 0; q < NHEAD; ++q)
+            if (q < d.out) se += expf(out[q] - mx);
+          const float lse = mx + logf(se);
+          const int a = p.action[flat];
+          const int u = (int)(j / p.mb_size);
+          const double cnt = (double)p.mb_size * d.A;
+          const double mean_d = p.adv_stats[2 * u] / cnt;
+          const double var_d = fmax(p.adv_stats[2 * u + 1] / cnt - mean_d * mean_d, 0.0);
+          const float mean = (float)mean_d, sd = (float)sqrt(var_d);
+          float logp[NHEAD], pr[NHEAD];
+          float la = 0.0f, ent = 0.0f;
+#pragma unroll
+          for (int q = 0; q < NHEAD; ++q) {
+            logp[q] = 0.0f;
+            pr[q] = 0.0f;
+            if (q < d.out) {
+              logp[q] = out[q] - lse;
+              pr[q] = expf(logp[q]);
+              if (pr[q] != 0.0f) ent -= pr[q] * logp[q];
+              if (q == a) la = logp[q];
+            }
           }
+          const float ratio = expf(la - p.old_logp[flat]);
+          const float g = (p.adv[flat] - mean) / (sd + 1e-8f);
+          const float lo = 1.0f - p.clip_eps, hi = 1.0f + p.clip_eps;
+          const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
+          const bool inside = ratio > lo && ratio < hi;
+          float dr;
+          if (t1 < t2) dr = -g;
+          else if (t1 > t2) dr = inside ? -g : 0.0f;
+          else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
+          const float dla = dr * ratio;
+#pragma unroll
+          for (int q = 0; q < NHEAD; ++q) {
+            if (q < d.out && ((mk >> q) & 1)) {
+              float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
+              if (pr[q] != 0.0f) dl += p.ent_coef * pr[q] * (logp[q] + ent);
+              dz[q] = dl * wrow;
+            }
+          }
+          l0 += (double)(-fminf(t1, t2));
+          l1 += (double)ent;
         }
-        l0 += (double)(-fminf(t1, t2));
-        l1 += (double)ent;
       }
-    }
-    st_shared_v4(dz3t.base + chunk_off(dz3t, t, 0), pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]),
-                 pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
-    st_shared_v4(dz3t.base + chunk_off(dz3t, t, 1), pack_bf16(dz[8], dz[9]), pack_bf16(dz[10], dz[11]),
-                 pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
-    // head bias gradient: column sums of dZ3 over the tile
+      st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 0), pack_bf16(dz[0], dz[1]),
+                   pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
+      st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 1), pack_bf16(dz[8], dz[9]),
+                   pack_bf16(dz[10], dz[11]), pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
+      // head bias gradient: column sums of dZ3 over the tile
 #pragma unroll
-    for (int q = 0; q < NHEAD; ++q) {
-      if (q < d.out) {
-        float sum = dz[q];
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) atomicAdd(&ctrl.db3[q], sum);
+      for (int q = 0; q < NHEAD; ++q) {
+        if (q < d.out) {
+          float sum = dz[q];
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) atomicAdd(&ctrl.db3[q], sum);
+        }
       }
     }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (p.debug_stop == 3) break;
     // ---- backward through the head: dH2 = dZ3 W3^T ; dW3 += H2^T dZ3
     if (t == 0) {
       fence_after_sync();
-      if (p.debug_stop != 42 && p.debug_stop != 44) issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
-      if (p.debug_stop != 41 && p.debug_stop != 44) issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
-      commit(&ctrl.mbar);
+      issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
+      issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, &ctrl.mbar);
     }
     mbar_wait(&ctrl.mbar, phase);
     phase ^= 1;
     fence_after_sync();
-    if (p.debug_stop == 43) { fence_before_sync(); __syncthreads(); break; }
-    grad_epilogue<false>(tmem + COL_ACC, m2, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
+    grad_epilogue<false>(L, tmem + COL_ACC, m2, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (p.debug_stop == 4 || (p.debug_stop >= 41 && p.debug_stop <= 49)) break;
     // ---- dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1]
     if (t == 0) {
       fence_after_sync();
@@ -302,7 +294,7 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_after_sync();
     unsigned char* gdst = (is_actor ? p.dz1_actor : p.dz1_critic) + (size_t)tile * tile_bytes(TM, HID);
     const Tile gimg{0u, 128u, 2048u};
-    grad_epilogue<true>(tmem + COL_ACC, m1, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
+    grad_epilogue<true>(L, tmem + COL_ACC, m1, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
     fence_before_sync();
     __syncthreads();
   }
@@ -313,27 +305,24 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
   float* gb2 = gw2 + (size_t)HID * HID;
   float* gw3 = gb2 + HID;
   float* gb3 = gw3 + (size_t)HID * d.out;
-  if (!first && (p.debug_stop == 0 || (p.debug_stop >= 6 && p.debug_stop < 40))) {
+  if (!first) {
     fence_after_sync();
-    {  // dW3: lane = hidden unit k, columns = outputs
+    // dW2^T: TMEM lane = output unit n, columns = input unit k (column HID = bias gradient)
+    {
+      float v[32];
+      ld32(tmem + L.tmem_lane() + COL_DW2 + (uint32_t)(L.q * 32), v);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(gw2 + (size_t)(L.q * 32 + c) * HID + L.r, v[c]);
+    }
+    if (L.q == 0) {
       float v[NHEAD];
-      ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW3, v);
+      ld16(tmem + L.tmem_lane() + COL_DW2 + HID, v);
+      atomicAdd(gb2 + L.r, v[0]);
+      // dW3: TMEM lane = hidden unit k, columns = outputs
+      ld16(tmem + L.tmem_lane() + COL_DW3, v);
 #pragma unroll
       for (int q = 0; q < NHEAD; ++q)
-        if (q < d.out) atomicAdd(gw3 + (size_t)t * d.out + q, v[q]);
-    }
-    // dW2^T: lane = output unit n, columns = input unit k (column HID = bias gradient)
-#pragma unroll
-    for (int q = 0; q < HID / 32; ++q) {
-      float v[32];
-      ld32(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW2 + (uint32_t)(q * 32), v);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) atomicAdd(gw2 + (size_t)(q * 32 + c) * HID + t, v[c]);
-    }
-    {
-      float v[16];
-      ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_DW2 + HID, v);
-      atomicAdd(gb2 + t, v[0]);
+        if (q < d.out) atomicAdd(gw3 + (size_t)L.r * d.out + q, v[q]);
     }
     if (t < d.out) atomicAdd(gb3 + t, ctrl.db3[t]);
   }
@@ -342,7 +331,7 @@ __global__ void __launch_bounds__(TM, 1) ppo_fused_kernel(const TrainArgs p) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, o);
     l1 += __shfl_xor_sync(0xffffffffu, l1, o);
   }
-  if (lane == 0) {
+  if (lane == 0 && L.q == 0) {
     if (is_actor) {
       atomicAdd(p.loss_acc + 0, l0);
       atomicAdd(p.loss_acc + 1, l1);
@@ -363,10 +352,11 @@ struct Wg1Ctrl {
   uint32_t tmem;
 };
 
-__global__ void __launch_bounds__(TM, 1) ppo_wgrad1_kernel(const TrainArgs p) {
+__global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Wg1Ctrl ctrl;
-  const int t = threadIdx.x, warp = t >> 5;
+  const Lane L;
+  const int t = L.t, warp = L.warp;
   const bool is_actor = (int)blockIdx.x < p.actor_ctas;
   const NetDesc& d = is_actor ? p.actor : p.critic;
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
@@ -376,9 +366,11 @@ __global__ void __launch_bounds__(TM, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   const int n_tiles = (int)ceil_div64(M, TM);
   const unsigned char* dz1 = is_actor ? p.dz1_actor : p.dz1_critic;
 
+  // shared memory: [dZ1 tile][X tile][gather staging]
   const uint32_t s0 = smem_u32(smem);
   const Tile dzt{s0, 128u, 2048u};
   const Tile xt{s0 + tile_bytes(TM, HID), 128u, 2048u};
+  unsigned char* stage = smem + tile_bytes(TM, HID) + tile_bytes(TM, d.k1p);
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
     mbar_init(&ctrl.lbar, 1);
@@ -398,7 +390,8 @@ __global__ void __launch_bounds__(TM, 1) ppo_wgrad1_kernel(const TrainArgs p) {
       mbar_expect_tx(&ctrl.lbar, tile_bytes(TM, HID));
       bulk_g2s(dzt.base, dz1 + (size_t)tile * tile_bytes(TM, HID), tile_bytes(TM, HID), &ctrl.lbar);
     }
-    build_x_tile(d, p.view, xt, row0, M, [&](int64_t r) { return (int64_t)p.rows[r / rows_per_step]; });
+    build_x_tile(d, p.view, xt, stage, row0, M,
+                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
     fence_proxy_async();
     mbar_wait(&ctrl.lbar, phase);
     fence_before_sync();
@@ -426,14 +419,15 @@ __global__ void __launch_bounds__(TM, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     float* g = is_actor ? p.grad_actor : p.grad_critic;
     float* gb1 = g + (size_t)d.in_dim * HID;
     fence_after_sync();
-    for (int c0 = 0; c0 < d.k1p; c0 += 16) {
+    // TMEM lane = hidden unit n, columns = input feature k (column in_dim = bias gradient)
+    for (int c0 = L.q * 16; c0 < d.k1p; c0 += 64) {
       float v[16];
-      ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      ld16(tmem + L.tmem_lane() + (uint32_t)c0, v);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int k = c0 + c;
-        if (k < d.in_dim) atomicAdd(g + (size_t)k * HID + t, v[c]);
-        else if (k == d.in_dim) atomicAdd(gb1 + t, v[c]);
+        if (k < d.in_dim) atomicAdd(g + (size_t)k * HID + L.r, v[c]);
+        else if (k == d.in_dim) atomicAdd(gb1 + L.r, v[c]);
       }
     }
   }
@@ -521,10 +515,6 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   a.grad_actor = grad_out;
   a.grad_critic = grad_out + na;
   a.loss_acc = loss_acc;
-  {
-    const char* dbg = getenv("MAVA_TC_DEBUG");
-    a.debug_stop = dbg ? atoi(dbg) : 0;
-  }
 
   // split the SMs between actor and critic tiles in proportion to their estimated cost
   const int64_t ta = tile_count(actor, R), tcn = tile_count(critic, R);
@@ -546,7 +536,8 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   const int k1p_max = a.actor.k1p > a.critic.k1p ? a.actor.k1p : a.critic.k1p;
   const size_t smem_fused = (size_t)WImage{k1p_max}.total() + region_bytes(k1p_max) +
                             tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
-  const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) + 128;
+  const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
+                          tile_bytes(TM, HCOLS) + 128;  // dZ1 tile, X tile, staging
   static size_t conf_fused = 0, conf_wg1 = 0;
   if (smem_fused > conf_fused) {
     e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -560,14 +551,12 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
     if (e != cudaSuccess) return (int)e;
     conf_wg1 = smem_wg1;
   }
-  ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem_fused, s>>>(a);
+  ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_fused, s>>>(a);
   rc = launch_status();
   if (rc) return rc;
-  if (a.debug_stop == 0 || (a.debug_stop >= 7 && a.debug_stop < 40)) {
-    ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, TM, smem_wg1, s>>>(a);
-    rc = launch_status();
-    if (rc) return rc;
-  }
+  ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_wg1, s>>>(a);
+  rc = launch_status();
+  if (rc) return rc;
   return launch_finalize_loss(loss_acc, (double)R * actor->num_agents, hyper->ent_coef,
                               hyper->vf_coef, grad_out + na + nc, s);
 }
