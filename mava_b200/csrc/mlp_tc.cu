@@ -23,27 +23,30 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ params, int in_dim, int k1p, int out,
                             unsigned char* __restrict__ image) {
-  // W1 [k1p][HID]
+  // flat flax order: W1 (in,H) | b1 | W2 (H,H) | b2 | W3 (H,out) | b3
   const float* w1 = params;
-  const float* w2 = w1 + (size_t)in_dim * HID + HID;
-  const float* w3 = w2 + (size_t)HID * HID + HID;
-  const int n1 = k1p * (HID / 8), n2 = HID * (HID / 8), n3 = HID * (NHEAD / 8);
+  const float* b1 = w1 + (size_t)in_dim * HID;
+  const float* w2 = b1 + HID;
+  const float* b2 = w2 + (size_t)HID * HID;
+  const float* w3 = b2 + HID;
+  const float* b3 = w3 + (size_t)HID * out;
+  const int n1 = k1p * (HID / 8), n2 = HCOLS * (HID / 8), n3 = HCOLS * (NHEAD / 8);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3;
        i += gridDim.x * blockDim.x) {
-    const float* src;
+    const float *src, *bias;
     int rows, r, cg, ld, rows_valid, cols_valid;
     size_t base;
     if (i < n1) {
-      rows = k1p; r = i % rows; cg = i / rows; src = w1; ld = HID; rows_valid = in_dim;
+      rows = k1p; r = i % rows; cg = i / rows; src = w1; bias = b1; ld = HID; rows_valid = in_dim;
       cols_valid = HID; base = 0;
     } else if (i < n1 + n2) {
       const int j = i - n1;
-      rows = HID; r = j % rows; cg = j / rows; src = w2; ld = HID; rows_valid = HID;
+      rows = HCOLS; r = j % rows; cg = j / rows; src = w2; bias = b2; ld = HID; rows_valid = HID;
       cols_valid = HID; base = (size_t)k1p * HID * 2;
     } else {
       const int j = i - n1 - n2;
-      rows = HID; r = j % rows; cg = j / rows; src = w3; ld = out; rows_valid = HID;
-      cols_valid = out; base = (size_t)k1p * HID * 2 + (size_t)HID * HID * 2;
+      rows = HCOLS; r = j % rows; cg = j / rows; src = w3; bias = b3; ld = out; rows_valid = HID;
+      cols_valid = out; base = (size_t)k1p * HID * 2 + (size_t)HCOLS * HID * 2;
     }
     uint32_t w[4];
 #pragma unroll
@@ -52,7 +55,12 @@ __global__ void pack_kernel(const float* __restrict__ params, int in_dim, int k1
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c = cg * 8 + h * 2 + q;
-        v[q] = (r < rows_valid && c < cols_valid) ? src[(size_t)r * ld + c] : 0.0f;
+        float x = 0.0f;
+        if (c < cols_valid) {
+          if (r < rows_valid) x = src[(size_t)r * ld + c];
+          else if (r == rows_valid) x = bias[c];  // the bias row, met by the tiles' ones column
+        }
+        v[q] = x;
       }
       w[h] = pack_bf16(v[0], v[1]);
     }
@@ -126,39 +134,36 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
     fence_after_sync();
     issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
   }
-  mbar_wait(&ctrl.mbar, phase);
+  wait_mma(&ctrl.mbar, phase);
   phase ^= 1;
-  fence_after_sync();
-  hidden_epilogue(L, tmem, d.b1, ht);
+  hidden_epilogue(L, tmem, ht);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   // ---- layer 2 (accumulator reused: every thread has drained its columns)
   if (t == 0) {
     fence_after_sync();
-    issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HID, false, &ctrl.mbar);
+    issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HCOLS, false, &ctrl.mbar);
   }
-  mbar_wait(&ctrl.mbar, phase);
+  wait_mma(&ctrl.mbar, phase);
   phase ^= 1;
-  fence_after_sync();
-  hidden_epilogue(L, tmem, d.b2, ht);  // layer-2 MMAs have completed: H1 may be overwritten
+  hidden_epilogue(L, tmem, ht);  // layer-2 MMAs have completed: H1 may be overwritten
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   // ---- head
   if (t == 0) {
     fence_after_sync();
-    issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HID, false, &ctrl.mbar);
+    issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HCOLS, false, &ctrl.mbar);
   }
-  mbar_wait(&ctrl.mbar, phase);
-  fence_after_sync();
+  wait_mma(&ctrl.mbar, phase);
   const int64_t row = row0 + L.r;
   if (L.q == 0) {  // the first four warps finish the rows (one thread per row)
     float out[NHEAD];
     ld16(tmem + L.tmem_lane() + (uint32_t)HID, out);
     if (row < M) {
       if (!is_actor) {
-        const float v = out[0] + __ldg(d.b3);
+        const float v = out[0];
         if (d.mode == MAVA_IN_GLOBAL) {
           for (int a = 0; a < d.A; ++a) p.value[row * d.A + a] = v;
         } else {
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
 #pragma unroll
         for (int j = 0; j < NHEAD; ++j) {
           if (j < d.out) {
-            out[j] = ((mk >> j) & 1) ? out[j] + __ldg(d.b3 + j) : kF32Min;
+            out[j] = ((mk >> j) & 1) ? out[j] : kF32Min;
             mx = fmaxf(mx, out[j]);
           }
         }
@@ -233,13 +238,7 @@ int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n) {
   if (n->k1p > 304) return MAVA_E_UNSUPPORTED;  // shared-memory budget of the training kernel
   if (stage_bytes(n->A, n->FR, n->mode == MAVA_IN_GLOBAL ? 1 : n->A) > tile_bytes(TM, HCOLS))
     return MAVA_E_UNSUPPORTED;  // the observation staging area aliases an activation tile
-  if (params) {
-    n->b1 = params + (size_t)d->in_dim * HID;
-    n->b2 = n->b1 + HID + (size_t)HID * HID;
-    n->b3 = n->b2 + HID + (size_t)HID * d->out_dim;
-  } else {
-    n->b1 = n->b2 = n->b3 = nullptr;
-  }
+  (void)params;
   return 0;
 }
 

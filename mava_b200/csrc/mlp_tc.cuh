@@ -27,12 +27,14 @@ constexpr float kF32Min = -3.402823466e38f;
 __host__ __device__ constexpr int pad16(int x) { return (x + 15) / 16 * 16; }
 
 // Byte layout of one network's packed weight image (bf16 core-matrix tiles, see tc.cuh):
-//   W1 [K1p][HID] | W2 [HID][HID] | W3 [HID][NHEAD]
+//   W1 [K1p][HID] | W2 [HCOLS][HID] | W3 [HCOLS][NHEAD]
+// Each matrix carries its bias as one extra input row (row in_dim of W1, row HID of W2 and W3):
+// the activation tiles have a ones column there, so the bias add is part of the GEMM.
 struct WImage {
   int k1p;
   __host__ __device__ uint32_t w1_bytes() const { return (uint32_t)k1p * HID * 2; }
-  __host__ __device__ uint32_t w2_bytes() const { return HID * HID * 2; }
-  __host__ __device__ uint32_t w3_bytes() const { return HID * NHEAD * 2; }
+  __host__ __device__ uint32_t w2_bytes() const { return HCOLS * HID * 2; }
+  __host__ __device__ uint32_t w3_bytes() const { return HCOLS * NHEAD * 2; }
   __host__ __device__ uint32_t total() const { return w1_bytes() + w2_bytes() + w3_bytes(); }
 };
 
@@ -41,15 +43,14 @@ __device__ __forceinline__ Tile w1_tile(uint32_t base, int k1p) {
   return Tile{base, 128u, (uint32_t)(k1p / 8) * 128u};
 }
 __device__ __forceinline__ Tile w2_tile(uint32_t base, int k1p) {
-  return Tile{base + (uint32_t)k1p * HID * 2, 128u, (uint32_t)(HID / 8) * 128u};
+  return Tile{base + (uint32_t)k1p * HID * 2, 128u, (uint32_t)(HCOLS / 8) * 128u};
 }
 __device__ __forceinline__ Tile w3_tile(uint32_t base, int k1p) {
-  return Tile{base + (uint32_t)k1p * HID * 2 + HID * HID * 2, 128u, (uint32_t)(HID / 8) * 128u};
+  return Tile{base + (uint32_t)k1p * HID * 2 + HCOLS * HID * 2, 128u, (uint32_t)(HCOLS / 8) * 128u};
 }
 
 struct NetDesc {
   int mode, add_id, A, FR, in_dim, k1p, out;  // k1p = pad16(in_dim + 1): room for the ones column
-  const float *b1, *b2, *b3;                  // fp32 biases inside the flat parameter vector
 };
 
 // Position of the calling thread inside the tile.
@@ -158,18 +159,30 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
   const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
   const signed char* mine = reinterpret_cast<const signed char*>(stage) +
                             (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
+  const uint32_t mine_s = smem_u32(mine);
   for (int cg = L.q; cg < d.k1p / 8; cg += 4) {
     float v[8];
+    const int k0 = cg * 8;
+    if (valid && k0 >= id_cols && k0 + 8 <= d.in_dim) {
+      // interior chunk: eight observation bytes, no boundary logic
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = cg * 8 + j;
-      float x = 0.0f;
-      if (valid) {
-        if (k < id_cols) x = k == a ? 1.0f : 0.0f;
-        else if (k < d.in_dim) x = (float)mine[k - id_cols];
-        else if (k == d.in_dim) x = 1.0f;
+      for (int j = 0; j < 8; ++j) {
+        int b;
+        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(b) : "r"(mine_s + (uint32_t)(k0 - id_cols + j)));
+        v[j] = (float)b;
       }
-      v[j] = x;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        float x = 0.0f;
+        if (valid) {
+          if (k < id_cols) x = k == a ? 1.0f : 0.0f;
+          else if (k < d.in_dim) x = (float)mine[k - id_cols];
+          else if (k == d.in_dim) x = 1.0f;
+        }
+        v[j] = x;
+      }
     }
     st_shared_v4(xt.base + chunk_off(xt, L.r, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                  pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -189,29 +202,50 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool 
   if (bar) commit(bar);
 }
 
-// Hidden-layer epilogue for thread (r, q): 32 accumulator columns -> (+bias, relu) -> bf16 into the
-// activation tile (quarter 0 also writes the ones column at HID).  Returns the relu mask of the 32
-// columns (bit c set = unit 32q + c active).
-__device__ __forceinline__ uint32_t hidden_epilogue(const Lane& L, uint32_t tmem_acc,
-                                                    const float* __restrict__ bias, const Tile& ht) {
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&x);
+  v = __hmax2(v, __floats2bfloat162_rn(0.0f, 0.0f));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// x * (h > 0) on packed bf16 pairs (the relu derivative read back from the activation tile)
+__device__ __forceinline__ uint32_t relu_grad_bf16x2(uint32_t x, uint32_t h) {
+  const __nv_bfloat162 xv = *reinterpret_cast<__nv_bfloat162*>(&x);
+  const __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&h);
+  __nv_bfloat162 o = __hmul2(xv, __hgt2(hv, __floats2bfloat162_rn(0.0f, 0.0f)));
+  return *reinterpret_cast<uint32_t*>(&o);
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&w)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+               : "r"(addr));
+}
+
+// Hidden-layer epilogue for thread (r, q): 32 accumulator columns (bias already added by the GEMM
+// through the ones column) -> relu -> bf16 into the activation tile; quarter 0 also writes the ones
+// column at HID that feeds the next layer's bias row and the bias gradient.
+__device__ __forceinline__ void hidden_epilogue(const Lane& L, uint32_t tmem_acc, const Tile& ht) {
   float v[32];
   ld32(tmem_acc + L.tmem_lane() + (uint32_t)(L.q * 32), v);
-  uint32_t bits = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    v[j] = fmaxf(v[j] + __ldg(bias + L.q * 32 + j), 0.0f);
-    bits |= (v[j] > 0.0f ? 1u : 0u) << j;
-  }
 #pragma unroll
   for (int cg = 0; cg < 4; ++cg)
-    st_shared_v4(ht.base + chunk_off(ht, L.r, L.q * 4 + cg), pack_bf16(v[cg * 8], v[cg * 8 + 1]),
-                 pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]), pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]),
-                 pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]));
-  if (L.q == 0) {  // ones column (bias gradient) + zero padding
+    st_shared_v4(ht.base + chunk_off(ht, L.r, L.q * 4 + cg),
+                 relu_bf16x2(pack_bf16(v[cg * 8], v[cg * 8 + 1])),
+                 relu_bf16x2(pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3])),
+                 relu_bf16x2(pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5])),
+                 relu_bf16x2(pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7])));
+  if (L.q == 0) {
     st_shared_v4(ht.base + chunk_off(ht, L.r, HID / 8), 0x00003F80u, 0u, 0u, 0u);
     st_shared_v4(ht.base + chunk_off(ht, L.r, HID / 8 + 1), 0u, 0u, 0u, 0u);
   }
-  return bits;
+}
+
+// Only warp 0 polls the mbarrier; everybody else parks at the CTA barrier.
+__device__ __forceinline__ void wait_mma(uint64_t* bar, uint32_t parity) {
+  if (threadIdx.x < 32) mbar_wait(bar, parity);
+  __syncthreads();
+  fence_after_sync();
 }
 
 }  // namespace tcmlp

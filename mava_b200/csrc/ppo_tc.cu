@@ -64,19 +64,22 @@ __host__ __device__ inline uint32_t region_bytes(int k1p) {
   return x > kRegionMin ? x : kRegionMin;
 }
 
-// dH (32 accumulator columns of row r) * relu mask -> bf16, written either into a shared-memory
-// tile or into a tile image in global memory (same core-matrix layout).
+// dH (32 accumulator columns of row r) * relu'(H) -> bf16, written either into a shared-memory tile
+// or into a tile image in global memory (same core-matrix layout).  The relu derivative is read back
+// from the activation tile H (bf16 > 0), so no mask has to be carried from the forward pass.
 template <bool TO_GLOBAL>
-__device__ __forceinline__ void grad_epilogue(const Lane& L, uint32_t tmem_acc, uint32_t relu_bits,
+__device__ __forceinline__ void grad_epilogue(const Lane& L, uint32_t tmem_acc, const Tile& h,
                                               const Tile& dst, unsigned char* gdst) {
   float v[32];
   ld32(tmem_acc + L.tmem_lane() + (uint32_t)(L.q * 32), v);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = ((relu_bits >> j) & 1u) ? v[j] : 0.0f;
-#pragma unroll
   for (int cg = 0; cg < 4; ++cg) {
-    const uint32_t a = pack_bf16(v[cg * 8], v[cg * 8 + 1]), b = pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]),
-                   c = pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]), d = pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]);
+    uint32_t hw[4];
+    ld_shared_v4(h.base + chunk_off(h, L.r, L.q * 4 + cg), hw);
+    const uint32_t a = relu_grad_bf16x2(pack_bf16(v[cg * 8], v[cg * 8 + 1]), hw[0]),
+                   b = relu_grad_bf16x2(pack_bf16(v[cg * 8 + 2], v[cg * 8 + 3]), hw[1]),
+                   c = relu_grad_bf16x2(pack_bf16(v[cg * 8 + 4], v[cg * 8 + 5]), hw[2]),
+                   d = relu_grad_bf16x2(pack_bf16(v[cg * 8 + 6], v[cg * 8 + 7]), hw[3]);
     const uint32_t off = chunk_off(dst, L.r, L.q * 4 + cg);
     if (TO_GLOBAL) *reinterpret_cast<uint4*>(gdst + off) = make_uint4(a, b, c, d);
     else st_shared_v4(dst.base + off, a, b, c, d);
@@ -138,31 +141,28 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);
+    wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    fence_after_sync();
-    const uint32_t m1 = hidden_epilogue(L, tmem + COL_ACC, d.b1, h1t);
+    hidden_epilogue(L, tmem + COL_ACC, h1t);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     if (t == 0) {
       fence_after_sync();
-      issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HID, false, &ctrl.mbar);
+      issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);
+    wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    fence_after_sync();
-    const uint32_t m2 = hidden_epilogue(L, tmem + COL_ACC, d.b2, h2t);  // X is dead: H2 replaces it
+    hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead: H2 replaces it
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     if (t == 0) {
       fence_after_sync();
-      issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HID, false, &ctrl.mbar);
+      issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);
+    wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    fence_after_sync();
     // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output)
     if (L.q == 0) {
       const int64_t row = row0 + L.r;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       if (valid) {
         if (!is_actor) {
           // _critic_loss_fn, ff_mappo.py:190-201
-          const float v = out[0] + __ldg(d.b3);
+          const float v = out[0];
           const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
           float dv = 0.0f;
           for (int a = 0; a < reps; ++a) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
 #pragma unroll
           for (int q = 0; q < NHEAD; ++q) {
             if (q < d.out) {
-              out[q] = ((mk >> q) & 1) ? out[q] + __ldg(d.b3 + q) : kF32Min;
+              out[q] = ((mk >> q) & 1) ? out[q] : kF32Min;
               mx = fmaxf(mx, out[q]);
             }
           }
@@ -276,10 +276,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
       issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, &ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);
+    wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    fence_after_sync();
-    grad_epilogue<false>(L, tmem + COL_ACC, m2, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
+    grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -289,12 +288,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, nullptr);
       issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, &ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);
+    wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    fence_after_sync();
     unsigned char* gdst = (is_actor ? p.dz1_actor : p.dz1_critic) + (size_t)tile * tile_bytes(TM, HID);
     const Tile gimg{0u, 128u, 2048u};
-    grad_epilogue<true>(L, tmem + COL_ACC, m1, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
+    grad_epilogue<true>(L, tmem + COL_ACC, h1t, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
     fence_before_sync();
     __syncthreads();
   }
@@ -409,11 +407,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
       }
       commit(&ctrl.mbar);
     }
-    mbar_wait(&ctrl.mbar, phase);  // operands are free again once the MMAs have completed
+    wait_mma(&ctrl.mbar, phase);  // operands are free again once the MMAs have completed
     phase ^= 1;
-    fence_after_sync();
-    fence_before_sync();
-    __syncthreads();
   }
   if (!first) {
     float* g = is_actor ? p.grad_actor : p.grad_critic;
