@@ -125,6 +125,19 @@ def loss_grad_flops(L) -> float:
     return net(L.actor_desc, R * L.A) + net(L.critic_desc, crows)
 
 
+def _finish(world: int, device) -> None:
+    """Leave a multi-rank run without tearing NCCL down: destroy_process_group blocks while CUDA
+    graphs that captured collectives are alive, so drain the device and exit the process."""
+    if world <= 1:
+        return
+    import torch
+
+    torch.cuda.synchronize(device)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
@@ -232,8 +245,7 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, lg_mean_ms = (float(x) for x in t.tolist())
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, device)
         return
 
     peaks = {}
@@ -274,8 +286,7 @@ def run_ours(args) -> None:
                          "launches_timed": len(lg_ms)},
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, device)
 
 
 def main() -> None:
@@ -287,6 +298,10 @@ def main() -> None:
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("MAVA_BENCH_DEBUG"):  # dump every thread's stack if the run gets stuck
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["MAVA_BENCH_DEBUG"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -192,6 +192,12 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
                    int64_t n, float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
                    int steps_per_update, mava_stream_t s);
 
+/* Both networks in one launch: params/mu/nu/grad hold [actor | critic], counts[2]. */
+int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, const float* grad,
+                        int64_t n_actor, int64_t n_critic, float grad_scale, float lr_actor,
+                        float lr_critic, float max_norm, int lr_decay_num_updates,
+                        int steps_per_update, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMEM).  Same regions as mava_ff_act / mava_ppo_loss_grad with
  * bf16 operands and fp32 accumulation (tolerance 2e-2, BASELINE.json).  Requires h1 == h2 == 128.

@@ -103,9 +103,98 @@ clip_adam_kernel(float* __restrict__ params, float* __restrict__ mu, float* __re
   if (threadIdx.x == 0) *count = c;
 }
 
+// Both networks in one launch, several CTAs per network: every CTA recomputes the (tiny) global
+// norm of its network, then updates its slice.  The step count is advanced by the last CTA to have
+// read it (ticket), so late CTAs never see the incremented value.
+__device__ unsigned int g_adam_ticket[2];
+
+struct AdamPairArgs {
+  float *params, *mu, *nu;
+  int32_t* counts;
+  const float* grad;
+  int64_t n[2];
+  float lr[2];
+  float grad_scale, max_norm;
+  int lr_decay_num_updates, steps_per_update;
+};
+
+__global__ void __launch_bounds__(512) clip_adam_pair_kernel(const AdamPairArgs a) {
+  const int net = blockIdx.y;
+  const int64_t off = net == 0 ? 0 : a.n[0];
+  const int64_t n = a.n[net];
+  const float* grad = a.grad + off;
+  float* params = a.params + off;
+  float* mu = a.mu + off;
+  float* nu = a.nu + off;
+  __shared__ double red[16];
+  __shared__ float s_norm;
+  __shared__ int s_count;
+  double ss = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = __ldg(grad + i) * a.grad_scale;
+    ss += (double)g * (double)g;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  if (threadIdx.x == 0) s_count = a.counts[net];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      s_norm = (float)sqrt(v);
+      __threadfence();
+      const unsigned int ticket = atomicAdd(&g_adam_ticket[net], 1u);
+      if (ticket == gridDim.x - 1) {  // every CTA of this network has read the count
+        g_adam_ticket[net] = 0u;
+        a.counts[net] = s_count + 1;
+      }
+    }
+  }
+  __syncthreads();
+  const float g_norm = s_norm;
+  const bool keep = g_norm < a.max_norm;
+  const int c0 = s_count, c = c0 + 1;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-5f;
+  const float bc1 = 1.0f - powf(b1, (float)c), bc2 = 1.0f - powf(b2, (float)c);
+  float step_lr = a.lr[net];
+  if (a.lr_decay_num_updates > 0)
+    step_lr *= 1.0f - (float)(c0 / a.steps_per_update) / (float)a.lr_decay_num_updates;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float g = grad[i] * a.grad_scale;
+    if (!keep) g = (g / g_norm) * a.max_norm;
+    const float m = (1.0f - b1) * g + b1 * mu[i];
+    const float v = (1.0f - b2) * g * g + b2 * nu[i];
+    mu[i] = m;
+    nu[i] = v;
+    params[i] += -step_lr * ((m / bc1) / (sqrtf(v / bc2) + eps));
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, const float* grad,
+                        int64_t n_actor, int64_t n_critic, float grad_scale, float lr_actor,
+                        float lr_critic, float max_norm, int lr_decay_num_updates,
+                        int steps_per_update, mava_stream_t s) {
+  MAVA_CHECK_PTR(params);
+  MAVA_CHECK_PTR(mu);
+  MAVA_CHECK_PTR(nu);
+  MAVA_CHECK_PTR(counts);
+  MAVA_CHECK_PTR(grad);
+  MAVA_CHECK_ARG(n_actor > 0 && n_critic > 0 && steps_per_update > 0);
+  AdamPairArgs a;
+  a.params = params; a.mu = mu; a.nu = nu; a.counts = counts; a.grad = grad;
+  a.n[0] = n_actor; a.n[1] = n_critic;
+  a.lr[0] = lr_actor; a.lr[1] = lr_critic;
+  a.grad_scale = grad_scale; a.max_norm = max_norm;
+  a.lr_decay_num_updates = lr_decay_num_updates; a.steps_per_update = steps_per_update;
+  clip_adam_pair_kernel<<<dim3(16, 2), 512, 0, as_stream(s)>>>(a);
+  return launch_status();
+}
 
 int mava_gae(const float* reward, const float* value, const uint8_t* done, const float* last_val,
              const uint8_t* last_done, float gamma, float gae_lambda, int T, int num_envs,

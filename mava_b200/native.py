@@ -141,7 +141,8 @@ class Env:
 
     def peek(self, state, field: int, num_envs: int) -> torch.Tensor:
         A = self.num_agents
-        width = {0: 1, 1: 2, 2: 4 * A, 3: 3 * self.dims.aux0, 4: self.dims.aux1}[field]
+        last = self.dims.aux0 if self.kind == ENV_LBF else self.dims.aux1  # eaten flags | queue
+        width = {0: 1, 1: 2, 2: 4 * A, 3: 3 * self.dims.aux0, 4: last}[field]
         out = torch.zeros(num_envs, width, dtype=torch.int32, device=state.device)
         check(_lib.load().mava_env_peek(self._h, _p(state, torch.uint8, None, "state"), field,
                                         _p(out, torch.int32), num_envs, _stream()), "mava_env_peek")
@@ -323,3 +324,15 @@ def ppo_loss_grad_bf16(actor: MlpDesc, actor_params, actor_image, critic: MlpDes
         _p(rows, torch.int32, num_replicas * mb_size, "rows"), num_replicas, mb_size,
         _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
         _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16")
+
+
+def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, grad_scale: float,
+                   lr_actor: float, lr_critic: float, max_norm: float,
+                   lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:
+    n = n_actor + n_critic
+    _count(1)
+    check(_lib.load().mava_clip_adam_pair(
+        _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
+        _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
+        _p(grad, torch.float32, n, "grad"), n_actor, n_critic, grad_scale, lr_actor, lr_critic,
+        max_norm, lr_decay_num_updates, steps_per_update, _stream()), "mava_clip_adam_pair")

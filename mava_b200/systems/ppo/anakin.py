@@ -219,12 +219,10 @@ class FFLearner:
                     self.time_loss_grad.append((e0, e1))
                 if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
                     dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
-                native.clip_adam(self.params[:na], self.mu[:na], self.nu[:na], self.counts[0:1],
-                                 self.grad[:na], na, scale, float(s.actor_lr),
-                                 float(s.max_grad_norm), self.lr_decay_updates, steps_per_update)
-                native.clip_adam(self.params[na:], self.mu[na:], self.nu[na:], self.counts[1:2],
-                                 self.grad[na:na + nc], nc, scale, float(s.critic_lr),
-                                 float(s.max_grad_norm), self.lr_decay_updates, steps_per_update)
+                native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na, nc,
+                                      scale, float(s.actor_lr), float(s.critic_lr),
+                                      float(s.max_grad_norm), self.lr_decay_updates,
+                                      steps_per_update)
                 self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
                 if self.bf16:
                     self._pack()

@@ -110,3 +110,27 @@ def test_clip_adam_matches_oracle(lib_built, gscale, decay):
     np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(tmu.cpu().numpy(), mu, rtol=1e-5, atol=1e-8)
     np.testing.assert_allclose(tnu.cpu().numpy(), nu, rtol=1e-5, atol=1e-10)
+
+
+def test_clip_adam_pair_matches_single(lib_built):
+    """The two-network multi-CTA Adam launch equals two single-network steps."""
+    from mava_b200 import native
+
+    rng = np.random.default_rng(9)
+    na, nc = 26245, 50561
+    p = torch.from_numpy(rng.normal(size=na + nc).astype(np.float32)).to(DEV)
+    p2 = p.clone()
+    mu, nu = torch.zeros_like(p), torch.zeros_like(p)
+    mu2, nu2 = torch.zeros_like(p), torch.zeros_like(p)
+    cnt = torch.zeros(2, dtype=torch.int32, device=DEV)
+    cnt2 = torch.zeros(2, dtype=torch.int32, device=DEV)
+    for step in range(5):
+        g = torch.from_numpy((rng.normal(size=na + nc) * (0.001 if step % 2 else 1.0)).astype(np.float32)).to(DEV)
+        native.clip_adam_pair(p, mu, nu, cnt, g, na, nc, 0.5, 2.5e-4, 1e-4, 0.5, 7, 4)
+        native.clip_adam(p2[:na], mu2[:na], nu2[:na], cnt2[0:1], g[:na], na, 0.5, 2.5e-4, 0.5, 7, 4)
+        native.clip_adam(p2[na:], mu2[na:], nu2[na:], cnt2[1:2], g[na:], nc, 0.5, 1e-4, 0.5, 7, 4)
+    torch.cuda.synchronize()
+    assert cnt.tolist() == [5, 5]
+    torch.testing.assert_close(p, p2, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(mu, mu2, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(nu, nu2, rtol=1e-6, atol=1e-12)
