@@ -307,8 +307,11 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
   const int el = threadIdx.x / G, g = threadIdx.x % G;
   const int env = env0 + el;
   const unsigned gmask = group_mask<G>();
-  if (el < nenv) {
-    EnvSmem m{srec + el * L.rec_stride, sgsh + el * L.grid_stride, sgag + el * L.grid_stride};
+  const bool active = el < nenv;
+  const EnvSmem m{srec + el * L.rec_stride, sgsh + el * L.grid_stride, sgag + el * L.grid_stride};
+  bool needs_reset = false;
+  Key key{0u, 0u};
+  if (active) {
     build_grids<G>(c, m, g, gmask);
 
     // --- validate the action against the mask of the current state (utils.get_valid_actions)
@@ -373,7 +376,6 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
     // --- deliveries at the goal cells; a delivered request is replaced by a uniformly drawn
     //     shelf that is not in the queue (env._update_reward_and_request_queue)
     float rew = 0.0f;
-    Key key;
     {
       const uint32_t* k = reinterpret_cast<const uint32_t*>(m.rec + c.off_key);
       key = Key{k[0], k[1]};
@@ -448,21 +450,36 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
       ep_length[env] = len_info;
     }
     if (g < c.A) reward[(size_t)env * c.A + g] = rew;
-    __syncwarp(gmask);
-    // --- AutoResetWrapper: on the last step the state and observation are those of a fresh
-    //     episode seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75)
-    if (is_done && auto_reset) {
+    needs_reset = is_done && auto_reset != 0;
+  }
+  // --- AutoResetWrapper: on the last step the state and observation are those of a fresh episode
+  //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare, so
+  //     the whole warp regenerates one finished env at a time: 32 lanes share the threefry draws
+  //     and the top-k selections instead of leaving G lanes with the long tail.
+  __syncwarp();
+  {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned pending = __ballot_sync(0xffffffffu, needs_reset && g == 0);
+    while (pending) {
+      const int leader = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const int rel = __shfl_sync(0xffffffffu, el, leader);
+      const uint32_t k0 = __shfl_sync(0xffffffffu, key.k0, leader);
+      const uint32_t k1 = __shfl_sync(0xffffffffu, key.k1, leader);
+      const EnvSmem mr{srec + rel * L.rec_stride, sgsh + rel * L.grid_stride,
+                       sgag + rel * L.grid_stride};
       Key nk, unused;
-      split2(key, nk, unused);
-      generate<G>(c, m, nk, g, gmask);
-      build_grids<G>(c, m, g, gmask);
+      split2(Key{k0, k1}, nk, unused);
+      generate<32>(c, mr, nk, (int)lane, 0xffffffffu);
+      build_grids<32>(c, mr, (int)lane, 0xffffffffu);
     }
-    // --- next observation and action mask
-    if (g < c.A) {
-      int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
-      const uint8_t mk = emit_obs_and_mask(c, m, g, row);
-      mask[(size_t)env * c.A + g] = mk;
-    }
+  }
+  __syncwarp();
+  // --- next observation and action mask
+  if (active && g < c.A) {
+    int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
+    const uint8_t mk = emit_obs_and_mask(c, m, g, row);
+    mask[(size_t)env * c.A + g] = mk;
   }
   __syncthreads();
   store_obs(c, sobs, view, env0, nenv);
