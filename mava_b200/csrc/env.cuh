@@ -10,12 +10,22 @@ constexpr int kMaxAgents = 8;
 constexpr int kMaxQueue = 8;
 
 // Immutable RobotWarehouse scenario constants, passed to kernels by value.
+// Packed per-env record (bytes, `stride` per env, stride/16 odd so that the records of the envs of
+// one warp start in different shared-memory banks):
+//   off_agents   A words   x | y << 8 | direction << 16 | carrying << 24
+//   off_queue    Q bytes   requested shelf ids (request_queue)
+//   off_reqbits  ceil(n/32) words, bit s = shelf s is requested
+//   off_step u32, off_key 2 x u32 (State.key), off_mkey 2 x u32 (RecordEpisodeMetrics key),
+//   off_run_ret f32, off_run_len i32, off_ep_ret f32, off_ep_len i32
+//   off_cells    HW bytes  the SHELVES grid channel: shelf id + 1 per cell, 0 = empty
+// The AGENTS grid channel is never stored: with agents on distinct cells it is a function of the
+// agent positions (see env_rware.cu).
 struct RwareConst {
   int H, W, HW, A, Q, n, R, FR, time_limit;
   int stride;  // bytes per env record in HBM (multiple of 16)
-  // byte offsets inside a record
-  int off_ax, off_ay, off_dir, off_carry, off_sx, off_sy, off_req, off_queue;
+  int off_agents, off_queue, off_reqbits;
   int off_step, off_key, off_mkey, off_run_ret, off_run_len, off_ep_ret, off_ep_len;
+  int off_cells, cells_words, req_words;
   int goal[2];                            // flat cell index, scan order
   uint32_t highway[kMaxCells / 32];       // bit per cell
   uint16_t shelf_home[kMaxShelves + 2];   // flat cell index of shelf s at reset

@@ -5,13 +5,21 @@
 // The inner dynamics follow the published Jumanji RobotWarehouse algorithm (third party, absent
 // from the reference tree).
 //
-// Mapping: G lanes cooperate on one env (G = 4 or 8, lane g < A is agent g), 256/G envs per CTA.
-// The packed per-env records of a CTA are contiguous in HBM: they are staged into shared memory
-// with 16-byte vector loads, worked on there (occupancy grids are rebuilt in shared memory, never
-// stored), and written back the same way; observations are assembled in shared memory and stored
-// as one contiguous int8 block per CTA.  Agents are advanced one after the other (lane i acts in
-// turn i) exactly like the reference's scan over agents; collisions use a sub-warp ballot; the
-// rare paths (delivery -> new request, episode end -> in-kernel reset) run threefry on all G lanes.
+// Mapping: G lanes cooperate on one env (G = 2, 4 or 8; lane g < A is agent g), 256/G envs per CTA.
+//   * The packed records of a CTA are contiguous in HBM: ONE bulk (TMA) copy stages them into
+//     shared memory, they are updated in place there, and one bulk copy writes them back.
+//   * The record holds the SHELVES grid itself (one byte per cell) instead of shelf coordinates,
+//     so nothing is rebuilt per step; the AGENTS grid is never materialised: with agents on
+//     distinct cells (always true while an episode is alive) the value the reference's sequential
+//     grid writes leave in a cell is a closed-form function of (old cell, new cell, moved) of the
+//     A agents, exchanged with sub-warp shuffles.
+//   * Agents still take their turns one after the other on the shelf grid (lane i in turn i),
+//     exactly like the reference's scan over agents.
+//   * Each lane assembles its whole observation row in registers as packed 32-bit words (the
+//     5-byte "other agent" blocks come from a bit mask expanded with one multiply per word) and
+//     writes it to a staging block that leaves the CTA as one contiguous bulk store.
+//   * Rare paths (delivery -> new request, episode end -> in-kernel reset) run threefry on all
+//     lanes of the group / warp.
 #include "env.cuh"
 #include "prng.cuh"
 
@@ -19,6 +27,57 @@ namespace mava {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef MAVA_RWARE_MINB
+#define MAVA_RWARE_MINB 6  // resident CTAs per SM the step kernel's register budget is sized for
+#endif
+
+// ---- small PTX helpers (mbarrier + bulk copies) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spins > (1u << 24)) __trap();  // a bug surfaces as an error instead of a hang
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
@@ -37,13 +96,6 @@ __device__ __forceinline__ unsigned long long group_min(unsigned long long v, un
   return v;
 }
 
-// Per-env shared-memory working set.
-struct EnvSmem {
-  uint8_t* rec;   // packed record
-  uint8_t* gsh;   // shelf id (+1) per cell
-  uint8_t* gag;   // agent id (+1) per cell
-};
-
 __device__ __forceinline__ bool is_highway(const RwareConst& c, int cell) {
   return (c.highway[cell >> 5] >> (cell & 31)) & 1u;
 }
@@ -58,23 +110,12 @@ __device__ __forceinline__ void forward_cell(const RwareConst& c, int x, int y, 
   else ny = max(0, y - 1);
 }
 
-// Rebuild both occupancy grids from the record.
-template <int G>
-__device__ __forceinline__ void build_grids(const RwareConst& c, const EnvSmem& m, int g,
-                                            unsigned gmask) {
-  const int words = (c.HW + 3) >> 2;
-  uint32_t* s32 = reinterpret_cast<uint32_t*>(m.gsh);
-  uint32_t* a32 = reinterpret_cast<uint32_t*>(m.gag);
-  for (int i = g; i < words; i += G) {
-    s32[i] = 0u;
-    a32[i] = 0u;
-  }
-  __syncwarp(gmask);
-  const uint8_t* sx = m.rec + c.off_sx;
-  const uint8_t* sy = m.rec + c.off_sy;
-  for (int s = g; s < c.n; s += G) m.gsh[sx[s] * c.W + sy[s]] = (uint8_t)(s + 1);
-  if (g < c.A) m.gag[m.rec[c.off_ax + g] * c.W + m.rec[c.off_ay + g]] = (uint8_t)(g + 1);
-  __syncwarp(gmask);
+__device__ __forceinline__ uint32_t pack_agent(int x, int y, int d, int carry) {
+  return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)d << 16) | ((uint32_t)carry << 24);
+}
+
+__device__ __forceinline__ bool requested(const RwareConst& c, const uint8_t* rec, int s) {
+  return (reinterpret_cast<const uint32_t*>(rec + c.off_reqbits)[s >> 5] >> (s & 31)) & 1u;
 }
 
 // K smallest of the composites (random_bits(sub, size)[i] << 32 | i), i.e. the first K entries of
@@ -126,166 +167,212 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
 }
 
 // jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
-// their home cells, Q distinct requested shelves.  Writes the inner-env part of the record and
-// returns the key left over (State.key).
-template <int G>
-__device__ __forceinline__ void generate(const RwareConst& c, const EnvSmem& m, Key key, int g,
+// their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
+// lanes cooperate; State.key is what is left of `key`).
+template <int GG>
+__device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
                                          unsigned gmask) {
   Key pos_key, dir_key, q_key, unused, sub;
   unsigned long long pick[kMaxAgents];
   split2(key, key, pos_key);
   split2(pos_key, unused, sub);
-  smallest_k<G, kMaxAgents>(sub, c.HW, c.A, g, gmask, pick);
+  smallest_k<GG, kMaxAgents>(sub, c.HW, c.A, g, gmask, pick);
   split2(key, key, dir_key);
   Key d_hi, d_lo;
   split2(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
   if (g == 0) {
+    uint32_t* agents = reinterpret_cast<uint32_t*>(rec + c.off_agents);
 #pragma unroll
     for (int i = 0; i < kMaxAgents; ++i) {
       if (i < c.A) {
-        int cell = (int)(pick[i] & 0xffffffffull);
-        m.rec[c.off_ax + i] = (uint8_t)(cell / c.W);
-        m.rec[c.off_ay + i] = (uint8_t)(cell % c.W);
-        m.rec[c.off_dir + i] = (uint8_t)(random_bits_at(d_lo, (uint32_t)i, (uint32_t)c.A) & 3u);
-        m.rec[c.off_carry + i] = 0;
+        const int cell = (int)(pick[i] & 0xffffffffull);
+        const int d = (int)(random_bits_at(d_lo, (uint32_t)i, (uint32_t)c.A) & 3u);
+        agents[i] = pack_agent(cell / c.W, cell % c.W, d, 0);
       }
     }
   }
   split2(key, key, q_key);
   split2(q_key, unused, sub);
   unsigned long long qpick[kMaxQueue];
-  smallest_k<G, kMaxQueue>(sub, c.n, c.Q, g, gmask, qpick);
-  for (int s = g; s < c.n; s += G) {
-    int cell = c.shelf_home[s];
-    m.rec[c.off_sx + s] = (uint8_t)(cell / c.W);
-    m.rec[c.off_sy + s] = (uint8_t)(cell % c.W);
-    m.rec[c.off_req + s] = 0;
-  }
+  smallest_k<GG, kMaxQueue>(sub, c.n, c.Q, g, gmask, qpick);
+  uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
+  for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
   __syncwarp(gmask);
+  uint8_t* cells = rec + c.off_cells;
+  for (int s = g; s < c.n; s += GG) cells[c.shelf_home[s]] = (uint8_t)(s + 1);
   if (g == 0) {
+    uint32_t* rq = reinterpret_cast<uint32_t*>(rec + c.off_reqbits);
+    for (int i = 0; i < c.req_words; ++i) rq[i] = 0u;
 #pragma unroll
     for (int i = 0; i < kMaxQueue; ++i) {
       if (i < c.Q) {
-        int s = (int)(qpick[i] & 0xffffffffull);
-        m.rec[c.off_queue + i] = (uint8_t)s;
-        m.rec[c.off_req + s] = 1;
+        const int s = (int)(qpick[i] & 0xffffffffull);
+        rec[c.off_queue + i] = (uint8_t)s;
+        rq[s >> 5] |= 1u << (s & 31);
       }
     }
-    *reinterpret_cast<uint32_t*>(m.rec + c.off_step) = 0u;
-    uint32_t* k = reinterpret_cast<uint32_t*>(m.rec + c.off_key);
+    *reinterpret_cast<uint32_t*>(rec + c.off_step) = 0u;
+    uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
     k[0] = key.k0;
     k[1] = key.k1;
   }
   __syncwarp(gmask);
 }
 
-// Action mask bits + int8 observation row of agent g (jumanji utils.make_agent_observation and
-// compute_action_mask); grids must be current.
-__device__ __forceinline__ uint8_t emit_obs_and_mask(const RwareConst& c, const EnvSmem& m, int g,
-                                                     int8_t* row) {
-  const int x = m.rec[c.off_ax + g], y = m.rec[c.off_ay + g];
-  const int d = m.rec[c.off_dir + g], carry = m.rec[c.off_carry + g];
-  row[0] = (int8_t)x;
-  row[1] = (int8_t)y;
-  row[2] = (int8_t)carry;
-  row[3] = d == 0;
-  row[4] = d == 1;
-  row[5] = d == 2;
-  row[6] = d == 3;
-  row[7] = is_highway(c, x * c.W + y);
-  int ia = 8;
-  const int loc = (2 * c.R + 1) * (2 * c.R + 1);
-  int is = 8 + (loc - 1) * 5;
-  for (int dx = -c.R; dx <= c.R; ++dx) {
-    for (int dy = -c.R; dy <= c.R; ++dy) {
-      const int cx = x + dx, cy = y + dy;
-      const bool inside = cx >= 0 && cx < c.H && cy >= 0 && cy < c.W;
-      const int cell = cx * c.W + cy;
-      const int aid = inside ? m.gag[cell] : 0;
-      const int sid = inside ? m.gsh[cell] : 0;
-      if (dx != 0 || dy != 0) {
-        const int od = aid ? m.rec[c.off_dir + aid - 1] : -1;
-        row[ia + 0] = aid != 0;
-        row[ia + 1] = od == 0;
-        row[ia + 2] = od == 1;
-        row[ia + 3] = od == 2;
-        row[ia + 4] = od == 3;
-        ia += 5;
-      }
-      row[is + 0] = sid != 0;
-      row[is + 1] = sid ? (int8_t)m.rec[c.off_req + sid - 1] : 0;
-      is += 2;
+// ---- observation rows --------------------------------------------------------------------------
+// jumanji utils.make_agent_observation: [x, y, carrying, onehot(dir, 4), on_highway] then, for the
+// (2R+1)^2 - 1 cells around the agent, [other agent present, onehot(its dir, 4)], then for all
+// (2R+1)^2 cells [shelf present, shelf requested]; int8, FR = 8 + 5 (L - 1) + 2 L bytes.
+template <int R>
+struct ObsDims {
+  static constexpr int SIDE = 2 * R + 1;
+  static constexpr int LOC = SIDE * SIDE;
+  static constexpr int CENTER = LOC / 2;
+  static constexpr int NAG = (LOC - 1) * 5;   // bytes of "other agent" features
+  static constexpr int FR = 8 + NAG + 2 * LOC;
+  static constexpr int NH = FR / 2;           // halfwords per row (odd)
+  static constexpr int NW = NH / 2 + 1;       // 32-bit words, the last one half used
+  static constexpr int MW = (NAG + 63) / 64;  // 64-bit words of the agent-feature bit mask
+  static constexpr int SH0 = (8 + NAG) / 4;   // first word of the shelf features
+  static_assert(FR % 4 == 2 && NAG % 4 == 0, "row layout assumptions");
+};
+
+// OR the 5-bit pattern p into bit position s of a multi-word mask.
+template <int MW>
+__device__ __forceinline__ void set5(unsigned long long (&M)[MW], int s, unsigned long long p) {
+  if (MW == 1) {
+    M[0] |= p << s;
+  } else {
+    const int w = s >> 6, b = s & 63;
+#pragma unroll
+    for (int i = 0; i < MW; ++i) {
+      if (i == w) M[i] |= p << b;
+      if (i == w + 1 && b > 59) M[i] |= p >> (64 - b);
     }
   }
+}
+
+// Builds the row of agent g from the (post-step) record and writes it, with the action mask bits
+// returned.  opk[j] = old cell | new cell << 10 | moved << 20 of agent j for this step; when
+// `replay` is set the AGENTS grid is evaluated exactly as the reference's sequence of grid writes
+// leaves it (needed only for the terminal observation of a collision without auto-reset), else
+// agents are on distinct cells and the grid is simply {cell of j -> j}.
+template <int G, int R>
+__device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* rec, int g,
+                                            uint8_t* row, int row_parity, bool replay,
+                                            const uint32_t (&opk)[G]) {
+  using O = ObsDims<R>;
+  const uint32_t* agents = reinterpret_cast<const uint32_t*>(rec + c.off_agents);
+  const uint8_t* cells = rec + c.off_cells;
+  const uint32_t me = agents[g];
+  const int x = me & 0xff, y = (me >> 8) & 0xff, d = (me >> 16) & 0xff, carry = me >> 24;
+  uint32_t w[O::NW];
+#pragma unroll
+  for (int i = 0; i < O::NW; ++i) w[i] = 0u;
+  w[0] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)carry << 16) | ((uint32_t)(d == 0) << 24);
+  w[1] = (uint32_t)(d == 1) | ((uint32_t)(d == 2) << 8) | ((uint32_t)(d == 3) << 16) |
+         ((uint32_t)is_highway(c, x * c.W + y) << 24);
+  unsigned long long M[O::MW];
+#pragma unroll
+  for (int i = 0; i < O::MW; ++i) M[i] = 0ull;
+  uint32_t ag[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) ag[j] = j < c.A ? agents[j] : 0u;
+  if (!replay) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (j < c.A && j != g) {
+        const int dx = (int)(ag[j] & 0xff) - x + R, dy = (int)((ag[j] >> 8) & 0xff) - y + R;
+        if ((unsigned)dx <= 2u * R && (unsigned)dy <= 2u * R) {
+          int k = dx * O::SIDE + dy;
+          if (k != O::CENTER) {
+            k -= k > O::CENTER;
+            set5<O::MW>(M, 5 * k, 1ull | (2ull << ((ag[j] >> 16) & 3u)));
+          }
+        }
+      }
+    }
+  } else {
+    int k = 0;
+    for (int dx = -R; dx <= R; ++dx) {
+      for (int dy = -R; dy <= R; ++dy) {
+        if (dx == 0 && dy == 0) continue;
+        const int cx = x + dx, cy = y + dy;
+        if (cx >= 0 && cx < c.H && cy >= 0 && cy < c.W) {
+          const uint32_t q = (uint32_t)(cx * c.W + cy);
+          int v = 0;
+#pragma unroll
+          for (int m = 0; m < G; ++m)
+            if (m < c.A && (opk[m] & 1023u) == q) v = m + 1;
+#pragma unroll
+          for (int m = 0; m < G; ++m) {
+            if (m < c.A && ((opk[m] >> 20) & 1u)) {
+              if ((opk[m] & 1023u) == q) v = 0;
+              if (((opk[m] >> 10) & 1023u) == q) v = m + 1;
+            }
+          }
+          if (v != 0) {
+            uint32_t dj = 0;
+#pragma unroll
+            for (int m = 0; m < G; ++m)
+              if (m + 1 == v) dj = (ag[m] >> 16) & 3u;
+            set5<O::MW>(M, 5 * k, 1ull | (2ull << dj));
+          }
+        }
+        ++k;
+      }
+    }
+  }
+  // bit b of the mask -> byte b of the feature block: 4 bits per word, spread with one multiply
+#pragma unroll
+  for (int i = 0; i < O::NAG / 4; ++i) {
+    const uint32_t nib = (uint32_t)(M[i >> 4] >> ((i & 15) * 4)) & 0xFu;
+    w[2 + i] = (nib * 0x00204081u) & 0x01010101u;
+  }
+#pragma unroll
+  for (int ci = 0; ci < O::LOC; ++ci) {
+    const int cx = x + ci / O::SIDE - R, cy = y + ci % O::SIDE - R;
+    uint32_t h = 0u;
+    if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
+      const int sid = cells[cx * c.W + cy];
+      if (sid != 0) h = 1u | ((uint32_t)requested(c, rec, sid - 1) << 8);
+    }
+    w[O::SH0 + ci / 2] |= h << (16 * (ci & 1));
+  }
+  // rows are FR = 2 (mod 4) bytes long: odd rows start on a half word
+  uint32_t* wp = reinterpret_cast<uint32_t*>(row + 2 * row_parity);
+  const int sh = 16 * row_parity;
+#pragma unroll
+  for (int k = 0; k + 1 < O::NW; ++k) wp[k] = __funnelshift_r(w[k], w[k + 1], sh);
+  uint16_t* hp = reinterpret_cast<uint16_t*>(row_parity ? row : row + 4 * (O::NW - 1));
+  *hp = (uint16_t)(row_parity ? w[0] : w[O::NW - 1]);
+  // utils.compute_action_mask: only FORWARD can be illegal
   int nx, ny;
   forward_cell(c, x, y, d, nx, ny);
   const bool stuck = nx == x && ny == y;
-  const bool blocked = carry && m.gsh[nx * c.W + ny] != 0;
+  const bool blocked = carry && cells[nx * c.W + ny] != 0;
   return (uint8_t)(0x1Du | ((stuck || blocked) ? 0u : 0x2u));
 }
 
-struct SmemLayout {
-  int rec_stride, grid_stride, obs_stride, per_cta_rec, per_cta_grid;
-};
-
-__host__ __device__ inline SmemLayout smem_layout(const RwareConst& c, int envs_per_cta) {
-  SmemLayout L;
-  L.rec_stride = c.stride + 16;
-  L.grid_stride = round_up(c.HW, 4) + 4;
-  L.obs_stride = c.A * c.FR;
-  L.per_cta_rec = envs_per_cta * L.rec_stride;
-  L.per_cta_grid = envs_per_cta * L.grid_stride;
-  return L;
-}
-
 __host__ inline size_t smem_bytes(const RwareConst& c, int envs_per_cta) {
-  SmemLayout L = smem_layout(c, envs_per_cta);
-  return (size_t)L.per_cta_rec + 2 * (size_t)L.per_cta_grid +
-         (size_t)round_up(envs_per_cta * L.obs_stride, 16);
+  return (size_t)envs_per_cta * c.stride + (size_t)round_up(envs_per_cta * c.A * c.FR, 16) + 16;
 }
 
-// Coalesced CTA-wide copies between HBM and the staged records / observation block.
-__device__ __forceinline__ void load_records(const RwareConst& c, const SmemLayout& L,
-                                             uint8_t* srec, const uint8_t* state, int env0,
-                                             int nenv) {
-  const int v = c.stride >> 4;
-  const uint4* src = reinterpret_cast<const uint4*>(state + (size_t)env0 * c.stride);
-  for (int i = threadIdx.x; i < nenv * v; i += blockDim.x) {
-    const int e = i / v, w = i - e * v;
-    reinterpret_cast<uint4*>(srec + e * L.rec_stride)[w] = src[i];
-  }
-}
-
-__device__ __forceinline__ void store_records(const RwareConst& c, const SmemLayout& L,
-                                              const uint8_t* srec, uint8_t* state, int env0,
-                                              int nenv) {
-  const int v = c.stride >> 4;
-  uint4* dst = reinterpret_cast<uint4*>(state + (size_t)env0 * c.stride);
-  for (int i = threadIdx.x; i < nenv * v; i += blockDim.x) {
-    const int e = i / v, w = i - e * v;
-    dst[i] = reinterpret_cast<const uint4*>(srec + e * L.rec_stride)[w];
-  }
-}
-
-__device__ __forceinline__ void store_obs(const RwareConst& c, const uint8_t* sobs, int8_t* view,
-                                          int env0, int nenv) {
-  const size_t base = (size_t)env0 * c.A * c.FR;
-  const int bytes = nenv * c.A * c.FR;
-  if (((base | (size_t)bytes) & 15) == 0) {
-    uint4* dst = reinterpret_cast<uint4*>(view + base);
-    for (int i = threadIdx.x; i < (bytes >> 4); i += blockDim.x)
-      dst[i] = reinterpret_cast<const uint4*>(sobs)[i];
-  } else if (((base | (size_t)bytes) & 3) == 0) {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(view + base);
+// Staged observation block / records -> HBM.  Bulk stores when size and address allow it.
+__device__ __forceinline__ void store_block(const uint8_t* src, uint8_t* dst, int bytes) {
+  // caller has synchronised the CTA and fenced the async proxy
+  if ((((size_t)dst | (size_t)bytes) & 15) == 0) {
+    if (threadIdx.x == 0) bulk_s2g(dst, src, (uint32_t)bytes);
+  } else if ((((size_t)dst | (size_t)bytes) & 3) == 0) {
     for (int i = threadIdx.x; i < (bytes >> 2); i += blockDim.x)
-      dst[i] = reinterpret_cast<const uint32_t*>(sobs)[i];
+      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
   } else {
-    for (int i = threadIdx.x; i < bytes; i += blockDim.x) view[base + i] = (int8_t)sobs[i];
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
   }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kThreads)
+template <int G, int R>
+__global__ void __launch_bounds__(kThreads, MAVA_RWARE_MINB)
 rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ state,
                   const int8_t* __restrict__ action, int8_t* __restrict__ view,
                   uint8_t* __restrict__ mask, float* __restrict__ reward,
@@ -293,96 +380,109 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
                   int32_t* __restrict__ ep_length, int num_envs, int auto_reset) {
   extern __shared__ uint4 smem_raw[];
   constexpr int EPC = kThreads / G;
-  const SmemLayout L = smem_layout(c, EPC);
   uint8_t* srec = reinterpret_cast<uint8_t*>(smem_raw);
-  uint8_t* sgsh = srec + L.per_cta_rec;
-  uint8_t* sgag = sgsh + L.per_cta_grid;
-  uint8_t* sobs = sgag + L.per_cta_grid;
+  uint8_t* sobs = srec + EPC * c.stride;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sobs + round_up(EPC * c.A * c.FR, 16));
 
   const int env0 = blockIdx.x * EPC;
   const int nenv = min(EPC, num_envs - env0);
-  load_records(c, L, srec, state, env0, nenv);
-  __syncthreads();
-
+  const uint32_t rec_bytes = (uint32_t)nenv * (uint32_t)c.stride;
+  uint8_t* gstate = state + (size_t)env0 * c.stride;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, rec_bytes);
+    bulk_g2s(srec, gstate, rec_bytes, bar);
+  }
   const int el = threadIdx.x / G, g = threadIdx.x % G;
   const int env = env0 + el;
   const unsigned gmask = group_mask<G>();
   const bool active = el < nenv;
-  const EnvSmem m{srec + el * L.rec_stride, sgsh + el * L.grid_stride, sgag + el * L.grid_stride};
-  bool needs_reset = false;
-  Key key{0u, 0u};
-  if (active) {
-    build_grids<G>(c, m, g, gmask);
+  const bool agent = active && g < c.A;
+  int act = agent ? (int)action[(size_t)env * c.A + g] : 0;
+  __syncthreads();  // the barrier is initialised for everyone
+  mbar_wait(bar, 0);
 
+  uint8_t* rec = srec + el * c.stride;
+  uint8_t* cells = rec + c.off_cells;
+  bool needs_reset = false, replay = false;
+  Key key{0u, 0u};
+  uint32_t opk[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) opk[j] = 0u;
+  if (active) {
     // --- validate the action against the mask of the current state (utils.get_valid_actions)
-    int x = 0, y = 0, d = 0, carry = 0, act = 0;
-    if (g < c.A) {
-      x = m.rec[c.off_ax + g];
-      y = m.rec[c.off_ay + g];
-      d = m.rec[c.off_dir + g];
-      carry = m.rec[c.off_carry + g];
-      act = action[(size_t)env * c.A + g];
+    int x = 0, y = 0, d = 0, carry = 0, nx = 0, ny = 0;
+    if (agent) {
+      const uint32_t me = reinterpret_cast<const uint32_t*>(rec + c.off_agents)[g];
+      x = me & 0xff;
+      y = (me >> 8) & 0xff;
+      d = (me >> 16) & 0xff;
+      carry = me >> 24;
+      forward_cell(c, x, y, d, nx, ny);
       if (act == 1) {
-        int nx, ny;
-        forward_cell(c, x, y, d, nx, ny);
         const bool stuck = nx == x && ny == y;
-        const bool blocked = carry && m.gsh[nx * c.W + ny] != 0;
+        const bool blocked = carry && cells[nx * c.W + ny] != 0;
         if (stuck || blocked) act = 0;
       }
     }
-    // --- agents act one after the other on the shared grids (scan over agents in env.step)
+    const int oldcell = x * c.W + y;
+    const bool moved = act == 1;
+    __syncwarp(gmask);
+    // --- agents act one after the other on the shelf grid (scan over agents in env.step)
     for (int i = 0; i < c.A; ++i) {
       if (g == i) {
-        const int cell = x * c.W + y;
         if (act == 2) {
           d = (d + 3) & 3;
         } else if (act == 3) {
           d = (d + 1) & 3;
         } else if (act == 1) {
-          int nx, ny;
-          forward_cell(c, x, y, d, nx, ny);
-          const int ncell = nx * c.W + ny;
-          m.gag[cell] = 0;
-          m.gag[ncell] = (uint8_t)(g + 1);
           if (carry) {
-            const int sid = m.gsh[cell];
-            const int s = sid ? sid - 1 : c.n - 1;  // jax .at[-1] wraps to the last shelf
-            m.rec[c.off_sx + s] = (uint8_t)nx;
-            m.rec[c.off_sy + s] = (uint8_t)ny;
-            m.gsh[cell] = 0;
-            m.gsh[ncell] = (uint8_t)sid;
+            const uint8_t sid = cells[oldcell];
+            cells[oldcell] = 0;
+            cells[nx * c.W + ny] = sid;
           }
           x = nx;
           y = ny;
         } else if (act == 4) {
-          const int sid = m.gsh[cell];
           if (!carry) {
-            if (sid != 0) carry = 1;
-          } else if (!is_highway(c, cell)) {
+            if (cells[oldcell] != 0) carry = 1;
+          } else if (!is_highway(c, oldcell)) {
             carry = 0;
           }
         }
-        m.rec[c.off_ax + g] = (uint8_t)x;
-        m.rec[c.off_ay + g] = (uint8_t)y;
-        m.rec[c.off_dir + g] = (uint8_t)d;
-        m.rec[c.off_carry + g] = (uint8_t)carry;
+        reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(x, y, d, carry);
       }
       __syncwarp(gmask);
     }
-    // --- collision: the id left on my cell is not mine (utils.is_collision)
-    const bool my_col = g < c.A && m.gag[x * c.W + y] != (uint8_t)(g + 1);
-    const bool collision = (__ballot_sync(gmask, my_col) & gmask) != 0u;
+    // --- collision (utils.is_collision): grid[AGENTS, pos_i] != i + 1 after the sequential writes
+    //     "old cell <- 0, new cell <- j + 1" of every agent j that moved.  The last write to my
+    //     cell is not mine iff some mover j entered or left it after my own write.
+    const int newcell = x * c.W + y;
+    const uint32_t pk = (uint32_t)oldcell | ((uint32_t)newcell << 10) | ((uint32_t)moved << 20);
+#pragma unroll
+    for (int j = 0; j < G; ++j) opk[j] = __shfl_sync(gmask, pk, j, G);
+    bool my_col = false;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (j < c.A && j != g) {
+        const uint32_t oj = opk[j] & 1023u, nj = (opk[j] >> 10) & 1023u;
+        const bool mj = (opk[j] >> 20) & 1u;
+        if (mj && (nj == (uint32_t)newcell || oj == (uint32_t)newcell) && (!moved || j > g))
+          my_col = true;
+      }
+    }
+    const bool collision = (__ballot_sync(gmask, my_col && agent) & gmask) != 0u;
 
     // --- deliveries at the goal cells; a delivered request is replaced by a uniformly drawn
     //     shelf that is not in the queue (env._update_reward_and_request_queue)
     float rew = 0.0f;
     {
-      const uint32_t* k = reinterpret_cast<const uint32_t*>(m.rec + c.off_key);
+      const uint32_t* k = reinterpret_cast<const uint32_t*>(rec + c.off_key);
       key = Key{k[0], k[1]};
     }
     for (int gi = 0; gi < 2; ++gi) {
-      const int sid = m.gsh[c.goal[gi]];
-      if (sid != 0 && m.rec[c.off_req + sid - 1] == 1) {
+      const int sid = cells[c.goal[gi]];
+      if (sid != 0 && requested(c, rec, sid - 1)) {
         Key rkey, unused, sub;
         split2(key, key, rkey);
         split2(rkey, unused, sub);
@@ -392,7 +492,7 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
           int below = 0;
           bool inq = false;
           for (int q = 0; q < c.Q; ++q) {
-            const int qs = m.rec[c.off_queue + q];
+            const int qs = rec[c.off_queue + q];
             inq |= qs == s;
             below += qs < s;
           }
@@ -409,33 +509,34 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
         __syncwarp(gmask);
         if (g == 0) {
           for (int q = 0; q < c.Q; ++q) {
-            if (m.rec[c.off_queue + q] == sid - 1) {
-              m.rec[c.off_queue + q] = (uint8_t)new_req;
+            if (rec[c.off_queue + q] == sid - 1) {
+              rec[c.off_queue + q] = (uint8_t)new_req;
               break;
             }
           }
-          m.rec[c.off_req + sid - 1] = 0;
-          m.rec[c.off_req + new_req] = 1;
+          uint32_t* rq = reinterpret_cast<uint32_t*>(rec + c.off_reqbits);
+          rq[(sid - 1) >> 5] &= ~(1u << ((sid - 1) & 31));
+          rq[new_req >> 5] |= 1u << (new_req & 31);
         }
         rew += 1.0f;
         __syncwarp(gmask);
       }
     }
     // --- step count, termination
-    uint32_t* pstep = reinterpret_cast<uint32_t*>(m.rec + c.off_step);
+    uint32_t* pstep = reinterpret_cast<uint32_t*>(rec + c.off_step);
     const int step = (int)(*pstep) + 1;
     const bool is_done = collision || step >= c.time_limit;
     __syncwarp(gmask);
     if (g == 0) {
       *pstep = (uint32_t)step;
-      uint32_t* k = reinterpret_cast<uint32_t*>(m.rec + c.off_key);
+      uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
       k[0] = key.k0;
       k[1] = key.k1;
       // RecordEpisodeMetrics.step (episode_metrics.py:83-110)
-      float* run_ret = reinterpret_cast<float*>(m.rec + c.off_run_ret);
-      int32_t* run_len = reinterpret_cast<int32_t*>(m.rec + c.off_run_len);
-      float* e_ret = reinterpret_cast<float*>(m.rec + c.off_ep_ret);
-      int32_t* e_len = reinterpret_cast<int32_t*>(m.rec + c.off_ep_len);
+      float* run_ret = reinterpret_cast<float*>(rec + c.off_run_ret);
+      int32_t* run_len = reinterpret_cast<int32_t*>(rec + c.off_run_len);
+      float* e_ret = reinterpret_cast<float*>(rec + c.off_ep_ret);
+      int32_t* e_len = reinterpret_cast<int32_t*>(rec + c.off_ep_len);
       const float new_ret = *run_ret + rew;  // mean over agents of a shared reward
       const int32_t new_len = *run_len + 1;
       const float nd = is_done ? 0.0f : 1.0f, dd = is_done ? 1.0f : 0.0f;
@@ -449,8 +550,9 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
       ep_return[env] = ret_info;
       ep_length[env] = len_info;
     }
-    if (g < c.A) reward[(size_t)env * c.A + g] = rew;
+    if (agent) reward[(size_t)env * c.A + g] = rew;
     needs_reset = is_done && auto_reset != 0;
+    replay = collision && !needs_reset;
   }
   // --- AutoResetWrapper: on the last step the state and observation are those of a fresh episode
   //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare, so
@@ -466,66 +568,69 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
       const int rel = __shfl_sync(0xffffffffu, el, leader);
       const uint32_t k0 = __shfl_sync(0xffffffffu, key.k0, leader);
       const uint32_t k1 = __shfl_sync(0xffffffffu, key.k1, leader);
-      const EnvSmem mr{srec + rel * L.rec_stride, sgsh + rel * L.grid_stride,
-                       sgag + rel * L.grid_stride};
       Key nk, unused;
       split2(Key{k0, k1}, nk, unused);
-      generate<32>(c, mr, nk, (int)lane, 0xffffffffu);
-      build_grids<32>(c, mr, (int)lane, 0xffffffffu);
+      generate<32>(c, srec + rel * c.stride, nk, (int)lane, 0xffffffffu);
     }
   }
   __syncwarp();
   // --- next observation and action mask
-  if (active && g < c.A) {
-    int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
-    const uint8_t mk = emit_obs_and_mask(c, m, g, row);
-    mask[(size_t)env * c.A + g] = mk;
+  if (agent) {
+    const int r = el * c.A + g;
+    mask[(size_t)env * c.A + g] = emit_row<G, R>(c, rec, g, sobs + r * c.FR, r & 1, replay, opk);
   }
+  fence_proxy_async();
   __syncthreads();
-  store_obs(c, sobs, view, env0, nenv);
-  store_records(c, L, srec, state, env0, nenv);
+  store_block(sobs, reinterpret_cast<uint8_t*>(view) + (size_t)env0 * c.A * c.FR,
+              nenv * c.A * c.FR);
+  store_block(srec, gstate, (int)rec_bytes);
+  if (threadIdx.x == 0) bulk_commit_wait_read();
 }
 
 // vmap(env.reset)(keys): RecordEpisodeMetrics.reset splits the key, the inner generator builds the
 // state, metrics start at zero (episode_metrics.py:59-76).
-template <int G>
+template <int G, int R>
 __global__ void __launch_bounds__(kThreads)
 rware_reset_kernel(const __grid_constant__ RwareConst c, const uint32_t* __restrict__ keys,
                    uint8_t* __restrict__ state, int8_t* __restrict__ view,
                    uint8_t* __restrict__ mask, int num_envs) {
   extern __shared__ uint4 smem_raw[];
   constexpr int EPC = kThreads / G;
-  const SmemLayout L = smem_layout(c, EPC);
   uint8_t* srec = reinterpret_cast<uint8_t*>(smem_raw);
-  uint8_t* sgsh = srec + L.per_cta_rec;
-  uint8_t* sgag = sgsh + L.per_cta_grid;
-  uint8_t* sobs = sgag + L.per_cta_grid;
+  uint8_t* sobs = srec + EPC * c.stride;
   const int env0 = blockIdx.x * EPC;
   const int nenv = min(EPC, num_envs - env0);
   const int el = threadIdx.x / G, g = threadIdx.x % G;
   const int env = env0 + el;
   const unsigned gmask = group_mask<G>();
+  uint32_t opk[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) opk[j] = 0u;
   if (el < nenv) {
-    EnvSmem m{srec + el * L.rec_stride, sgsh + el * L.grid_stride, sgag + el * L.grid_stride};
-    for (int i = g; i < (c.stride >> 2); i += G) reinterpret_cast<uint32_t*>(m.rec)[i] = 0u;
+    uint8_t* rec = srec + el * c.stride;
+    for (int i = g; i < (c.stride >> 2); i += G) reinterpret_cast<uint32_t*>(rec)[i] = 0u;
     __syncwarp(gmask);
     Key key{keys[2 * (size_t)env], keys[2 * (size_t)env + 1]}, reset_key;
     split2(key, key, reset_key);
-    generate<G>(c, m, reset_key, g, gmask);
+    generate<G>(c, rec, reset_key, g, gmask);
     if (g == 0) {
-      uint32_t* mk = reinterpret_cast<uint32_t*>(m.rec + c.off_mkey);
+      uint32_t* mk = reinterpret_cast<uint32_t*>(rec + c.off_mkey);
       mk[0] = key.k0;
       mk[1] = key.k1;
     }
-    build_grids<G>(c, m, g, gmask);
+    __syncwarp(gmask);
     if (g < c.A) {
-      int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
-      mask[(size_t)env * c.A + g] = emit_obs_and_mask(c, m, g, row);
+      const int r = el * c.A + g;
+      mask[(size_t)env * c.A + g] =
+          emit_row<G, R>(c, rec, g, sobs + r * c.FR, r & 1, false, opk);
     }
   }
+  fence_proxy_async();
   __syncthreads();
-  store_obs(c, sobs, view, env0, nenv);
-  store_records(c, L, srec, state, env0, nenv);
+  store_block(sobs, reinterpret_cast<uint8_t*>(view) + (size_t)env0 * c.A * c.FR,
+              nenv * c.A * c.FR);
+  store_block(srec, state + (size_t)env0 * c.stride, nenv * c.stride);
+  if (threadIdx.x == 0) bulk_commit_wait_read();
 }
 
 __global__ void rware_peek_kernel(const __grid_constant__ RwareConst c,
@@ -541,19 +646,25 @@ __global__ void rware_peek_kernel(const __grid_constant__ RwareConst c,
     out[2 * env] = (int32_t)k[0];
     out[2 * env + 1] = (int32_t)k[1];
   } else if (field == 2) {
+    const uint32_t* agents = reinterpret_cast<const uint32_t*>(r + c.off_agents);
     for (int i = 0; i < c.A; ++i) {
       int32_t* o = out + ((size_t)env * c.A + i) * 4;
-      o[0] = r[c.off_ax + i];
-      o[1] = r[c.off_ay + i];
-      o[2] = r[c.off_dir + i];
-      o[3] = r[c.off_carry + i];
+      o[0] = agents[i] & 0xff;
+      o[1] = (agents[i] >> 8) & 0xff;
+      o[2] = (agents[i] >> 16) & 0xff;
+      o[3] = agents[i] >> 24;
     }
-  } else if (field == 3) {  // shelves: x, y, requested
-    for (int s = 0; s < c.n; ++s) {
-      int32_t* o = out + ((size_t)env * c.n + s) * 3;
-      o[0] = r[c.off_sx + s];
-      o[1] = r[c.off_sy + s];
-      o[2] = r[c.off_req + s];
+  } else if (field == 3) {  // shelves: x, y, requested (positions read back from the grid)
+    const uint8_t* cells = r + c.off_cells;
+    for (int cell = 0; cell < c.HW; ++cell) {
+      const int sid = cells[cell];
+      if (sid != 0) {
+        int32_t* o = out + ((size_t)env * c.n + sid - 1) * 3;
+        o[0] = cell / c.W;
+        o[1] = cell % c.W;
+        o[2] = (reinterpret_cast<const uint32_t*>(r + c.off_reqbits)[(sid - 1) >> 5] >>
+                ((sid - 1) & 31)) & 1u;
+      }
     }
   } else if (field == 4) {  // request queue
     for (int q = 0; q < c.Q; ++q) out[(size_t)env * c.Q + q] = r[c.off_queue + q];
@@ -611,16 +722,12 @@ int rware_create(const mava_rware_config* cfg, mava_env_s* env) {
   MAVA_CHECK_ARG(c.Q <= c.n && c.A <= c.HW);
   c.goal[0] = (c.H - 1) * c.W + c.W / 2 - 1;
   c.goal[1] = (c.H - 1) * c.W + c.W / 2;
+  c.cells_words = (c.HW + 3) / 4;
+  c.req_words = (c.n + 31) / 32;
   int o = 0;
-  c.off_ax = o; o += c.A;
-  c.off_ay = o; o += c.A;
-  c.off_dir = o; o += c.A;
-  c.off_carry = o; o += c.A;
-  c.off_sx = o; o += c.n;
-  c.off_sy = o; o += c.n;
-  c.off_req = o; o += c.n;
-  c.off_queue = o; o += c.Q;
-  o = round_up(o, 4);
+  c.off_agents = o; o += 4 * c.A;
+  c.off_queue = o; o += round_up(c.Q, 4);
+  c.off_reqbits = o; o += 4 * c.req_words;
   c.off_step = o; o += 4;
   c.off_key = o; o += 8;
   c.off_mkey = o; o += 8;
@@ -628,7 +735,9 @@ int rware_create(const mava_rware_config* cfg, mava_env_s* env) {
   c.off_run_len = o; o += 4;
   c.off_ep_ret = o; o += 4;
   c.off_ep_len = o; o += 4;
+  c.off_cells = o; o += 4 * c.cells_words;
   c.stride = round_up(o, 16);
+  if ((c.stride / 16) % 2 == 0) c.stride += 16;  // odd multiple of 16: bank-conflict-free records
 
   mava_env_dims& d = env->dims;
   d.kind = MAVA_ENV_RWARE;
@@ -647,21 +756,25 @@ int rware_create(const mava_rware_config* cfg, mava_env_s* env) {
   return 0;
 }
 
-#define MAVA_RWARE_DISPATCH(KERNEL, ...)                                              \
-  do {                                                                                \
-    if (c.A <= 4) {                                                                   \
-      constexpr int G = 4;                                                            \
-      const size_t smem = smem_bytes(c, kThreads / G);                                \
-      int rc = prepare(KERNEL<G>, smem);                                              \
-      if (rc) return rc;                                                              \
-      KERNEL<G><<<ceil_div(num_envs, kThreads / G), kThreads, smem, s>>>(__VA_ARGS__); \
-    } else {                                                                          \
-      constexpr int G = 8;                                                            \
-      const size_t smem = smem_bytes(c, kThreads / G);                                \
-      int rc = prepare(KERNEL<G>, smem);                                              \
-      if (rc) return rc;                                                              \
-      KERNEL<G><<<ceil_div(num_envs, kThreads / G), kThreads, smem, s>>>(__VA_ARGS__); \
-    }                                                                                 \
+#define MAVA_RWARE_LAUNCH(KERNEL, G_, R_, ...)                                              \
+  do {                                                                                      \
+    const size_t smem = smem_bytes(c, kThreads / G_);                                       \
+    int rc = prepare(KERNEL<G_, R_>, smem);                                                 \
+    if (rc) return rc;                                                                      \
+    KERNEL<G_, R_><<<ceil_div(num_envs, kThreads / G_), kThreads, smem, s>>>(__VA_ARGS__);  \
+  } while (0)
+
+#define MAVA_RWARE_DISPATCH(KERNEL, ...)                                   \
+  do {                                                                     \
+    if (c.R == 1) {                                                        \
+      if (c.A <= 2) MAVA_RWARE_LAUNCH(KERNEL, 2, 1, __VA_ARGS__);          \
+      else if (c.A <= 4) MAVA_RWARE_LAUNCH(KERNEL, 4, 1, __VA_ARGS__);     \
+      else MAVA_RWARE_LAUNCH(KERNEL, 8, 1, __VA_ARGS__);                   \
+    } else {                                                               \
+      if (c.A <= 2) MAVA_RWARE_LAUNCH(KERNEL, 2, 2, __VA_ARGS__);          \
+      else if (c.A <= 4) MAVA_RWARE_LAUNCH(KERNEL, 4, 2, __VA_ARGS__);     \
+      else MAVA_RWARE_LAUNCH(KERNEL, 8, 2, __VA_ARGS__);                   \
+    }                                                                      \
   } while (0)
 
 int rware_reset(const mava_env_s* env, const uint32_t* keys, uint8_t* state, int8_t* view,
