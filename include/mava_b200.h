@@ -229,6 +229,70 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor_host, const float* actor_
                             void* workspace, mava_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * Recurrent systems - RecurrentActor / RecurrentValueNet / ScannedRNN (mava/networks.py:238-331)
+ * as rec_ippo / rec_mappo use them (mava/systems/ppo/rec_mappo.py:91-149,208-293,334-360).
+ * Network: Dense(in,H)+relu -> reset-masked GRU(H) -> Dense(H,post)+relu -> Dense(post,out).
+ * Parameters are one flat f32 vector per network:
+ *   [pre.kernel (in,H) | pre.bias | Wi (H,3H) = [ir|iz|in] kernels | bi (3H) = [ir|iz|in] biases |
+ *    Wh (H,3H) = [hr|hz|hn] kernels | hn.bias (H) | post.kernel (H,post) | post.bias |
+ *    head.kernel (post,out) | head.bias]            (flax GRUCell: hr and hz carry no bias)
+ * Hidden states are f32 [num_envs * rows_per_env][H].
+ * ---------------------------------------------------------------------------------------- */
+#define MAVA_IN_DENSE 2 /* x = obs[step][row][:] given as f32 (e.g. SMAX-shaped observations)   */
+
+typedef struct mava_rnn_desc {
+  int32_t input_mode;   /* MAVA_IN_AGENT_VIEW | MAVA_IN_GLOBAL | MAVA_IN_DENSE                   */
+  int32_t add_agent_id; /* AGENT_VIEW only                                                       */
+  int32_t num_agents, view_dim;
+  int32_t in_dim;       /* derived for the view modes; the feature count for DENSE               */
+  int32_t rows_per_env; /* A, or 1 for a centralised critic (identical rows are evaluated once)  */
+  int32_t hidden;       /* pre_torso width == GRU width (flax: features = ins.shape[-1])         */
+  int32_t post;         /* post_torso width                                                      */
+  int32_t out_dim;      /* action_dim for the actor, 1 for the critic                            */
+} mava_rnn_desc;
+
+int64_t mava_rnn_param_count(const mava_rnn_desc* d_host);
+
+/* One acting step (rec_mappo.py:91-134): both networks advance their hidden state from
+ * h_*_in to h_*_out (out may alias in, or be NULL to discard the new state - the bootstrap value
+ * of rec_mappo.py:165 does that), the carry being zeroed first where done_in[env] is set
+ * (ScannedRNN, networks.py:249-253).  actor_host == NULL evaluates the critic only.
+ * view is the int8 observation of the env kernels; obs_actor / obs_critic are the f32 inputs of
+ * MAVA_IN_DENSE networks ([num_envs][rows_per_env][in_dim]).  Sampling as mava_ff_act. */
+int64_t mava_rec_act_workspace_bytes(const mava_rnn_desc* actor_host,
+                                     const mava_rnn_desc* critic_host, int num_envs);
+int mava_rec_act(const mava_rnn_desc* actor_host, const float* actor_params,
+                 const mava_rnn_desc* critic_host, const float* critic_params, const int8_t* view,
+                 const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                 const uint8_t* done_in, const float* h_actor_in, float* h_actor_out,
+                 const float* h_critic_in, float* h_critic_out, const uint32_t* policy_key,
+                 int envs_per_replica, int num_envs, int greedy, const int8_t* actions_in,
+                 int8_t* action, float* logp, float* value, void* workspace, mava_stream_t s);
+
+/* Gradients of the recurrent actor and critic losses for one minibatch (rec_mappo.py:208-312),
+ * averaged over the update_batch_size replicas on this GPU.  The batch is the rollout reshaped
+ * exactly like the reference does it (rec_mappo.py:339-349): (T, E) -> (chunk, E*num_chunks), so
+ * column col = c*E + e holds env e at times t = l*num_chunks + c, l = 0..chunk-1, and starts from
+ * the hidden state stored at time c.  cols[mb_cols] are the (shuffled) columns of this minibatch,
+ * shared by all replicas.  Rollout buffers have a leading [T] axis over NE = num_replicas *
+ * envs_per_replica envs; done_in[T][NE] is the flag ENTERING each step; hs_* are the hidden
+ * states entering steps 0..num_chunks-1: [num_chunks][NE*rows_per_env][H].
+ * grad_out: [actor grads | critic grads | total_actor, actor_loss, entropy, total_critic,
+ * value_loss | pad]. */
+int64_t mava_rec_ppo_workspace_bytes(const mava_rnn_desc* actor_host,
+                                     const mava_rnn_desc* critic_host, int seq_envs_total,
+                                     int chunk);
+int mava_rec_ppo_loss_grad(const mava_rnn_desc* actor_host, const float* actor_params,
+                           const mava_rnn_desc* critic_host, const float* critic_params,
+                           const mava_ppo_hyper* hyper_host, const int8_t* view,
+                           const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                           const int8_t* action, const float* old_logp, const float* old_value,
+                           const float* adv, const float* targets, const uint8_t* done_in,
+                           const float* hs_actor, const float* hs_critic, const int32_t* cols,
+                           int num_replicas, int envs_per_replica, int mb_cols, int chunk,
+                           int num_chunks, float* grad_out, void* workspace, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics.  One 128 x N x K bf16 GEMM on the tcgen05 tensor cores in each operand arrangement
  * the fused MLP kernels use (0: X W, 1: dZ W^T, 2: H^T dZ); A, B, D are row-major f32.
  * ---------------------------------------------------------------------------------------- */

@@ -37,6 +37,12 @@ class MlpDesc(C.Structure):
         "input_mode", "add_agent_id", "num_agents", "view_dim", "in_dim", "h1", "h2", "out_dim")]
 
 
+class RnnDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "input_mode", "add_agent_id", "num_agents", "view_dim", "in_dim", "rows_per_env", "hidden",
+        "post", "out_dim")]
+
+
 class PpoHyper(C.Structure):
     _fields_ = [("clip_eps", c_f32), ("ent_coef", c_f32), ("vf_coef", c_f32)]
 
@@ -78,6 +84,13 @@ SIGNATURES = {
                                         P(PpoHyper)] + [c_void] * 8 +
                                 [c_int, c_int, c_void, c_void, c_void]),
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
+    "mava_rnn_param_count": (c_i64, [P(RnnDesc)]),
+    "mava_rec_act_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int]),
+    "mava_rec_act": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void] + [c_void] * 10 +
+                     [c_int, c_int, c_int] + [c_void] * 6),
+    "mava_rec_ppo_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int, c_int]),
+    "mava_rec_ppo_loss_grad": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void, P(PpoHyper)] +
+                               [c_void] * 13 + [c_int] * 5 + [c_void] * 3),
     "mava_clip_adam": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32,
                                c_int, c_int, c_void]),
 }

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EnvDims, LbfConfig, MlpDesc, PpoHyper, RwareConfig, check
+from ._lib import EnvDims, LbfConfig, MlpDesc, PpoHyper, RnnDesc, RwareConfig, check
 
 ENV_RWARE, ENV_LBF = 1, 2
 # Number of mava_b200 kernels launched through this module (the benchmark's `gpu_launches`).
@@ -23,7 +23,7 @@ def _count(n: int) -> None:
     global LAUNCHES
     LAUNCHES += n
 
-IN_AGENT_VIEW, IN_GLOBAL = 0, 1
+IN_AGENT_VIEW, IN_GLOBAL, IN_DENSE = 0, 1, 2
 OMAX = 16
 
 
@@ -336,3 +336,82 @@ def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, gr
         _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
         _p(grad, torch.float32, n, "grad"), n_actor, n_critic, grad_scale, lr_actor, lr_critic,
         max_norm, lr_decay_num_updates, steps_per_update, _stream()), "mava_clip_adam_pair")
+
+
+# ---------------------------------------------------------------------------------------------
+# recurrent systems (rec_ippo / rec_mappo)
+# ---------------------------------------------------------------------------------------------
+def rnn_desc(input_mode: int, add_agent_id: bool, num_agents: int, view_dim: int, hidden: int,
+             post: int, out_dim: int, dense_in_dim: int = 0, rows_per_env: Optional[int] = None
+             ) -> RnnDesc:
+    if input_mode == IN_DENSE:
+        in_dim = int(dense_in_dim)
+        rpe = num_agents if rows_per_env is None else int(rows_per_env)
+    elif input_mode == IN_GLOBAL:
+        in_dim, rpe = num_agents * view_dim, 1
+    else:
+        in_dim, rpe = view_dim + (num_agents if add_agent_id else 0), num_agents
+    return RnnDesc(input_mode, int(add_agent_id), num_agents, view_dim, in_dim, rpe, hidden, post,
+                   out_dim)
+
+
+def rnn_param_count(d: RnnDesc) -> int:
+    return int(_lib.load().mava_rnn_param_count(C.byref(d)))
+
+
+def rec_act_workspace_bytes(actor: Optional[RnnDesc], critic: RnnDesc, num_envs: int) -> int:
+    return int(_lib.load().mava_rec_act_workspace_bytes(
+        C.byref(actor) if actor is not None else None, C.byref(critic), num_envs))
+
+
+def rec_act(actor: Optional[RnnDesc], actor_params, critic: Optional[RnnDesc], critic_params, view,
+            obs_actor, obs_critic, mask, done_in, h_actor_in, h_actor_out, h_critic_in,
+            h_critic_out, policy_key, envs_per_replica: int, num_envs: int, action, logp, value,
+            workspace, greedy: bool = False, actions_in=None) -> None:
+    """One acting step of the recurrent systems (actor=None: critic only, the bootstrap value)."""
+    _count((9 if actor is not None else 0) + (9 if critic is not None and value is not None else 0))
+    check(_lib.load().mava_rec_act(
+        C.byref(actor) if actor is not None else None,
+        _p(actor_params, torch.float32, rnn_param_count(actor) if actor is not None else None,
+           "actor_params"),
+        C.byref(critic) if critic is not None else None,
+        _p(critic_params, torch.float32, rnn_param_count(critic) if critic is not None else None,
+           "critic_params"),
+        _p(view, torch.int8, None, "view"), _p(obs_actor, torch.float32, None, "obs_actor"),
+        _p(obs_critic, torch.float32, None, "obs_critic"), _p(mask, torch.uint8, None, "mask"),
+        _p(done_in, torch.uint8, num_envs, "done_in"),
+        _p(h_actor_in, torch.float32, None, "h_actor_in"),
+        _p(h_actor_out, torch.float32, None, "h_actor_out"),
+        _p(h_critic_in, torch.float32, None, "h_critic_in"),
+        _p(h_critic_out, torch.float32, None, "h_critic_out"),
+        _p(policy_key, torch.uint32, 2, "policy_key"), envs_per_replica, num_envs, int(greedy),
+        _p(actions_in, torch.int8, None, "actions_in"), _p(action, torch.int8, None, "action"),
+        _p(logp, torch.float32, None, "logp"), _p(value, torch.float32, None, "value"),
+        _p(workspace, torch.uint8, None, "workspace"), _stream()), "mava_rec_act")
+
+
+def rec_ppo_workspace_bytes(actor: RnnDesc, critic: RnnDesc, seq_envs_total: int, chunk: int) -> int:
+    return int(_lib.load().mava_rec_ppo_workspace_bytes(C.byref(actor), C.byref(critic),
+                                                        seq_envs_total, chunk))
+
+
+def rec_ppo_loss_grad(actor: RnnDesc, actor_params, critic: RnnDesc, critic_params,
+                      hyper: PpoHyper, view, obs_actor, obs_critic, mask, action, old_logp,
+                      old_value, adv, targets, done_in, hs_actor, hs_critic, cols,
+                      num_replicas: int, envs_per_replica: int, mb_cols: int, chunk: int,
+                      num_chunks: int, grad_out, workspace) -> None:
+    na, nc = rnn_param_count(actor), rnn_param_count(critic)
+    need = rec_ppo_workspace_bytes(actor, critic, num_replicas * mb_cols, chunk)
+    _count(2 * (4 * chunk + 24) + 3)
+    check(_lib.load().mava_rec_ppo_loss_grad(
+        C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"), C.byref(critic),
+        _p(critic_params, torch.float32, nc, "critic_params"), C.byref(hyper),
+        _p(view, torch.int8, None, "view"), _p(obs_actor, torch.float32, None, "obs_actor"),
+        _p(obs_critic, torch.float32, None, "obs_critic"), _p(mask, torch.uint8, None, "mask"),
+        _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
+        _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
+        _p(targets, torch.float32, None, "targets"), _p(done_in, torch.uint8, None, "done_in"),
+        _p(hs_actor, torch.float32, None, "hs_actor"), _p(hs_critic, torch.float32, None, "hs_critic"),
+        _p(cols, torch.int32, mb_cols, "cols"), num_replicas, envs_per_replica, mb_cols, chunk,
+        num_chunks, _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
+        _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_rec_ppo_loss_grad")

@@ -159,3 +159,45 @@ def clip_adam(params: np.ndarray, grads: np.ndarray, mu: np.ndarray, nu: np.ndar
 def linear_lr(init_lr: float, count: int, ppo_epochs: int, num_minibatches: int, num_updates: int):
     """make_learning_rate_schedule, mava/utils/training.py:39-47."""
     return init_lr * (1.0 - (count // (ppo_epochs * num_minibatches)) / num_updates)
+
+
+# ------------------------------------------------------------------------------------------
+# recurrent systems (mava/networks.py:238-331, mava/systems/ppo/rec_mappo.py)
+# ------------------------------------------------------------------------------------------
+def rnn_unflatten(flat: torch.Tensor, in_dim: int, H: int, Q: int, out: int) -> Dict[str, torch.Tensor]:
+    """Split the flat parameter vector of include/mava_b200.h (mava_rnn_desc) into named blocks."""
+    shapes = [("pre_w", (in_dim, H)), ("pre_b", (H,)), ("wi", (H, 3 * H)), ("bi", (3 * H,)),
+              ("wh", (H, 3 * H)), ("hn_b", (H,)), ("post_w", (H, Q)), ("post_b", (Q,)),
+              ("head_w", (Q, out)), ("head_b", (out,))]
+    p, off = {}, 0
+    for name, s in shapes:
+        n = int(np.prod(s))
+        p[name] = flat[off:off + n].reshape(s)
+        off += n
+    assert off == flat.numel()
+    return p
+
+
+def _gru_params(p: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    H = p["hn_b"].shape[0]
+    wi, bi, wh = p["wi"], p["bi"], p["wh"]
+    return {"ir_w": wi[:, :H], "iz_w": wi[:, H:2 * H], "in_w": wi[:, 2 * H:],
+            "ir_b": bi[:H], "iz_b": bi[H:2 * H], "in_b": bi[2 * H:],
+            "hr_w": wh[:, :H], "hz_w": wh[:, H:2 * H], "hn_w": wh[:, 2 * H:], "hn_b": p["hn_b"]}
+
+
+def rec_net(p: Dict[str, torch.Tensor], h0: torch.Tensor, xs: torch.Tensor, resets: torch.Tensor):
+    """RecurrentActor / RecurrentValueNet body, networks.py:281-294,314-331: pre_torso ->
+    ScannedRNN -> post_torso -> head.  xs (L, S, in), resets (L, S) bool.  Returns (h_L, out)."""
+    emb = torch.relu(xs @ p["pre_w"] + p["pre_b"])
+    h, ys = scanned_rnn(h0, emb, resets, _gru_params(p))
+    post = torch.relu(ys @ p["post_w"] + p["post_b"])
+    return h, post @ p["head_w"] + p["head_b"]
+
+
+def rec_chunk_batch(x: torch.Tensor, chunk: int, cols: torch.Tensor) -> torch.Tensor:
+    """The reference's minibatch view of a (T, E, ...) rollout array, rec_mappo.py:339-357:
+    reshape to (chunk, E * num_chunks, ...) and take the minibatch's columns."""
+    T, E = x.shape[:2]
+    nc = T // chunk
+    return x.reshape(chunk, E * nc, *x.shape[2:])[:, cols.long()]
