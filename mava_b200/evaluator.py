@@ -35,6 +35,30 @@ def make_ff_eval_act_fn(actor_desc, config) -> Callable:
     return eval_act_fn
 
 
+def make_rec_eval_act_fn(actor_desc, config) -> Callable:
+    """evaluator.py:189-209: the recurrent actor carries a hidden state through the episode
+    (zeros at the start, evaluator's ``init_act_state``) and resets it on ``timestep.last()``."""
+    greedy = bool(config.arch.evaluation_greedy)
+    st: Dict[str, torch.Tensor] = {}
+
+    def reset(num_envs: int, device) -> None:
+        if "h" not in st or st["h"].shape[0] != num_envs * actor_desc.num_agents:
+            st["h"] = torch.zeros(num_envs * actor_desc.num_agents, actor_desc.hidden, device=device)
+            st["ws"] = torch.zeros(native.rec_act_workspace_bytes(actor_desc, actor_desc, num_envs),
+                                   dtype=torch.uint8, device=device)
+            st["zero"] = torch.zeros(num_envs, dtype=torch.uint8, device=device)
+        st["h"].zero_()
+
+    def eval_act_fn(params, view, mask, key, num_envs, action, logp, last_done=None):
+        native.rec_act(actor_desc, params, None, None, view, None, None, mask,
+                       st["zero"] if last_done is None else last_done, st["h"], st["h"], None, None,
+                       key, num_envs, num_envs, action, logp, None, st["ws"], greedy=greedy)
+
+    eval_act_fn.reset = reset  # type: ignore[attr-defined]
+    eval_act_fn.recurrent = True  # type: ignore[attr-defined]
+    return eval_act_fn
+
+
 def get_eval_fn(env, act_fn: Callable, config, absolute_metric: bool):
     """evaluator.py:80-172.  Returns ``evaluator(params, key, init_act_state) -> metrics`` where
     ``key`` is this rank's uint32[2] evaluation key (host array)."""
@@ -71,8 +95,15 @@ def get_eval_fn(env, act_fn: Callable, config, absolute_metric: bool):
             env.native.reset(torch.from_numpy(reset_keys.copy()).to(dev), state, view, mask, n_envs)
             key_dev.copy_(torch.from_numpy(np.ascontiguousarray(key)).to(dev))
             native.prng_split_chain(key_dev, act_keys, T)  # key, act_key = split(key) per step
+            recurrent = bool(getattr(act_fn, "recurrent", False))
+            if recurrent:
+                act_fn.reset(n_envs, dev)
             for t in range(T):
-                act_fn(params, view, mask, act_keys[t], n_envs, action, logp)
+                if recurrent:
+                    act_fn(params, view, mask, act_keys[t], n_envs, action, logp,
+                           done[t - 1] if t > 0 else None)
+                else:
+                    act_fn(params, view, mask, act_keys[t], n_envs, action, logp)
                 env.native.step(state, action, view, mask, reward, done[t], ep_ret[t], ep_len[t],
                                 n_envs, False)
             key = key_dev.cpu().numpy()
