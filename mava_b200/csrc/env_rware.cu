@@ -86,14 +86,15 @@ __device__ __forceinline__ unsigned group_mask() {
   return ((1u << G) - 1u) << ((lane / G) * G);
 }
 
+// Minimum of a 64-bit composite over the lanes of a group: two hardware warp reductions
+// (redux.sync) instead of a shuffle tree -- high word first, then the low word among the ties.
 template <int G>
 __device__ __forceinline__ unsigned long long group_min(unsigned long long v, unsigned gmask) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
-    unsigned long long w = __shfl_xor_sync(gmask, v, o, G);
-    v = w < v ? w : v;
-  }
-  return v;
+  const uint32_t hi = (uint32_t)(v >> 32);
+  const uint32_t m = __reduce_min_sync(gmask, hi);
+  const uint32_t lo = hi == m ? (uint32_t)v : 0xffffffffu;
+  const uint32_t l = __reduce_min_sync(gmask, lo);
+  return ((unsigned long long)m << 32) | l;
 }
 
 __device__ __forceinline__ bool is_highway(const RwareConst& c, int cell) {
@@ -355,7 +356,8 @@ __device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* 
 }
 
 __host__ inline size_t smem_bytes(const RwareConst& c, int envs_per_cta) {
-  return (size_t)envs_per_cta * c.stride + (size_t)round_up(envs_per_cta * c.A * c.FR, 16) + 16;
+  return (size_t)envs_per_cta * c.stride + (size_t)round_up(envs_per_cta * c.A * c.FR, 16) + 16 +
+         2 * (size_t)envs_per_cta;  // mbarrier + reset counter, reset queue
 }
 
 // Staged observation block / records -> HBM.  Bulk stores when size and address allow it.
@@ -383,12 +385,15 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
   uint8_t* srec = reinterpret_cast<uint8_t*>(smem_raw);
   uint8_t* sobs = srec + EPC * c.stride;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sobs + round_up(EPC * c.A * c.FR, 16));
+  int* rcount = reinterpret_cast<int*>(bar + 1);
+  uint16_t* rlist = reinterpret_cast<uint16_t*>(bar + 2);
 
   const int env0 = blockIdx.x * EPC;
   const int nenv = min(EPC, num_envs - env0);
   const uint32_t rec_bytes = (uint32_t)nenv * (uint32_t)c.stride;
   uint8_t* gstate = state + (size_t)env0 * c.stride;
   if (threadIdx.x == 0) {
+    *rcount = 0;
     mbar_init(bar, 1);
     mbar_expect_tx(bar, rec_bytes);
     bulk_g2s(srec, gstate, rec_bytes, bar);
@@ -555,25 +560,25 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
     replay = collision && !needs_reset;
   }
   // --- AutoResetWrapper: on the last step the state and observation are those of a fresh episode
-  //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare, so
-  //     the whole warp regenerates one finished env at a time: 32 lanes share the threefry draws
-  //     and the top-k selections instead of leaving G lanes with the long tail.
-  __syncwarp();
+  //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare and a
+  //     regeneration is a long dependent chain of threefry calls, so finished envs go into a CTA
+  //     queue and every warp takes one at a time with all 32 lanes: the tail is one regeneration
+  //     per warp instead of all of a warp's finished envs back to back.
+  if (needs_reset && g == 0) rlist[atomicAdd(rcount, 1)] = (uint16_t)el;
+  __syncthreads();
   {
+    const int nreset = *rcount;
     const unsigned lane = threadIdx.x & 31u;
-    unsigned pending = __ballot_sync(0xffffffffu, needs_reset && g == 0);
-    while (pending) {
-      const int leader = __ffs(pending) - 1;
-      pending &= pending - 1;
-      const int rel = __shfl_sync(0xffffffffu, el, leader);
-      const uint32_t k0 = __shfl_sync(0xffffffffu, key.k0, leader);
-      const uint32_t k1 = __shfl_sync(0xffffffffu, key.k1, leader);
+    for (int i = threadIdx.x >> 5; i < nreset; i += kThreads / 32) {
+      uint8_t* rrec = srec + (int)rlist[i] * c.stride;
+      const uint32_t* k = reinterpret_cast<const uint32_t*>(rrec + c.off_key);
       Key nk, unused;
-      split2(Key{k0, k1}, nk, unused);
-      generate<32>(c, srec + rel * c.stride, nk, (int)lane, 0xffffffffu);
+      split2(Key{k[0], k[1]}, nk, unused);
+      __syncwarp();
+      generate<32>(c, rrec, nk, (int)lane, 0xffffffffu);
     }
   }
-  __syncwarp();
+  __syncthreads();
   // --- next observation and action mask
   if (agent) {
     const int r = el * c.A + g;
