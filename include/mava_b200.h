@@ -228,6 +228,22 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor_host, const float* actor_
                             const int32_t* rows, int num_replicas, int mb_size, float* grad_out,
                             void* workspace, mava_stream_t s);
 
+/* The whole rollout scan of ff_ippo / ff_mappo (ff_mappo.py:76-106) in one persistent kernel:
+ * rollout_length x (actor forward + masked categorical sample + env step through the wrapper
+ * stack), env records, observation rows and the actor weights resident in shared memory for the
+ * whole rollout.  view / mask have rollout_length + 1 time slots: slot 0 holds the observation the
+ * first step acts on, slot t + 1 receives the observation after step t.  policy_keys[T][2] are the
+ * per-step sampling keys (mava_prng_split_chain).  action, logp, reward: [T][NE][A]; done,
+ * ep_return, ep_length: [T][NE].  The critic values are computed afterwards with one batched
+ * mava_ff_act_bf16(actor = NULL) call over the T + 1 observation slots.
+ * Returns MAVA_E_UNSUPPORTED unless the env is RobotWarehouse with 2, 4 or 8 agents and
+ * sensor_range 1 (callers then fall back to mava_ff_act_bf16 + mava_env_step per step). */
+int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor_host, const float* actor_params,
+                         const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,
+                         const uint32_t* policy_keys, int envs_per_replica, int num_envs,
+                         int rollout_length, int8_t* action, float* logp, float* reward,
+                         uint8_t* done, float* ep_return, int32_t* ep_length, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Recurrent systems - RecurrentActor / RecurrentValueNet / ScannedRNN (mava/networks.py:238-331)
  * as rec_ippo / rec_mappo use them (mava/systems/ppo/rec_mappo.py:91-149,208-293,334-360).

@@ -84,6 +84,8 @@ SIGNATURES = {
                                         P(PpoHyper)] + [c_void] * 8 +
                                 [c_int, c_int, c_void, c_void, c_void]),
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
+    "mava_ff_rollout_bf16": (c_int, [c_void, P(MlpDesc)] + [c_void] * 6 + [c_int] * 3 +
+                             [c_void] * 7),
     "mava_rnn_param_count": (c_i64, [P(RnnDesc)]),
     "mava_rec_act_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int]),
     "mava_rec_act": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void] + [c_void] * 10 +

@@ -20,340 +20,17 @@
 //     writes it to a staging block that leaves the CTA as one contiguous bulk store.
 //   * Rare paths (delivery -> new request, episode end -> in-kernel reset) run threefry on all
 //     lanes of the group / warp.
-#include "env.cuh"
-#include "prng.cuh"
+#include "env_rware.cuh"
 
 namespace mava {
 namespace {
+
+using namespace rware;
 
 constexpr int kThreads = 256;
 #ifndef MAVA_RWARE_MINB
 #define MAVA_RWARE_MINB 6  // resident CTAs per SM the step kernel's register budget is sized for
 #endif
-
-// ---- small PTX helpers (mbarrier + bulk copies) ------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (spins > (1u << 24)) __trap();  // a bug surfaces as an error instead of a hang
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-               "r"(smem_u32(src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-  if (G == 32) return 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  return ((1u << G) - 1u) << ((lane / G) * G);
-}
-
-// Minimum of a 64-bit composite over the lanes of a group: two hardware warp reductions
-// (redux.sync) instead of a shuffle tree -- high word first, then the low word among the ties.
-template <int G>
-__device__ __forceinline__ unsigned long long group_min(unsigned long long v, unsigned gmask) {
-  const uint32_t hi = (uint32_t)(v >> 32);
-  const uint32_t m = __reduce_min_sync(gmask, hi);
-  const uint32_t lo = hi == m ? (uint32_t)v : 0xffffffffu;
-  const uint32_t l = __reduce_min_sync(gmask, lo);
-  return ((unsigned long long)m << 32) | l;
-}
-
-__device__ __forceinline__ bool is_highway(const RwareConst& c, int cell) {
-  return (c.highway[cell >> 5] >> (cell & 31)) & 1u;
-}
-
-__device__ __forceinline__ void forward_cell(const RwareConst& c, int x, int y, int d, int& nx,
-                                             int& ny) {
-  nx = x;
-  ny = y;
-  if (d == 0) nx = max(0, x - 1);
-  else if (d == 1) ny = min(c.W - 1, y + 1);
-  else if (d == 2) nx = min(c.H - 1, x + 1);
-  else ny = max(0, y - 1);
-}
-
-__device__ __forceinline__ uint32_t pack_agent(int x, int y, int d, int carry) {
-  return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)d << 16) | ((uint32_t)carry << 24);
-}
-
-__device__ __forceinline__ bool requested(const RwareConst& c, const uint8_t* rec, int s) {
-  return (reinterpret_cast<const uint32_t*>(rec + c.off_reqbits)[s >> 5] >> (s & 31)) & 1u;
-}
-
-// K smallest of the composites (random_bits(sub, size)[i] << 32 | i), i.e. the first K entries of
-// jax.random.permutation-by-stable-sort.  Every lane returns the same out[].
-template <int G, int KMAX>
-__device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsigned gmask,
-                                           unsigned long long (&out)[KMAX]) {
-  unsigned long long top[KMAX];
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) top[j] = ~0ull;
-  const int half = (size + 1) >> 1;
-  for (int p = g; p < half; p += G) {
-    uint32_t lo, hi;
-    random_bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
-    unsigned long long v = ((unsigned long long)lo << 32) | (unsigned)p;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (v < top[j]) {
-        unsigned long long t = top[j];
-        top[j] = v;
-        v = t;
-      }
-    }
-    if (p + half < size) {
-      v = ((unsigned long long)hi << 32) | (unsigned)(p + half);
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (v < top[j]) {
-          unsigned long long t = top[j];
-          top[j] = v;
-          v = t;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < KMAX; ++r) {
-    out[r] = ~0ull;
-    if (r < K) {
-      unsigned long long mn = group_min<G>(top[0], gmask);
-      if (top[0] == mn) {
-#pragma unroll
-        for (int j = 0; j + 1 < KMAX; ++j) top[j] = top[j + 1];
-        top[KMAX - 1] = ~0ull;
-      }
-      out[r] = mn;
-    }
-  }
-}
-
-// jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
-// their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
-// lanes cooperate; State.key is what is left of `key`).
-template <int GG>
-__device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
-                                         unsigned gmask) {
-  Key pos_key, dir_key, q_key, unused, sub;
-  unsigned long long pick[kMaxAgents];
-  split2(key, key, pos_key);
-  split2(pos_key, unused, sub);
-  smallest_k<GG, kMaxAgents>(sub, c.HW, c.A, g, gmask, pick);
-  split2(key, key, dir_key);
-  Key d_hi, d_lo;
-  split2(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
-  if (g == 0) {
-    uint32_t* agents = reinterpret_cast<uint32_t*>(rec + c.off_agents);
-#pragma unroll
-    for (int i = 0; i < kMaxAgents; ++i) {
-      if (i < c.A) {
-        const int cell = (int)(pick[i] & 0xffffffffull);
-        const int d = (int)(random_bits_at(d_lo, (uint32_t)i, (uint32_t)c.A) & 3u);
-        agents[i] = pack_agent(cell / c.W, cell % c.W, d, 0);
-      }
-    }
-  }
-  split2(key, key, q_key);
-  split2(q_key, unused, sub);
-  unsigned long long qpick[kMaxQueue];
-  smallest_k<GG, kMaxQueue>(sub, c.n, c.Q, g, gmask, qpick);
-  uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
-  for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
-  __syncwarp(gmask);
-  uint8_t* cells = rec + c.off_cells;
-  for (int s = g; s < c.n; s += GG) cells[c.shelf_home[s]] = (uint8_t)(s + 1);
-  if (g == 0) {
-    uint32_t* rq = reinterpret_cast<uint32_t*>(rec + c.off_reqbits);
-    for (int i = 0; i < c.req_words; ++i) rq[i] = 0u;
-#pragma unroll
-    for (int i = 0; i < kMaxQueue; ++i) {
-      if (i < c.Q) {
-        const int s = (int)(qpick[i] & 0xffffffffull);
-        rec[c.off_queue + i] = (uint8_t)s;
-        rq[s >> 5] |= 1u << (s & 31);
-      }
-    }
-    *reinterpret_cast<uint32_t*>(rec + c.off_step) = 0u;
-    uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
-    k[0] = key.k0;
-    k[1] = key.k1;
-  }
-  __syncwarp(gmask);
-}
-
-// ---- observation rows --------------------------------------------------------------------------
-// jumanji utils.make_agent_observation: [x, y, carrying, onehot(dir, 4), on_highway] then, for the
-// (2R+1)^2 - 1 cells around the agent, [other agent present, onehot(its dir, 4)], then for all
-// (2R+1)^2 cells [shelf present, shelf requested]; int8, FR = 8 + 5 (L - 1) + 2 L bytes.
-template <int R>
-struct ObsDims {
-  static constexpr int SIDE = 2 * R + 1;
-  static constexpr int LOC = SIDE * SIDE;
-  static constexpr int CENTER = LOC / 2;
-  static constexpr int NAG = (LOC - 1) * 5;   // bytes of "other agent" features
-  static constexpr int FR = 8 + NAG + 2 * LOC;
-  static constexpr int NH = FR / 2;           // halfwords per row (odd)
-  static constexpr int NW = NH / 2 + 1;       // 32-bit words, the last one half used
-  static constexpr int MW = (NAG + 63) / 64;  // 64-bit words of the agent-feature bit mask
-  static constexpr int SH0 = (8 + NAG) / 4;   // first word of the shelf features
-  static_assert(FR % 4 == 2 && NAG % 4 == 0, "row layout assumptions");
-};
-
-// OR the 5-bit pattern p into bit position s of a multi-word mask.
-template <int MW>
-__device__ __forceinline__ void set5(unsigned long long (&M)[MW], int s, unsigned long long p) {
-  if (MW == 1) {
-    M[0] |= p << s;
-  } else {
-    const int w = s >> 6, b = s & 63;
-#pragma unroll
-    for (int i = 0; i < MW; ++i) {
-      if (i == w) M[i] |= p << b;
-      if (i == w + 1 && b > 59) M[i] |= p >> (64 - b);
-    }
-  }
-}
-
-// Builds the row of agent g from the (post-step) record and writes it, with the action mask bits
-// returned.  opk[j] = old cell | new cell << 10 | moved << 20 of agent j for this step; when
-// `replay` is set the AGENTS grid is evaluated exactly as the reference's sequence of grid writes
-// leaves it (needed only for the terminal observation of a collision without auto-reset), else
-// agents are on distinct cells and the grid is simply {cell of j -> j}.
-template <int G, int R>
-__device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* rec, int g,
-                                            uint8_t* row, int row_parity, bool replay,
-                                            const uint32_t (&opk)[G]) {
-  using O = ObsDims<R>;
-  const uint32_t* agents = reinterpret_cast<const uint32_t*>(rec + c.off_agents);
-  const uint8_t* cells = rec + c.off_cells;
-  const uint32_t me = agents[g];
-  const int x = me & 0xff, y = (me >> 8) & 0xff, d = (me >> 16) & 0xff, carry = me >> 24;
-  uint32_t w[O::NW];
-#pragma unroll
-  for (int i = 0; i < O::NW; ++i) w[i] = 0u;
-  w[0] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)carry << 16) | ((uint32_t)(d == 0) << 24);
-  w[1] = (uint32_t)(d == 1) | ((uint32_t)(d == 2) << 8) | ((uint32_t)(d == 3) << 16) |
-         ((uint32_t)is_highway(c, x * c.W + y) << 24);
-  unsigned long long M[O::MW];
-#pragma unroll
-  for (int i = 0; i < O::MW; ++i) M[i] = 0ull;
-  uint32_t ag[G];
-#pragma unroll
-  for (int j = 0; j < G; ++j) ag[j] = j < c.A ? agents[j] : 0u;
-  if (!replay) {
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      if (j < c.A && j != g) {
-        const int dx = (int)(ag[j] & 0xff) - x + R, dy = (int)((ag[j] >> 8) & 0xff) - y + R;
-        if ((unsigned)dx <= 2u * R && (unsigned)dy <= 2u * R) {
-          int k = dx * O::SIDE + dy;
-          if (k != O::CENTER) {
-            k -= k > O::CENTER;
-            set5<O::MW>(M, 5 * k, 1ull | (2ull << ((ag[j] >> 16) & 3u)));
-          }
-        }
-      }
-    }
-  } else {
-    int k = 0;
-    for (int dx = -R; dx <= R; ++dx) {
-      for (int dy = -R; dy <= R; ++dy) {
-        if (dx == 0 && dy == 0) continue;
-        const int cx = x + dx, cy = y + dy;
-        if (cx >= 0 && cx < c.H && cy >= 0 && cy < c.W) {
-          const uint32_t q = (uint32_t)(cx * c.W + cy);
-          int v = 0;
-#pragma unroll
-          for (int m = 0; m < G; ++m)
-            if (m < c.A && (opk[m] & 1023u) == q) v = m + 1;
-#pragma unroll
-          for (int m = 0; m < G; ++m) {
-            if (m < c.A && ((opk[m] >> 20) & 1u)) {
-              if ((opk[m] & 1023u) == q) v = 0;
-              if (((opk[m] >> 10) & 1023u) == q) v = m + 1;
-            }
-          }
-          if (v != 0) {
-            uint32_t dj = 0;
-#pragma unroll
-            for (int m = 0; m < G; ++m)
-              if (m + 1 == v) dj = (ag[m] >> 16) & 3u;
-            set5<O::MW>(M, 5 * k, 1ull | (2ull << dj));
-          }
-        }
-        ++k;
-      }
-    }
-  }
-  // bit b of the mask -> byte b of the feature block: 4 bits per word, spread with one multiply
-#pragma unroll
-  for (int i = 0; i < O::NAG / 4; ++i) {
-    const uint32_t nib = (uint32_t)(M[i >> 4] >> ((i & 15) * 4)) & 0xFu;
-    w[2 + i] = (nib * 0x00204081u) & 0x01010101u;
-  }
-#pragma unroll
-  for (int ci = 0; ci < O::LOC; ++ci) {
-    const int cx = x + ci / O::SIDE - R, cy = y + ci % O::SIDE - R;
-    uint32_t h = 0u;
-    if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
-      const int sid = cells[cx * c.W + cy];
-      if (sid != 0) h = 1u | ((uint32_t)requested(c, rec, sid - 1) << 8);
-    }
-    w[O::SH0 + ci / 2] |= h << (16 * (ci & 1));
-  }
-  // rows are FR = 2 (mod 4) bytes long: odd rows start on a half word
-  uint32_t* wp = reinterpret_cast<uint32_t*>(row + 2 * row_parity);
-  const int sh = 16 * row_parity;
-#pragma unroll
-  for (int k = 0; k + 1 < O::NW; ++k) wp[k] = __funnelshift_r(w[k], w[k + 1], sh);
-  uint16_t* hp = reinterpret_cast<uint16_t*>(row_parity ? row : row + 4 * (O::NW - 1));
-  *hp = (uint16_t)(row_parity ? w[0] : w[O::NW - 1]);
-  // utils.compute_action_mask: only FORWARD can be illegal
-  int nx, ny;
-  forward_cell(c, x, y, d, nx, ny);
-  const bool stuck = nx == x && ny == y;
-  const bool blocked = carry && cells[nx * c.W + ny] != 0;
-  return (uint8_t)(0x1Du | ((stuck || blocked) ? 0u : 0x2u));
-}
 
 __host__ inline size_t smem_bytes(const RwareConst& c, int envs_per_cta) {
   return (size_t)envs_per_cta * c.stride + (size_t)round_up(envs_per_cta * c.A * c.FR, 16) + 16 +
@@ -414,151 +91,9 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
   uint32_t opk[G];
 #pragma unroll
   for (int j = 0; j < G; ++j) opk[j] = 0u;
-  if (active) {
-    // --- validate the action against the mask of the current state (utils.get_valid_actions)
-    int x = 0, y = 0, d = 0, carry = 0, nx = 0, ny = 0;
-    if (agent) {
-      const uint32_t me = reinterpret_cast<const uint32_t*>(rec + c.off_agents)[g];
-      x = me & 0xff;
-      y = (me >> 8) & 0xff;
-      d = (me >> 16) & 0xff;
-      carry = me >> 24;
-      forward_cell(c, x, y, d, nx, ny);
-      if (act == 1) {
-        const bool stuck = nx == x && ny == y;
-        const bool blocked = carry && cells[nx * c.W + ny] != 0;
-        if (stuck || blocked) act = 0;
-      }
-    }
-    const int oldcell = x * c.W + y;
-    const bool moved = act == 1;
-    __syncwarp(gmask);
-    // --- agents act one after the other on the shelf grid (scan over agents in env.step)
-    for (int i = 0; i < c.A; ++i) {
-      if (g == i) {
-        if (act == 2) {
-          d = (d + 3) & 3;
-        } else if (act == 3) {
-          d = (d + 1) & 3;
-        } else if (act == 1) {
-          if (carry) {
-            const uint8_t sid = cells[oldcell];
-            cells[oldcell] = 0;
-            cells[nx * c.W + ny] = sid;
-          }
-          x = nx;
-          y = ny;
-        } else if (act == 4) {
-          if (!carry) {
-            if (cells[oldcell] != 0) carry = 1;
-          } else if (!is_highway(c, oldcell)) {
-            carry = 0;
-          }
-        }
-        reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(x, y, d, carry);
-      }
-      __syncwarp(gmask);
-    }
-    // --- collision (utils.is_collision): grid[AGENTS, pos_i] != i + 1 after the sequential writes
-    //     "old cell <- 0, new cell <- j + 1" of every agent j that moved.  The last write to my
-    //     cell is not mine iff some mover j entered or left it after my own write.
-    const int newcell = x * c.W + y;
-    const uint32_t pk = (uint32_t)oldcell | ((uint32_t)newcell << 10) | ((uint32_t)moved << 20);
-#pragma unroll
-    for (int j = 0; j < G; ++j) opk[j] = __shfl_sync(gmask, pk, j, G);
-    bool my_col = false;
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      if (j < c.A && j != g) {
-        const uint32_t oj = opk[j] & 1023u, nj = (opk[j] >> 10) & 1023u;
-        const bool mj = (opk[j] >> 20) & 1u;
-        if (mj && (nj == (uint32_t)newcell || oj == (uint32_t)newcell) && (!moved || j > g))
-          my_col = true;
-      }
-    }
-    const bool collision = (__ballot_sync(gmask, my_col && agent) & gmask) != 0u;
-
-    // --- deliveries at the goal cells; a delivered request is replaced by a uniformly drawn
-    //     shelf that is not in the queue (env._update_reward_and_request_queue)
-    float rew = 0.0f;
-    {
-      const uint32_t* k = reinterpret_cast<const uint32_t*>(rec + c.off_key);
-      key = Key{k[0], k[1]};
-    }
-    for (int gi = 0; gi < 2; ++gi) {
-      const int sid = cells[c.goal[gi]];
-      if (sid != 0 && requested(c, rec, sid - 1)) {
-        Key rkey, unused, sub;
-        split2(key, key, rkey);
-        split2(rkey, unused, sub);
-        const int msize = c.n - c.Q;
-        unsigned long long best = ~0ull;
-        for (int s = g; s < c.n; s += G) {
-          int below = 0;
-          bool inq = false;
-          for (int q = 0; q < c.Q; ++q) {
-            const int qs = rec[c.off_queue + q];
-            inq |= qs == s;
-            below += qs < s;
-          }
-          if (!inq) {
-            const int p = s - below;  // position in the sorted not-in-queue list
-            const uint32_t b = random_bits_at(sub, (uint32_t)p, (uint32_t)msize);
-            const unsigned long long v =
-                ((unsigned long long)b << 32) | ((unsigned long long)p << 16) | (unsigned)s;
-            best = v < best ? v : best;
-          }
-        }
-        best = group_min<G>(best, gmask);
-        const int new_req = (int)(best & 0xffffull);
-        __syncwarp(gmask);
-        if (g == 0) {
-          for (int q = 0; q < c.Q; ++q) {
-            if (rec[c.off_queue + q] == sid - 1) {
-              rec[c.off_queue + q] = (uint8_t)new_req;
-              break;
-            }
-          }
-          uint32_t* rq = reinterpret_cast<uint32_t*>(rec + c.off_reqbits);
-          rq[(sid - 1) >> 5] &= ~(1u << ((sid - 1) & 31));
-          rq[new_req >> 5] |= 1u << (new_req & 31);
-        }
-        rew += 1.0f;
-        __syncwarp(gmask);
-      }
-    }
-    // --- step count, termination
-    uint32_t* pstep = reinterpret_cast<uint32_t*>(rec + c.off_step);
-    const int step = (int)(*pstep) + 1;
-    const bool is_done = collision || step >= c.time_limit;
-    __syncwarp(gmask);
-    if (g == 0) {
-      *pstep = (uint32_t)step;
-      uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
-      k[0] = key.k0;
-      k[1] = key.k1;
-      // RecordEpisodeMetrics.step (episode_metrics.py:83-110)
-      float* run_ret = reinterpret_cast<float*>(rec + c.off_run_ret);
-      int32_t* run_len = reinterpret_cast<int32_t*>(rec + c.off_run_len);
-      float* e_ret = reinterpret_cast<float*>(rec + c.off_ep_ret);
-      int32_t* e_len = reinterpret_cast<int32_t*>(rec + c.off_ep_len);
-      const float new_ret = *run_ret + rew;  // mean over agents of a shared reward
-      const int32_t new_len = *run_len + 1;
-      const float nd = is_done ? 0.0f : 1.0f, dd = is_done ? 1.0f : 0.0f;
-      const float ret_info = *e_ret * nd + new_ret * dd;
-      const int32_t len_info = is_done ? new_len : *e_len;
-      *run_ret = new_ret * nd;
-      *run_len = is_done ? 0 : new_len;
-      *e_ret = ret_info;
-      *e_len = len_info;
-      done[env] = is_done ? 1 : 0;
-      ep_return[env] = ret_info;
-      ep_length[env] = len_info;
-    }
-    if (agent) reward[(size_t)env * c.A + g] = rew;
-    needs_reset = is_done && auto_reset != 0;
-    replay = collision && !needs_reset;
-  }
+  if (active)
+    rware::step_group<G>(c, rec, g, gmask, agent, act, env, auto_reset, reward, done, ep_return,
+                         ep_length, needs_reset, replay, opk);
   // --- AutoResetWrapper: on the last step the state and observation are those of a fresh episode
   //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare and a
   //     regeneration is a long dependent chain of threefry calls, so finished envs go into a CTA

@@ -109,6 +109,41 @@ __host__ __device__ inline uint32_t stage_bytes(int A, int FR, int rows_per_step
   return ((uint32_t)(TM / rows_per_step + 2) * A * FR + 15) / 16 * 16 + TM * 4 + 16;
 }
 
+// Thread (r, q) expands every fourth 8-column chunk of tile row r from the int8 observation bytes
+// at `mine` (shared memory) to bf16: [onehot(agent a) if add_id | view bytes | 1 | 0...].
+__device__ __forceinline__ void expand_x_row(const NetDesc& d, const Tile& xt, const Lane& L,
+                                             const signed char* mine, bool valid, int a) {
+  const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
+  const uint32_t mine_s = smem_u32(mine);
+  for (int cg = L.q; cg < d.k1p / 8; cg += 4) {
+    float v[8];
+    const int k0 = cg * 8;
+    if (valid && k0 >= id_cols && k0 + 8 <= d.in_dim) {
+      // interior chunk: eight observation bytes, no boundary logic
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int b;
+        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(b) : "r"(mine_s + (uint32_t)(k0 - id_cols + j)));
+        v[j] = (float)b;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        float x = 0.0f;
+        if (valid) {
+          if (k < id_cols) x = k == a ? 1.0f : 0.0f;
+          else if (k < d.in_dim) x = (float)mine[k - id_cols];
+          else if (k == d.in_dim) x = 1.0f;
+        }
+        v[j] = x;
+      }
+    }
+    st_shared_v4(xt.base + chunk_off(xt, L.r, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 template <class StepFn>
 __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __restrict__ view,
                                              const Tile& xt, unsigned char* stage, int64_t row0,
@@ -156,37 +191,9 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
   const int64_t row = row0 + L.r;
   const bool valid = row < M;
   const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
-  const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
   const signed char* mine = reinterpret_cast<const signed char*>(stage) +
                             (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
-  const uint32_t mine_s = smem_u32(mine);
-  for (int cg = L.q; cg < d.k1p / 8; cg += 4) {
-    float v[8];
-    const int k0 = cg * 8;
-    if (valid && k0 >= id_cols && k0 + 8 <= d.in_dim) {
-      // interior chunk: eight observation bytes, no boundary logic
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int b;
-        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(b) : "r"(mine_s + (uint32_t)(k0 - id_cols + j)));
-        v[j] = (float)b;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k0 + j;
-        float x = 0.0f;
-        if (valid) {
-          if (k < id_cols) x = k == a ? 1.0f : 0.0f;
-          else if (k < d.in_dim) x = (float)mine[k - id_cols];
-          else if (k == d.in_dim) x = 1.0f;
-        }
-        v[j] = x;
-      }
-    }
-    st_shared_v4(xt.base + chunk_off(xt, L.r, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-  }
+  expand_x_row(d, xt, L, mine, valid, a);
 }
 
 // One thread issues the K/16 MMAs of a GEMM (M = 128) and optionally commits to `bar`.

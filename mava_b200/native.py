@@ -301,6 +301,32 @@ def ff_act_bf16(actor: Optional[MlpDesc], actor_params, actor_image, critic: Opt
         _p(value, torch.float32, num_envs * A, "value"), _stream()), "mava_ff_act_bf16")
 
 
+def ff_rollout_supported(env: "Env") -> bool:
+    """Whether mava_ff_rollout_bf16 handles this env (RobotWarehouse, 2/4/8 agents, range 1)."""
+    return (env.kind == ENV_RWARE and env.num_agents in (2, 4, 8) and env.view_dim == 66)
+
+
+def ff_rollout_bf16(env: "Env", actor: MlpDesc, actor_params, actor_image, state, view, mask,
+                    policy_keys, envs_per_replica: int, num_envs: int, T: int, action, logp, reward,
+                    done, ep_return, ep_length) -> None:
+    """The whole rollout scan in one persistent kernel (see include/mava_b200.h)."""
+    A, F = actor.num_agents, actor.view_dim
+    _count(1)
+    check(_lib.load().mava_ff_rollout_bf16(
+        env._h, C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"),
+        _p(state, torch.uint8, num_envs * env.state_stride, "state"),
+        _p(view, torch.int8, (T + 1) * num_envs * A * F, "view"),
+        _p(mask, torch.uint8, (T + 1) * num_envs * A, "mask"),
+        _p(policy_keys, torch.uint32, 2 * T, "policy_keys"), envs_per_replica, num_envs, T,
+        _p(action, torch.int8, T * num_envs * A, "action"),
+        _p(logp, torch.float32, T * num_envs * A, "logp"),
+        _p(reward, torch.float32, T * num_envs * A, "reward"),
+        _p(done, torch.uint8, T * num_envs, "done"),
+        _p(ep_return, torch.float32, T * num_envs, "ep_return"),
+        _p(ep_length, torch.int32, T * num_envs, "ep_length"), _stream()), "mava_ff_rollout_bf16")
+
+
 def ppo_workspace_bytes_bf16(actor: MlpDesc, critic: MlpDesc, rows_total: int) -> int:
     return int(_lib.load().mava_ppo_workspace_bytes_bf16(C.byref(actor), C.byref(critic),
                                                          rows_total))

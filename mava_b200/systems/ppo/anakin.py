@@ -77,11 +77,12 @@ class FFLearner:
         self.view = z(T + 1, NE, A, self.FR, dtype=torch.int8)
         self.mask = z(T + 1, NE, A, dtype=torch.uint8)
         self.action = z(T, NE, A, dtype=torch.int8)
-        self.logp, self.value, self.reward = z(T, NE, A), z(T, NE, A), z(T, NE, A)
+        self.logp, self.reward = z(T, NE, A), z(T, NE, A)
+        self.value_all = z(T + 1, NE, A)  # slot T is the bootstrap value
+        self.value, self.last_val = self.value_all[:T], self.value_all[T]
         self.done = z(T, NE, dtype=torch.uint8)
         self.ep_ret = z(T, NE)
         self.ep_len = z(T, NE, dtype=torch.int32)
-        self.last_val = z(NE, A)
         self.adv, self.targets = z(T, NE, A), z(T, NE, A)
         # scratch
         self.policy_keys = z(T, 2, dtype=torch.uint32)
@@ -99,6 +100,9 @@ class FFLearner:
         if self.precision == "bf16" and not tc_ok:
             raise ValueError("arch.precision=bf16 needs MLP torsos with layer_sizes [128, 128]")
         self.bf16 = tc_ok and self.precision != "fp32"
+        # one persistent kernel for the whole rollout scan where the env kernel supports it
+        self.fused_rollout = (self.bf16 and native.ff_rollout_supported(env.native)
+                              and bool(config.arch.get("fused_rollout", True)))
         if self.bf16:
             self.actor_img = z(native.mlp_pack_bytes(self.actor_desc), dtype=torch.uint8)
             self.critic_img = z(native.mlp_pack_bytes(self.critic_desc), dtype=torch.uint8)
@@ -147,6 +151,16 @@ class FFLearner:
         native.prng_split_chain(self.key, self.policy_keys, self.T)
         if self.bf16:
             self._pack()
+        if self.fused_rollout:
+            native.ff_rollout_bf16(envn, self.actor_desc, self.actor_params, self.actor_img,
+                                   self.env_buf, self.view, self.mask, self.policy_keys, self.E,
+                                   self.NE, self.T, self.action, self.logp, self.reward, self.done,
+                                   self.ep_ret, self.ep_len)
+            # the critic is not needed to act: all T + 1 slots in one batched launch
+            native.ff_act_bf16(None, None, None, self.critic_desc, self.critic_params,
+                               self.critic_img, self.view, None, None, self.E,
+                               (self.T + 1) * self.NE, None, None, self.value_all)
+            return
         for t in range(self.T):
             if self.bf16:
                 native.ff_act_bf16(self.actor_desc, self.actor_params, self.actor_img,
