@@ -34,6 +34,7 @@ namespace {
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t COL_ACC = 0, COL_HEAD = 128, COL_DW3 = 144, COL_DW2 = 160;  // dW2: 144 columns
+constexpr uint32_t COL_DW1 = 304;  // folded first-layer gradient of the actor: up to 208 columns
 constexpr uint32_t kRegionMin = tile_bytes(TM, HCOLS) + tile_bytes(TM, HID);   // H2 + dZ2
 
 struct TrainArgs {
@@ -48,6 +49,7 @@ struct TrainArgs {
   int R, mb_size, num_replicas;
   float clip_eps, ent_coef, vf_coef;
   int actor_ctas, critic_ctas;
+  int fold_actor_w1;  // the actor's [dW1^T | db1] accumulates in TMEM inside the fused kernel
   float *grad_actor, *grad_critic;
   double* loss_acc;
   unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
@@ -100,13 +102,19 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   const int n_tiles = (int)ceil_div64(M, TM);
 
   // shared memory: [weights][region: X, later H2 + dZ2][H1 (also the gather staging area)][dZ3]
+  // fold mode (actor): [weights][X ping][X pong][region: H2 (later dZ1) + dZ2][H1][dZ3] -- X stays
+  // alive to the end of the tile so that [dW1^T | db1] += dZ1^T [X | 1] runs here, in TMEM, while the
+  // next tile is gathered into the other X buffer.
+  const bool fold = is_actor && p.fold_actor_w1 != 0;
   const WImage wi{d.k1p};
   const uint32_t s_w = smem_u32(smem);
-  const uint32_t s_region = s_w + wi.total();
-  const Tile xt{s_region, 128u, 2048u};
+  const uint32_t x_bytes = tile_bytes(TM, d.k1p);
+  const uint32_t s_x0 = s_w + wi.total();
+  const uint32_t s_region = fold ? s_x0 + 2 * x_bytes : s_x0;
   const Tile h2t{s_region, 128u, 2048u};
+  const Tile dz1t{s_region, 128u, 2048u};
   const Tile dz2t{s_region + tile_bytes(TM, HCOLS), 128u, 2048u};
-  const Tile h1t{s_region + region_bytes(d.k1p), 128u, 2048u};
+  const Tile h1t{s_region + (fold ? kRegionMin : region_bytes(d.k1p)), 128u, 2048u};
   const Tile dz3t{h1t.base + tile_bytes(TM, HCOLS), 128u, 2048u};
   const Tile w1 = w1_tile(s_w, d.k1p), w2 = w2_tile(s_w, d.k1p), w3 = w3_tile(s_w, d.k1p);
 
@@ -128,8 +136,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   double l0 = 0.0, l1 = 0.0;
   const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
   bool first = true;
-  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
+  int it = 0;
+  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
     const int64_t row0 = (int64_t)tile * TM;
+    const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
 
     build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M,
                  [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
@@ -290,11 +300,34 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    unsigned char* gdst = (is_actor ? p.dz1_actor : p.dz1_critic) + (size_t)tile * tile_bytes(TM, HID);
-    const Tile gimg{0u, 128u, 2048u};
-    grad_epilogue<true>(L, tmem + COL_ACC, h1t, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
-    fence_before_sync();
-    __syncthreads();
+    if (fold) {
+      // dZ1 stays on chip (H2 is dead): [dW1^T | db1] += dZ1^T [X | 1], A = dZ1 and B = X MN-major.
+      // Not waited for here: the MMAs run under the next tile's gather (other X buffer, H1 as the
+      // staging area) and complete, in issue order, before that tile's second hidden epilogue
+      // writes this region again.
+      grad_epilogue<false>(L, tmem + COL_ACC, h1t, dz1t, nullptr);
+      fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (t == 0) {
+        fence_after_sync();
+        const uint32_t idesc = instr_desc(TM, d.k1p, true, true);
+        for (int k = 0; k < TM / 16; ++k)
+          mma(tmem + COL_DW1, desc_mnmajor(dz1t, k), desc_mnmajor(xt, k), idesc, !first || k > 0);
+      }
+    } else {
+      unsigned char* gdst = p.dz1_critic + (size_t)tile * tile_bytes(TM, HID);
+      if (is_actor) gdst = p.dz1_actor + (size_t)tile * tile_bytes(TM, HID);
+      const Tile gimg{0u, 128u, 2048u};
+      grad_epilogue<true>(L, tmem + COL_ACC, h1t, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
+      fence_before_sync();
+      __syncthreads();
+    }
+  }
+  if (fold && !first) {  // the last tile's dW1 MMAs
+    if (t == 0) commit(&ctrl.mbar);
+    wait_mma(&ctrl.mbar, phase);
+    phase ^= 1;
   }
 
   // ---- flush: TMEM weight-gradient accumulators -> global fp32 gradient (atomics)
@@ -323,6 +356,20 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
         if (q < d.out) atomicAdd(gw3 + (size_t)L.r * d.out + q, v[q]);
     }
     if (t < d.out) atomicAdd(gb3 + t, ctrl.db3[t]);
+    if (fold) {
+      // dW1^T: TMEM lane = hidden unit n, columns = input feature k (column in_dim = db1)
+      float* gb1 = g + (size_t)d.in_dim * HID;
+      for (int c0 = L.q * 16; c0 < d.k1p; c0 += 64) {
+        float v[16];
+        ld16(tmem + L.tmem_lane() + COL_DW1 + (uint32_t)c0, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int k = c0 + c;
+          if (k < d.in_dim) atomicAdd(g + (size_t)k * HID + L.r, v[c]);
+          else if (k == d.in_dim) atomicAdd(gb1 + L.r, v[c]);
+        }
+      }
+    }
   }
   // loss sums
   for (int o = 16; o > 0; o >>= 1) {
@@ -529,8 +576,14 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   if (rc) return rc;
 
   const int k1p_max = a.actor.k1p > a.critic.k1p ? a.actor.k1p : a.critic.k1p;
-  const size_t smem_fused = (size_t)WImage{k1p_max}.total() + region_bytes(k1p_max) +
-                            tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
+  size_t smem_fused = (size_t)WImage{k1p_max}.total() + region_bytes(k1p_max) +
+                      tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
+  // actor first-layer gradient folded into the fused kernel when TMEM (208 free columns) and
+  // shared memory (two X buffers on top of the activation tiles) have room for it
+  const size_t smem_fold = (size_t)WImage{a.actor.k1p}.total() + 2 * tile_bytes(TM, a.actor.k1p) +
+                           kRegionMin + tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
+  a.fold_actor_w1 = a.actor.k1p <= 208 && smem_fold <= 227 * 1024;
+  if (a.fold_actor_w1 && smem_fold > smem_fused) smem_fused = smem_fold;
   const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
                           tile_bytes(TM, HCOLS) + 128;  // dZ1 tile, X tile, staging
   static size_t conf_fused = 0, conf_wg1 = 0;
@@ -549,6 +602,10 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_fused, s>>>(a);
   rc = launch_status();
   if (rc) return rc;
+  if (a.fold_actor_w1) {  // only the critic's first layer is left: give it every SM
+    a.actor_ctas = 0;
+    a.critic_ctas = (int)(tcn < sms ? tcn : sms);
+  }
   ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_wg1, s>>>(a);
   rc = launch_status();
   if (rc) return rc;
