@@ -31,10 +31,41 @@ OVERRIDES = ["env=rware", "env/scenario=tiny-4ag", "arch.num_envs=1024",
              "system.num_minibatches=2", "logger.use_console=False"]
 
 
-def workload_config(n_gpus: int) -> dict:
-    return {"workload": "ff_mappo RWARE tiny-4ag, 2048 envs/GPU (update_batch_size 2 x num_envs "
-                        "1024), rollout 128, 4 epochs x 2 minibatches (BASELINE.json configs[1])",
-            "envs_per_gpu": 2048, "global_envs": 2048 * n_gpus, "rollout_length": 128,
+_COMMON = ["system.rollout_length=128", "system.ppo_epochs=4", "system.num_minibatches=2",
+           "system.update_batch_size=2", "logger.use_console=False"]
+# The default is the headline (BASELINE.json configs[1]); the others are the remaining single-GPU
+# configurations of BASELINE.json, selectable with --workload (their lines go to profiles/).
+WORKLOADS = {
+    "ff_mappo_rware": dict(
+        system="ff_mappo", metric=METRIC, envs_per_gpu=2048,
+        overrides=OVERRIDES,
+        text="ff_mappo RWARE tiny-4ag, 2048 envs/GPU (update_batch_size 2 x num_envs 1024), "
+             "rollout 128, 4 epochs x 2 minibatches (BASELINE.json configs[1])"),
+    "ff_ippo_lbf": dict(
+        system="ff_ippo", metric="LBF ff_ippo env-steps/sec (rollout+GAE+PPO)", envs_per_gpu=65536,
+        overrides=["env=lbf", "env/scenario=8x8-2p-2f-coop", "arch.num_envs=32768"] + _COMMON,
+        text="ff_ippo Level-Based Foraging 8x8-2p-2f-coop, 65536 envs/GPU (update_batch_size 2 x "
+             "num_envs 32768), rollout 128, 4 epochs x 2 minibatches (BASELINE.json configs[2])"),
+    "rec_mappo_smax": dict(
+        system="rec_mappo", metric="SMAX-shaped rec_mappo env-steps/sec (rollout+GAE+PPO)",
+        envs_per_gpu=4096,
+        overrides=["env=smax_synthetic", "arch.num_envs=2048"] + _COMMON,
+        text="rec_mappo (GRU 128) on synthetic SMAX 3s5z-shaped tensors (8 agents, obs 205, state "
+             "168, 13 actions), 4096 envs/GPU (update_batch_size 2 x num_envs 2048), rollout 128, "
+             "4 epochs x 2 minibatches (BASELINE.json configs[3]; no SMAX dynamics, see DESIGN.md)"),
+    "rec_mappo_rware": dict(
+        system="rec_mappo", metric="RWARE rec_mappo env-steps/sec (rollout+GAE+PPO)",
+        envs_per_gpu=2048,
+        overrides=["env=rware", "env/scenario=tiny-4ag", "arch.num_envs=1024"] + _COMMON,
+        text="rec_mappo (GRU 128) RWARE tiny-4ag, 2048 envs/GPU (update_batch_size 2 x num_envs "
+             "1024), rollout 128, 4 epochs x 2 minibatches"),
+}
+
+
+def workload_config(n_gpus: int, name: str = "ff_mappo_rware") -> dict:
+    w = WORKLOADS[name]
+    return {"workload": w["text"], "envs_per_gpu": w["envs_per_gpu"],
+            "global_envs": w["envs_per_gpu"] * n_gpus, "rollout_length": 128,
             "parallelism": f"dp{n_gpus}", "l2": "inputs are rewritten by every update; "
             "a 256 MiB buffer is written between timed steps to flush L2"}
 
@@ -115,6 +146,13 @@ class ClockSampler:
 
 def loss_grad_flops(L) -> float:
     """Executed FLOPs of one ppo_loss_grad call (forward + backward of both networks)."""
+    if hasattr(L, "chunk"):  # recurrent: pre, x-gates, h-gates, post, head; backward = 2 x forward
+        def rnet(d, rows):
+            H, Q = d.hidden, d.post
+            return 3.0 * rows * 2.0 * (d.in_dim * H + 2 * H * 3 * H + H * Q + Q * d.out_dim)
+        S = L.U * L.mbc * L.chunk
+        return rnet(L.actor_desc, S * L.A) + rnet(L.critic_desc, S * L.critic_desc.rows_per_env)
+
     def net(d, rows):
         fwd = 2.0 * (d.in_dim * d.h1 + d.h1 * d.h2 + d.h2 * d.out_dim)
         bwd = 2.0 * (d.h2 * d.out_dim + d.h1 * d.h2)          # dZ2, dZ1
@@ -145,7 +183,9 @@ def run_ours(args) -> None:
 
     from mava_b200 import native, prng
     from mava_b200.config import compose
-    from mava_b200.systems.ppo import _runner, ff_mappo
+    import importlib
+
+    from mava_b200.systems.ppo import _runner
     from mava_b200.utils import make_env
     from mava_b200.utils.logger import get_final_step_metrics
 
@@ -154,10 +194,12 @@ def run_ours(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
-    cfg = compose(ff_mappo.CONFIG_NAME, OVERRIDES + [f"+arch.precision={args.precision}"])
-    env, _ = make_env.make(cfg, add_global_state=True, device=device)
+    wl = WORKLOADS[args.workload]
+    system = importlib.import_module(f"mava_b200.systems.ppo.{wl['system']}")
+    cfg = compose(system.CONFIG_NAME, wl["overrides"] + [f"+arch.precision={args.precision}"])
+    env, _ = make_env.make(cfg, add_global_state=system.CENTRALISED_CRITIC, device=device)
     key, _, ak, ck = prng.split(prng.PRNGKey(cfg.system.seed), 4)
-    learn, _, state = ff_mappo.learner_setup(env, (key, ak, ck), cfg)
+    learn, _, state = system.learner_setup(env, (key, ak, ck), cfg)
     L = learn.learner
     cfg.system.num_updates_per_eval = 1
     steps_per_update = L.T * L.NE  # per GPU
@@ -262,7 +304,7 @@ def run_ours(args) -> None:
     e2e_value = world * steps_per_update * args.steps / (e2e_ms * 1e-3)
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.workload == "ff_mappo_rware":
         from oracle import cpu_baseline as cb
 
         res = cb.run(TASK, num_envs=512, updates=1, warmup=0)
@@ -271,10 +313,12 @@ def run_ours(args) -> None:
                         "sample": "1 update of 512 envs x 128 steps, 4 epochs x 2 minibatches "
                                   "(1/4 of one GPU's share), oracle port on all host cores"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": L.compute_dtype, "data": "synthetic", "config": workload_config(world),
+            "dtype": L.compute_dtype, "data": "synthetic",
+            "config": workload_config(world, args.workload),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
@@ -297,6 +341,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ff_mappo_rware", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     if os.environ.get("MAVA_BENCH_DEBUG"):  # dump every thread's stack if the run gets stuck
         import faulthandler

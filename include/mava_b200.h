@@ -274,12 +274,13 @@ int64_t mava_rnn_param_count(const mava_rnn_desc* d_host);
  * of rec_mappo.py:165 does that), the carry being zeroed first where done_in[env] is set
  * (ScannedRNN, networks.py:249-253).  actor_host == NULL evaluates the critic only.
  * view is the int8 observation of the env kernels; obs_actor / obs_critic are the f32 inputs of
- * MAVA_IN_DENSE networks ([num_envs][rows_per_env][in_dim]).  Sampling as mava_ff_act. */
+ * MAVA_IN_DENSE networks ([num_envs][rows_per_env][in_dim]).  mask holds uint8 entries (bit k =
+ * action k legal) for out_dim <= 8 and uint16 entries above.  Sampling as mava_ff_act. */
 int64_t mava_rec_act_workspace_bytes(const mava_rnn_desc* actor_host,
                                      const mava_rnn_desc* critic_host, int num_envs);
 int mava_rec_act(const mava_rnn_desc* actor_host, const float* actor_params,
                  const mava_rnn_desc* critic_host, const float* critic_params, const int8_t* view,
-                 const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                 const float* obs_actor, const float* obs_critic, const void* mask,
                  const uint8_t* done_in, const float* h_actor_in, float* h_actor_out,
                  const float* h_critic_in, float* h_critic_out, const uint32_t* policy_key,
                  int envs_per_replica, int num_envs, int greedy, const int8_t* actions_in,
@@ -301,12 +302,34 @@ int64_t mava_rec_ppo_workspace_bytes(const mava_rnn_desc* actor_host,
 int mava_rec_ppo_loss_grad(const mava_rnn_desc* actor_host, const float* actor_params,
                            const mava_rnn_desc* critic_host, const float* critic_params,
                            const mava_ppo_hyper* hyper_host, const int8_t* view,
-                           const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                           const float* obs_actor, const float* obs_critic, const void* mask,
                            const int8_t* action, const float* old_logp, const float* old_value,
                            const float* adv, const float* targets, const uint8_t* done_in,
                            const float* hs_actor, const float* hs_critic, const int32_t* cols,
                            int num_replicas, int envs_per_replica, int mb_cols, int chunk,
                            int num_chunks, float* grad_out, void* workspace, mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic SMAX-shaped step source (benchmark only; BASELINE.json configs[3]).  SMAX's dynamics
+ * live in jaxmarl, which is neither under the reference tree nor installable here, so the
+ * rec_mappo workload is driven by device-generated tensors of the SMAX 3s5z shape: f32 per-agent
+ * observations [NE][A][obs_dim] ~ U(0,1), one world-state row per env [NE][state_dim], uint16
+ * action masks (bits ~ Bernoulli(0.7), actions 0..4 always legal), team reward ~ N(0, reward_std),
+ * done ~ Bernoulli(done_prob), with RecordEpisodeMetrics applied for real.  `key` (2 words, device)
+ * seeds the step; the actions are accepted and ignored.  state: uint8 [NE][16].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mava_synth_config {
+  int32_t num_agents, obs_dim, state_dim, num_actions;
+  float done_prob, reward_std;
+} mava_synth_config;
+
+int mava_synth_reset(const mava_synth_config* cfg_host, const uint32_t* key, uint8_t* state,
+                     float* obs_actor, float* obs_critic, uint16_t* mask, int num_envs,
+                     mava_stream_t s);
+int mava_synth_step(const mava_synth_config* cfg_host, const uint32_t* key, uint8_t* state,
+                    const int8_t* action, float* obs_actor, float* obs_critic, uint16_t* mask,
+                    float* reward, uint8_t* done, float* ep_return, int32_t* ep_length,
+                    int num_envs, mava_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics.  One 128 x N x K bf16 GEMM on the tcgen05 tensor cores in each operand arrangement

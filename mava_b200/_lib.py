@@ -43,6 +43,11 @@ class RnnDesc(C.Structure):
         "post", "out_dim")]
 
 
+class SynthConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_agents", "obs_dim", "state_dim", "num_actions")] + [
+        ("done_prob", C.c_float), ("reward_std", C.c_float)]
+
+
 class PpoHyper(C.Structure):
     _fields_ = [("clip_eps", c_f32), ("ent_coef", c_f32), ("vf_coef", c_f32)]
 
@@ -86,6 +91,8 @@ SIGNATURES = {
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
     "mava_ff_rollout_bf16": (c_int, [c_void, P(MlpDesc)] + [c_void] * 6 + [c_int] * 3 +
                              [c_void] * 7),
+    "mava_synth_reset": (c_int, [P(SynthConfig)] + [c_void] * 5 + [c_int, c_void]),
+    "mava_synth_step": (c_int, [P(SynthConfig)] + [c_void] * 10 + [c_int, c_void]),
     "mava_rnn_param_count": (c_i64, [P(RnnDesc)]),
     "mava_rec_act_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int]),
     "mava_rec_act": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void] + [c_void] * 10 +

@@ -141,6 +141,15 @@ def _builtin_tree() -> Dict[str, Dict]:
                      "eval_metric": "win_rate", "implicit_agent_id": False, "log_win_rate": True,
                      "kwargs": {"see_enemy_actions": True, "walls_cause_death": True,
                                 "attack_mode": "closest"}}
+    # SMAX-shaped synthetic step source (benchmark only, see wrappers/synthetic.py); 3s5z: 8 allies
+    # vs 8 enemies -> 5 + 8 actions; obs / state sizes are parameters (jaxmarl is not available)
+    t["env/smax_synthetic"] = {"defaults": ["_self_", {"scenario": "synthetic-3s5z"}],
+                               "env_name": "SmaxSynthetic", "eval_metric": "episode_return",
+                               "implicit_agent_id": False, "log_win_rate": False,
+                               "kwargs": {"time_limit": 100}}
+    t["env/scenario/synthetic-3s5z"] = dict(
+        name="SmaxSynthetic", task_name="synthetic-3s5z",
+        task_config=dict(num_agents=8, obs_dim=205, state_dim=168, num_actions=13), env_kwargs={})
     t["env/scenario/tiny-2ag"] = _rware_scenario("tiny-2ag", 2, 2)
     t["env/scenario/tiny-4ag"] = _rware_scenario("tiny-4ag", 4, 4)
     t["env/scenario/tiny-4ag-easy"] = _rware_scenario("tiny-4ag-easy", 4, 8)

@@ -417,7 +417,7 @@ struct HeadArgs {
   int rpe, A, N;
   const int32_t* steps;  // env-step per row / rpe (null: identity)
   // acting
-  const uint8_t* mask;   // [steps][A]
+  const void* mask;      // [steps][A]: uint8 entries, uint16 when N > 8 (bit k = action k legal)
   const uint32_t* policy_key;
   int envs_per_replica, greedy;
   const int8_t* actions_in;
@@ -440,6 +440,11 @@ struct HeadArgs {
   double* loss_acc;  // [5]
 };
 
+__device__ __forceinline__ uint32_t mask_at(const HeadArgs& p, int64_t flat) {
+  return p.N > 8 ? (uint32_t)static_cast<const uint16_t*>(p.mask)[flat]
+                 : (uint32_t)static_cast<const uint8_t*>(p.mask)[flat];
+}
+
 // masked categorical: sample / mode / replay, log-prob (acting)
 __global__ void __launch_bounds__(256) rec_sample_kernel(const HeadArgs p) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(256) rec_sample_kernel(const HeadArgs p) {
   const int64_t q = row / p.A;
   const int a = (int)(row - q * p.A);
   const int64_t flat = (p.steps ? p.steps[q] : q) * p.A + a;
-  const uint8_t mk = p.mask[flat];
+  const uint32_t mk = mask_at(p, flat);
   float out[OMAX];
   float mx = kF32Min;
 #pragma unroll
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(256) rec_actor_loss_kernel(const HeadArgs p) {
     const int a = (int)(row - q * p.A);
     const int64_t flat = (int64_t)p.steps[q] * p.A + a;
     const int u = (int)((row % p.rows_per_pos) / p.rows_per_replica);
-    const uint8_t mk = p.mask[flat];
+    const uint32_t mk = mask_at(p, flat);
     float out[OMAX], logp[OMAX], pr[OMAX];
     float mx = kF32Min;
 #pragma unroll
@@ -808,7 +813,7 @@ int64_t mava_rec_act_workspace_bytes(const mava_rnn_desc* actor, const mava_rnn_
 
 int mava_rec_act(const mava_rnn_desc* actor, const float* actor_params,
                  const mava_rnn_desc* critic, const float* critic_params, const int8_t* view,
-                 const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                 const float* obs_actor, const float* obs_critic, const void* mask,
                  const uint8_t* done_in, const float* h_actor_in, float* h_actor_out,
                  const float* h_critic_in, float* h_critic_out, const uint32_t* policy_key,
                  int envs_per_replica, int num_envs, int greedy, const int8_t* actions_in,
@@ -888,7 +893,7 @@ int64_t mava_rec_ppo_workspace_bytes(const mava_rnn_desc* actor, const mava_rnn_
 int mava_rec_ppo_loss_grad(const mava_rnn_desc* actor, const float* actor_params,
                            const mava_rnn_desc* critic, const float* critic_params,
                            const mava_ppo_hyper* hyper, const int8_t* view,
-                           const float* obs_actor, const float* obs_critic, const uint8_t* mask,
+                           const float* obs_actor, const float* obs_critic, const void* mask,
                            const int8_t* action, const float* old_logp, const float* old_value,
                            const float* adv, const float* targets, const uint8_t* done_in,
                            const float* hs_actor, const float* hs_critic, const int32_t* cols,

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EnvDims, LbfConfig, MlpDesc, PpoHyper, RnnDesc, RwareConfig, check
+from ._lib import (EnvDims, LbfConfig, MlpDesc, PpoHyper, RnnDesc, RwareConfig, SynthConfig,
+                   check)
 
 ENV_RWARE, ENV_LBF = 1, 2
 # Number of mava_b200 kernels launched through this module (the benchmark's `gpu_launches`).
@@ -381,6 +382,54 @@ def rnn_desc(input_mode: int, add_agent_id: bool, num_agents: int, view_dim: int
                    out_dim)
 
 
+def _pmask(mask, actor: Optional[RnnDesc]):
+    """Action masks are uint8 per (env, agent) up to 8 actions and uint16 above."""
+    if mask is None:
+        return None
+    wide = actor is not None and actor.out_dim > 8
+    return _p(mask, torch.uint16 if wide else torch.uint8, None, "mask")
+
+
+class SynthEnv:
+    """Synthetic SMAX-shaped step source (include/mava_b200.h, benchmark only)."""
+
+    def __init__(self, num_agents=8, obs_dim=205, state_dim=168, num_actions=13,
+                 done_prob=0.01, reward_std=0.1):
+        self.cfg = SynthConfig(num_agents, obs_dim, state_dim, num_actions, done_prob, reward_std)
+        self.num_agents, self.obs_dim, self.state_dim = num_agents, obs_dim, state_dim
+        self.num_actions = num_actions
+        self.state_stride = 16
+
+    def alloc_state(self, num_envs: int, device) -> torch.Tensor:
+        return torch.zeros(num_envs, 16, dtype=torch.uint8, device=device)
+
+    def reset(self, key, state, obs_actor, obs_critic, mask, num_envs: int) -> None:
+        _count(1)
+        check(_lib.load().mava_synth_reset(
+            C.byref(self.cfg), _p(key, torch.uint32, 2, "key"),
+            _p(state, torch.uint8, num_envs * 16, "state"),
+            _p(obs_actor, torch.float32, num_envs * self.num_agents * self.obs_dim, "obs_actor"),
+            _p(obs_critic, torch.float32, num_envs * self.state_dim, "obs_critic"),
+            _p(mask, torch.uint16, num_envs * self.num_agents, "mask"), num_envs, _stream()),
+            "mava_synth_reset")
+
+    def step(self, key, state, action, obs_actor, obs_critic, mask, reward, done, ep_return,
+             ep_length, num_envs: int) -> None:
+        A = self.num_agents
+        _count(1)
+        check(_lib.load().mava_synth_step(
+            C.byref(self.cfg), _p(key, torch.uint32, 2, "key"),
+            _p(state, torch.uint8, num_envs * 16, "state"),
+            _p(action, torch.int8, num_envs * A, "action"),
+            _p(obs_actor, torch.float32, num_envs * A * self.obs_dim, "obs_actor"),
+            _p(obs_critic, torch.float32, num_envs * self.state_dim, "obs_critic"),
+            _p(mask, torch.uint16, num_envs * A, "mask"),
+            _p(reward, torch.float32, num_envs * A, "reward"), _p(done, torch.uint8, num_envs, "done"),
+            _p(ep_return, torch.float32, num_envs, "ep_return"),
+            _p(ep_length, torch.int32, num_envs, "ep_length"), num_envs, _stream()),
+            "mava_synth_step")
+
+
 def rnn_param_count(d: RnnDesc) -> int:
     return int(_lib.load().mava_rnn_param_count(C.byref(d)))
 
@@ -404,7 +453,7 @@ def rec_act(actor: Optional[RnnDesc], actor_params, critic: Optional[RnnDesc], c
         _p(critic_params, torch.float32, rnn_param_count(critic) if critic is not None else None,
            "critic_params"),
         _p(view, torch.int8, None, "view"), _p(obs_actor, torch.float32, None, "obs_actor"),
-        _p(obs_critic, torch.float32, None, "obs_critic"), _p(mask, torch.uint8, None, "mask"),
+        _p(obs_critic, torch.float32, None, "obs_critic"), _pmask(mask, actor),
         _p(done_in, torch.uint8, num_envs, "done_in"),
         _p(h_actor_in, torch.float32, None, "h_actor_in"),
         _p(h_actor_out, torch.float32, None, "h_actor_out"),
@@ -433,7 +482,7 @@ def rec_ppo_loss_grad(actor: RnnDesc, actor_params, critic: RnnDesc, critic_para
         C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"), C.byref(critic),
         _p(critic_params, torch.float32, nc, "critic_params"), C.byref(hyper),
         _p(view, torch.int8, None, "view"), _p(obs_actor, torch.float32, None, "obs_actor"),
-        _p(obs_critic, torch.float32, None, "obs_critic"), _p(mask, torch.uint8, None, "mask"),
+        _p(obs_critic, torch.float32, None, "obs_critic"), _pmask(mask, actor),
         _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
         _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
         _p(targets, torch.float32, None, "targets"), _p(done_in, torch.uint8, None, "done_in"),

@@ -46,6 +46,9 @@ def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
 
     env, eval_env = environments.make(config=config, add_global_state=add_global_state,
                                       device=device)
+    if getattr(env, "dense", False):
+        raise ValueError("env=smax_synthetic is a benchmark-only step source (no dynamics, no "
+                         "evaluator): use bench.py --workload rec_mappo_smax")
     key, key_e, actor_net_key, critic_net_key = prng.split(prng.PRNGKey(config.system.seed), 4)
     learn, actor_network, learner_state = learner_setup(
         env, (key, actor_net_key, critic_net_key), config)

@@ -42,7 +42,9 @@ class RecLearner:
         self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
             config.arch.num_envs)
         self.NE = self.U * self.E
-        self.A, self.FR, self.N = env.num_agents, env.native.view_dim, env.action_dim
+        self.dense = bool(getattr(env, "dense", False))  # f32 observation rows (synthetic SMAX)
+        self.A, self.N = env.num_agents, env.action_dim
+        self.FR = 1 if self.dense else env.native.view_dim
         self.epochs, self.nmb = int(s.ppo_epochs), int(s.num_minibatches)
         chunk = s.get("recurrent_chunk_size", None)
         self.chunk = int(chunk) if chunk else self.T
@@ -53,9 +55,18 @@ class RecLearner:
             raise ValueError("num_envs * num_chunks must be divisible by num_minibatches")
         self.mbc = self.E * self.nc // self.nmb
         add_id = bool(s.add_agent_id)
-        self.actor_desc = actor.desc(self.A, self.FR, add_id, native.IN_AGENT_VIEW)
-        self.critic_desc = critic.desc(
-            self.A, self.FR, add_id, native.IN_GLOBAL if centralised_critic else native.IN_AGENT_VIEW)
+        if self.dense:
+            # AgentIDWrapper appends nothing here: the synthetic rows already have their width
+            self.actor_desc = actor.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A)
+            self.critic_desc = (critic.desc(self.A, 1, False, native.IN_DENSE, env.state_dim, 1)
+                                if centralised_critic else
+                                critic.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A))
+        else:
+            self.actor_desc = actor.desc(self.A, self.FR, add_id, native.IN_AGENT_VIEW)
+            self.critic_desc = critic.desc(
+                self.A, self.FR, add_id,
+                native.IN_GLOBAL if centralised_critic else native.IN_AGENT_VIEW)
+        self.centralised_critic = centralised_critic
         self.H = self.actor_desc.hidden
         self.rpc = self.critic_desc.rows_per_env
         self.na = native.rnn_param_count(self.actor_desc)
@@ -73,8 +84,15 @@ class RecLearner:
         self.h_actor = z(NE * A, self.H)
         self.h_critic = z(NE * self.rpc, self.H)
         # rollout buffers; done_in[t] is the flag entering step t, slot T is last_done
-        self.view = z(T + 1, NE, A, self.FR, dtype=torch.int8)
-        self.mask = z(T + 1, NE, A, dtype=torch.uint8)
+        if self.dense:
+            self.view = None
+            self.obs_a = z(T + 1, NE, A, env.obs_dim)
+            self.obs_c = (z(T + 1, NE, 1, env.state_dim) if centralised_critic else self.obs_a)
+            self.mask = z(T + 1, NE, A, dtype=torch.uint16 if self.N > 8 else torch.uint8)
+        else:
+            self.view = z(T + 1, NE, A, self.FR, dtype=torch.int8)
+            self.obs_a = self.obs_c = None
+            self.mask = z(T + 1, NE, A, dtype=torch.uint8)
         self.done_in = z(T + 1, NE, dtype=torch.uint8)
         self.action = z(T, NE, A, dtype=torch.int8)
         self.logp, self.value, self.reward = z(T, NE, A), z(T, NE, A), z(T, NE, A)
@@ -97,6 +115,7 @@ class RecLearner:
         self.workspace = z(native.rec_ppo_workspace_bytes(self.actor_desc, self.critic_desc,
                                                           self.U * self.mbc, self.chunk),
                            dtype=torch.uint8)
+        self._scratch_state = z(NE, env.state_dim) if self.dense and not centralised_critic else None
         self.perm_rounds = int(math.ceil(3 * math.log(max(1, self.ncols)) / math.log(2 ** 32 - 1)))
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0
@@ -119,9 +138,14 @@ class RecLearner:
         params = Params(self.params[:na], self.params[na:])
         opt = OptStates({"mu": self.mu[:na], "nu": self.nu[:na], "count": self.counts[0:1]},
                         {"mu": self.mu[na:], "nu": self.nu[na:], "count": self.counts[1:2]})
-        env_state = EnvState(self.env_buf, self.view[0], self.mask[0])
-        steps = self.env.step_count(env_state)
-        obs = self.env.decode_observation(self.view[0], self.mask[0], steps)
+        if self.dense:
+            env_state = EnvState(self.env_buf, self.obs_a[0], self.mask[0])
+            obs = {"agents_view": self.obs_a[0], "action_mask": self.mask[0],
+                   "global_state": self.obs_c[0]}
+        else:
+            env_state = EnvState(self.env_buf, self.view[0], self.mask[0])
+            steps = self.env.step_count(env_state)
+            obs = self.env.decode_observation(self.view[0], self.mask[0], steps)
         ts = TimeStep(torch.full((self.NE,), StepType.MID, dtype=torch.int8, device=self.device),
                       self.reward[-1], torch.ones(self.NE, self.A, device=self.device), obs, {})
         dones = self.done_in[0].bool().unsqueeze(-1).expand(self.NE, self.A)
@@ -138,17 +162,28 @@ class RecLearner:
             if t < self.nc:  # the hidden state entering a column's first position (:221,254)
                 self.hs_actor[t].copy_(self.h_actor)
                 self.hs_critic[t].copy_(self.h_critic)
+            view_t = None if self.dense else self.view[t]
+            oa_t = self.obs_a[t] if self.dense else None
+            oc_t = self.obs_c[t] if self.dense else None
             native.rec_act(self.actor_desc, self.actor_params, self.critic_desc, self.critic_params,
-                           self.view[t], None, None, self.mask[t], self.done_in[t], self.h_actor,
+                           view_t, oa_t, oc_t, self.mask[t], self.done_in[t], self.h_actor,
                            self.h_actor, self.h_critic, self.h_critic, self.policy_keys[t], self.E,
                            self.NE, self.action[t], self.logp[t], self.value[t], self.act_ws)
-            envn.step(self.env_buf, self.action[t], self.view[t + 1], self.mask[t + 1],
-                      self.reward[t], self.done_in[t + 1], self.ep_ret[t], self.ep_len[t], self.NE,
-                      True)
+            if self.dense:
+                oc_next = self.obs_c[t + 1] if self.centralised_critic else self._scratch_state
+                envn.step(self.policy_keys[t], self.env_buf, self.action[t], self.obs_a[t + 1],
+                          oc_next, self.mask[t + 1], self.reward[t], self.done_in[t + 1],
+                          self.ep_ret[t], self.ep_len[t], self.NE)
+            else:
+                envn.step(self.env_buf, self.action[t], self.view[t + 1], self.mask[t + 1],
+                          self.reward[t], self.done_in[t + 1], self.ep_ret[t], self.ep_len[t],
+                          self.NE, True)
         # bootstrap value; the advanced critic state is discarded (rec_mappo.py:165)
-        native.rec_act(None, None, self.critic_desc, self.critic_params, self.view[self.T], None,
-                       None, None, self.done_in[self.T], None, None, self.h_critic, None, None,
-                       self.E, self.NE, None, None, self.last_val, self.act_ws)
+        native.rec_act(None, None, self.critic_desc, self.critic_params,
+                       None if self.dense else self.view[self.T], None,
+                       self.obs_c[self.T] if self.dense else None, None, self.done_in[self.T], None,
+                       None, self.h_critic, None, None, self.E, self.NE, None, None, self.last_val,
+                       self.act_ws)
 
     def _permutation(self, shuffle_key: torch.Tensor) -> torch.Tensor:
         """jax.random.permutation(shuffle_key, num_envs * num_chunks) (rec_mappo.py:350-352)."""
@@ -180,7 +215,7 @@ class RecLearner:
                     e0.record()
                 native.rec_ppo_loss_grad(
                     self.actor_desc, self.actor_params, self.critic_desc, self.critic_params,
-                    self.hyper, self.view, None, None, self.mask, self.action, self.logp,
+                    self.hyper, self.view, self.obs_a, self.obs_c, self.mask, self.action, self.logp,
                     self.value, self.adv, self.targets, self.done_in, self.hs_actor,
                     self.hs_critic, cols, self.U, self.E, self.mbc, self.chunk, self.nc, self.grad,
                     self.workspace)
@@ -206,15 +241,22 @@ class RecLearner:
                    float(self.config.system.gamma), float(self.config.system.gae_lambda), self.T,
                    self.NE, self.A, self.adv, self.targets, last_done=self.done_in[self.T])
         self._update_epochs()
-        self.view[0].copy_(self.view[self.T])
+        if self.dense:
+            self.obs_a[0].copy_(self.obs_a[self.T])
+            if self.centralised_critic:
+                self.obs_c[0].copy_(self.obs_c[self.T])
+        else:
+            self.view[0].copy_(self.view[self.T])
         self.mask[0].copy_(self.mask[self.T])
         self.done_in[0].copy_(self.done_in[self.T])
         self.launches_per_update = native.LAUNCHES - n0
 
     # -- CUDA graph -----------------------------------------------------------------------------
     def _state_tensors(self):
-        return [self.params, self.mu, self.nu, self.counts, self.key, self.env_buf, self.view,
-                self.mask, self.done_in, self.h_actor, self.h_critic]
+        obs = [self.obs_a] + ([self.obs_c] if self.centralised_critic else []) if self.dense \
+            else [self.view]
+        return [self.params, self.mu, self.nu, self.counts, self.key, self.env_buf, self.mask,
+                self.done_in, self.h_actor, self.h_critic] + obs
 
     def _capture(self) -> None:
         snap = [t.clone() for t in self._state_tensors()]
@@ -277,7 +319,8 @@ def _adopt(learner: RecLearner, st: RNNLearnerState) -> None:
     pairs = [(learner.params[: learner.na], st.params.actor_params),
              (learner.params[learner.na:], st.params.critic_params),
              (learner.key, st.key), (learner.env_buf, st.env_state.buf),
-             (learner.view[0], st.env_state.view), (learner.mask[0], st.env_state.mask)]
+             (learner.obs_a[0] if learner.dense else learner.view[0], st.env_state.view),
+             (learner.mask[0], st.env_state.mask)]
     if st.hstates is not None:
         pairs += [(learner.h_actor, st.hstates.policy_hidden_state.reshape(learner.h_actor.shape)),
                   (learner.h_critic, st.hstates.critic_hidden_state.reshape(learner.h_critic.shape))]
@@ -317,8 +360,13 @@ def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
     per_dev = learner.U * learner.E
     all_keys = prng.split(key, n_devices * per_dev + 1)
     key, env_keys = all_keys[0], all_keys[1 + rank * per_dev: 1 + (rank + 1) * per_dev]
-    env.native.reset(_u32(env_keys, device), learner.env_buf, learner.view[0], learner.mask[0],
-                     learner.NE)
+    if learner.dense:
+        oc0 = learner.obs_c[0] if centralised_critic else learner._scratch_state
+        env.native.reset(_u32(env_keys[0], device), learner.env_buf, learner.obs_a[0], oc0,
+                         learner.mask[0], learner.NE)
+    else:
+        env.native.reset(_u32(env_keys, device), learner.env_buf, learner.view[0], learner.mask[0],
+                         learner.NE)
     key, step_key = prng.split(key)
     learner.key.copy_(_u32(step_key, device))
 

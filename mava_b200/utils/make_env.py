@@ -42,6 +42,16 @@ def make(config, add_global_state: bool = False, device: torch.device = None
     env_name = config.env.scenario.name
     if env_name in _jumanji_registry:
         return make_jumanji_env(env_name, config, add_global_state, device)
+    if env_name == "SmaxSynthetic":
+        from ..wrappers import SyntheticSmaxEnv
+
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        tc = dict(config.env.scenario.task_config)
+        add_extra_wrappers(config)
+        mk = lambda: SyntheticSmaxEnv(int(tc["num_agents"]), int(tc["obs_dim"]),
+                                      int(tc["state_dim"]), int(tc["num_actions"]),
+                                      int(config.env.kwargs.get("time_limit", 100)), device)
+        return mk(), mk()
     raise ValueError(
         f"{env_name} is not supported by the mava_b200 env kernels "
         f"(supported: {sorted(_jumanji_registry)})")
