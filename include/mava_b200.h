@@ -265,6 +265,8 @@ typedef struct mava_rnn_desc {
   int32_t hidden;       /* pre_torso width == GRU width (flax: features = ins.shape[-1])         */
   int32_t post;         /* post_torso width                                                      */
   int32_t out_dim;      /* action_dim for the actor, 1 for the critic                            */
+  int32_t precision;    /* 0: fp32 contractions (rtol 1e-5 path); 1: bf16 operands on the tcgen05
+                           tensor cores with fp32 accumulation (tolerance 2e-2, BASELINE.json)   */
 } mava_rnn_desc;
 
 int64_t mava_rnn_param_count(const mava_rnn_desc* d_host);
@@ -337,6 +339,13 @@ int mava_synth_step(const mava_synth_config* cfg_host, const uint32_t* key, uint
  * ---------------------------------------------------------------------------------------- */
 int mava_tc_selftest(int mode, const float* A, const float* B, float* D, int N, int K,
                      mava_stream_t s);
+/* The dense contraction the recurrent path is built from, exposed for tests:
+ *   C[M][N] (mode 0: =, 1: +=, 2: atomic +=) opA(A)[M][K] opB(B)[K][N] (+ bias[N]) (relu)
+ *   (zeroed where relu_ref[M][ldr] <= 0);  ta: A is stored [K][lda];  tb: B is stored [N][ldb].
+ * use_tc = 0: fp32 SIMT kernel; 1: bf16 tcgen05 kernel.  k_splits > 1 splits K over CTAs (mode 2). */
+int mava_gemm(int use_tc, const float* A, int ta, int64_t lda, const float* B, int tb, int64_t ldb,
+              float* C, int64_t ldc, int M, int N, int K, const float* bias, int relu,
+              const float* relu_ref, int64_t ldr, int mode, int k_splits, mava_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ class MlpDesc(C.Structure):
 class RnnDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "input_mode", "add_agent_id", "num_agents", "view_dim", "in_dim", "rows_per_env", "hidden",
-        "post", "out_dim")]
+        "post", "out_dim", "precision")]
 
 
 class SynthConfig(C.Structure):
@@ -93,6 +93,8 @@ SIGNATURES = {
                              [c_void] * 7),
     "mava_synth_reset": (c_int, [P(SynthConfig)] + [c_void] * 5 + [c_int, c_void]),
     "mava_synth_step": (c_int, [P(SynthConfig)] + [c_void] * 10 + [c_int, c_void]),
+    "mava_gemm": (c_int, [c_int, c_void, c_int, c_i64, c_void, c_int, c_i64, c_void, c_i64, c_int,
+                          c_int, c_int, c_void, c_int, c_void, c_i64, c_int, c_int, c_void]),
     "mava_rnn_param_count": (c_i64, [P(RnnDesc)]),
     "mava_rec_act_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int]),
     "mava_rec_act": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void] + [c_void] * 10 +

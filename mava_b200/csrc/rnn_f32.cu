@@ -17,6 +17,7 @@
 // are element-wise kernels.  A tensor-core (tcgen05) version of the scan is the next step; this
 // path is the rtol-1e-5 one the bf16 kernels will be checked against.
 #include "common.cuh"
+#include "gemm.cuh"
 #include "prng.cuh"
 
 namespace mava {
@@ -31,23 +32,6 @@ constexpr int OMAX = 16;  // max head width, also the row stride of logits buffe
 // SGEMM: C[M][N] (op)= alpha * opA(A)[M][K] * opB(B)[K][N] (+ bias) (relu) (* relu_ref > 0)
 // ------------------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBK = 16, GT = 256;
-
-struct GemmArgs {
-  const float* A;
-  const float* B;
-  float* C;
-  int M, N, K;
-  int64_t lda, ldb, ldc;
-  int ta;  // 0: A(i,k) = A[i*lda + k]   1: A(i,k) = A[k*lda + i]
-  int tb;  // 0: B(k,j) = B[k*ldb + j]   1: B(k,j) = B[j*ldb + k]
-  const float* bias;      // [N] or null
-  const float* relu_ref;  // [M][ldr] or null: result zeroed where relu_ref <= 0
-  int64_t ldr;
-  int relu;
-  int mode;  // 0 store, 1 accumulate (+=), 2 atomicAdd
-  float alpha;
-  int kchunk;  // K range per blockIdx.z (multiple of GBK)
-};
 
 template <int TN>
 __global__ void __launch_bounds__(GT, 2) sgemm_kernel(const GemmArgs p) {
@@ -162,37 +146,45 @@ __global__ void __launch_bounds__(GT, 2) sgemm_kernel(const GemmArgs p) {
 
 struct Gemm {
   GemmArgs a{};
+  bool use_tc = false;
   Gemm(const float* A, int ta, int64_t lda, const float* B, int tb, int64_t ldb, float* C,
        int64_t ldc, int M, int N, int K) {
     a.A = A; a.ta = ta; a.lda = lda; a.B = B; a.tb = tb; a.ldb = ldb; a.C = C; a.ldc = ldc;
-    a.M = M; a.N = N; a.K = K; a.alpha = 1.0f; a.kchunk = ((K + GBK - 1) / GBK) * GBK;
+    a.M = M; a.N = N; a.K = K; a.alpha = 1.0f; a.kchunk = round_up(K, 64);
     a.bias = nullptr; a.relu_ref = nullptr; a.ldr = 0; a.relu = 0; a.mode = 0;
   }
   Gemm& bias(const float* b) { a.bias = b; return *this; }
   Gemm& relu() { a.relu = 1; return *this; }
   Gemm& relu_ref(const float* r, int64_t ldr) { a.relu_ref = r; a.ldr = ldr; return *this; }
   Gemm& accumulate() { a.mode = 1; return *this; }
+  Gemm& tc(bool on) { use_tc = on; return *this; }
   // reduction over a very long K (weight gradients): split K over CTAs, combine with atomics
   Gemm& split_k_atomic() {
     a.mode = 2;
     const int tiles = ceil_div(a.M, GBM) * ceil_div(a.N, a.N > 32 ? 128 : 32);
     int splits = max(1, min(ceil_div(4 * sm_count(), tiles), ceil_div(a.K, 8 * GBK)));
-    a.kchunk = round_up(ceil_div(a.K, splits), GBK);
+    a.kchunk = round_up(ceil_div(a.K, splits), 64);
     return *this;
   }
-  int run(cudaStream_t s) const {
-    if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
-    const int splits = ceil_div(a.K, a.kchunk);
-    if (a.N > 32) {
-      dim3 grid(ceil_div(a.M, GBM), ceil_div(a.N, 128), splits);
-      sgemm_kernel<8><<<grid, GT, 0, s>>>(a);
-    } else {
-      dim3 grid(ceil_div(a.M, GBM), ceil_div(a.N, 32), splits);
-      sgemm_kernel<2><<<grid, GT, 0, s>>>(a);
-    }
-    return launch_status();
-  }
+  int run(cudaStream_t s) const { return use_tc ? launch_tc_gemm(a, s) : launch_sgemm(a, s); }
 };
+
+}  // namespace
+
+int launch_sgemm(const GemmArgs& a, cudaStream_t s) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
+  const int splits = ceil_div(a.K, a.kchunk);
+  if (a.N > 32) {
+    dim3 grid(ceil_div(a.M, GBM), ceil_div(a.N, 128), splits);
+    sgemm_kernel<8><<<grid, GT, 0, s>>>(a);
+  } else {
+    dim3 grid(ceil_div(a.M, GBM), ceil_div(a.N, 32), splits);
+    sgemm_kernel<2><<<grid, GT, 0, s>>>(a);
+  }
+  return launch_status();
+}
+
+namespace {
 
 // db[j] += sum_i D[i][j]
 __global__ void __launch_bounds__(256)
@@ -228,6 +220,7 @@ int launch_colsum(const float* D, int64_t ldd, int64_t M, int N, float* db, cuda
 // ------------------------------------------------------------------------------------------------
 struct Net {
   int in_dim, H, Q, out, rows_per_env, mode, add_id, A, FR;
+  bool tc;  // bf16 tensor-core contractions (mava_rnn_desc.precision == 1)
   const float *w_pre, *b_pre, *w_i, *b_i, *w_h, *b_hn, *w_post, *b_post, *w_head, *b_head;
 };
 
@@ -236,6 +229,7 @@ int check_desc(const mava_rnn_desc* d) {
   if (d->hidden < 1 || d->hidden > 1024 || d->post < 1 || d->post > 1024) return MAVA_E_UNSUPPORTED;
   if (d->out_dim < 1 || d->out_dim > OMAX) return MAVA_E_UNSUPPORTED;
   if (d->num_agents < 1) return MAVA_E_BADARG;
+  if (d->precision != 0 && d->precision != 1) return MAVA_E_BADARG;
   if (d->input_mode == MAVA_IN_DENSE) {
     if (d->in_dim < 1) return MAVA_E_BADARG;
     if (d->rows_per_env != 1 && d->rows_per_env != d->num_agents) return MAVA_E_BADARG;
@@ -258,6 +252,7 @@ Net make_net(const mava_rnn_desc* d, T* p) {
   n.in_dim = d->in_dim; n.H = d->hidden; n.Q = d->post; n.out = d->out_dim;
   n.rows_per_env = d->rows_per_env; n.mode = d->input_mode; n.add_id = d->add_agent_id;
   n.A = d->num_agents; n.FR = d->view_dim;
+  n.tc = d->precision == 1;
   const int H = n.H;
   n.w_pre = p; p += (int64_t)n.in_dim * H;
   n.b_pre = p; p += H;
@@ -378,10 +373,11 @@ gru_fwd_kernel(const float* __restrict__ Gx, const float* __restrict__ Gh,
 
 // Backward of the gates of one time step.  dh = dHout (+ carry where the next step did not reset).
 // Overwrites the stash row with dGh = [da_r | da_z | dq | .], writes dGx = [da_r | da_z | da_n]
-// and dHin = dh * z (the W_h term is added by the GEMM that follows).
+// and dHin = dh * z; the W_h term dGh W_h^T is produced by the GEMM that follows into its own buffer
+// (carry2 of the next call), so that GEMM is a plain store instead of a read-modify-write.
 __global__ void __launch_bounds__(256)
 gru_bwd_kernel(const float* __restrict__ dHout, const float* __restrict__ carry,
-               const int32_t* __restrict__ next_steps, const uint8_t* __restrict__ done_in, int rpe,
+               const float* __restrict__ carry2, const int32_t* __restrict__ next_steps, const uint8_t* __restrict__ done_in, int rpe,
                const float* __restrict__ Hin, float* __restrict__ gates, float* __restrict__ dGx,
                float* __restrict__ dHin, int64_t rows, int H) {
   const int64_t total = rows * H;
@@ -390,7 +386,7 @@ gru_bwd_kernel(const float* __restrict__ dHout, const float* __restrict__ carry,
     const int64_t row = idx / H;
     const int j = (int)(idx - row * H);
     float dh = dHout[idx];
-    if (carry != nullptr && !done_in[next_steps[row / rpe]]) dh += carry[idx];
+    if (carry != nullptr && !done_in[next_steps[row / rpe]]) dh += carry[idx] + carry2[idx];
     float* g = gates + row * 4 * H;
     const float r = g[j], z = g[H + j], n = g[2 * H + j], q = g[3 * H + j];
     const float hin = Hin[idx];
@@ -659,7 +655,7 @@ int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 // forward of one network over `L` time positions of `S` sequences (rows = S per position)
 // ------------------------------------------------------------------------------------------------
 struct Work {
-  float *X, *E1, *Gx, *gates, *Hin, *Hout, *P, *out, *Gh, *dH0, *dH1;
+  float *X, *E1, *Gx, *gates, *Hin, *Hout, *P, *out, *Gh, *dH0, *dH1, *dT0, *dT1;
 };
 
 int64_t work_floats(const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
@@ -668,7 +664,7 @@ int64_t work_floats(const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
   f += align256(R * d->in_dim) + align256(R * H) + align256(R * 3 * H);  // X, E1, Gx
   f += train ? align256(R * 4 * H) : 0;                                   // gates
   f += align256(R * H) * 2 + align256(R * Q) + align256(R * OMAX);        // Hin, Hout, P, out
-  f += align256(S * 3 * H) + 2 * align256(S * H);                         // Gh, dH0, dH1
+  f += align256(S * 3 * H) + 4 * align256(S * H);                         // Gh, dH0/1, dT0/1
   return f;
 }
 
@@ -685,7 +681,9 @@ Work carve(float* w, const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
   k.out = w; w += align256(R * OMAX);
   k.Gh = w; w += align256(S * 3 * H);
   k.dH0 = w; w += align256(S * H);
-  k.dH1 = w;
+  k.dH1 = w; w += align256(S * H);
+  k.dT0 = w; w += align256(S * H);
+  k.dT1 = w;
   return k;
 }
 
@@ -706,15 +704,15 @@ int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
   const int64_t S = in.Senv * n.rows_per_env, R = S * L;
   expand_obs_kernel<<<ew_blocks(R * n.in_dim), 256, 0, s>>>(
       in.view, in.dense, in.steps, R, n.rows_per_env, n.mode, n.add_id, n.A, n.FR, n.in_dim, k.X);
-  int rc = Gemm(k.X, 0, n.in_dim, n.w_pre, 0, H, k.E1, H, (int)R, H, n.in_dim).bias(n.b_pre).relu().run(s);
+  int rc = Gemm(k.X, 0, n.in_dim, n.w_pre, 0, H, k.E1, H, (int)R, H, n.in_dim).bias(n.b_pre).relu().tc(n.tc).run(s);
   if (rc) return rc;
-  rc = Gemm(k.E1, 0, H, n.w_i, 0, 3 * H, k.Gx, 3 * H, (int)R, 3 * H, H).bias(n.b_i).run(s);
+  rc = Gemm(k.E1, 0, H, n.w_i, 0, 3 * H, k.Gx, 3 * H, (int)R, 3 * H, H).bias(n.b_i).tc(n.tc).run(s);
   if (rc) return rc;
   mask_hidden_kernel<<<ew_blocks(S * H), 256, 0, s>>>(in.h0, in.steps, in.done_in, S,
                                                        n.rows_per_env, H, 0, in.h0_gather, k.Hin);
   for (int l = 0; l < L; ++l) {
     const float* hin = k.Hin + (int64_t)l * S * H;
-    rc = Gemm(hin, 0, H, n.w_h, 0, 3 * H, k.Gh, 3 * H, (int)S, 3 * H, H).run(s);
+    rc = Gemm(hin, 0, H, n.w_h, 0, 3 * H, k.Gh, 3 * H, (int)S, 3 * H, H).tc(n.tc).run(s);
     if (rc) return rc;
     const bool more = l + 1 < L;
     gru_fwd_kernel<<<ew_blocks(S * H), 256, 0, s>>>(
@@ -723,10 +721,10 @@ int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
         more ? in.steps + (int64_t)(l + 1) * in.Senv : nullptr, in.done_in, n.rows_per_env,
         more ? k.Hin + (int64_t)(l + 1) * S * H : nullptr);
   }
-  rc = Gemm(k.Hout, 0, H, n.w_post, 0, n.Q, k.P, n.Q, (int)R, n.Q, H).bias(n.b_post).relu().run(s);
+  rc = Gemm(k.Hout, 0, H, n.w_post, 0, n.Q, k.P, n.Q, (int)R, n.Q, H).bias(n.b_post).relu().tc(n.tc).run(s);
   if (rc) return rc;
   const int ldo = n.out == 1 ? 1 : OMAX;
-  rc = Gemm(k.P, 0, n.Q, n.w_head, 0, n.out, k.out, ldo, (int)R, n.out, n.Q).bias(n.b_head).run(s);
+  rc = Gemm(k.P, 0, n.Q, n.w_head, 0, n.out, k.out, ldo, (int)R, n.out, n.Q).bias(n.b_head).tc(n.tc).run(s);
   if (rc) return rc;
   return launch_status();
 }
@@ -739,49 +737,50 @@ int backward(const Net& n, const Net& g, const SeqInput& in, const Work& k, cuda
   auto G = [](const float* p) { return const_cast<float*>(p); };
   int rc;
   // head
-  rc = Gemm(k.P, 1, Q, k.out, 0, ldo, G(g.w_head), n.out, Q, n.out, (int)R).split_k_atomic().run(s);
+  rc = Gemm(k.P, 1, Q, k.out, 0, ldo, G(g.w_head), n.out, Q, n.out, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   rc = launch_colsum(k.out, ldo, R, n.out, G(g.b_head), s);
   if (rc) return rc;
   // dP = (dOut W_head^T) * relu'(P), in place over P
-  rc = Gemm(k.out, 0, ldo, n.w_head, 1, n.out, k.P, Q, (int)R, Q, n.out).relu_ref(k.P, Q).run(s);
+  rc = Gemm(k.out, 0, ldo, n.w_head, 1, n.out, k.P, Q, (int)R, Q, n.out).relu_ref(k.P, Q).tc(n.tc).run(s);
   if (rc) return rc;
-  rc = Gemm(k.Hout, 1, H, k.P, 0, Q, G(g.w_post), Q, H, Q, (int)R).split_k_atomic().run(s);
+  rc = Gemm(k.Hout, 1, H, k.P, 0, Q, G(g.w_post), Q, H, Q, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   rc = launch_colsum(k.P, Q, R, Q, G(g.b_post), s);
   if (rc) return rc;
   // dHout = dP W_post^T, in place over Hout
-  rc = Gemm(k.P, 0, Q, n.w_post, 1, Q, k.Hout, H, (int)R, H, Q).run(s);
+  rc = Gemm(k.P, 0, Q, n.w_post, 1, Q, k.Hout, H, (int)R, H, Q).tc(n.tc).run(s);
   if (rc) return rc;
   // reverse scan
   float* dH[2] = {k.dH0, k.dH1};
+  float* dT[2] = {k.dT0, k.dT1};
   for (int l = L - 1; l >= 0; --l) {
     const bool has_next = l + 1 < L;
-    float* cur = dH[l & 1];
     gru_bwd_kernel<<<ew_blocks(S * H), 256, 0, s>>>(
         k.Hout + (int64_t)l * S * H, has_next ? dH[(l + 1) & 1] : nullptr,
+        has_next ? dT[(l + 1) & 1] : nullptr,
         has_next ? in.steps + (int64_t)(l + 1) * in.Senv : nullptr, in.done_in, n.rows_per_env,
         k.Hin + (int64_t)l * S * H, k.gates + (int64_t)l * S * 4 * H,
-        k.Gx + (int64_t)l * S * 3 * H, cur, S, H);
-    if (l > 0) {  // dHin += dGh W_h^T (the chunk-start state carries no gradient)
-      rc = Gemm(k.gates + (int64_t)l * S * 4 * H, 0, 4 * H, n.w_h, 1, 3 * H, cur, H, (int)S, H,
-                3 * H).accumulate().run(s);
+        k.Gx + (int64_t)l * S * 3 * H, dH[l & 1], S, H);
+    if (l > 0) {  // dGh W_h^T (the chunk-start state carries no gradient)
+      rc = Gemm(k.gates + (int64_t)l * S * 4 * H, 0, 4 * H, n.w_h, 1, 3 * H, dT[l & 1], H, (int)S, H,
+                3 * H).tc(n.tc).run(s);
       if (rc) return rc;
     }
   }
   // recurrent and input weights of the cell: one contraction over all (position, sequence) rows
-  rc = Gemm(k.Hin, 1, H, k.gates, 0, 4 * H, G(g.w_h), 3 * H, H, 3 * H, (int)R).split_k_atomic().run(s);
+  rc = Gemm(k.Hin, 1, H, k.gates, 0, 4 * H, G(g.w_h), 3 * H, H, 3 * H, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   rc = launch_colsum(k.gates + 2 * H, 4 * H, R, H, G(g.b_hn), s);
   if (rc) return rc;
-  rc = Gemm(k.E1, 1, H, k.Gx, 0, 3 * H, G(g.w_i), 3 * H, H, 3 * H, (int)R).split_k_atomic().run(s);
+  rc = Gemm(k.E1, 1, H, k.Gx, 0, 3 * H, G(g.w_i), 3 * H, H, 3 * H, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   rc = launch_colsum(k.Gx, 3 * H, R, 3 * H, G(g.b_i), s);
   if (rc) return rc;
   // dE1 = (dGx W_i^T) * relu'(E1), in place over E1
-  rc = Gemm(k.Gx, 0, 3 * H, n.w_i, 1, 3 * H, k.E1, H, (int)R, H, 3 * H).relu_ref(k.E1, H).run(s);
+  rc = Gemm(k.Gx, 0, 3 * H, n.w_i, 1, 3 * H, k.E1, H, (int)R, H, 3 * H).relu_ref(k.E1, H).tc(n.tc).run(s);
   if (rc) return rc;
-  rc = Gemm(k.X, 1, n.in_dim, k.E1, 0, H, G(g.w_pre), H, n.in_dim, H, (int)R).split_k_atomic().run(s);
+  rc = Gemm(k.X, 1, n.in_dim, k.E1, 0, H, G(g.w_pre), H, n.in_dim, H, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   return launch_colsum(k.E1, H, R, H, G(g.b_pre), s);
 }
@@ -792,6 +791,22 @@ int backward(const Net& n, const Net& g, const SeqInput& in, const Work& k, cuda
 using namespace mava;
 
 extern "C" {
+
+int mava_gemm(int use_tc, const float* A, int ta, int64_t lda, const float* B, int tb, int64_t ldb,
+              float* C, int64_t ldc, int M, int N, int K, const float* bias, int relu,
+              const float* relu_ref, int64_t ldr, int mode, int k_splits, mava_stream_t s) {
+  MAVA_CHECK_PTR(A);
+  MAVA_CHECK_PTR(B);
+  MAVA_CHECK_PTR(C);
+  MAVA_CHECK_ARG(M > 0 && N > 0 && K > 0 && mode >= 0 && mode <= 2 && k_splits >= 1);
+  MAVA_CHECK_ARG(k_splits == 1 || mode == 2);
+  GemmArgs a{};
+  a.A = A; a.ta = ta; a.lda = lda; a.B = B; a.tb = tb; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.relu = relu; a.relu_ref = relu_ref; a.ldr = ldr;
+  a.mode = mode; a.alpha = 1.0f;
+  a.kchunk = round_up(ceil_div(K, k_splits), 64);
+  return use_tc ? launch_tc_gemm(a, as_stream(s)) : launch_sgemm(a, as_stream(s));
+}
 
 int64_t mava_rnn_param_count(const mava_rnn_desc* d) {
   if (!d) return -1;

@@ -369,8 +369,8 @@ def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, gr
 # recurrent systems (rec_ippo / rec_mappo)
 # ---------------------------------------------------------------------------------------------
 def rnn_desc(input_mode: int, add_agent_id: bool, num_agents: int, view_dim: int, hidden: int,
-             post: int, out_dim: int, dense_in_dim: int = 0, rows_per_env: Optional[int] = None
-             ) -> RnnDesc:
+             post: int, out_dim: int, dense_in_dim: int = 0, rows_per_env: Optional[int] = None,
+             precision: int = 0) -> RnnDesc:
     if input_mode == IN_DENSE:
         in_dim = int(dense_in_dim)
         rpe = num_agents if rows_per_env is None else int(rows_per_env)
@@ -379,7 +379,25 @@ def rnn_desc(input_mode: int, add_agent_id: bool, num_agents: int, view_dim: int
     else:
         in_dim, rpe = view_dim + (num_agents if add_agent_id else 0), num_agents
     return RnnDesc(input_mode, int(add_agent_id), num_agents, view_dim, in_dim, rpe, hidden, post,
-                   out_dim)
+                   out_dim, int(precision))
+
+
+def _p2d(t: torch.Tensor, name: str):
+    """Row-major 2-D float32 matrix whose rows may be strided (leading dimension = stride(0))."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a CUDA float32 matrix with unit column stride")
+    return C.c_void_p(t.data_ptr())
+
+
+def gemm(use_tc: bool, A, ta: bool, B, tb: bool, C, M: int, N: int, K: int, bias=None,
+         relu: bool = False, relu_ref=None, mode: int = 0, k_splits: int = 1) -> None:
+    """The recurrent path's dense contraction on row-major 2-D tensors (tests / diagnostics)."""
+    _count(1)
+    check(_lib.load().mava_gemm(
+        int(use_tc), _p2d(A, "A"), int(ta), A.stride(0), _p2d(B, "B"), int(tb), B.stride(0),
+        _p2d(C, "C"), C.stride(0), M, N, K, _p(bias, torch.float32, None, "bias"), int(relu),
+        _p2d(relu_ref, "relu_ref") if relu_ref is not None else None,
+        relu_ref.stride(0) if relu_ref is not None else 0, mode, k_splits, _stream()), "mava_gemm")
 
 
 def _pmask(mask, actor: Optional[RnnDesc]):

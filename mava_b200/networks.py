@@ -186,10 +186,10 @@ class _Recurrent:
         return H, Q
 
     def desc(self, num_agents: int, view_dim: int, add_agent_id: bool, input_mode: int,
-             dense_in_dim: int = 0, rows_per_env=None):
+             dense_in_dim: int = 0, rows_per_env=None, precision: int = 0):
         H, Q = self._dims()
         return native.rnn_desc(input_mode, add_agent_id, num_agents, view_dim, H, Q, self.out_dim,
-                               dense_in_dim, rows_per_env)
+                               dense_in_dim, rows_per_env, precision)
 
     def shapes(self, in_dim: int):
         H, Q = self._dims()

@@ -55,17 +55,23 @@ class RecLearner:
             raise ValueError("num_envs * num_chunks must be divisible by num_minibatches")
         self.mbc = self.E * self.nc // self.nmb
         add_id = bool(s.add_agent_id)
+        # precision: bf16 tensor-core contractions unless fp32 is asked for (as the ff learner)
+        self.precision = str(config.arch.get("precision", "auto"))
+        if self.precision not in ("auto", "fp32", "bf16"):
+            raise ValueError(f"arch.precision must be auto, fp32 or bf16, got {self.precision}")
+        self.bf16 = self.precision != "fp32"
+        pr = 1 if self.bf16 else 0
         if self.dense:
             # AgentIDWrapper appends nothing here: the synthetic rows already have their width
-            self.actor_desc = actor.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A)
-            self.critic_desc = (critic.desc(self.A, 1, False, native.IN_DENSE, env.state_dim, 1)
+            self.actor_desc = actor.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A, pr)
+            self.critic_desc = (critic.desc(self.A, 1, False, native.IN_DENSE, env.state_dim, 1, pr)
                                 if centralised_critic else
-                                critic.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A))
+                                critic.desc(self.A, 1, False, native.IN_DENSE, env.obs_dim, self.A, pr))
         else:
-            self.actor_desc = actor.desc(self.A, self.FR, add_id, native.IN_AGENT_VIEW)
+            self.actor_desc = actor.desc(self.A, self.FR, add_id, native.IN_AGENT_VIEW, precision=pr)
             self.critic_desc = critic.desc(
                 self.A, self.FR, add_id,
-                native.IN_GLOBAL if centralised_critic else native.IN_AGENT_VIEW)
+                native.IN_GLOBAL if centralised_critic else native.IN_AGENT_VIEW, precision=pr)
         self.centralised_critic = centralised_critic
         self.H = self.actor_desc.hidden
         self.rpc = self.critic_desc.rows_per_env
@@ -120,8 +126,9 @@ class RecLearner:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0
         self.time_loss_grad = None
-        self.compute_dtype = "f32"
-        self.dominant_kernel = "sgemm_kernel (fp32 GRU scan + dense layers)"
+        self.compute_dtype = "bf16" if self.bf16 else "f32"
+        self.dominant_kernel = ("tc_gemm_kernel (tcgen05 bf16 GRU scan + dense layers)" if self.bf16
+                                else "sgemm_kernel (fp32 GRU scan + dense layers)")
         self.lr_decay_updates = int(s.num_updates) if bool(s.decay_learning_rates) else 0
 
     # -- views of the state ---------------------------------------------------------------------

@@ -28,7 +28,7 @@ def test_one_recurrent_update_matches_oracle(lib_built, system, chunk, use_graph
     over = ["env/scenario=tiny-2ag", "arch.num_envs=8", "system.rollout_length=16",
             "system.ppo_epochs=2", "system.num_minibatches=2", "system.update_batch_size=2",
             "env.kwargs.time_limit=10", f"+arch.use_cuda_graph={use_graph}",
-            "network.hidden_state_dim=32", "network.actor_network.pre_torso.layer_sizes=[32]",
+            "+arch.precision=fp32", "network.hidden_state_dim=32", "network.actor_network.pre_torso.layer_sizes=[32]",
             "network.actor_network.post_torso.layer_sizes=[24]",
             "network.critic_network.pre_torso.layer_sizes=[32]",
             "network.critic_network.post_torso.layer_sizes=[24]"]

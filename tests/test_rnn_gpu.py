@@ -30,10 +30,10 @@ def _inputs(mode, view, dense, A, add_id):
     return v
 
 
-def _make(rng, mode, A, FR, H, Q, out, dense_dim=0, rpe=None):
+def _make(rng, mode, A, FR, H, Q, out, dense_dim=0, rpe=None, precision=0):
     from mava_b200 import native
 
-    d = native.rnn_desc(mode, True, A, FR, H, Q, out, dense_dim, rpe)
+    d = native.rnn_desc(mode, True, A, FR, H, Q, out, dense_dim, rpe, precision)
     n = native.rnn_param_count(d)
     flat = (rng.standard_normal(n) * 0.3).astype(np.float32)
     return d, flat
@@ -100,8 +100,9 @@ def test_rec_act_matches_oracle(lib_built, critic_mode):
     np.testing.assert_allclose(value.cpu().numpy(), v, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("critic_mode,chunk", [("global", 8), ("agent", 4), ("dense", 2)])
-def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk):
+@pytest.mark.parametrize("critic_mode,chunk,precision", [
+    ("global", 8, 0), ("agent", 4, 0), ("dense", 2, 0), ("global", 8, 1), ("dense", 4, 1)])
+def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, precision):
     from mava_b200 import native
     from mava_b200._lib import PpoHyper
 
@@ -111,12 +112,12 @@ def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk):
     NE, nc = U * E, T // chunk
     dense_dim = 10
     if critic_mode == "dense":
-        ad, ap = _make(rng, native.IN_DENSE, A, FR, H, Q, N, dense_dim, A)
-        cd, cp = _make(rng, native.IN_DENSE, A, FR, H, Q, 1, dense_dim + 3, 1)
+        ad, ap = _make(rng, native.IN_DENSE, A, FR, H, Q, N, dense_dim, A, precision)
+        cd, cp = _make(rng, native.IN_DENSE, A, FR, H, Q, 1, dense_dim + 3, 1, precision)
     else:
-        ad, ap = _make(rng, native.IN_AGENT_VIEW, A, FR, H, Q, N)
+        ad, ap = _make(rng, native.IN_AGENT_VIEW, A, FR, H, Q, N, precision=precision)
         cd, cp = _make(rng, native.IN_GLOBAL if critic_mode == "global" else native.IN_AGENT_VIEW,
-                       A, FR, H, Q, 1)
+                       A, FR, H, Q, 1, precision=precision)
     rpc = cd.rows_per_env
     f32 = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
     view = torch.from_numpy(rng.integers(-2, 3, (T, NE, A, FR)).astype(np.int8))
@@ -182,6 +183,15 @@ def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk):
     ga, = torch.autograd.grad(tot_a, pa_flat)
     gc, = torch.autograd.grad(tot_c, pc_flat)
     scale_a, scale_c = float(ga.abs().max()), float(gc.abs().max())
+    if precision == 1:
+        # bf16 tensor-core contractions (fp32 accumulation): 2e-2 tolerance of BASELINE.json on the
+        # losses, gradient blocks within 5e-2 in Frobenius norm (chains of 3 to 5 bf16 GEMMs)
+        for got, want in ((grad[:na], ga.numpy()), (grad[na:na + ncr], gc.numpy())):
+            err = np.linalg.norm(got - want) / np.linalg.norm(want)
+            assert err < 5e-2, err
+        np.testing.assert_allclose(grad[na + ncr:na + ncr + 5],
+                                   [tot_a.item(), la, ent, tot_c.item(), vl], rtol=2e-2, atol=2e-3)
+        return
     np.testing.assert_allclose(grad[:na], ga.numpy(), rtol=2e-4, atol=2e-5 * scale_a)
     np.testing.assert_allclose(grad[na:na + ncr], gc.numpy(), rtol=2e-4, atol=2e-5 * scale_c)
     np.testing.assert_allclose(grad[na + ncr:na + ncr + 5],
