@@ -196,6 +196,56 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
   expand_x_row(d, xt, L, mine, valid, a);
 }
 
+// Split form of build_x_tile for kernels that prefetch the next tile's observations while the
+// current tile is in the tensor pipe: gather_issue() starts the asynchronous copies of the
+// env-steps a tile touches into `stage` (no CTA barrier inside: every lane of a warp reads the
+// warp's env-step index itself), gather_expand() is called after cp.async.wait_group 0 + a CTA
+// barrier and builds the bf16 X tile.  Requires A * FR to be a multiple of 4 bytes.
+template <class StepFn>
+__device__ __forceinline__ void gather_issue(const NetDesc& d, const int8_t* __restrict__ view,
+                                             unsigned char* stage, int64_t row0, int64_t M,
+                                             StepFn step_at) {
+  const Lane L;
+  const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
+  const int step_bytes = d.A * d.FR;
+  const int64_t last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
+  const int64_t j0 = row0 / rps;
+  const int nsteps = (int)(last / rps - j0) + 1;
+  const int unit = (step_bytes & 7) == 0 ? 8 : 4;
+  const int units = step_bytes / unit;
+  for (int js = L.warp; js < nsteps; js += NWARPS) {
+    const int8_t* src = view + (size_t)step_at(j0 + js) * step_bytes;
+    const uint32_t dst = smem_u32(stage) + (uint32_t)js * step_bytes;
+    for (int i = L.lane; i < units; i += 32) {
+      if (unit == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 8), "l"(src + i * 8)
+                     : "memory");
+      else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * 4), "l"(src + i * 4)
+                     : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void gather_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
+                                              const unsigned char* stage, int64_t row0, int64_t M) {
+  const Lane L;
+  const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
+  const int step_bytes = d.A * d.FR;
+  const int64_t j0 = row0 / rps;
+  const int64_t row = row0 + L.r;
+  const bool valid = row < M;
+  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
+  const signed char* mine = reinterpret_cast<const signed char*>(stage) +
+                            (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
+  expand_x_row(d, xt, L, mine, valid, a);
+}
+
 // One thread issues the K/16 MMAs of a GEMM (M = 128) and optionally commits to `bar`.
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool a_mn, const Tile& b,
                                            bool b_mn, int N, int K, bool accumulate,

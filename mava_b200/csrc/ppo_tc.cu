@@ -50,6 +50,7 @@ struct TrainArgs {
   float clip_eps, ent_coef, vf_coef;
   int actor_ctas, critic_ctas;
   int fold_actor_w1;  // the actor's [dW1^T | db1] accumulates in TMEM inside the fused kernel
+  int prefetch_actor; // fold mode: next tile's observation rows are gathered one tile ahead
   float *grad_actor, *grad_critic;
   double* loss_acc;
   unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
@@ -59,6 +60,17 @@ struct Ctrl {
   uint64_t wbar, mbar;
   uint32_t tmem;
   float db3[NHEAD];
+};
+
+constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava: num_agents <= 8)
+
+// per-row loss inputs, fetched at the start of a tile
+struct LossIn {
+  bool valid;
+  int64_t j, flat;
+  uint32_t mk;
+  int act;
+  float f0[kMaxReps], f1[kMaxReps];  // actor: old_logp, adv in [0]; critic: old_value, targets
 };
 
 __host__ __device__ inline uint32_t region_bytes(int k1p) {
@@ -117,6 +129,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   const Tile h1t{s_region + (fold ? kRegionMin : region_bytes(d.k1p)), 128u, 2048u};
   const Tile dz3t{h1t.base + tile_bytes(TM, HCOLS), 128u, 2048u};
   const Tile w1 = w1_tile(s_w, d.k1p), w2 = w2_tile(s_w, d.k1p), w3 = w3_tile(s_w, d.k1p);
+  // fold mode also prefetches: the next tile's observation rows are gathered (cp.async) into a
+  // dedicated staging buffer while this tile runs, so the two dependent HBM latencies of the
+  // gather (row index -> observation bytes) leave the critical path
+  const bool prefetch = fold && p.prefetch_actor != 0;
+  unsigned char* pf_stage = smem + (dz3t.base - s_w) + tile_bytes(TM, NHEAD);
+  auto step_at = [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); };
 
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
@@ -130,6 +148,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
+  if (prefetch && cta < n_tiles) gather_issue(d, p.view, pf_stage, (int64_t)cta * TM, M, step_at);
   mbar_wait(&ctrl.wbar, 0);
 
   uint32_t phase = 0;
@@ -141,8 +160,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     const int64_t row0 = (int64_t)tile * TM;
     const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
 
-    build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M,
-                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
+    if (prefetch) {
+      gather_wait();
+      __syncthreads();
+      gather_expand(d, xt, pf_stage, row0, M);
+    } else {
+      build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M, step_at);
+    }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -150,6 +174,36 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
+    }
+    if (prefetch && tile + n_ctas < n_tiles)  // staging buffer is free again: next tile's rows
+      gather_issue(d, p.view, pf_stage, (int64_t)(tile + n_ctas) * TM, M, step_at);
+    // loss inputs of this row: in flight during the forward pass instead of after it
+    LossIn li{};
+    if (L.q == 0) {
+      const int64_t row = row0 + L.r;
+      li.valid = row < M;
+      const int64_t j = li.valid ? row / rows_per_step : 0;
+      const int ag = (int)(row - j * rows_per_step);
+      const int64_t sidx = li.valid ? __ldg(p.rows + j) : 0;
+      li.j = j;
+      li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
+      if (li.valid) {
+        if (is_actor) {
+          li.mk = p.mask[li.flat];
+          li.act = p.action[li.flat];
+          li.f0[0] = p.old_logp[li.flat];
+          li.f1[0] = p.adv[li.flat];
+        } else {
+          const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
+#pragma unroll
+          for (int a = 0; a < kMaxReps; ++a) {
+            if (a < reps) {
+              li.f0[a] = p.old_value[li.flat + a];
+              li.f1[a] = p.targets[li.flat + a];
+            }
+          }
+        }
+      }
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
@@ -175,12 +229,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     phase ^= 1;
     // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output)
     if (L.q == 0) {
-      const int64_t row = row0 + L.r;
-      const bool valid = row < M;
-      const int64_t j = valid ? row / rows_per_step : 0;  // position in the minibatch
-      const int ag = (int)(row - j * rows_per_step);
-      const int64_t s = valid ? __ldg(p.rows + j) : 0;    // env-step index in the rollout buffers
-      const int64_t flat = s * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
+      const bool valid = li.valid;
+      const int64_t j = li.j;  // position in the minibatch
       float out[NHEAD], dz[NHEAD];
       ld16(tmem + L.tmem_lane() + COL_HEAD, out);
 #pragma unroll
@@ -191,8 +241,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
           const float v = out[0];
           const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
           float dv = 0.0f;
-          for (int a = 0; a < reps; ++a) {
-            const float vo = p.old_value[flat + a], tg = p.targets[flat + a];
+#pragma unroll
+          for (int a = 0; a < kMaxReps; ++a) {
+            if (a >= reps) break;
+            const float vo = li.f0[a], tg = li.f1[a];
             const float diff = v - vo;
             const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
             const float e1 = v - tg, e2 = vc - tg;
@@ -208,7 +260,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
           dz[0] = dv * wrow * p.vf_coef;
         } else {
           // _actor_loss_fn, ff_mappo.py:159-180
-          const uint8_t mk = p.mask[flat];
+          const uint32_t mk = li.mk;
           float mx = kF32Min;
 #pragma unroll
           for (int q = 0; q < NHEAD; ++q) {
@@ -222,7 +274,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
           for (int q = 0; q < NHEAD; ++q)
             if (q < d.out) se += expf(out[q] - mx);
           const float lse = mx + logf(se);
-          const int a = p.action[flat];
+          const int a = li.act;
           const int u = (int)(j / p.mb_size);
           const double cnt = (double)p.mb_size * d.A;
           const double mean_d = p.adv_stats[2 * u] / cnt;
@@ -241,8 +293,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
               if (q == a) la = logp[q];
             }
           }
-          const float ratio = expf(la - p.old_logp[flat]);
-          const float g = (p.adv[flat] - mean) / (sd + 1e-8f);
+          const float ratio = expf(la - li.f0[0]);
+          const float g = (li.f1[0] - mean) / (sd + 1e-8f);
           const float lo = 1.0f - p.clip_eps, hi = 1.0f + p.clip_eps;
           const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
           const bool inside = ratio > lo && ratio < hi;
@@ -584,6 +636,10 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
                            kRegionMin + tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
   a.fold_actor_w1 = a.actor.k1p <= 208 && smem_fold <= 227 * 1024;
   if (a.fold_actor_w1 && smem_fold > smem_fused) smem_fused = smem_fold;
+  const size_t smem_pf = smem_fold + stage_bytes(a.actor.A, a.actor.FR, a.actor.A);
+  a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && ((a.actor.A * a.actor.FR) & 3) == 0;
+  if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
+  MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
   const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
                           tile_bytes(TM, HCOLS) + 128;  // dZ1 tile, X tile, staging
   static size_t conf_fused = 0, conf_wg1 = 0;
