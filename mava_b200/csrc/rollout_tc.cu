@@ -45,6 +45,7 @@ struct RolloutArgs {
   float* ep_return;             // [T][NE]
   int32_t* ep_length;           // [T][NE]
   int num_envs, envs_per_replica, T;
+  int epc;  // envs per CTA (<= TM / A): fewer than a full tile when that fills more SMs
 };
 
 struct RCtrl {
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(NT, 1)
 rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ RCtrl ctrl;
-  constexpr int EPC = TM / G;  // envs per CTA; agents == G, so tile row r = el * G + g = thread r
+  constexpr int EPC = TM / G;  // max envs per CTA; agents == G, so tile row r = el * G + g = thread r
   const RwareConst& c = p.c;
   const NetDesc& d = p.actor;
   const Lane L;
@@ -87,9 +88,10 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   const Tile ht{xt.base + tile_bytes(TM, d.k1p), 128u, (uint32_t)(TM / 8) * 128u};
   uint8_t* srec = smem + wi.total() + tile_bytes(TM, d.k1p) + tile_bytes(TM, HCOLS);
   uint8_t* sobs = srec + EPC * c.stride;
+  float* snoise = reinterpret_cast<float*>(sobs + round_up(EPC * G * c.FR, 16));  // [2][TM][NHEAD]
 
-  const int env0 = blockIdx.x * EPC;
-  const int nenv = min(EPC, p.num_envs - env0);
+  const int env0 = blockIdx.x * p.epc;
+  const int nenv = min(p.epc, p.num_envs - env0);
   const int rows_valid = nenv * G;
   const uint32_t rec_bytes = (uint32_t)nenv * (uint32_t)c.stride;
   uint8_t* gstate = p.state + (size_t)env0 * c.stride;
@@ -127,6 +129,21 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   const unsigned gmask = rware::group_mask<G>();
   uint8_t* rec = srec + el * c.stride;
   uint32_t mk = agent ? p.mask[(size_t)env * G + g] : 0u;
+  // Gumbel noise of a step: depends only on the step's policy key and (env, agent, action), so it
+  // is produced one step ahead by the warps that idle during the env step (noise laid out
+  // (envs_per_replica, A, N) as tfd.Categorical.sample draws it)
+  auto make_noise = [&](int step, int first, int nthreads) {
+    const Key key{__ldg(p.policy_keys + 2 * step), __ldg(p.policy_keys + 2 * step + 1)};
+    const uint32_t size = (uint32_t)p.envs_per_replica * G * d.out;
+    float* dst = snoise + (step & 1) * TM * NHEAD;
+    for (int idx = first; idx < rows_valid * d.out; idx += nthreads) {
+      const int row = idx / d.out, j = idx - row * d.out;
+      const int e = (env0 + row / G) % p.envs_per_replica;
+      const uint32_t base = (uint32_t)((e * G + row % G) * d.out);
+      dst[row * NHEAD + j] = bits_to_gumbel(random_bits_at(key, base + j, size));
+    }
+  };
+  make_noise(0, t, NT);
   mbar_wait(&ctrl.wbar, 0);
   mbar_wait(&ctrl.rbar, 0);
   __syncthreads();
@@ -190,16 +207,13 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
         for (int j = 0; j < NHEAD; ++j)
           if (j < d.out) se += expf(out[j] - mx);
         const float lse = mx + logf(se);
-        // Gumbel arg-max; noise laid out (envs_per_replica, A, N) as tfd.Categorical.sample
-        const Key key{__ldg(p.policy_keys + 2 * step), __ldg(p.policy_keys + 2 * step + 1)};
-        const int e = env % p.envs_per_replica;
-        const uint32_t size = (uint32_t)p.envs_per_replica * G * d.out;
-        const uint32_t base = (uint32_t)((e * G + g) * d.out);
+        // Gumbel arg-max on the noise prepared during the previous step
+        const float* nz = snoise + (step & 1) * TM * NHEAD + L.r * NHEAD;
         float best = 0.0f;
 #pragma unroll
         for (int j = 0; j < NHEAD; ++j) {
           if (j < d.out) {
-            const float z = bits_to_gumbel(random_bits_at(key, base + j, size)) + out[j];
+            const float z = nz[j] + out[j];
             if (j == 0 || z > best) { best = z; act = j; }
           }
         }
@@ -217,6 +231,8 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
                              p.ep_return + (size_t)step * p.num_envs,
                              p.ep_length + (size_t)step * p.num_envs, needs_reset, replay, opk);
       if (needs_reset && g == 0) ctrl.rlist[atomicAdd(&ctrl.rcount, 1)] = (uint16_t)el;
+    } else if (step + 1 < p.T) {
+      make_noise(step + 1, t - TM, NT - TM);  // warps 4..15: next step's noise
     }
     // the previous step's observation block must have left shared memory before it is rewritten
     if (t == 0 && pending_store) rware::bulk_commit_wait_read();
@@ -264,7 +280,7 @@ int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
   constexpr int EPC = TM / G;
   const size_t smem = (size_t)WImage{a.actor.k1p}.total() + tile_bytes(TM, a.actor.k1p) +
                       tile_bytes(TM, HCOLS) + (size_t)EPC * a.c.stride +
-                      (size_t)round_up(EPC * G * a.c.FR, 16) + 128;
+                      (size_t)round_up(EPC * G * a.c.FR, 16) + 2 * TM * NHEAD * 4 + 128;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rware_rollout_kernel<G, 1>,
@@ -272,7 +288,12 @@ int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  rware_rollout_kernel<G, 1><<<ceil_div(a.num_envs, EPC), NT, smem, s>>>(a);
+  // spread the envs over the SMs: a CTA takes whole warps of envs (32 / G each), at most a tile
+  RolloutArgs b = a;
+  const int per_warp = 32 / G;
+  int epc = round_up(ceil_div(a.num_envs, sm_count()), per_warp);
+  b.epc = epc < per_warp ? per_warp : (epc > EPC ? EPC : epc);
+  rware_rollout_kernel<G, 1><<<ceil_div(a.num_envs, b.epc), NT, smem, s>>>(b);
   return launch_status();
 }
 
