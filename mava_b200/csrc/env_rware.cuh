@@ -307,14 +307,17 @@ __device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* 
     const uint32_t nib = (uint32_t)(M[i >> 4] >> ((i & 15) * 4)) & 0xFu;
     w[2 + i] = (nib * 0x00204081u) & 0x01010101u;
   }
+  const uint32_t* rq = reinterpret_cast<const uint32_t*>(rec + c.off_reqbits);
 #pragma unroll
   for (int ci = 0; ci < O::LOC; ++ci) {
     const int cx = x + ci / O::SIDE - R, cy = y + ci % O::SIDE - R;
-    uint32_t h = 0u;
-    if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
-      const int sid = cells[cx * c.W + cy];
-      if (sid != 0) h = 1u | ((uint32_t)requested(c, rec, sid - 1) << 8);
-    }
+    const bool inside = (unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W;
+    const int sid = inside ? (int)cells[cx * c.W + cy] : 0;
+    // s = sid - 1 is -1 for an empty cell: read word 0 and mask the result instead of branching
+    const int s1 = sid - 1;
+    const uint32_t word = rq[sid ? s1 >> 5 : 0];
+    const uint32_t present = sid != 0;
+    const uint32_t h = present | (((word >> (s1 & 31)) & present) << 8);
     w[O::SH0 + ci / 2] |= h << (16 * (ci & 1));
   }
   // rows are FR = 2 (mod 4) bytes long: odd rows start on a half word
@@ -363,41 +366,18 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
   }
   const int oldcell = x * c.W + y;
   const bool moved = act == 1;
-  __syncwarp(gmask);
-  // --- agents act one after the other on the shelf grid (scan over agents in env.step)
-  for (int i = 0; i < c.A; ++i) {
-    if (g == i) {
-      if (act == 2) {
-        d = (d + 3) & 3;
-      } else if (act == 3) {
-        d = (d + 1) & 3;
-      } else if (act == 1) {
-        if (carry) {
-          const uint8_t sid = cells[oldcell];
-          cells[oldcell] = 0;
-          cells[nx * c.W + ny] = sid;
-        }
-        x = nx;
-        y = ny;
-      } else if (act == 4) {
-        if (!carry) {
-          if (cells[oldcell] != 0) carry = 1;
-        } else if (!is_highway(c, oldcell)) {
-          carry = 0;
-        }
-      }
-      reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(x, y, d, carry);
-    }
-    __syncwarp(gmask);
-  }
-  // --- collision (utils.is_collision): grid[AGENTS, pos_i] != i + 1 after the sequential writes
-  //     "old cell <- 0, new cell <- j + 1" of every agent j that moved.  The last write to my
-  //     cell is not mine iff some mover j entered or left it after my own write.
-  const int newcell = x * c.W + y;
+  // where everybody is and goes is known before anybody acts: the forward cell depends only on the
+  // agent's own state.  (old cell, new cell, moved) of all agents, exchanged with shuffles:
+  const int newcell = moved ? nx * c.W + ny : oldcell;
   const uint32_t pk = (uint32_t)oldcell | ((uint32_t)newcell << 10) | ((uint32_t)moved << 20);
 #pragma unroll
   for (int j = 0; j < G; ++j) opk[j] = __shfl_sync(gmask, pk, j, G);
-  bool my_col = false;
+  // --- collision (utils.is_collision): grid[AGENTS, pos_i] != i + 1 after the sequential writes
+  //     "old cell <- 0, new cell <- j + 1" of every agent j that moved.  The last write to my
+  //     cell is not mine iff some mover j entered or left it after my own write.
+  //     `touch`: my move lands on a cell another agent occupies or enters -- only then can the order
+  //     of the agents' turns matter for the shelf grid.
+  bool my_col = false, touch = false;
 #pragma unroll
   for (int j = 0; j < G; ++j) {
     if (j < c.A && j != g) {
@@ -405,8 +385,45 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
       const bool mj = (opk[j] >> 20) & 1u;
       if (mj && (nj == (uint32_t)newcell || oj == (uint32_t)newcell) && (!moved || j > g))
         my_col = true;
+      if (moved && (nj == (uint32_t)newcell || oj == (uint32_t)newcell)) touch = true;
     }
   }
+  const bool ordered = (__ballot_sync(gmask, touch && agent) & gmask) != 0u;
+  // rotations and the position update do not depend on the other agents
+  if (act == 2) d = (d + 3) & 3;
+  else if (act == 3) d = (d + 1) & 3;
+  if (moved) {
+    x = nx;
+    y = ny;
+  }
+  if (!ordered) {
+    // every cell this step reads or writes belongs to exactly one agent: the turns commute
+    if (moved && carry) {
+      const uint8_t sid = cells[oldcell];
+      cells[oldcell] = 0;
+      cells[newcell] = sid;
+    } else if (act == 4) {
+      if (!carry) carry = cells[oldcell] != 0;
+      else if (!is_highway(c, oldcell)) carry = 0;
+    }
+  } else {
+    // --- agents act one after the other on the shelf grid (scan over agents in env.step)
+    for (int i = 0; i < c.A; ++i) {
+      if (g == i) {
+        if (moved && carry) {
+          const uint8_t sid = cells[oldcell];
+          cells[oldcell] = 0;
+          cells[newcell] = sid;
+        } else if (act == 4) {
+          if (!carry) carry = cells[oldcell] != 0;
+          else if (!is_highway(c, oldcell)) carry = 0;
+        }
+      }
+      __syncwarp(gmask);
+    }
+  }
+  if (agent) reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(x, y, d, carry);
+  __syncwarp(gmask);
   const bool collision = (__ballot_sync(gmask, my_col && agent) & gmask) != 0u;
 
   // --- deliveries at the goal cells; a delivered request is replaced by a uniformly drawn
