@@ -250,11 +250,20 @@ __device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool a_mn, const Tile& b,
                                            bool b_mn, int N, int K, bool accumulate,
                                            uint64_t* bar) {
+  // The K=16 steps of an operand differ only in the 14-bit start-address field of its descriptor:
+  // build the descriptors once and step them by a constant.  The issuing thread is on the critical
+  // path of every phase of every tile (one thread, dependent instruction stream), so the per-MMA
+  // issue cost matters as much as the MMA itself.
   const uint32_t idesc = instr_desc(TM, N, a_mn, b_mn);
-  for (int k = 0; k < K / 16; ++k) {
-    const uint64_t ad = a_mn ? desc_mnmajor(a, k) : desc_kmajor(a, k);
-    const uint64_t bd = b_mn ? desc_mnmajor(b, k) : desc_kmajor(b, k);
+  uint64_t ad = a_mn ? desc_mnmajor(a, 0) : desc_kmajor(a, 0);
+  uint64_t bd = b_mn ? desc_mnmajor(b, 0) : desc_kmajor(b, 0);
+  const uint64_t a_inc = (uint64_t)(((a_mn ? a.s_r : a.s_c) * 2u) >> 4);
+  const uint64_t b_inc = (uint64_t)(((b_mn ? b.s_r : b.s_c) * 2u) >> 4);
+  const int steps = K / 16;
+  for (int k = 0; k < steps; ++k) {
     mma(d_tmem, ad, bd, idesc, accumulate || k > 0);
+    ad += a_inc;
+    bd += b_inc;
   }
   if (bar) commit(bar);
 }

@@ -32,6 +32,19 @@ int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n);
 
 namespace {
 
+// Phase timing (development aid): compile with -DMAVA_PROFILE_PHASES to have thread 0 of CTA 0
+// record clock64() at the phase boundaries of its first tiles (read back with
+// mava_debug_phases).  Compiled out by default.
+#ifdef MAVA_PROFILE_PHASES
+__device__ long long g_phase_clock[16 * 16];
+#define MAVA_STAMP(k)                                                              \
+  do {                                                                             \
+    if (t == 0 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock[(it - 2) * 16 + (k)] = clock64(); \
+  } while (0)
+#else
+#define MAVA_STAMP(k) do { } while (0)
+#endif
+
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t COL_ACC = 0, COL_HEAD = 128, COL_DW3 = 144, COL_DW2 = 160;  // dW2: 144 columns
 constexpr uint32_t COL_DW1 = 304;  // folded first-layer gradient of the actor: up to 208 columns
@@ -60,6 +73,8 @@ struct Ctrl {
   uint64_t wbar, mbar;
   uint32_t tmem;
   float db3[NHEAD];
+  float adv_mean[8], adv_sd[8];  // per replica, from the fp64 sums (once per CTA, not per row)
+  int32_t steps[2][TM + 2];      // env-step index of each minibatch position of a prefetched tile
 };
 
 constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava: num_agents <= 8)
@@ -135,6 +150,23 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   const bool prefetch = fold && p.prefetch_actor != 0;
   unsigned char* pf_stage = smem + (dz3t.base - s_w) + tile_bytes(TM, NHEAD);
   auto step_at = [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); };
+  // prefetch: ONE coalesced load of the tile's env-step indices into ctrl.steps[buf] (also read by
+  // the loss epilogue), then the asynchronous copies of their observation rows
+  auto load_steps = [&](int tile_idx) -> int32_t {  // this thread's entry of a tile's index list
+    const int64_t r0 = (int64_t)tile_idx * TM;
+    const int64_t last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
+    const int64_t j0 = r0 / rows_per_step;
+    const int nsteps = (int)(last / rows_per_step - j0) + 1;
+    return t < nsteps ? __ldg(p.rows + j0 + t) : 0;
+  };
+  auto prefetch_tile = [&](int tile_idx, int buf, int32_t my_step) {
+    const int64_t r0 = (int64_t)tile_idx * TM;
+    const int64_t j0 = r0 / rows_per_step;
+    if (t < TM + 2) ctrl.steps[buf][t] = my_step;
+    __syncthreads();
+    gather_issue(d, p.view, pf_stage, r0, M,
+                 [&](int64_t jj) { return (int64_t)ctrl.steps[buf][jj - j0]; });
+  };
 
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
@@ -143,22 +175,36 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_mbar_init();
   }
   if (t < NHEAD) ctrl.db3[t] = 0.0f;
+  if (t < p.num_replicas && t < 8) {
+    const double cnt = (double)p.mb_size * d.A;
+    const double mean_d = p.adv_stats[2 * t] / cnt;
+    const double var_d = fmax(p.adv_stats[2 * t + 1] / cnt - mean_d * mean_d, 0.0);
+    ctrl.adv_mean[t] = (float)mean_d;
+    ctrl.adv_sd[t] = (float)sqrt(var_d);
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
-  if (prefetch && cta < n_tiles) gather_issue(d, p.view, pf_stage, (int64_t)cta * TM, M, step_at);
+  if (prefetch && cta < n_tiles) prefetch_tile(cta, 0, load_steps(cta));
   mbar_wait(&ctrl.wbar, 0);
 
   uint32_t phase = 0;
-  double l0 = 0.0, l1 = 0.0;
+  float l0f = 0.0f, l1f = 0.0f;
+  float db3_acc[NHEAD];
+#pragma unroll
+  for (int q = 0; q < NHEAD; ++q) db3_acc[q] = 0.0f;
   const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
   bool first = true;
   int it = 0;
   for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
     const int64_t row0 = (int64_t)tile * TM;
     const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
+    MAVA_STAMP(0);
+    // the next tile's env-step indices: requested now, needed after GEMM 1 has been issued
+    const bool has_next = prefetch && tile + n_ctas < n_tiles;
+    const int32_t next_step = has_next ? load_steps(tile + n_ctas) : 0;
 
     if (prefetch) {
       gather_wait();
@@ -170,13 +216,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_STAMP(1);
     // ---- forward
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
     }
-    if (prefetch && tile + n_ctas < n_tiles)  // staging buffer is free again: next tile's rows
-      gather_issue(d, p.view, pf_stage, (int64_t)(tile + n_ctas) * TM, M, step_at);
+    MAVA_STAMP(13);
+    if (has_next)  // staging buffer is free again: next tile's rows
+      prefetch_tile(tile + n_ctas, (it + 1) & 1, next_step);
+    MAVA_STAMP(14);
     // loss inputs of this row: in flight during the forward pass instead of after it
     LossIn li{};
     if (L.q == 0) {
@@ -184,7 +233,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       li.valid = row < M;
       const int64_t j = li.valid ? row / rows_per_step : 0;
       const int ag = (int)(row - j * rows_per_step);
-      const int64_t sidx = li.valid ? __ldg(p.rows + j) : 0;
+      const int64_t sidx = !li.valid ? 0
+                           : prefetch ? (int64_t)ctrl.steps[it & 1][j - row0 / rows_per_step]
+                                      : (int64_t)__ldg(p.rows + j);
       li.j = j;
       li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
       if (li.valid) {
@@ -205,12 +256,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
         }
       }
     }
+    MAVA_STAMP(2);
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
+    MAVA_STAMP(3);
     hidden_epilogue(L, tmem + COL_ACC, h1t);
+    MAVA_STAMP(4);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_STAMP(5);
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
@@ -221,12 +276,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_STAMP(6);
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
+    MAVA_STAMP(7);
     // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output)
     if (L.q == 0) {
       const bool valid = li.valid;
@@ -255,7 +312,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
             else if (a2 > a1) g = inside ? e2 : 0.0f;
             else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
             dv += g;
-            l0 += 0.5 * (double)fmaxf(a1, a2);
+            l0f += 0.5f * fmaxf(a1, a2);
           }
           dz[0] = dv * wrow * p.vf_coef;
         } else {
@@ -269,17 +326,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
               mx = fmaxf(mx, out[q]);
             }
           }
-          float se = 0.0f;
+          float se = 0.0f, ex[NHEAD];
 #pragma unroll
-          for (int q = 0; q < NHEAD; ++q)
-            if (q < d.out) se += expf(out[q] - mx);
-          const float lse = mx + logf(se);
+          for (int q = 0; q < NHEAD; ++q) {
+            ex[q] = q < d.out ? expf(out[q] - mx) : 0.0f;
+            se += ex[q];
+          }
+          const float lse = mx + logf(se), inv_se = 1.0f / se;
           const int a = li.act;
           const int u = (int)(j / p.mb_size);
-          const double cnt = (double)p.mb_size * d.A;
-          const double mean_d = p.adv_stats[2 * u] / cnt;
-          const double var_d = fmax(p.adv_stats[2 * u + 1] / cnt - mean_d * mean_d, 0.0);
-          const float mean = (float)mean_d, sd = (float)sqrt(var_d);
+          const float mean = ctrl.adv_mean[u], sd = ctrl.adv_sd[u];
           float logp[NHEAD], pr[NHEAD];
           float la = 0.0f, ent = 0.0f;
 #pragma unroll
@@ -288,7 +344,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
             pr[q] = 0.0f;
             if (q < d.out) {
               logp[q] = out[q] - lse;
-              pr[q] = expf(logp[q]);
+              pr[q] = ex[q] * inv_se;
               if (pr[q] != 0.0f) ent -= pr[q] * logp[q];
               if (q == a) la = logp[q];
             }
@@ -311,27 +367,23 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
               dz[q] = dl * wrow;
             }
           }
-          l0 += (double)(-fminf(t1, t2));
-          l1 += (double)ent;
+          l0f += -fminf(t1, t2);
+          l1f += ent;
         }
       }
       st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 0), pack_bf16(dz[0], dz[1]),
                    pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
       st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 1), pack_bf16(dz[8], dz[9]),
                    pack_bf16(dz[10], dz[11]), pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
-      // head bias gradient: column sums of dZ3 over the tile
+      MAVA_STAMP(15);
+      // head bias gradient: column sums of dZ3, kept per thread across tiles (reduced at the end)
 #pragma unroll
-      for (int q = 0; q < NHEAD; ++q) {
-        if (q < d.out) {
-          float sum = dz[q];
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) atomicAdd(&ctrl.db3[q], sum);
-        }
-      }
+      for (int q = 0; q < NHEAD; ++q) db3_acc[q] += dz[q];
     }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_STAMP(8);
     // ---- backward through the head: dH2 = dZ3 W3^T ; dW3 += H2^T dZ3
     if (t == 0) {
       fence_after_sync();
@@ -340,10 +392,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
+    MAVA_STAMP(9);
     grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_STAMP(10);
     // ---- dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1]
     if (t == 0) {
       fence_after_sync();
@@ -352,6 +406,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
+    MAVA_STAMP(11);
     if (fold) {
       // dZ1 stays on chip (H2 is dead): [dW1^T | db1] += dZ1^T [X | 1], A = dZ1 and B = X MN-major.
       // Not waited for here: the MMAs run under the next tile's gather (other X buffer, H1 as the
@@ -363,10 +418,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       __syncthreads();
       if (t == 0) {
         fence_after_sync();
-        const uint32_t idesc = instr_desc(TM, d.k1p, true, true);
-        for (int k = 0; k < TM / 16; ++k)
-          mma(tmem + COL_DW1, desc_mnmajor(dz1t, k), desc_mnmajor(xt, k), idesc, !first || k > 0);
+        issue_gemm(tmem + COL_DW1, dz1t, true, xt, true, d.k1p, TM, !first, nullptr);
       }
+      MAVA_STAMP(12);
     } else {
       unsigned char* gdst = p.dz1_critic + (size_t)tile * tile_bytes(TM, HID);
       if (is_actor) gdst = p.dz1_actor + (size_t)tile * tile_bytes(TM, HID);
@@ -382,6 +436,18 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     phase ^= 1;
   }
 
+  // head bias gradient: one reduction per CTA
+  if (L.q == 0) {
+#pragma unroll
+    for (int q = 0; q < NHEAD; ++q) {
+      if (q < d.out) {
+        float sum = db3_acc[q];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) atomicAdd(&ctrl.db3[q], sum);
+      }
+    }
+  }
+  __syncthreads();
   // ---- flush: TMEM weight-gradient accumulators -> global fp32 gradient (atomics)
   float* g = is_actor ? p.grad_actor : p.grad_critic;
   float* gw2 = g + (size_t)d.in_dim * HID + HID;
@@ -424,6 +490,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
   }
   // loss sums
+  double l0 = (double)l0f, l1 = (double)l1f;
   for (int o = 16; o > 0; o >>= 1) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, o);
     l1 += __shfl_xor_sync(0xffffffffu, l1, o);
@@ -543,6 +610,12 @@ using namespace mava;
 using namespace mava::tcmlp;
 
 extern "C" {
+
+#ifdef MAVA_PROFILE_PHASES
+int mava_debug_phases(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 256);
+}
+#endif
 
 int64_t mava_ppo_workspace_bytes_bf16(const mava_mlp_desc* actor, const mava_mlp_desc* critic,
                                       int rows_total) {

@@ -1,0 +1,39 @@
+#!/bin/bash
+# development aid: per-phase clock64() stamps of ppo_fused_kernel (CTA 0, tiles 2..17)
+set -e
+cd "$(dirname "$0")/.."
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -I include"
+nvcc $FLAGS -DMAVA_PROFILE_PHASES -c mava_b200/csrc/ppo_tc.cu -o mava_b200/build/ppo_tc.o
+nvcc -shared -o mava_b200/libmava_b200.so mava_b200/build/*.o -lcudart
+python - <<'PY'
+import ctypes, sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from mava_b200 import prng, _lib
+from mava_b200.config import compose
+from mava_b200.systems.ppo import ff_mappo
+from mava_b200.utils import make_env
+import bench
+cfg = compose(ff_mappo.CONFIG_NAME, bench.OVERRIDES + ["+arch.use_cuda_graph=False"])
+env, _ = make_env.make(cfg, add_global_state=True)
+key, _, ak, ck = prng.split(prng.PRNGKey(42), 4)
+learn, _, state = ff_mappo.learner_setup(env, (key, ak, ck), cfg)
+cfg.system.num_updates_per_eval = 1
+learn(state); learn(state)
+torch.cuda.synchronize()
+lib = _lib.load()
+buf = (ctypes.c_longlong * 256)()
+lib.mava_debug_phases.restype = ctypes.c_int
+assert lib.mava_debug_phases(buf) == 0
+a = np.array(buf[:]).reshape(16, 16)
+names = ["start", "x_built", "gemm1_issued", "gemm1_done", "epi1", "epi1_sync", "epi2_sync(gemm2+epi2)",
+         "gemm3_done", "loss_sync", "dh2_done", "dz2_sync", "dh1_done", "dz1+dw1_issued"]
+d = np.diff(a[:, :13], axis=1)
+print("cycles per phase, mean over 16 tiles (actor CTA 0):")
+for n, v in zip(names[1:], d.mean(0)):
+    print(f"  {n:28s} {v:9.0f}")
+print("tile total (start->start):", np.diff(a[:, 0]).mean())
+print("x_built -> gemm1 issued:", (a[:, 13] - a[:, 1]).mean(), " -> prefetch issued:", (a[:, 14] - a[:, 13]).mean(),
+      " -> loss inputs requested:", (a[:, 2] - a[:, 14]).mean())
+print("gemm3_done -> dz3 stored:", (a[:, 15] - a[:, 7]).mean(), " -> db3 reduced + sync:", (a[:, 8] - a[:, 15]).mean())
+PY
