@@ -204,8 +204,10 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
 template <class StepFn>
 __device__ __forceinline__ void gather_issue(const NetDesc& d, const int8_t* __restrict__ view,
                                              unsigned char* stage, int64_t row0, int64_t M,
-                                             StepFn step_at) {
+                                             StepFn step_at, int first_warp = 0,
+                                             int num_warps = NWARPS) {
   const Lane L;
+  if (L.warp < first_warp || L.warp >= first_warp + num_warps) return;
   const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
   const int step_bytes = d.A * d.FR;
   const int64_t last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
@@ -213,7 +215,7 @@ __device__ __forceinline__ void gather_issue(const NetDesc& d, const int8_t* __r
   const int nsteps = (int)(last / rps - j0) + 1;
   const int unit = (step_bytes & 7) == 0 ? 8 : 4;
   const int units = step_bytes / unit;
-  for (int js = L.warp; js < nsteps; js += NWARPS) {
+  for (int js = L.warp - first_warp; js < nsteps; js += num_warps) {
     const int8_t* src = view + (size_t)step_at(j0 + js) * step_bytes;
     const uint32_t dst = smem_u32(stage) + (uint32_t)js * step_bytes;
     for (int i = L.lane; i < units; i += 32) {

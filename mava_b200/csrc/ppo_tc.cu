@@ -159,13 +159,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     const int nsteps = (int)(last / rows_per_step - j0) + 1;
     return t < nsteps ? __ldg(p.rows + j0 + t) : 0;
   };
-  auto prefetch_tile = [&](int tile_idx, int buf, int32_t my_step) {
+  // the index list goes to shared memory right away; the asynchronous copies are issued later, by
+  // the twelve warps that have nothing to do during the loss epilogue
+  auto publish_steps = [&](int buf, int32_t my_step) {
+    if (t < TM + 2) ctrl.steps[buf][t] = my_step;
+  };
+  auto issue_copies = [&](int tile_idx, int buf, int first_warp, int num_warps) {
     const int64_t r0 = (int64_t)tile_idx * TM;
     const int64_t j0 = r0 / rows_per_step;
-    if (t < TM + 2) ctrl.steps[buf][t] = my_step;
-    __syncthreads();
     gather_issue(d, p.view, pf_stage, r0, M,
-                 [&](int64_t jj) { return (int64_t)ctrl.steps[buf][jj - j0]; });
+                 [&](int64_t jj) { return (int64_t)ctrl.steps[buf][jj - j0]; }, first_warp,
+                 num_warps);
   };
 
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
@@ -187,7 +191,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
-  if (prefetch && cta < n_tiles) prefetch_tile(cta, 0, load_steps(cta));
+  if (prefetch && cta < n_tiles) {
+    publish_steps(0, load_steps(cta));
+    __syncthreads();
+    issue_copies(cta, 0, 0, NWARPS);
+  }
   mbar_wait(&ctrl.wbar, 0);
 
   uint32_t phase = 0;
@@ -223,8 +231,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
     }
     MAVA_STAMP(13);
-    if (has_next)  // staging buffer is free again: next tile's rows
-      prefetch_tile(tile + n_ctas, (it + 1) & 1, next_step);
+    if (has_next) publish_steps((it + 1) & 1, next_step);  // read after several CTA barriers
     MAVA_STAMP(14);
     // loss inputs of this row: in flight during the forward pass instead of after it
     LossIn li{};
@@ -284,8 +291,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
     MAVA_STAMP(7);
-    // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output)
-    if (L.q == 0) {
+    // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output);
+    //      the other twelve warps start the next tile's observation copies meanwhile (the staging
+    //      buffer has been free since this tile's X was built)
+    if (L.q != 0) {
+      if (has_next) issue_copies(tile + n_ctas, (it + 1) & 1, 4, NWARPS - 4);
+    } else {
       const bool valid = li.valid;
       const int64_t j = li.j;  // position in the minibatch
       float out[NHEAD], dz[NHEAD];
