@@ -112,35 +112,53 @@ __host__ __device__ inline uint32_t stage_bytes(int A, int FR, int rows_per_step
 // Thread (r, q) expands every fourth 8-column chunk of tile row r from the int8 observation bytes
 // at `mine` (shared memory) to bf16: [onehot(agent a) if add_id | view bytes | 1 | 0...].
 __device__ __forceinline__ void expand_x_row(const NetDesc& d, const Tile& xt, const Lane& L,
-                                             const signed char* mine, bool valid, int a) {
+                                             const signed char* mine, bool valid, int a,
+                                             int cg0 = -1, int cg_step = 4) {
   const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
   const uint32_t mine_s = smem_u32(mine);
-  for (int cg = L.q; cg < d.k1p / 8; cg += 4) {
-    float v[8];
+  for (int cg = cg0 < 0 ? L.q : cg0; cg < d.k1p / 8; cg += cg_step) {
     const int k0 = cg * 8;
-    if (valid && k0 >= id_cols && k0 + 8 <= d.in_dim) {
-      // interior chunk: eight observation bytes, no boundary logic
+    const uint32_t dst = xt.base + chunk_off(xt, L.r, cg);
+    if (!valid || k0 > d.in_dim) {  // rows past the end of the minibatch, padding columns
+      st_shared_v4(dst, 0u, 0u, 0u, 0u);
+      continue;
+    }
+    float v[8];
+    if (k0 >= id_cols && k0 + 8 <= d.in_dim) {
+      // interior chunk: eight observation bytes as four 16-bit loads (rows are 2-byte aligned:
+      // A * FR and FR are even for every supported env; odd FR falls back to byte loads below)
+      const uint32_t src = mine_s + (uint32_t)(k0 - id_cols);
+      if ((src & 1u) == 0u) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int b;
-        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(b) : "r"(mine_s + (uint32_t)(k0 - id_cols + j)));
-        v[j] = (float)b;
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(src + 2u * j));
+          v[2 * j] = (float)(int)(signed char)(h & 0xffu);
+          v[2 * j + 1] = (float)(int)(signed char)(h >> 8);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int b;
+          asm volatile("ld.shared.s8 %0, [%1];" : "=r"(b) : "r"(src + (uint32_t)j));
+          v[j] = (float)b;
+        }
       }
     } else {
+      // boundary chunk (agent-id columns in front, the ones column behind): clamped loads and
+      // selects instead of per-element branches
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = k0 + j;
-        float x = 0.0f;
-        if (valid) {
-          if (k < id_cols) x = k == a ? 1.0f : 0.0f;
-          else if (k < d.in_dim) x = (float)mine[k - id_cols];
-          else if (k == d.in_dim) x = 1.0f;
-        }
+        const int idx = min(max(k - id_cols, 0), d.FR * (d.mode == MAVA_IN_GLOBAL ? d.A : 1) - 1);
+        float x = (float)mine[idx];
+        x = k < id_cols ? (k == a ? 1.0f : 0.0f) : x;
+        x = k >= d.in_dim ? (k == d.in_dim ? 1.0f : 0.0f) : x;
         v[j] = x;
       }
     }
-    st_shared_v4(xt.base + chunk_off(xt, L.r, cg), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    st_shared_v4(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                 pack_bf16(v[6], v[7]));
   }
 }
 
@@ -235,7 +253,8 @@ __device__ __forceinline__ void gather_wait() {
 }
 
 __device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
-                                              const unsigned char* stage, int64_t row0, int64_t M) {
+                                              const unsigned char* stage, int64_t row0, int64_t M,
+                                              int cg0 = -1, int cg_step = 4) {
   const Lane L;
   const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
   const int step_bytes = d.A * d.FR;
@@ -245,7 +264,7 @@ __device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
   const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
   const signed char* mine = reinterpret_cast<const signed char*>(stage) +
                             (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
-  expand_x_row(d, xt, L, mine, valid, a);
+  expand_x_row(d, xt, L, mine, valid, a, cg0, cg_step);
 }
 
 // One thread issues the K/16 MMAs of a GEMM (M = 128) and optionally commits to `bar`.

@@ -74,7 +74,7 @@ struct Ctrl {
   uint32_t tmem;
   float db3[NHEAD];
   float adv_mean[8], adv_sd[8];  // per replica, from the fp64 sums (once per CTA, not per row)
-  int32_t steps[2][TM + 2];      // env-step index of each minibatch position of a prefetched tile
+  int32_t steps[3][TM + 2];      // env-step index of each minibatch position of the tiles in flight
 };
 
 constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava: num_agents <= 8)
@@ -191,10 +191,20 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
+  // Prefetch pipeline (fold mode): while tile i is in its loss epilogue (four warps busy), the other
+  // twelve warps expand the raw rows of tile i+1 -- copied during tile i-1 -- into the other X
+  // buffer and then start the copies of tile i+2 into the (single) staging buffer.  A tile therefore
+  // finds its X tile ready.  Prologue: tile 0 is built by everybody, tile 1's copies are started.
   if (prefetch && cta < n_tiles) {
     publish_steps(0, load_steps(cta));
+    if (cta + n_ctas < n_tiles) publish_steps(1, load_steps(cta + n_ctas));
     __syncthreads();
     issue_copies(cta, 0, 0, NWARPS);
+    gather_wait();
+    __syncthreads();
+    gather_expand(d, Tile{s_x0, 128u, 2048u}, pf_stage, (int64_t)cta * TM, M);
+    __syncthreads();
+    if (cta + n_ctas < n_tiles) issue_copies(cta + n_ctas, 1, 4, NWARPS - 4);
   }
   mbar_wait(&ctrl.wbar, 0);
 
@@ -212,13 +222,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     MAVA_STAMP(0);
     // the next tile's env-step indices: requested now, needed after GEMM 1 has been issued
     const bool has_next = prefetch && tile + n_ctas < n_tiles;
-    const int32_t next_step = has_next ? load_steps(tile + n_ctas) : 0;
+    const bool has_next2 = prefetch && tile + 2 * n_ctas < n_tiles;
+    const int32_t next2_step = has_next2 ? load_steps(tile + 2 * n_ctas) : 0;
 
-    if (prefetch) {
-      gather_wait();
-      __syncthreads();
-      gather_expand(d, xt, pf_stage, row0, M);
-    } else {
+    if (!prefetch) {
       build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M, step_at);
     }
     fence_proxy_async();
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
     }
     MAVA_STAMP(13);
-    if (has_next) publish_steps((it + 1) & 1, next_step);  // read after several CTA barriers
+    if (has_next2) publish_steps((it + 2) % 3, next2_step);  // read after several CTA barriers
     MAVA_STAMP(14);
     // loss inputs of this row: in flight during the forward pass instead of after it
     LossIn li{};
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       const int64_t j = li.valid ? row / rows_per_step : 0;
       const int ag = (int)(row - j * rows_per_step);
       const int64_t sidx = !li.valid ? 0
-                           : prefetch ? (int64_t)ctrl.steps[it & 1][j - row0 / rows_per_step]
+                           : prefetch ? (int64_t)ctrl.steps[it % 3][j - row0 / rows_per_step]
                                       : (int64_t)__ldg(p.rows + j);
       li.j = j;
       li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
@@ -295,7 +302,15 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     //      the other twelve warps start the next tile's observation copies meanwhile (the staging
     //      buffer has been free since this tile's X was built)
     if (L.q != 0) {
-      if (has_next) issue_copies(tile + n_ctas, (it + 1) & 1, 4, NWARPS - 4);
+      if (has_next) {
+        gather_wait();                                  // my copies of tile i+1 (issued a tile ago)
+        asm volatile("bar.sync 1, 384;" ::: "memory");  // ... and those of the other eleven warps
+        const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
+        gather_expand(d, xn, pf_stage, (int64_t)(tile + n_ctas) * TM, M, L.q - 1, 3);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 384;" ::: "memory");  // the staging buffer is free again
+        if (has_next2) issue_copies(tile + 2 * n_ctas, (it + 2) % 3, 4, NWARPS - 4);
+      }
     } else {
       const bool valid = li.valid;
       const int64_t j = li.j;  // position in the minibatch
