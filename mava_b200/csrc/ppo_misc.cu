@@ -129,11 +129,22 @@ __global__ void __launch_bounds__(512) clip_adam_pair_kernel(const AdamPairArgs 
   __shared__ double red[16];
   __shared__ float s_norm;
   __shared__ int s_count;
-  double ss = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float g = __ldg(grad + i) * a.grad_scale;
-    ss += (double)g * (double)g;
+  // per-thread partial sums in fp32 (about n / 512 terms each, four independent chains; B200's
+  // fp64 pipe is far too slow for an element-wise pass), cross-thread reduction in fp64
+  float p4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  int64_t i0 = threadIdx.x;
+  for (; i0 + 3 * (int64_t)blockDim.x < n; i0 += 4 * (int64_t)blockDim.x) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float g = __ldg(grad + i0 + u * (int64_t)blockDim.x) * a.grad_scale;
+      p4[u] = fmaf(g, g, p4[u]);
+    }
   }
+  for (; i0 < n; i0 += blockDim.x) {
+    const float g = __ldg(grad + i0) * a.grad_scale;
+    p4[0] = fmaf(g, g, p4[0]);
+  }
+  double ss = ((double)p4[0] + (double)p4[1]) + ((double)p4[2] + (double)p4[3]);
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   if (threadIdx.x == 0) s_count = a.counts[net];

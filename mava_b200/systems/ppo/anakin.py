@@ -87,6 +87,8 @@ class FFLearner:
         # scratch
         self.policy_keys = z(T, 2, dtype=torch.uint32)
         self.key3 = z(3, 2, dtype=torch.uint32)
+        self.key3_ep = z(int(s.ppo_epochs), 3, 2, dtype=torch.uint32)
+        self._side = torch.cuda.Stream(device=dev)
         self.key2 = z(2, 2, dtype=torch.uint32)
         self.bits = z(T * self.E, dtype=torch.uint32)
         self.rows = z(self.U * self.mb, dtype=torch.int32)
@@ -148,7 +150,6 @@ class FFLearner:
     def _rollout(self) -> None:
         """ff_mappo.py:76-106: T acting + env steps, then the bootstrap value (:110)."""
         envn = self.env.native
-        native.prng_split_chain(self.key, self.policy_keys, self.T)
         if self.bf16:
             self._pack()
         if self.fused_rollout:
@@ -201,16 +202,26 @@ class FFLearner:
             x = x[order]
         return x
 
-    def _update_epochs(self) -> None:
+    def _epoch_permutations(self):
+        """The shuffles of all epochs (ff_mappo.py:269-273).  They depend only on the key left by
+        the rollout's split chain, not on the rollout or on training, so they run on a side stream
+        (a parallel branch of the CUDA graph) next to the rollout kernel, which leaves SMs idle."""
+        k = self.key
+        perms = []
+        for ep in range(self.epochs):
+            native.prng_split(k, self.key3_ep[ep], 3)  # key, shuffle_key, entropy_key (:269)
+            k = self.key3_ep[ep][0]
+            perms.append(self._permutation(self.key3_ep[ep][1]))
+        return perms
+
+    def _update_epochs(self, perms) -> None:
         """ff_mappo.py:141-295."""
         s = self.config.system
         na, nc = self.na, self.nc
         scale = 1.0 / self.world
         steps_per_update = self.epochs * self.nmb
         for ep in range(self.epochs):
-            native.prng_split(self.key, self.key3, 3)  # key, shuffle_key, entropy_key (:269)
-            self.key.copy_(self.key3[0])
-            perm = self._permutation(self.key3[1])
+            perm = perms[ep]
             for m in range(self.nmb):
                 native.ppo_minibatch_rows(perm, m, self.mb, self.U, self.E, self.rows)
                 if self.time_loss_grad is not None:
@@ -240,17 +251,24 @@ class FFLearner:
                 self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
                 if self.bf16:
                     self._pack()
+        self.key.copy_(self.key3_ep[self.epochs - 1][0])
         if self.world > 1:
             self.loss_buf.mul_(scale)
 
     def _update_step(self) -> None:
         """One ``_update_step`` of the reference (ff_mappo.py:56-300) for all U replicas."""
         n0 = native.LAUNCHES
+        native.prng_split_chain(self.key, self.policy_keys, self.T)  # key, policy_key per step (:81)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            perms = self._epoch_permutations()
         self._rollout()
         native.gae(self.reward, self.value, self.done, self.last_val, float(self.config.system.gamma),
                    float(self.config.system.gae_lambda), self.T, self.NE, self.A, self.adv,
                    self.targets)
-        self._update_epochs()
+        main.wait_stream(self._side)
+        self._update_epochs(perms)
         self.view[0].copy_(self.view[self.T])
         self.mask[0].copy_(self.mask[self.T])
         self.launches_per_update = native.LAUNCHES - n0
