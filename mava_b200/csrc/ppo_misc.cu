@@ -103,10 +103,13 @@ clip_adam_kernel(float* __restrict__ params, float* __restrict__ mu, float* __re
   if (threadIdx.x == 0) *count = c;
 }
 
-// Both networks in one launch, several CTAs per network: every CTA recomputes the (tiny) global
-// norm of its network, then updates its slice.  The step count is advanced by the last CTA to have
-// read it (ticket), so late CTAs never see the incremented value.
+// clip_by_global_norm -> adam -> apply_updates for both networks: a first launch accumulates the
+// squared global norms (one slice per CTA, fp32 partial sums -- B200's fp64 pipe is far too slow for
+// an element-wise pass -- combined in fp64), a second launch applies the update slice by slice.
+// The last CTA of the second launch to have read norm and step count (ticket) resets the norm
+// accumulator and advances the count, so late CTAs never see the new values.
 __device__ unsigned int g_adam_ticket[2];
+__device__ double g_adam_norm2[2];
 
 struct AdamPairArgs {
   float *params, *mu, *nu;
@@ -118,7 +121,37 @@ struct AdamPairArgs {
   int lr_decay_num_updates, steps_per_update;
 };
 
-__global__ void __launch_bounds__(512) clip_adam_pair_kernel(const AdamPairArgs a) {
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(const AdamPairArgs a) {
+  const int net = blockIdx.y;
+  const float* grad = a.grad + (net == 0 ? 0 : a.n[0]);
+  const int64_t n = a.n[net];
+  float p4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float g = __ldg(grad + i + u * stride) * a.grad_scale;
+      p4[u] = fmaf(g, g, p4[u]);
+    }
+  }
+  for (; i < n; i += stride) {
+    const float g = __ldg(grad + i) * a.grad_scale;
+    p4[0] = fmaf(g, g, p4[0]);
+  }
+  double ss = ((double)p4[0] + (double)p4[1]) + ((double)p4[2] + (double)p4[3]);
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+    atomicAdd(&g_adam_norm2[net], v);
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_adam_pair_kernel(const AdamPairArgs a) {
   const int net = blockIdx.y;
   const int64_t off = net == 0 ? 0 : a.n[0];
   const int64_t n = a.n[net];
@@ -126,40 +159,17 @@ __global__ void __launch_bounds__(512) clip_adam_pair_kernel(const AdamPairArgs 
   float* params = a.params + off;
   float* mu = a.mu + off;
   float* nu = a.nu + off;
-  __shared__ double red[16];
   __shared__ float s_norm;
   __shared__ int s_count;
-  // per-thread partial sums in fp32 (about n / 512 terms each, four independent chains; B200's
-  // fp64 pipe is far too slow for an element-wise pass), cross-thread reduction in fp64
-  float p4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  int64_t i0 = threadIdx.x;
-  for (; i0 + 3 * (int64_t)blockDim.x < n; i0 += 4 * (int64_t)blockDim.x) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float g = __ldg(grad + i0 + u * (int64_t)blockDim.x) * a.grad_scale;
-      p4[u] = fmaf(g, g, p4[u]);
-    }
-  }
-  for (; i0 < n; i0 += blockDim.x) {
-    const float g = __ldg(grad + i0) * a.grad_scale;
-    p4[0] = fmaf(g, g, p4[0]);
-  }
-  double ss = ((double)p4[0] + (double)p4[1]) + ((double)p4[2] + (double)p4[3]);
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-  if (threadIdx.x == 0) s_count = a.counts[net];
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) {
-      s_norm = (float)sqrt(v);
-      __threadfence();
-      const unsigned int ticket = atomicAdd(&g_adam_ticket[net], 1u);
-      if (ticket == gridDim.x - 1) {  // every CTA of this network has read the count
-        g_adam_ticket[net] = 0u;
-        a.counts[net] = s_count + 1;
-      }
+  if (threadIdx.x == 0) {
+    s_count = a.counts[net];
+    s_norm = (float)sqrt(*reinterpret_cast<volatile double*>(&g_adam_norm2[net]));
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&g_adam_ticket[net], 1u);
+    if (ticket == gridDim.x - 1) {  // every CTA of this network has read norm and count
+      g_adam_ticket[net] = 0u;
+      g_adam_norm2[net] = 0.0;
+      a.counts[net] = s_count + 1;
     }
   }
   __syncthreads();
@@ -203,7 +213,9 @@ int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, co
   a.lr[0] = lr_actor; a.lr[1] = lr_critic;
   a.grad_scale = grad_scale; a.max_norm = max_norm;
   a.lr_decay_num_updates = lr_decay_num_updates; a.steps_per_update = steps_per_update;
-  clip_adam_pair_kernel<<<dim3(16, 2), 512, 0, as_stream(s)>>>(a);
+  const unsigned ctas = (unsigned)max((int64_t)1, min((int64_t)64, ceil_div64(max(n_actor, n_critic), 1024)));
+  grad_sqnorm_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
+  clip_adam_pair_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
   return launch_status();
 }
 

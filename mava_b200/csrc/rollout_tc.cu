@@ -150,6 +150,9 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
 
   uint32_t phase = 0;
   bool pending_store = false;
+  // warps whose 32 tile rows are all beyond this CTA's envs skip the hidden-layer epilogues (TMEM
+  // reads are 64 B/clk per SM: half a tile of dead rows would cost as much as the live half)
+  const bool live = (warp & 3) * 32 < rows_valid;
   for (int step = 0; step < p.T; ++step) {
     // ---- 1. X tile from the observation rows in shared memory
     expand_x_row(d, xt, L, reinterpret_cast<const signed char*>(sobs) + L.r * c.FR,
@@ -164,7 +167,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    hidden_epilogue(L, tmem, ht);
+    if (live) hidden_epilogue(L, tmem, ht);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -174,7 +177,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
-    hidden_epilogue(L, tmem, ht);
+    if (live) hidden_epilogue(L, tmem, ht);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();

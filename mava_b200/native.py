@@ -357,7 +357,7 @@ def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, gr
                    lr_actor: float, lr_critic: float, max_norm: float,
                    lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:
     n = n_actor + n_critic
-    _count(1)
+    _count(2)  # squared-norm pass + update pass
     check(_lib.load().mava_clip_adam_pair(
         _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
         _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
