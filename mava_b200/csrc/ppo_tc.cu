@@ -37,12 +37,18 @@ namespace {
 // mava_debug_phases).  Compiled out by default.
 #ifdef MAVA_PROFILE_PHASES
 __device__ long long g_phase_clock[16 * 16];
+__device__ long long g_phase_clock2[16 * 8];
+#define MAVA_STAMP2(k)                                                             \
+  do {                                                                             \
+    if (t == 128 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock2[(it - 2) * 8 + (k)] = clock64(); \
+  } while (0)
 #define MAVA_STAMP(k)                                                              \
   do {                                                                             \
     if (t == 0 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock[(it - 2) * 16 + (k)] = clock64(); \
   } while (0)
 #else
 #define MAVA_STAMP(k) do { } while (0)
+#define MAVA_STAMP2(k) do { } while (0)
 #endif
 
 constexpr uint32_t kTmemCols = 512;
@@ -148,6 +154,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   // dedicated staging buffer while this tile runs, so the two dependent HBM latencies of the
   // gather (row index -> observation bytes) leave the critical path
   const bool prefetch = fold && p.prefetch_actor != 0;
+  int pf_total = 0;
   unsigned char* pf_stage = smem + (dz3t.base - s_w) + tile_bytes(TM, NHEAD);
   auto step_at = [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); };
   // prefetch: ONE coalesced load of the tile's env-step indices into ctrl.steps[buf] (also read by
@@ -163,6 +170,37 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   // the twelve warps that have nothing to do during the loss epilogue
   auto publish_steps = [&](int buf, int32_t my_step) {
     if (t < TM + 2) ctrl.steps[buf][t] = my_step;
+  };
+  // Register-staged prefetch by the twelve warps that idle during the loss epilogue: the raw
+  // observation rows of the next tile are REQUESTED (plain loads, 4 bytes per thread and slot)
+  // while GEMM 1 runs and only consumed -- stored to the staging buffer and expanded into the
+  // other X buffer -- during the loss epilogue, so neither the HBM latency nor the copy issue is
+  // on the tile's critical path.
+  constexpr int kPfSlots = 8;
+  uint32_t pf_reg[kPfSlots];
+  auto pf_load = [&](int tile_idx, int buf) {
+    const int64_t r0 = (int64_t)tile_idx * TM;
+    const int64_t last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
+    const int64_t j0 = r0 / rows_per_step;
+    const int nsteps = (int)(last / rows_per_step - j0) + 1;
+    const int units = (d.A * d.FR) >> 2, total = nsteps * units;
+#pragma unroll
+    for (int k = 0; k < kPfSlots; ++k) {
+      const int idx = k * (NT - TM) + (t - TM);
+      if (idx < total) {
+        const int js = idx / units, u = idx - js * units;
+        pf_reg[k] = __ldg(reinterpret_cast<const uint32_t*>(
+                              p.view + (size_t)ctrl.steps[buf][js] * (size_t)(d.A * d.FR)) + u);
+      }
+    }
+    pf_total = total;
+  };
+  auto pf_store = [&]() {
+#pragma unroll
+    for (int k = 0; k < kPfSlots; ++k) {
+      const int idx = k * (NT - TM) + (t - TM);
+      if (idx < pf_total) reinterpret_cast<uint32_t*>(pf_stage)[idx] = pf_reg[k];
+    }
   };
   auto issue_copies = [&](int tile_idx, int buf, int first_warp, int num_warps) {
     const int64_t r0 = (int64_t)tile_idx * TM;
@@ -204,7 +242,6 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     __syncthreads();
     gather_expand(d, Tile{s_x0, 128u, 2048u}, pf_stage, (int64_t)cta * TM, M);
     __syncthreads();
-    if (cta + n_ctas < n_tiles) issue_copies(cta + n_ctas, 1, 4, NWARPS - 4);
   }
   mbar_wait(&ctrl.wbar, 0);
 
@@ -239,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     MAVA_STAMP(13);
     if (has_next2) publish_steps((it + 2) % 3, next2_step);  // read after several CTA barriers
+    if (has_next && L.q != 0) pf_load(tile + n_ctas, (it + 1) % 3);
     MAVA_STAMP(14);
     // loss inputs of this row: in flight during the forward pass instead of after it
     LossIn li{};
@@ -302,14 +340,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     //      the other twelve warps start the next tile's observation copies meanwhile (the staging
     //      buffer has been free since this tile's X was built)
     if (L.q != 0) {
+      MAVA_STAMP2(0);
       if (has_next) {
-        gather_wait();                                  // my copies of tile i+1 (issued a tile ago)
+        pf_store();                                     // raw rows of tile i+1 (loaded since GEMM 1)
         asm volatile("bar.sync 1, 384;" ::: "memory");  // ... and those of the other eleven warps
+        MAVA_STAMP2(1);
         const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
         gather_expand(d, xn, pf_stage, (int64_t)(tile + n_ctas) * TM, M, L.q - 1, 3);
+        MAVA_STAMP2(2);
         fence_proxy_async();
-        asm volatile("bar.sync 1, 384;" ::: "memory");  // the staging buffer is free again
-        if (has_next2) issue_copies(tile + 2 * n_ctas, (it + 2) % 3, 4, NWARPS - 4);
+        MAVA_STAMP2(3);
+        MAVA_STAMP2(4);
       }
     } else {
       const bool valid = li.valid;
@@ -641,6 +682,9 @@ extern "C" {
 int mava_debug_phases(long long* out_host) {
   return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 256);
 }
+int mava_debug_phases2(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock2, sizeof(long long) * 128);
+}
 #endif
 
 int64_t mava_ppo_workspace_bytes_bf16(const mava_mlp_desc* actor, const mava_mlp_desc* critic,
@@ -709,15 +753,8 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   a.grad_critic = grad_out + na;
   a.loss_acc = loss_acc;
 
-  // split the SMs between actor and critic tiles in proportion to their estimated cost
   const int64_t ta = tile_count(actor, R), tcn = tile_count(critic, R);
-  const double ca = (double)ta * ((a.actor.k1p / 16 + 27) * 64.0 + 4500.0);
-  const double cc = (double)tcn * ((a.critic.k1p / 16 + 27) * 64.0 + 4500.0 + 4.0 * a.critic.k1p);
   const int sms = sm_count();
-  int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
-  n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
-  a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
-  a.critic_ctas = (int)(tcn < sms - n_actor ? tcn : sms - n_actor);
 
   cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
   if (e != cudaSuccess) return (int)e;
@@ -736,9 +773,23 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   a.fold_actor_w1 = a.actor.k1p <= 208 && smem_fold <= 227 * 1024;
   if (a.fold_actor_w1 && smem_fold > smem_fused) smem_fused = smem_fold;
   const size_t smem_pf = smem_fold + stage_bytes(a.actor.A, a.actor.FR, a.actor.A);
-  a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && ((a.actor.A * a.actor.FR) & 3) == 0;
+  a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && ((a.actor.A * a.actor.FR) & 3) == 0 &&
+                     (TM / a.actor.A + 2) * ((a.actor.A * a.actor.FR) >> 2) <= 8 * (NT - TM);
   if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
+  // split the SMs between actor and critic tiles in proportion to their measured cost per tile
+  // (cycles, scripts/exp_phase_clock.sh): an actor tile with the folded first-layer gradient and
+  // the prefetch pipeline ~13.9 K at k1p = 80, a tile on the plain path ~15.5 K + 30 per input column
+  {
+    const double tile_a = (a.prefetch_actor ? 11500.0 : 15500.0) + 30.0 * a.actor.k1p;
+    const double tile_c = 15500.0 + 30.0 * a.critic.k1p;
+    const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
+    int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
+    n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
+    a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
+    a.critic_ctas = (int)(tcn < sms - n_actor ? tcn : sms - n_actor);
+  }
+
   const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
                           tile_bytes(TM, HCOLS) + 128;  // dZ1 tile, X tile, staging
   static size_t conf_fused = 0, conf_wg1 = 0;
