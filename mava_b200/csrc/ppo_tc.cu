@@ -37,7 +37,7 @@ namespace {
 // mava_debug_phases).  Compiled out by default.
 #ifdef MAVA_PROFILE_PHASES
 __device__ long long g_phase_clock[16 * 16];
-__device__ long long g_phase_clock2[16 * 8];
+__device__ long long g_phase_clock2[16 * 8 + 32];
 #define MAVA_STAMP2(k)                                                             \
   do {                                                                             \
     if (t == 128 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock2[(it - 2) * 8 + (k)] = clock64(); \
@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     const int64_t row0 = (int64_t)tile * TM;
     const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
     MAVA_STAMP(0);
+#ifdef MAVA_PROFILE_PHASES
+    if (t == 0 && blockIdx.x == gridDim.x - 1 && it < 16) g_phase_clock2[128 + it] = clock64();
+#endif
     // the next tile's env-step indices: requested now, needed after GEMM 1 has been issued
     const bool has_next = prefetch && tile + n_ctas < n_tiles;
     const bool has_next2 = prefetch && tile + 2 * n_ctas < n_tiles;
@@ -683,7 +686,7 @@ int mava_debug_phases(long long* out_host) {
   return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 256);
 }
 int mava_debug_phases2(long long* out_host) {
-  return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock2, sizeof(long long) * 128);
+  return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock2, sizeof(long long) * 160);
 }
 #endif
 
@@ -779,10 +782,11 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
   // split the SMs between actor and critic tiles in proportion to their measured cost per tile
   // (cycles, scripts/exp_phase_clock.sh): an actor tile with the folded first-layer gradient and
-  // the prefetch pipeline ~13.9 K at k1p = 80, a tile on the plain path ~15.5 K + 30 per input column
+  // the prefetch pipeline ~13.8 K at k1p = 80, a tile on the plain path ~13.8 K + 30 per input
+  // column (22 K for the 272-wide MAPPO critic)
   {
-    const double tile_a = (a.prefetch_actor ? 11500.0 : 15500.0) + 30.0 * a.actor.k1p;
-    const double tile_c = 15500.0 + 30.0 * a.critic.k1p;
+    const double tile_a = (a.prefetch_actor ? 11400.0 : 13800.0) + 30.0 * a.actor.k1p;
+    const double tile_c = 13800.0 + 30.0 * a.critic.k1p;
     const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
     int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
     n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);

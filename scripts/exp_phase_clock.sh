@@ -35,11 +35,13 @@ for n, v in zip(names[1:], d.mean(0)):
 print("tile total (start->start):", np.diff(a[:, 0]).mean())
 print("x_built -> gemm1 issued:", (a[:, 13] - a[:, 1]).mean(), " -> prefetch issued:", (a[:, 14] - a[:, 13]).mean(),
       " -> loss inputs requested:", (a[:, 2] - a[:, 14]).mean())
-buf2 = (ctypes.c_longlong * 128)()
+buf2 = (ctypes.c_longlong * 160)()
 lib.mava_debug_phases2.restype = ctypes.c_int
 assert lib.mava_debug_phases2(buf2) == 0
-b = np.array(buf2[:]).reshape(16, 8)
+b = np.array(buf2[:128]).reshape(16, 8)
 print("idle-warp branch of the loss phase (warp 4): wait+bar %.0f, expand %.0f, fence+bar %.0f, issue copies %.0f" %
       tuple(np.diff(b[:, :5], axis=1).mean(0)))
+c = np.array(buf2[128:144])
+print("critic tile (last CTA), start->start: %.0f cycles" % np.diff(c[2:]).mean())
 print("gemm3_done -> dz3 stored:", (a[:, 15] - a[:, 7]).mean(), " -> db3 reduced + sync:", (a[:, 8] - a[:, 15]).mean())
 PY
