@@ -36,6 +36,8 @@ struct LbfConst {
   int stride;
   int off_ax, off_ay, off_alvl, off_fx, off_fy, off_flvl, off_featen;
   int off_step, off_key, off_mkey, off_run_ret, off_run_len, off_ep_ret, off_ep_len;
+  uint32_t interior[8];  // bit per cell (grid up to 16 x 16): not on the border (food may spawn)
+  uint32_t allcells[8];  // bit per cell of the grid
 };
 
 }  // namespace mava

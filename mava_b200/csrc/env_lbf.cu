@@ -22,6 +22,7 @@ constexpr int kMaxCellsLbf = 256;  // grid up to 16 x 16
 
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
+  if (G == 32) return 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   return ((1u << G) - 1u) << ((lane / G) * G);
 }
@@ -33,14 +34,15 @@ __device__ __forceinline__ int group_sum(int v, unsigned gmask) {
   return v;
 }
 
+// Minimum of a 64-bit composite over the lanes of a group: two hardware warp reductions
+// (redux.sync), high word first, then the low word among the ties.
 template <int G>
 __device__ __forceinline__ unsigned long long group_min(unsigned long long v, unsigned gmask) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
-    const unsigned long long w = __shfl_xor_sync(gmask, v, o, G);
-    v = w < v ? w : v;
-  }
-  return v;
+  const uint32_t hi = (uint32_t)(v >> 32);
+  const uint32_t m = __reduce_min_sync(gmask, hi);
+  const uint32_t lo = hi == m ? (uint32_t)v : 0xffffffffu;
+  const uint32_t l = __reduce_min_sync(gmask, lo);
+  return ((unsigned long long)m << 32) | l;
 }
 
 __device__ __forceinline__ void move_of(int a, int& dx, int& dy) {
@@ -69,12 +71,57 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
             k_flevel = split_n(key, 5, 2), k_alevel = split_n(key, 5, 3),
             k_state = split_n(key, 5, 4);
   // ---- food: inverse CDF over the cells that are not on the border / next to an earlier food
-  if (g == 0) {
-    for (int w = 0; w < kMaxCellsLbf / 32; ++w) cellmask[w] = 0u;
-    for (int i = 0; i < flat; ++i) {
-      const int x = i / S, y = i - x * S;
-      if (x > 0 && x < S - 1 && y > 0 && y < S - 1) cellmask[i >> 5] |= 1u << (i & 31);
+  if constexpr (G == 32) {
+    // warp-cooperative form (in-step regeneration): lane w < 8 owns mask word w; the cumulative
+    // count is a prefix sum over the word popcounts and the hit is the k-th set bit of one word
+    uint32_t word = g < kMaxCellsLbf / 32 ? c.interior[g] : 0u;
+    for (int f = 0; f < c.NF; ++f) {
+      const Key kf = split_n(k_food, (uint32_t)c.NF, (uint32_t)f);
+      const uint32_t bits = random_bits_at(kf, 0u, 1u);
+      const float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+      const int pc = __popc(word);
+      int incl = pc;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (g >= o) incl += v;
+      }
+      const int count = __shfl_sync(0xffffffffu, incl, 7);
+      const float r = (float)count * (1.0f - u);
+      const int k = r <= 0.0f ? 0 : (int)ceilf(r);  // first i with (float)cumsum[i] >= r
+      const int excl = incl - pc;
+      const bool hit = g < 8 && k > excl && k <= incl;
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      int pos = flat;
+      if (k == 0) {
+        pos = 0;
+      } else if (b != 0u) {
+        const int src = __ffs(b) - 1;
+        const int local = hit ? (int)__fns(word, 0u, k - excl) : 0;
+        pos = 32 * src + __shfl_sync(0xffffffffu, local, src);
+      }
+      const int adj[5] = {pos, pos + 1, pos - 1, pos + S, pos - S};
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (adj[q] >= 0 && adj[q] < flat && (adj[q] >> 5) == g) word &= ~(1u << (adj[q] & 31));
+      if (g == 0) {
+        rec[c.off_fx + f] = (uint8_t)(pos / S);
+        rec[c.off_fy + f] = (uint8_t)(pos % S);
+        rec[c.off_featen + f] = 0;
+      }
     }
+    __syncwarp(gmask);
+    // ---- the agents may stand anywhere but on food
+    if (g < kMaxCellsLbf / 32) {
+      uint32_t w = c.allcells[g];
+      for (int f = 0; f < c.NF; ++f) {
+        const int cell = rec[c.off_fx + f] * S + rec[c.off_fy + f];
+        if ((cell >> 5) == g) w &= ~(1u << (cell & 31));
+      }
+      cellmask[g] = w;
+    }
+  } else if (g == 0) {
+    for (int w = 0; w < kMaxCellsLbf / 32; ++w) cellmask[w] = c.interior[w];
     for (int f = 0; f < c.NF; ++f) {
       const Key kf = split_n(k_food, (uint32_t)c.NF, (uint32_t)f);
       const uint32_t bits = random_bits_at(kf, 0u, 1u);
@@ -95,8 +142,7 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
       rec[c.off_featen + f] = 0;
     }
     // ---- the agents may stand anywhere but on food
-    for (int w = 0; w < kMaxCellsLbf / 32; ++w) cellmask[w] = 0u;
-    for (int i = 0; i < flat; ++i) cellmask[i >> 5] |= 1u << (i & 31);
+    for (int w = 0; w < kMaxCellsLbf / 32; ++w) cellmask[w] = c.allcells[w];
     for (int f = 0; f < c.NF; ++f) {
       const int cell = rec[c.off_fx + f] * S + rec[c.off_fy + f];
       cellmask[cell >> 5] &= ~(1u << (cell & 31));
@@ -269,11 +315,15 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
   uint8_t* sobs = srec + L.per_cta_rec + L.per_cta_mask;
   const int env0 = blockIdx.x * EPC;
   const int nenv = min(EPC, num_envs - env0);
+  __shared__ int rcount;
+  __shared__ uint16_t rlist[kThreads / 2];
+  if (threadIdx.x == 0) rcount = 0;
   load_records(c, L, srec, state, env0, nenv);
   __syncthreads();
   const int el = threadIdx.x / G, g = threadIdx.x % G;
   const int env = env0 + el;
   const unsigned gmask = group_mask<G>();
+  bool needs_reset = false;
   if (el < nenv) {
     uint8_t* rec = srec + el * L.rec_stride;
     const bool is_agent = g < c.A;
@@ -360,15 +410,31 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
     }
     if (is_agent) reward[(size_t)env * c.A + g] = my_reward;
     __syncwarp(gmask);
-    if (is_done && auto_reset) {
+    needs_reset = is_done && auto_reset != 0;
+  }
+  // ---- AutoResetWrapper (auto_reset_wrapper.py:74-75): finished envs go into a CTA queue and every
+  //      warp regenerates one at a time with all 32 lanes (warp-cooperative generator), instead of
+  //      the G lanes of the env holding up the other envs of their warp
+  if (needs_reset && g == 0) rlist[atomicAdd(&rcount, 1)] = (uint16_t)el;
+  __syncthreads();
+  {
+    const int nreset = rcount;
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x >> 5; i < nreset; i += kThreads / 32) {
+      const int rel = rlist[i];
+      uint8_t* rrec = srec + rel * L.rec_stride;
+      const uint32_t* k = reinterpret_cast<const uint32_t*>(rrec + c.off_key);
       Key nk, unused;
-      split2(key, nk, unused);
-      generate<G>(c, rec, smask + el * (kMaxCellsLbf / 32), nk, g, gmask);
+      split2(Key{k[0], k[1]}, nk, unused);
+      __syncwarp();
+      generate<32>(c, rrec, smask + rel * (kMaxCellsLbf / 32), nk, lane, 0xffffffffu);
     }
-    if (is_agent) {
-      int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
-      mask[(size_t)env * c.A + g] = emit_obs_and_mask(c, rec, g, row);
-    }
+  }
+  __syncthreads();
+  if (el < nenv && g < c.A) {
+    const uint8_t* rec = srec + el * L.rec_stride;
+    int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
+    mask[(size_t)env * c.A + g] = emit_obs_and_mask(c, rec, g, row);
   }
   __syncthreads();
   store_obs(c, sobs, view, env0, nenv);
@@ -464,6 +530,12 @@ int lbf_create(const mava_lbf_config* cfg, mava_env_s* env) {
   c.time_limit = cfg->time_limit;
   c.individual_rewards = cfg->use_individual_rewards;
   c.FR = 3 * (c.NF + c.A);
+  for (int w = 0; w < kMaxCellsLbf / 32; ++w) c.interior[w] = c.allcells[w] = 0u;
+  for (int i = 0; i < c.S * c.S; ++i) {
+    const int x = i / c.S, y = i % c.S;
+    c.allcells[i >> 5] |= 1u << (i & 31);
+    if (x > 0 && x < c.S - 1 && y > 0 && y < c.S - 1) c.interior[i >> 5] |= 1u << (i & 31);
+  }
   int o = 0;
   c.off_ax = o; o += c.A;
   c.off_ay = o; o += c.A;
@@ -499,7 +571,11 @@ int lbf_create(const mava_lbf_config* cfg, mava_env_s* env) {
 
 #define MAVA_LBF_DISPATCH(KERNEL, ...)                                                \
   do {                                                                                \
-    if (c.A <= 4) {                                                                   \
+    if (c.A <= 2) {                                                                   \
+      constexpr int G = 2;                                                            \
+      const size_t smem = smem_bytes(c, kThreads / G);                                \
+      KERNEL<G><<<ceil_div(num_envs, kThreads / G), kThreads, smem, s>>>(__VA_ARGS__); \
+    } else if (c.A <= 4) {                                                            \
       constexpr int G = 4;                                                            \
       const size_t smem = smem_bytes(c, kThreads / G);                                \
       KERNEL<G><<<ceil_div(num_envs, kThreads / G), kThreads, smem, s>>>(__VA_ARGS__); \
