@@ -303,6 +303,12 @@ def run_ours(args) -> None:
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[args.workload]
+        traffic = int(tr["dram_read_bytes"]) + int(tr["dram_write_bytes"])
+    except Exception:
+        pass
     flops = loss_grad_flops(L)
     achieved = flops / (lg_mean_ms * 1e-3) / 1e12
     value = world * steps_per_update * args.steps / (dev_ms * 1e-3)
@@ -330,7 +336,7 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches_per_update * args.steps),
             "roofline": {"kernel": L.dominant_kernel, "bound": "tensor", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "flops_per_launch": flops, "ms_per_launch": lg_mean_ms,
                          "launches_timed": len(lg_ms)},
             "cpu_baseline": cpu_baseline}

@@ -43,7 +43,14 @@ def run(task: Dict, num_envs: int, rollout_length: int = 128, ppo_epochs: int = 
     """Time ``updates`` full updates on ``num_envs`` envs.  Returns env-steps/s and the cores used."""
     cores = threads or len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline must still use every core
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except OSError:
+        pass
     env = RwareC(time_limit=time_limit, **task)
     A, FR, N, E, T = env.A, env.FR, 5, num_envs, rollout_length
     gen = torch.Generator().manual_seed(0)
