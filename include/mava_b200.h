@@ -61,6 +61,15 @@ int mava_prng_split(const uint32_t* key, uint32_t* out, int num, mava_stream_t s
  * (ff_mappo.py:273). */
 int mava_prng_random_bits(const uint32_t* key, uint32_t* out, int64_t n, mava_stream_t s);
 
+/* One round of jax.random.permutation's sort (ff_mappo.py:273; jax: sort_key_val(random_bits, x)):
+ * val_out = val_in stably sorted by the uint32 keys (mava_prng_random_bits).  Keys are assumed to be
+ * (close to) uniform: a two-level bucket + shared-memory bitonic sort; *overflow_flag (device int,
+ * zero it once) is set if a bucket ever exceeds its capacity, in which case val_out is invalid.
+ * workspace: mava_sort_workspace_bytes(n) bytes.  val_in and val_out must not alias. */
+int64_t mava_sort_workspace_bytes(int64_t n);
+int mava_sort_by_key(const uint32_t* keys, const int32_t* val_in, int32_t* val_out, int64_t n,
+                     void* workspace, int* overflow_flag, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * Environments - replaces jax.vmap(env.step) / jax.vmap(env.reset) through the whole wrapper
  * stack RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(RwareWrapper|LbfWrapper(env))))

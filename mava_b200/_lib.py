@@ -61,6 +61,8 @@ SIGNATURES = {
     "mava_prng_split_chain": (c_int, [c_void, c_void, c_int, c_void]),
     "mava_prng_split": (c_int, [c_void, c_void, c_int, c_void]),
     "mava_prng_random_bits": (c_int, [c_void, c_void, c_i64, c_void]),
+    "mava_sort_workspace_bytes": (c_i64, [c_i64]),
+    "mava_sort_by_key": (c_int, [c_void, c_void, c_void, c_i64, c_void, c_void, c_void]),
     "mava_env_create": (c_int, [c_int, c_void, C.c_size_t, P(c_void)]),
     "mava_env_destroy": (c_int, [c_void]),
     "mava_env_dims_of": (c_int, [c_void, P(EnvDims)]),

@@ -171,6 +171,20 @@ def prng_random_bits(key: torch.Tensor, out: torch.Tensor, n: int) -> None:
           "mava_prng_random_bits")
 
 
+def sort_workspace_bytes(n: int) -> int:
+    return int(_lib.load().mava_sort_workspace_bytes(n))
+
+
+def sort_by_key(keys, val_in, val_out, n: int, workspace, overflow) -> None:
+    """val_out = val_in stably sorted by uint32 keys (one round of jax.random.permutation)."""
+    _count(4)
+    check(_lib.load().mava_sort_by_key(
+        _p(keys, torch.uint32, n, "keys"), _p(val_in, torch.int32, n, "val_in"),
+        _p(val_out, torch.int32, n, "val_out"), n,
+        _p(workspace, torch.uint8, sort_workspace_bytes(n), "workspace"),
+        _p(overflow, torch.int32, 1, "overflow"), _stream()), "mava_sort_by_key")
+
+
 def ff_act(actor: MlpDesc, actor_params, critic: Optional[MlpDesc], critic_params, view, mask,
            policy_key, envs_per_replica: int, num_envs: int, action, logp, value=None,
            greedy: bool = False, actions_in=None) -> None:

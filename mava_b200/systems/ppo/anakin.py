@@ -89,6 +89,14 @@ class FFLearner:
         self.key3 = z(3, 2, dtype=torch.uint32)
         self.key3_ep = z(int(s.ppo_epochs), 3, 2, dtype=torch.uint32)
         self._side = torch.cuda.Stream(device=dev)
+        n_perm = T * self.E
+        self.perm_rounds = int(math.ceil(3 * math.log(max(1, n_perm)) / math.log(2 ** 32 - 1)))
+        self.arange_n = torch.arange(n_perm, dtype=torch.int32, device=dev)
+        self.perm_buf = z(int(s.ppo_epochs), 2, n_perm, dtype=torch.int32)
+        self.key2_r = z(int(s.ppo_epochs), max(1, self.perm_rounds), 2, 2, dtype=torch.uint32)
+        self.sort_ws = z(native.sort_workspace_bytes(n_perm), dtype=torch.uint8)
+        self.sort_overflow = z(1, dtype=torch.int32)
+        self._ovf_host = None
         self.key2 = z(2, 2, dtype=torch.uint32)
         self.bits = z(T * self.E, dtype=torch.uint32)
         self.rows = z(self.U * self.mb, dtype=torch.int32)
@@ -187,20 +195,21 @@ class FFLearner:
         native.mlp_pack_bf16(self.actor_desc, self.actor_params, self.actor_img)
         native.mlp_pack_bf16(self.critic_desc, self.critic_params, self.critic_img)
 
-    def _permutation(self, shuffle_key: torch.Tensor) -> torch.Tensor:
-        """jax.random.permutation(shuffle_key, T*E) (ff_mappo.py:273): rounds of a stable sort by
-        fresh threefry bits.  The bits come from our kernel; the sort is torch's radix sort."""
+    def _permutation(self, shuffle_key: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """jax.random.permutation(shuffle_key, n): rounds of a stable sort of the running permutation
+        by fresh threefry bits (ff_mappo.py:273, rec_mappo.py:350-352).  Bits and sort are kernels of
+        this library (csrc/env.cu, csrc/sort.cu); `slot` selects the output buffers so that the
+        permutations of several epochs can be alive at once."""
         n = self.T * self.E
-        x = torch.arange(n, dtype=torch.int32, device=self.device)
-        k = shuffle_key
-        for _ in range(self.perm_rounds):
-            native.prng_split(k, self.key2, 2)
-            k = self.key2[0].clone()
-            native.prng_random_bits(self.key2[1], self.bits, n)
-            # unsigned order under a signed sort: flip the top bit
-            order = torch.sort(self.bits.view(torch.int32) ^ (-2 ** 31), stable=True).indices
-            x = x[order]
-        return x
+        src, k = self.arange_n, shuffle_key
+        for r in range(self.perm_rounds):
+            native.prng_split(k, self.key2_r[slot][r], 2)
+            k = self.key2_r[slot][r][0]
+            native.prng_random_bits(self.key2_r[slot][r][1], self.bits, n)
+            dst = self.perm_buf[slot][r & 1]
+            native.sort_by_key(self.bits, src, dst, n, self.sort_ws, self.sort_overflow)
+            src = dst
+        return src
 
     def _epoch_permutations(self):
         """The shuffles of all epochs (ff_mappo.py:269-273).  They depend only on the key left by
@@ -211,7 +220,7 @@ class FFLearner:
         for ep in range(self.epochs):
             native.prng_split(k, self.key3_ep[ep], 3)  # key, shuffle_key, entropy_key (:269)
             k = self.key3_ep[ep][0]
-            perms.append(self._permutation(self.key3_ep[ep][1]))
+            perms.append(self._permutation(self.key3_ep[ep][1], ep))
         return perms
 
     def _update_epochs(self, perms) -> None:
@@ -295,6 +304,20 @@ class FFLearner:
             t.copy_(c)
         self._graph = g
 
+    def check_sort(self) -> None:
+        """The permutation sort assumes uniform keys; a bucket overflow is reported here.  The flag
+        is read without stalling the stream: the copy issued by the previous call is checked, then
+        a new one is issued."""
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._ovf_event = torch.cuda.Event()
+        else:
+            self._ovf_event.synchronize()
+            if int(self._ovf_host[0]) != 0:
+                raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys)")
+        self._ovf_host.copy_(self.sort_overflow, non_blocking=True)
+        self._ovf_event.record()
+
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
         dev, T, NE = self.device, self.T, self.NE
@@ -329,6 +352,7 @@ def get_learner_fn(learner: FFLearner, config):
         _adopt(learner, learner_state)
         n = int(config.system.get("num_updates_per_eval", 1))
         episode_metrics, train_metrics = learner.learn(n)
+        learner.check_sort()
         return ExperimentOutput(learner.learner_state(), episode_metrics, train_metrics)
 
     return learner_fn

@@ -123,6 +123,12 @@ class RecLearner:
                            dtype=torch.uint8)
         self._scratch_state = z(NE, env.state_dim) if self.dense and not centralised_critic else None
         self.perm_rounds = int(math.ceil(3 * math.log(max(1, self.ncols)) / math.log(2 ** 32 - 1)))
+        self.arange_n = torch.arange(self.ncols, dtype=torch.int32, device=dev)
+        self.perm_buf = z(1, 2, self.ncols, dtype=torch.int32)
+        self.key2_r = z(1, max(1, self.perm_rounds), 2, 2, dtype=torch.uint32)
+        self.sort_ws = z(native.sort_workspace_bytes(self.ncols), dtype=torch.uint8)
+        self.sort_overflow = z(1, dtype=torch.int32)
+        self._ovf_host = None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0
         self.time_loss_grad = None
@@ -192,18 +198,21 @@ class RecLearner:
                        None, self.h_critic, None, None, self.E, self.NE, None, None, self.last_val,
                        self.act_ws)
 
-    def _permutation(self, shuffle_key: torch.Tensor) -> torch.Tensor:
-        """jax.random.permutation(shuffle_key, num_envs * num_chunks) (rec_mappo.py:350-352)."""
+    def _permutation(self, shuffle_key: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """jax.random.permutation(shuffle_key, n): rounds of a stable sort of the running permutation
+        by fresh threefry bits (ff_mappo.py:273, rec_mappo.py:350-352).  Bits and sort are kernels of
+        this library (csrc/env.cu, csrc/sort.cu); `slot` selects the output buffers so that the
+        permutations of several epochs can be alive at once."""
         n = self.ncols
-        x = torch.arange(n, dtype=torch.int32, device=self.device)
-        k = shuffle_key
-        for _ in range(self.perm_rounds):
-            native.prng_split(k, self.key2, 2)
-            k = self.key2[0].clone()
-            native.prng_random_bits(self.key2[1], self.bits, n)
-            order = torch.sort(self.bits.view(torch.int32) ^ (-2 ** 31), stable=True).indices
-            x = x[order]
-        return x
+        src, k = self.arange_n, shuffle_key
+        for r in range(self.perm_rounds):
+            native.prng_split(k, self.key2_r[slot][r], 2)
+            k = self.key2_r[slot][r][0]
+            native.prng_random_bits(self.key2_r[slot][r][1], self.bits, n)
+            dst = self.perm_buf[slot][r & 1]
+            native.sort_by_key(self.bits, src, dst, n, self.sort_ws, self.sort_overflow)
+            src = dst
+        return src
 
     def _update_epochs(self) -> None:
         """rec_mappo.py:201-383."""
@@ -214,7 +223,7 @@ class RecLearner:
         for ep in range(self.epochs):
             native.prng_split(self.key, self.key3, 3)  # key, shuffle_key, entropy_key (:332)
             self.key.copy_(self.key3[0])
-            perm = self._permutation(self.key3[1])
+            perm = self._permutation(self.key3[1], 0)
             for m in range(self.nmb):
                 cols = perm[m * self.mbc:(m + 1) * self.mbc]
                 if self.time_loss_grad is not None:
@@ -282,6 +291,18 @@ class RecLearner:
             t.copy_(c)
         self._graph = g
 
+    def check_sort(self) -> None:
+        """Bucket overflow of the permutation sort, read one call late (no stream stall)."""
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._ovf_event = torch.cuda.Event()
+        else:
+            self._ovf_event.synchronize()
+            if int(self._ovf_host[0]) != 0:
+                raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys)")
+        self._ovf_host.copy_(self.sort_overflow, non_blocking=True)
+        self._ovf_event.record()
+
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
         dev, T, NE = self.device, self.T, self.NE
@@ -317,6 +338,7 @@ def get_learner_fn(learner: RecLearner, config):
         _adopt(learner, learner_state)
         n = int(config.system.get("num_updates_per_eval", 1))
         episode_metrics, train_metrics = learner.learn(n)
+        learner.check_sort()
         return ExperimentOutput(learner.learner_state(), episode_metrics, train_metrics)
 
     return learner_fn

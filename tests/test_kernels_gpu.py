@@ -134,3 +134,24 @@ def test_clip_adam_pair_matches_single(lib_built):
     torch.testing.assert_close(p, p2, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(mu, mu2, rtol=1e-6, atol=1e-9)
     torch.testing.assert_close(nu, nu2, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 37, 1000, 16384, 131072, 1 << 20, 4194304])
+def test_sort_by_key_matches_stable_sort(lib_built, n):
+    """One round of jax.random.permutation's sort_key_val: stable on ties, any size."""
+    from mava_b200 import native
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(n)
+    keys = torch.randint(0, 2 ** 32, (n,), generator=g, device=dev, dtype=torch.int64)
+    if n > 8:  # equal keys in distant positions: stability decides
+        idx = torch.randint(0, n, (min(n // 4, 5000),), generator=g, device=dev)
+        keys[idx] = keys[(idx * 7 + 3) % n]
+    vals = torch.randperm(n, generator=g, device=dev).to(torch.int32)
+    out = torch.empty_like(vals)
+    ws = torch.zeros(native.sort_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    native.sort_by_key(keys.to(torch.uint32), vals, out, n, ws, ovf)
+    order = torch.sort(keys, stable=True).indices
+    assert int(ovf.item()) == 0
+    assert torch.equal(out, vals[order])
