@@ -150,29 +150,32 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
 template <int GG>
 __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
                                          unsigned gmask) {
-  Key pos_key, dir_key, q_key, unused, sub;
-  unsigned long long pick[kMaxAgents];
-  split2(key, key, pos_key);
-  split2(pos_key, unused, sub);
-  smallest_k<GG, kMaxAgents>(sub, c.HW, c.A, g, gmask, pick);
-  split2(key, key, dir_key);
-  Key d_hi, d_lo;
+  // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
+  // steps under random actions), and a regeneration is a chain of dependent threefry calls.  All
+  // keys are therefore derived first, in an order that leaves the independent splits next to each
+  // other for the scheduler (critical path: 4 splits instead of 7), and the per-agent direction
+  // draws run on the agents' own lanes.
+  Key k1, pos_key, k2, dir_key, k3, q_key, unused, sub_pos, sub_q, d_hi, d_lo;
+  split2(key, k1, pos_key);
+  split2(k1, k2, dir_key);
+  split2(pos_key, unused, sub_pos);
+  split2(k2, k3, q_key);
   split2(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
-  if (g == 0) {
-    uint32_t* agents = reinterpret_cast<uint32_t*>(rec + c.off_agents);
+  split2(q_key, unused, sub_q);
+  const int my_dir =
+      g < c.A ? (int)(random_bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
+  unsigned long long pick[kMaxAgents];
+  smallest_k<GG, kMaxAgents>(sub_pos, c.HW, c.A, g, gmask, pick);
+  if (g < c.A) {
+    unsigned long long mine = 0ull;
 #pragma unroll
-    for (int i = 0; i < kMaxAgents; ++i) {
-      if (i < c.A) {
-        const int cell = (int)(pick[i] & 0xffffffffull);
-        const int d = (int)(random_bits_at(d_lo, (uint32_t)i, (uint32_t)c.A) & 3u);
-        agents[i] = pack_agent(cell / c.W, cell % c.W, d, 0);
-      }
-    }
+    for (int i = 0; i < kMaxAgents; ++i)
+      if (i == g) mine = pick[i];
+    const int cell = (int)(mine & 0xffffffffull);
+    reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(cell / c.W, cell % c.W, my_dir, 0);
   }
-  split2(key, key, q_key);
-  split2(q_key, unused, sub);
   unsigned long long qpick[kMaxQueue];
-  smallest_k<GG, kMaxQueue>(sub, c.n, c.Q, g, gmask, qpick);
+  smallest_k<GG, kMaxQueue>(sub_q, c.n, c.Q, g, gmask, qpick);
   uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
   for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
   __syncwarp(gmask);
@@ -191,8 +194,8 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     }
     *reinterpret_cast<uint32_t*>(rec + c.off_step) = 0u;
     uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
-    k[0] = key.k0;
-    k[1] = key.k1;
+    k[0] = k3.k0;
+    k[1] = k3.k1;
   }
   __syncwarp(gmask);
 }

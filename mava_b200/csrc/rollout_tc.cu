@@ -30,6 +30,18 @@ int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n);
 
 namespace {
 
+// Phase timing (development aid, -DMAVA_PROFILE_PHASES): thread 0 of CTA 0 records clock64() at the
+// phase boundaries of steps 16..31 (read back with mava_debug_rollout_phases).
+#ifdef MAVA_PROFILE_PHASES
+__device__ long long g_rollout_clock[16 * 16];
+#define MAVA_RSTAMP(k)                                                                        \
+  do {                                                                                        \
+    if (t == 0 && blockIdx.x == 0 && step >= 16 && step < 32) g_rollout_clock[(step - 16) * 16 + (k)] = clock64(); \
+  } while (0)
+#else
+#define MAVA_RSTAMP(k) do { } while (0)
+#endif
+
 struct RolloutArgs {
   RwareConst c;
   NetDesc actor;
@@ -154,38 +166,45 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   // reads are 64 B/clk per SM: half a tile of dead rows would cost as much as the live half)
   const bool live = (warp & 3) * 32 < rows_valid;
   for (int step = 0; step < p.T; ++step) {
+    MAVA_RSTAMP(0);
     // ---- 1. X tile from the observation rows in shared memory
     expand_x_row(d, xt, L, reinterpret_cast<const signed char*>(sobs) + L.r * c.FR,
                  L.r < rows_valid, g);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_RSTAMP(1);
     // ---- 2. actor MLP
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
     }
     wait_mma(&ctrl.mbar, phase);
+    MAVA_RSTAMP(2);
     phase ^= 1;
     if (live) hidden_epilogue(L, tmem, ht);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_RSTAMP(3);
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HCOLS, false, &ctrl.mbar);
     }
     wait_mma(&ctrl.mbar, phase);
+    MAVA_RSTAMP(4);
     phase ^= 1;
     if (live) hidden_epilogue(L, tmem, ht);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    MAVA_RSTAMP(5);
     if (t == 0) {
       fence_after_sync();
       issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HCOLS, false, &ctrl.mbar);
     }
     wait_mma(&ctrl.mbar, phase);
+    MAVA_RSTAMP(6);
     phase ^= 1;
     // ---- 3 + 4. head epilogue and env step (threads 0 .. TM-1)
     bool needs_reset = false, replay = false;
@@ -241,6 +260,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     if (t == 0 && pending_store) rware::bulk_commit_wait_read();
     fence_before_sync();
     __syncthreads();
+    MAVA_RSTAMP(7);
     // ---- finished envs: one regeneration per warp at a time, all 16 warps take part
     {
       const int nreset = ctrl.rcount;
@@ -254,6 +274,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
       }
     }
     __syncthreads();
+    MAVA_RSTAMP(8);
     if (t == 0) ctrl.rcount = 0;
     // ---- next observation rows and masks
     if (agent) {
@@ -262,11 +283,13 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     }
     fence_proxy_async();
     __syncthreads();
+    MAVA_RSTAMP(9);
     pending_store = store_block(
         sobs, reinterpret_cast<uint8_t*>(p.view) + (size_t)(step + 1) * obs_slot +
                   (size_t)env0 * G * c.FR,
         obs_bytes);
     if (t == 0 && pending_store) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    MAVA_RSTAMP(10);
   }
   // ---- records back to HBM
   fence_proxy_async();
@@ -308,6 +331,12 @@ using namespace mava;
 using namespace mava::tcmlp;
 
 extern "C" {
+
+#ifdef MAVA_PROFILE_PHASES
+int mava_debug_rollout_phases(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_rollout_clock, sizeof(long long) * 256);
+}
+#endif
 
 int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor, const float* actor_params,
                          const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,

@@ -4,6 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -I include"
 nvcc $FLAGS -DMAVA_PROFILE_PHASES -c mava_b200/csrc/ppo_tc.cu -o mava_b200/build/ppo_tc.o
+nvcc $FLAGS -DMAVA_PROFILE_PHASES -c mava_b200/csrc/rollout_tc.cu -o mava_b200/build/rollout_tc.o
 nvcc -shared -o mava_b200/libmava_b200.so mava_b200/build/*.o -lcudart
 python - <<'PY'
 import ctypes, sys, os
@@ -44,4 +45,13 @@ print("idle-warp branch of the loss phase (warp 4): wait+bar %.0f, expand %.0f, 
 c = np.array(buf2[128:144])
 print("critic tile (last CTA), start->start: %.0f cycles" % np.diff(c[2:]).mean())
 print("gemm3_done -> dz3 stored:", (a[:, 15] - a[:, 7]).mean(), " -> db3 reduced + sync:", (a[:, 8] - a[:, 15]).mean())
+rb = (ctypes.c_longlong * 256)()
+lib.mava_debug_rollout_phases.restype = ctypes.c_int
+assert lib.mava_debug_rollout_phases(rb) == 0
+ra = np.array(rb[:]).reshape(16, 16)
+rn = ["x_expand+sync", "gemm1", "epi1+sync", "gemm2", "epi2+sync", "gemm3", "head+env_step", "resets", "emit_rows+sync", "store_issue"]
+print("rollout kernel, cycles per phase of a step (CTA 0, steps 16..31):")
+for n_, v in zip(rn, np.diff(ra[:, :11], axis=1).mean(0)):
+    print(f"  {n_:18s} {v:8.0f}")
+print("  step total (start->start):", np.diff(ra[:, 0]).mean())
 PY
