@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NT, 2) tc_gemm_kernel(const GemmArgs p) {
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
 #pragma unroll
       for (int k = 0; k < BK / 16; ++k) {

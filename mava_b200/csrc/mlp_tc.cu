@@ -123,14 +123,14 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
 
   // while acting, rows are (env, agent) for AGENT_VIEW and env for GLOBAL, in buffer order
   // (the H tile doubles as the staging area: it is not live before layer 1)
-  build_x_tile(d, p.view, xt, smem + (ht.base - s_w), row0, M, [](int64_t j) { return j; });
+  build_x_tile(d, p.view, xt, smem + (ht.base - s_w), (int)row0, (int)M, [](int64_t j) { return j; });
   fence_proxy_async();
   mbar_wait(&ctrl.wbar, 0);
   fence_before_sync();
   __syncthreads();
   uint32_t phase = 0;
   // ---- layer 1
-  if (t == 0) {
+  if (mma_issuer()) {
     fence_after_sync();
     issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
   }
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
   fence_before_sync();
   __syncthreads();
   // ---- layer 2 (accumulator reused: every thread has drained its columns)
-  if (t == 0) {
+  if (mma_issuer()) {
     fence_after_sync();
     issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HCOLS, false, &ctrl.mbar);
   }
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
   fence_before_sync();
   __syncthreads();
   // ---- head
-  if (t == 0) {
+  if (mma_issuer()) {
     fence_after_sync();
     issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HCOLS, false, &ctrl.mbar);
   }
@@ -278,6 +278,7 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, cons
   int rc = 0;
   MAVA_CHECK_PTR(view);
   MAVA_CHECK_ARG(num_envs > 0 && envs_per_replica > 0);
+  MAVA_CHECK_ARG((int64_t)num_envs * 8 < ((int64_t)1 << 31));  // tile rows are indexed in 32 bits
   MAVA_CHECK_ARG(actor != nullptr || value != nullptr);
   if (actor) {  // actor == NULL: critic only (bootstrap value, ff_mappo.py:110)
     rc = make_net(actor, actor_params, &a.actor);

@@ -164,14 +164,14 @@ __device__ __forceinline__ void expand_x_row(const NetDesc& d, const Tile& xt, c
 
 template <class StepFn>
 __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __restrict__ view,
-                                             const Tile& xt, unsigned char* stage, int64_t row0,
-                                             int64_t M, StepFn step_at) {
+                                             const Tile& xt, unsigned char* stage, int row0,
+                                             int M, StepFn step_at) {
   const Lane L;
   const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
   const int step_bytes = d.A * d.FR;
-  const int64_t last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
-  const int64_t j0 = row0 / rps;
-  const int nsteps = (int)(last / rps - j0) + 1;
+  const int last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
+  const int j0 = row0 / rps;
+  const int nsteps = last / rps - j0 + 1;
   // the env-step indices first (one coalesced load), so that the copies below are independent
   int* steps = reinterpret_cast<int*>(stage + ((size_t)(TM / rps + 2) * step_bytes + 15) / 16 * 16);
   if (L.t < nsteps) steps[L.t] = (int)step_at(j0 + L.t);
@@ -206,9 +206,9 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
     }
   }
   __syncthreads();
-  const int64_t row = row0 + L.r;
+  const int row = row0 + L.r;
   const bool valid = row < M;
-  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
+  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : row % rps;
   const signed char* mine = reinterpret_cast<const signed char*>(stage) +
                             (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
   expand_x_row(d, xt, L, mine, valid, a);
@@ -221,16 +221,16 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
 // barrier and builds the bf16 X tile.  Requires A * FR to be a multiple of 4 bytes.
 template <class StepFn>
 __device__ __forceinline__ void gather_issue(const NetDesc& d, const int8_t* __restrict__ view,
-                                             unsigned char* stage, int64_t row0, int64_t M,
+                                             unsigned char* stage, int row0, int M,
                                              StepFn step_at, int first_warp = 0,
                                              int num_warps = NWARPS) {
   const Lane L;
   if (L.warp < first_warp || L.warp >= first_warp + num_warps) return;
   const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
   const int step_bytes = d.A * d.FR;
-  const int64_t last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
-  const int64_t j0 = row0 / rps;
-  const int nsteps = (int)(last / rps - j0) + 1;
+  const int last = (row0 + TM - 1 < M ? row0 + TM - 1 : M - 1);
+  const int j0 = row0 / rps;
+  const int nsteps = last / rps - j0 + 1;
   const int unit = (step_bytes & 7) == 0 ? 8 : 4;
   const int units = step_bytes / unit;
   for (int js = L.warp - first_warp; js < nsteps; js += num_warps) {
@@ -253,15 +253,15 @@ __device__ __forceinline__ void gather_wait() {
 }
 
 __device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
-                                              const unsigned char* stage, int64_t row0, int64_t M,
+                                              const unsigned char* stage, int row0, int M,
                                               int cg0 = -1, int cg_step = 4) {
   const Lane L;
   const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
   const int step_bytes = d.A * d.FR;
-  const int64_t j0 = row0 / rps;
-  const int64_t row = row0 + L.r;
+  const int j0 = row0 / rps;
+  const int row = row0 + L.r;
   const bool valid = row < M;
-  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : (int)(row % rps);
+  const int a = d.mode == MAVA_IN_GLOBAL ? 0 : row % rps;
   const signed char* mine = reinterpret_cast<const signed char*>(stage) +
                             (valid ? (size_t)(row / rps - j0) * step_bytes + (size_t)a * d.FR : 0);
   expand_x_row(d, xt, L, mine, valid, a, cg0, cg_step);

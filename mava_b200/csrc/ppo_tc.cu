@@ -79,7 +79,7 @@ struct Ctrl {
   uint64_t wbar, mbar;
   uint32_t tmem;
   float db3[NHEAD];
-  float adv_mean[8], adv_sd[8];  // per replica, from the fp64 sums (once per CTA, not per row)
+  float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
   int32_t steps[3][TM + 2];      // env-step index of each minibatch position of the tiles in flight
 };
 
@@ -88,7 +88,8 @@ constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava
 // per-row loss inputs, fetched at the start of a tile
 struct LossIn {
   bool valid;
-  int64_t j, flat;
+  int j;
+  int64_t flat;
   uint32_t mk;
   int act;
   float f0[kMaxReps], f1[kMaxReps];  // actor: old_logp, adv in [0]; critic: old_value, targets
@@ -121,6 +122,58 @@ __device__ __forceinline__ void grad_epilogue(const Lane& L, uint32_t tmem_acc, 
   }
 }
 
+// One row of _actor_loss_fn (ff_mappo.py:159-180) over NO head columns (8 when the action space
+// fits, else 16): masked log-softmax, clipped ratio, entropy.  dz = d(total loss)/d(logits) * wrow.
+// exp / log are the hardware approximations (2 ulp of a bf16 forward pass is 2^-8).
+template <int NO>
+__device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, int nout, uint32_t mk,
+                                               int a, float old_logp, float g, float clip_eps,
+                                               float ent_coef, float wrow, float (&dz)[NHEAD],
+                                               float& l0f, float& l1f) {
+  float out[NO];
+  if constexpr (NO == 8) ld8(tmem_head, out);
+  else ld16(tmem_head, out);
+  if (!valid) return;
+  float mx = kF32Min;
+#pragma unroll
+  for (int q = 0; q < NO; ++q) {
+    out[q] = (q < nout && ((mk >> q) & 1u)) ? out[q] : kF32Min;
+    mx = fmaxf(mx, out[q]);
+  }
+  float se = 0.0f, ex[NO];
+#pragma unroll
+  for (int q = 0; q < NO; ++q) {
+    ex[q] = q < nout ? __expf(out[q] - mx) : 0.0f;
+    se += ex[q];
+  }
+  const float lse = mx + __logf(se), inv_se = __fdividef(1.0f, se);
+  float la = 0.0f, ent = 0.0f, logp[NO], pr[NO];
+#pragma unroll
+  for (int q = 0; q < NO; ++q) {
+    logp[q] = out[q] - lse;
+    pr[q] = ex[q] * inv_se;
+    ent -= pr[q] != 0.0f ? pr[q] * logp[q] : 0.0f;
+    la = q == a ? logp[q] : la;
+  }
+  const float ratio = __expf(la - old_logp);
+  const float lo = 1.0f - clip_eps, hi = 1.0f + clip_eps;
+  const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
+  const bool inside = ratio > lo && ratio < hi;
+  float dr;
+  if (t1 < t2) dr = -g;
+  else if (t1 > t2) dr = inside ? -g : 0.0f;
+  else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
+  const float dla = dr * ratio;
+#pragma unroll
+  for (int q = 0; q < NO; ++q) {
+    float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
+    dl += pr[q] != 0.0f ? ent_coef * pr[q] * (logp[q] + ent) : 0.0f;
+    dz[q] = (q < nout && ((mk >> q) & 1u)) ? dl * wrow : 0.0f;
+  }
+  l0f += -fminf(t1, t2);
+  l1f += ent;
+}
+
 __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Ctrl ctrl;
@@ -131,8 +184,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
   const int n_ctas = is_actor ? p.actor_ctas : p.critic_ctas;
   const int rows_per_step = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
-  const int64_t M = (int64_t)p.R * rows_per_step;
-  const int n_tiles = (int)ceil_div64(M, TM);
+  const int M = p.R * rows_per_step;  // < 2^31 (checked by the host entry)
+  const int n_tiles = ceil_div(M, TM);
 
   // shared memory: [weights][region: X, later H2 + dZ2][H1 (also the gather staging area)][dZ3]
   // fold mode (actor): [weights][X ping][X pong][region: H2 (later dZ1) + dZ2][H1][dZ3] -- X stays
@@ -160,10 +213,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   // prefetch: ONE coalesced load of the tile's env-step indices into ctrl.steps[buf] (also read by
   // the loss epilogue), then the asynchronous copies of their observation rows
   auto load_steps = [&](int tile_idx) -> int32_t {  // this thread's entry of a tile's index list
-    const int64_t r0 = (int64_t)tile_idx * TM;
-    const int64_t last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
-    const int64_t j0 = r0 / rows_per_step;
-    const int nsteps = (int)(last / rows_per_step - j0) + 1;
+    const int r0 = tile_idx * TM;
+    const int last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
+    const int j0 = r0 / rows_per_step;
+    const int nsteps = last / rows_per_step - j0 + 1;
     return t < nsteps ? __ldg(p.rows + j0 + t) : 0;
   };
   // the index list goes to shared memory right away; the asynchronous copies are issued later, by
@@ -179,10 +232,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   constexpr int kPfSlots = 8;
   uint32_t pf_reg[kPfSlots];
   auto pf_load = [&](int tile_idx, int buf) {
-    const int64_t r0 = (int64_t)tile_idx * TM;
-    const int64_t last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
-    const int64_t j0 = r0 / rows_per_step;
-    const int nsteps = (int)(last / rows_per_step - j0) + 1;
+    const int r0 = tile_idx * TM;
+    const int last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
+    const int j0 = r0 / rows_per_step;
+    const int nsteps = last / rows_per_step - j0 + 1;
     const int units = (d.A * d.FR) >> 2, total = nsteps * units;
 #pragma unroll
     for (int k = 0; k < kPfSlots; ++k) {
@@ -203,8 +256,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
   };
   auto issue_copies = [&](int tile_idx, int buf, int first_warp, int num_warps) {
-    const int64_t r0 = (int64_t)tile_idx * TM;
-    const int64_t j0 = r0 / rows_per_step;
+    const int r0 = tile_idx * TM;
+    const int j0 = r0 / rows_per_step;
     gather_issue(d, p.view, pf_stage, r0, M,
                  [&](int64_t jj) { return (int64_t)ctrl.steps[buf][jj - j0]; }, first_warp,
                  num_warps);
@@ -222,7 +275,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     const double mean_d = p.adv_stats[2 * t] / cnt;
     const double var_d = fmax(p.adv_stats[2 * t + 1] / cnt - mean_d * mean_d, 0.0);
     ctrl.adv_mean[t] = (float)mean_d;
-    ctrl.adv_sd[t] = (float)sqrt(var_d);
+    ctrl.adv_isd[t] = 1.0f / ((float)sqrt(var_d) + 1e-8f);
   }
   fence_before_sync();
   __syncthreads();
@@ -240,7 +293,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     issue_copies(cta, 0, 0, NWARPS);
     gather_wait();
     __syncthreads();
-    gather_expand(d, Tile{s_x0, 128u, 2048u}, pf_stage, (int64_t)cta * TM, M);
+    gather_expand(d, Tile{s_x0, 128u, 2048u}, pf_stage, cta * TM, M);
     __syncthreads();
   }
   mbar_wait(&ctrl.wbar, 0);
@@ -254,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   bool first = true;
   int it = 0;
   for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
-    const int64_t row0 = (int64_t)tile * TM;
+    const int row0 = tile * TM;
     const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
     MAVA_STAMP(0);
 #ifdef MAVA_PROFILE_PHASES
@@ -273,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     __syncthreads();
     MAVA_STAMP(1);
     // ---- forward
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
     }
@@ -284,10 +337,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     // loss inputs of this row: in flight during the forward pass instead of after it
     LossIn li{};
     if (L.q == 0) {
-      const int64_t row = row0 + L.r;
+      const int row = row0 + L.r;
       li.valid = row < M;
-      const int64_t j = li.valid ? row / rows_per_step : 0;
-      const int ag = (int)(row - j * rows_per_step);
+      const int j = li.valid ? row / rows_per_step : 0;
+      const int ag = row - j * rows_per_step;
       const int64_t sidx = !li.valid ? 0
                            : prefetch ? (int64_t)ctrl.steps[it % 3][j - row0 / rows_per_step]
                                       : (int64_t)__ldg(p.rows + j);
@@ -321,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_before_sync();
     __syncthreads();
     MAVA_STAMP(5);
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
     }
@@ -332,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     fence_before_sync();
     __syncthreads();
     MAVA_STAMP(6);
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
     }
@@ -349,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
         asm volatile("bar.sync 1, 384;" ::: "memory");  // ... and those of the other eleven warps
         MAVA_STAMP2(1);
         const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-        gather_expand(d, xn, pf_stage, (int64_t)(tile + n_ctas) * TM, M, L.q - 1, 3);
+        gather_expand(d, xn, pf_stage, (tile + n_ctas) * TM, M, L.q - 1, 3);
         MAVA_STAMP2(2);
         fence_proxy_async();
         MAVA_STAMP2(3);
@@ -357,14 +410,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       }
     } else {
       const bool valid = li.valid;
-      const int64_t j = li.j;  // position in the minibatch
-      float out[NHEAD], dz[NHEAD];
-      ld16(tmem + L.tmem_lane() + COL_HEAD, out);
+      float dz[NHEAD];
 #pragma unroll
       for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
-      if (valid) {
-        if (!is_actor) {
-          // _critic_loss_fn, ff_mappo.py:190-201
+      if (!is_actor) {
+        // _critic_loss_fn, ff_mappo.py:190-201
+        float out[8];
+        ld8(tmem + L.tmem_lane() + COL_HEAD, out);
+        if (valid) {
           const float v = out[0];
           const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
           float dv = 0.0f;
@@ -385,61 +438,16 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
             l0f += 0.5f * fmaxf(a1, a2);
           }
           dz[0] = dv * wrow * p.vf_coef;
-        } else {
-          // _actor_loss_fn, ff_mappo.py:159-180
-          const uint32_t mk = li.mk;
-          float mx = kF32Min;
-#pragma unroll
-          for (int q = 0; q < NHEAD; ++q) {
-            if (q < d.out) {
-              out[q] = ((mk >> q) & 1) ? out[q] : kF32Min;
-              mx = fmaxf(mx, out[q]);
-            }
-          }
-          float se = 0.0f, ex[NHEAD];
-#pragma unroll
-          for (int q = 0; q < NHEAD; ++q) {
-            ex[q] = q < d.out ? expf(out[q] - mx) : 0.0f;
-            se += ex[q];
-          }
-          const float lse = mx + logf(se), inv_se = 1.0f / se;
-          const int a = li.act;
-          const int u = (int)(j / p.mb_size);
-          const float mean = ctrl.adv_mean[u], sd = ctrl.adv_sd[u];
-          float logp[NHEAD], pr[NHEAD];
-          float la = 0.0f, ent = 0.0f;
-#pragma unroll
-          for (int q = 0; q < NHEAD; ++q) {
-            logp[q] = 0.0f;
-            pr[q] = 0.0f;
-            if (q < d.out) {
-              logp[q] = out[q] - lse;
-              pr[q] = ex[q] * inv_se;
-              if (pr[q] != 0.0f) ent -= pr[q] * logp[q];
-              if (q == a) la = logp[q];
-            }
-          }
-          const float ratio = expf(la - li.f0[0]);
-          const float g = (li.f1[0] - mean) / (sd + 1e-8f);
-          const float lo = 1.0f - p.clip_eps, hi = 1.0f + p.clip_eps;
-          const float t1 = ratio * g, t2 = fminf(fmaxf(ratio, lo), hi) * g;
-          const bool inside = ratio > lo && ratio < hi;
-          float dr;
-          if (t1 < t2) dr = -g;
-          else if (t1 > t2) dr = inside ? -g : 0.0f;
-          else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
-          const float dla = dr * ratio;
-#pragma unroll
-          for (int q = 0; q < NHEAD; ++q) {
-            if (q < d.out && ((mk >> q) & 1)) {
-              float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
-              if (pr[q] != 0.0f) dl += p.ent_coef * pr[q] * (logp[q] + ent);
-              dz[q] = dl * wrow;
-            }
-          }
-          l0f += -fminf(t1, t2);
-          l1f += ent;
         }
+      } else {
+        const int u = li.j / p.mb_size;  // replica of this minibatch position
+        const float g = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
+        if (d.out <= 8)
+          actor_loss_row<8>(tmem + L.tmem_lane() + COL_HEAD, valid, d.out, li.mk, li.act, li.f0[0],
+                            g, p.clip_eps, p.ent_coef, wrow, dz, l0f, l1f);
+        else
+          actor_loss_row<16>(tmem + L.tmem_lane() + COL_HEAD, valid, d.out, li.mk, li.act, li.f0[0],
+                             g, p.clip_eps, p.ent_coef, wrow, dz, l0f, l1f);
       }
       st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 0), pack_bf16(dz[0], dz[1]),
                    pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
@@ -455,10 +463,15 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     __syncthreads();
     MAVA_STAMP(8);
     // ---- backward through the head: dH2 = dZ3 W3^T ; dW3 += H2^T dZ3
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
+#ifdef MAVA_EARLY_COMMIT
+      issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, &ctrl.mbar);
+      issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
+#else
       issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
       issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, &ctrl.mbar);
+#endif
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
@@ -469,10 +482,15 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     __syncthreads();
     MAVA_STAMP(10);
     // ---- dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1]
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
+#ifdef MAVA_EARLY_COMMIT
+      issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
+      issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, nullptr);
+#else
       issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, nullptr);
       issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, &ctrl.mbar);
+#endif
     }
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
       fence_proxy_async();
       fence_before_sync();
       __syncthreads();
-      if (t == 0) {
+      if (mma_issuer()) {
         fence_after_sync();
         issue_gemm(tmem + COL_DW1, dz1t, true, xt, true, d.k1p, TM, !first, nullptr);
       }
@@ -501,7 +519,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     }
   }
   if (fold && !first) {  // the last tile's dW1 MMAs
-    if (t == 0) commit(&ctrl.mbar);
+    if (mma_issuer()) commit(&ctrl.mbar);
     wait_mma(&ctrl.mbar, phase);
     phase ^= 1;
   }
@@ -596,8 +614,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
   const int n_ctas = is_actor ? p.actor_ctas : p.critic_ctas;
   const int rows_per_step = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
-  const int64_t M = (int64_t)p.R * rows_per_step;
-  const int n_tiles = (int)ceil_div64(M, TM);
+  const int M = p.R * rows_per_step;
+  const int n_tiles = ceil_div(M, TM);
   const unsigned char* dz1 = is_actor ? p.dz1_actor : p.dz1_critic;
 
   // shared memory: [dZ1 tile][X tile][gather staging]
@@ -619,7 +637,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   uint32_t phase = 0;
   bool first = true;
   for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
-    const int64_t row0 = (int64_t)tile * TM;
+    const int row0 = tile * TM;
     if (t == 0) {
       mbar_expect_tx(&ctrl.lbar, tile_bytes(TM, HID));
       bulk_g2s(dzt.base, dz1 + (size_t)tile * tile_bytes(TM, HID), tile_bytes(TM, HID), &ctrl.lbar);
@@ -630,7 +648,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     mbar_wait(&ctrl.lbar, phase);
     fence_before_sync();
     __syncthreads();
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       // D[n][k] += sum_rows dZ1[row][n] * X[row][k]: A = dZ1 (MN-major), B = X (MN-major)
       const uint32_t idesc_lo = instr_desc(TM, n_lo, true, true);
@@ -726,6 +744,7 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   MAVA_CHECK_PTR(grad_out);
   MAVA_CHECK_PTR(workspace);
   MAVA_CHECK_ARG(num_replicas > 0 && num_replicas <= 8 && mb_size > 0 && critic->out_dim == 1);
+  MAVA_CHECK_ARG((int64_t)num_replicas * mb_size * actor->num_agents < ((int64_t)1 << 31));
   MAVA_CHECK_ARG(actor->input_mode == MAVA_IN_AGENT_VIEW);
   cudaStream_t s = as_stream(stream);
   const int R = num_replicas * mb_size;

@@ -175,7 +175,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     __syncthreads();
     MAVA_RSTAMP(1);
     // ---- 2. actor MLP
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
     }
@@ -187,7 +187,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     fence_before_sync();
     __syncthreads();
     MAVA_RSTAMP(3);
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HCOLS, false, &ctrl.mbar);
     }
@@ -199,7 +199,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     fence_before_sync();
     __syncthreads();
     MAVA_RSTAMP(5);
-    if (t == 0) {
+    if (mma_issuer()) {
       fence_after_sync();
       issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HCOLS, false, &ctrl.mbar);
     }

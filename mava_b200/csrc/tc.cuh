@@ -105,6 +105,21 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, uint64_t adesc, uint64_t bd
       : "memory");
 }
 
+// True in exactly one lane of warp 0 (call with warp 0 converged).  A warp-uniform condition plus
+// a hardware election instead of `threadIdx.x == 0`: under a thread-index branch nvcc treats the
+// MMA descriptors as per-lane values and rebuilds each one through an R2UR waterfall loop (~13
+// dependent instructions per tcgen05.mma, on the critical path of every phase); here they stay in
+// uniform registers.
+__device__ __forceinline__ bool mma_issuer() {
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp_u != 0) return false;
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -142,6 +157,18 @@ __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ---- mbarrier --------------------------------------------------------------------------------------
