@@ -162,7 +162,14 @@ __device__ __forceinline__ void expand_x_row(const NetDesc& d, const Tile& xt, c
   }
 }
 
-template <class StepFn>
+// BAR = 0: called by the whole CTA (__syncthreads); else the named barrier the NT calling threads use
+template <int BAR>
+__device__ __forceinline__ void tile_sync() {
+  if constexpr (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+
+template <int BAR = 0, class StepFn>
 __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __restrict__ view,
                                              const Tile& xt, unsigned char* stage, int row0,
                                              int M, StepFn step_at) {
@@ -175,7 +182,7 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
   // the env-step indices first (one coalesced load), so that the copies below are independent
   int* steps = reinterpret_cast<int*>(stage + ((size_t)(TM / rps + 2) * step_bytes + 15) / 16 * 16);
   if (L.t < nsteps) steps[L.t] = (int)step_at(j0 + L.t);
-  __syncthreads();
+  tile_sync<BAR>();
   if ((step_bytes & 3) == 0) {
     const int unit = (step_bytes & 7) == 0 ? 8 : 4;
     const int units = step_bytes / unit;
@@ -205,7 +212,7 @@ __device__ __forceinline__ void build_x_tile(const NetDesc& d, const int8_t* __r
       }
     }
   }
-  __syncthreads();
+  tile_sync<BAR>();
   const int row = row0 + L.r;
   const bool valid = row < M;
   const int a = d.mode == MAVA_IN_GLOBAL ? 0 : row % rps;

@@ -122,28 +122,30 @@ __device__ __forceinline__ void grad_epilogue(const Lane& L, uint32_t tmem_acc, 
   }
 }
 
-// One row of _actor_loss_fn (ff_mappo.py:159-180) over NO head columns (8 when the action space
-// fits, else 16): masked log-softmax, clipped ratio, entropy.  dz = d(total loss)/d(logits) * wrow.
-// exp / log are the hardware approximations (2 ulp of a bf16 forward pass is 2^-8).
-template <int NO>
+// One row of _actor_loss_fn (ff_mappo.py:159-180): masked log-softmax, clipped ratio, entropy.
+// NLD = head columns read from TMEM (8 or 16), NO = columns looked at; EXACT: NO is the action count
+// (instantiated for the action spaces of the supported envs), else columns q >= nout are skipped at
+// run time.  dz = d(total loss)/d(logits) * wrow, also accumulated into db3 (head bias gradient).
+// exp / log are the hardware approximations (the forward pass is bf16: 2^-8 relative).
+template <int NLD, int NO, bool EXACT>
 __device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, int nout, uint32_t mk,
                                                int a, float old_logp, float g, float clip_eps,
                                                float ent_coef, float wrow, float (&dz)[NHEAD],
-                                               float& l0f, float& l1f) {
-  float out[NO];
-  if constexpr (NO == 8) ld8(tmem_head, out);
+                                               float (&db3)[NHEAD], float& l0f, float& l1f) {
+  float out[NLD];
+  if constexpr (NLD == 8) ld8(tmem_head, out);
   else ld16(tmem_head, out);
   if (!valid) return;
   float mx = kF32Min;
 #pragma unroll
   for (int q = 0; q < NO; ++q) {
-    out[q] = (q < nout && ((mk >> q) & 1u)) ? out[q] : kF32Min;
-    mx = fmaxf(mx, out[q]);
+    out[q] = ((mk >> q) & 1u) ? out[q] : kF32Min;
+    if (EXACT || q < nout) mx = fmaxf(mx, out[q]);
   }
   float se = 0.0f, ex[NO];
 #pragma unroll
   for (int q = 0; q < NO; ++q) {
-    ex[q] = q < nout ? __expf(out[q] - mx) : 0.0f;
+    ex[q] = (EXACT || q < nout) ? __expf(out[q] - mx) : 0.0f;
     se += ex[q];
   }
   const float lse = mx + __logf(se), inv_se = __fdividef(1.0f, se);
@@ -163,29 +165,77 @@ __device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, i
   if (t1 < t2) dr = -g;
   else if (t1 > t2) dr = inside ? -g : 0.0f;
   else dr = -g * (0.5f + (inside ? 0.5f : 0.0f));
-  const float dla = dr * ratio;
+  const float dla = dr * ratio * wrow, ec = ent_coef * wrow;
 #pragma unroll
   for (int q = 0; q < NO; ++q) {
     float dl = dla * ((q == a ? 1.0f : 0.0f) - pr[q]);
-    dl += pr[q] != 0.0f ? ent_coef * pr[q] * (logp[q] + ent) : 0.0f;
-    dz[q] = (q < nout && ((mk >> q) & 1u)) ? dl * wrow : 0.0f;
+    dl += pr[q] != 0.0f ? ec * pr[q] * (logp[q] + ent) : 0.0f;
+    dz[q] = ((EXACT || q < nout) && ((mk >> q) & 1u)) ? dl : 0.0f;
+    db3[q] += dz[q];
   }
   l0f += -fminf(t1, t2);
   l1f += ent;
 }
 
-__global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
+// 16 epilogue warps (thread mapping of mlp_tc.cuh) + ONE MMA-issue warp.  tcgen05.mma issue blocks
+// at the execution rate of the tensor pipe (scripts/mma_rate.cu: ~68 cycles per 128x128x16 MMA plus
+// ~250 cycles from the first issue to the observed completion), so a thread that issues MMAs cannot
+// also finish rows: the issue warp waits on a named barrier for "operands ready", issues the GEMM the
+// next epilogue needs, commits, and then issues the weight-gradient GEMMs of the phase behind the
+// commit, so that they run while the epilogue warps are already working on the accumulator.
+constexpr int NT_F = NT + 32;
+constexpr int BAR_EXPAND = 1, BAR_READY = 2, BAR_EPI = 3;
+
+// epilogue side: my shared-memory / TMEM accesses of this phase are done
+__device__ __forceinline__ void epi_arrive() {
+  fence_proxy_async();
+  fence_before_sync();
+  asm volatile("bar.arrive %0, %1;" ::"n"(BAR_READY), "n"(NT_F) : "memory");
+}
+// issue side: all 512 epilogue threads have arrived
+__device__ __forceinline__ void issuer_wait() {
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR_READY), "n"(NT_F) : "memory");
+  fence_after_sync();
+}
+// barrier among the 16 epilogue warps only
+__device__ __forceinline__ void epi_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR_EPI), "n"(NT) : "memory");
+}
+// every epilogue thread polls the MMA-completion barrier itself (no CTA barrier behind it)
+__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t& phase) {
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  fence_after_sync();
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(pred));
+  return pred != 0;
+}
+
+constexpr int kPfSlots = 6;  // 6 x 384 words >= one aligned tile of 66-byte rows (32 * FR words)
+
+// two int8 (low half word) -> packed bf16 pair (exact: |x| <= 128)
+__device__ __forceinline__ uint32_t s8x2_bf16x2(uint32_t h) {
+  return pack_bf16((float)(int)(signed char)(h & 0xffu), (float)(int)(signed char)((h >> 8) & 0xffu));
+}
+
+__global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Ctrl ctrl;
   const Lane L;
   const int t = L.t, warp = L.warp, lane = L.lane;
+  // warp-uniform role (the shuffle tells the compiler so: descriptors stay in uniform registers)
+  const bool issue_warp = __shfl_sync(0xffffffffu, warp, 0) == NWARPS;
   const bool is_actor = (int)blockIdx.x < p.actor_ctas;
   const NetDesc& d = is_actor ? p.actor : p.critic;
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
   const int n_ctas = is_actor ? p.actor_ctas : p.critic_ctas;
-  const int rows_per_step = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;
-  const int M = p.R * rows_per_step;  // < 2^31 (checked by the host entry)
+  const int rps = d.mode == MAVA_IN_GLOBAL ? 1 : d.A;  // tile rows per env-step
+  const int M = p.R * rps;  // < 2^31 (checked by the host entry)
   const int n_tiles = ceil_div(M, TM);
+  const int step_bytes = d.A * d.FR;
 
   // shared memory: [weights][region: X, later H2 + dZ2][H1 (also the gather staging area)][dZ3]
   // fold mode (actor): [weights][X ping][X pong][region: H2 (later dZ1) + dZ2][H1][dZ3] -- X stays
@@ -203,24 +253,33 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   const Tile h1t{s_region + (fold ? kRegionMin : region_bytes(d.k1p)), 128u, 2048u};
   const Tile dz3t{h1t.base + tile_bytes(TM, HCOLS), 128u, 2048u};
   const Tile w1 = w1_tile(s_w, d.k1p), w2 = w2_tile(s_w, d.k1p), w3 = w3_tile(s_w, d.k1p);
-  // fold mode also prefetches: the next tile's observation rows are gathered (cp.async) into a
-  // dedicated staging buffer while this tile runs, so the two dependent HBM latencies of the
-  // gather (row index -> observation bytes) leave the critical path
+  // fold mode also prefetches: the next tile's observation rows are gathered into a dedicated
+  // staging buffer while this tile runs, so the two dependent HBM latencies of the gather (row
+  // index -> observation bytes) leave the critical path
   const bool prefetch = fold && p.prefetch_actor != 0;
-  int pf_total = 0;
   unsigned char* pf_stage = smem + (dz3t.base - s_w) + tile_bytes(TM, NHEAD);
-  auto step_at = [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); };
-  // prefetch: ONE coalesced load of the tile's env-step indices into ctrl.steps[buf] (also read by
-  // the loss epilogue), then the asynchronous copies of their observation rows
-  auto load_steps = [&](int tile_idx) -> int32_t {  // this thread's entry of a tile's index list
+
+  // Tile geometry without divisions on the per-tile path: when a tile holds whole env-steps (rps
+  // divides 128: every supported env) the step and agent of a tile row do not depend on the tile.
+  const bool aligned = (TM % rps) == 0;
+  const int spt = TM / rps;
+  const int r_j = L.r / rps, r_a = L.r - r_j * rps;
+  auto tile_span = [&](int tile_idx, int& j0, int& nsteps) {
     const int r0 = tile_idx * TM;
-    const int last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
-    const int j0 = r0 / rows_per_step;
-    const int nsteps = last / rows_per_step - j0 + 1;
+    const int rows = M - r0 < TM ? M - r0 : TM;
+    if (aligned) {
+      j0 = tile_idx * spt;
+      nsteps = rows == TM ? spt : rows / rps;
+    } else {
+      j0 = r0 / rps;
+      nsteps = (r0 + rows - 1) / rps - j0 + 1;
+    }
+  };
+  auto load_steps = [&](int tile_idx) -> int32_t {  // this thread's entry of a tile's index list
+    int j0, nsteps;
+    tile_span(tile_idx, j0, nsteps);
     return t < nsteps ? __ldg(p.rows + j0 + t) : 0;
   };
-  // the index list goes to shared memory right away; the asynchronous copies are issued later, by
-  // the twelve warps that have nothing to do during the loss epilogue
   auto publish_steps = [&](int buf, int32_t my_step) {
     if (t < TM + 2) ctrl.steps[buf][t] = my_step;
   };
@@ -228,39 +287,78 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   // observation rows of the next tile are REQUESTED (plain loads, 4 bytes per thread and slot)
   // while GEMM 1 runs and only consumed -- stored to the staging buffer and expanded into the
   // other X buffer -- during the loss epilogue, so neither the HBM latency nor the copy issue is
-  // on the tile's critical path.
-  constexpr int kPfSlots = 8;
-  uint32_t pf_reg[kPfSlots];
-  auto pf_load = [&](int tile_idx, int buf) {
-    const int r0 = tile_idx * TM;
-    const int last = (r0 + TM - 1 < M ? r0 + TM - 1 : M - 1);
-    const int j0 = r0 / rows_per_step;
-    const int nsteps = last / rows_per_step - j0 + 1;
-    const int units = (d.A * d.FR) >> 2, total = nsteps * units;
+  // on the tile's critical path.  Slot k of thread t is word u of step js of the tile, the same
+  // (js, u) for every tile.
+  // Staging layout: one padded byte row per tile row, [onehot(agent) | view bytes | 1 | 0...] of k1p
+  // bytes -- the int8 image of the X row.  Agent-id, ones and padding bytes do not depend on the
+  // tile and are written once; the prefetch only replaces the view bytes (two 16-bit stores per
+  // 32-bit word: FR is even, so a half word never straddles two rows).  The expansion is then the
+  // same for every 8-column chunk: one 8-byte load, eight conversions, one 16-byte store.
+  // Slot metadata, one register: bit 0 = the word straddles two rows, bits 1..13 = destination half
+  // word, bits 14..21 = word u of the step, bits 22..27 = step js of the tile.
+  uint32_t pf_reg[kPfSlots], pf_meta[kPfSlots];
+  const int pf_units = step_bytes >> 2;
+  const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
+  const uint32_t pf_gap = d.mode == MAVA_IN_GLOBAL ? 0u : (uint32_t)(d.k1p - d.FR) >> 1;
+  int pf_total = 0;
+  if (prefetch && !issue_warp && L.q != 0) {
 #pragma unroll
     for (int k = 0; k < kPfSlots; ++k) {
       const int idx = k * (NT - TM) + (t - TM);
-      if (idx < total) {
-        const int js = idx / units, u = idx - js * units;
-        pf_reg[k] = __ldg(reinterpret_cast<const uint32_t*>(
-                              p.view + (size_t)ctrl.steps[buf][js] * (size_t)(d.A * d.FR)) + u);
+      const int js = idx / pf_units, u = idx - js * pf_units;
+      const int sbyte = 4 * u;
+      int row = js, b0 = sbyte;
+      if (d.mode != MAVA_IN_GLOBAL) {
+        const int a0 = sbyte / d.FR;
+        b0 = sbyte - a0 * d.FR;
+        row = js * d.A + a0;
       }
+      const uint32_t dst0 = (uint32_t)(row * d.k1p + id_cols + b0) >> 1;
+      const uint32_t straddle = (d.mode != MAVA_IN_GLOBAL && b0 + 2 >= d.FR) ? 1u : 0u;
+      pf_meta[k] = straddle | (dst0 << 1) | ((uint32_t)u << 14) | ((uint32_t)js << 22);
+    }
+  }
+  auto pf_load = [&](int tile_idx, int buf) {
+    int j0, nsteps;
+    tile_span(tile_idx, j0, nsteps);
+    const int total = nsteps * pf_units;
+#pragma unroll
+    for (int k = 0; k < kPfSlots; ++k) {
+      const int idx = k * (NT - TM) + (t - TM);
+      if (idx < total)
+        pf_reg[k] = __ldg(reinterpret_cast<const uint32_t*>(
+                              p.view + (size_t)ctrl.steps[buf][pf_meta[k] >> 22] * (size_t)step_bytes) +
+                          ((pf_meta[k] >> 14) & 0xffu));
     }
     pf_total = total;
   };
   auto pf_store = [&]() {
+    const uint32_t base = smem_u32(pf_stage);
 #pragma unroll
     for (int k = 0; k < kPfSlots; ++k) {
       const int idx = k * (NT - TM) + (t - TM);
-      if (idx < pf_total) reinterpret_cast<uint32_t*>(pf_stage)[idx] = pf_reg[k];
+      if (idx < pf_total) {
+        const uint32_t h0 = (pf_meta[k] >> 1) & 0x1fffu;
+        const uint32_t h1 = h0 + 1u + (pf_meta[k] & 1u) * pf_gap;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + 2u * h0), "r"(pf_reg[k] & 0xffffu) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + 2u * h1), "r"(pf_reg[k] >> 16) : "memory");
+      }
     }
   };
-  auto issue_copies = [&](int tile_idx, int buf, int first_warp, int num_warps) {
-    const int r0 = tile_idx * TM;
-    const int j0 = r0 / rows_per_step;
-    gather_issue(d, p.view, pf_stage, r0, M,
-                 [&](int64_t jj) { return (int64_t)ctrl.steps[buf][jj - j0]; }, first_warp,
-                 num_warps);
+  // bf16 X rows of tile `tile_idx` from the padded staging rows (thread: row L.r, chunks cg0,
+  // cg0 + cg_step, ...)
+  auto expand_rows = [&](int tile_idx, const Tile& xn, int cg0, int cg_step,
+                         const unsigned char* stage) {
+    const bool valid = tile_idx * TM + L.r < M;
+    const uint32_t src = smem_u32(stage) + (uint32_t)(L.r * d.k1p);
+    const int nchunks = d.k1p >> 3;
+    for (int cg = cg0; cg < nchunks; cg += cg_step) {
+      uint32_t w0 = 0u, w1 = 0u;
+      if (valid)
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src + 8u * cg));
+      st_shared_v4(xn.base + chunk_off(xn, L.r, cg), s8x2_bf16x2(w0), s8x2_bf16x2(w0 >> 16),
+                   s8x2_bf16x2(w1), s8x2_bf16x2(w1 >> 16));
+    }
   };
 
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
@@ -282,250 +380,307 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
-  // Prefetch pipeline (fold mode): while tile i is in its loss epilogue (four warps busy), the other
-  // twelve warps expand the raw rows of tile i+1 -- copied during tile i-1 -- into the other X
-  // buffer and then start the copies of tile i+2 into the (single) staging buffer.  A tile therefore
-  // finds its X tile ready.  Prologue: tile 0 is built by everybody, tile 1's copies are started.
-  if (prefetch && cta < n_tiles) {
-    publish_steps(0, load_steps(cta));
-    if (cta + n_ctas < n_tiles) publish_steps(1, load_steps(cta + n_ctas));
-    __syncthreads();
-    issue_copies(cta, 0, 0, NWARPS);
-    gather_wait();
-    __syncthreads();
-    gather_expand(d, Tile{s_x0, 128u, 2048u}, pf_stage, cta * TM, M);
-    __syncthreads();
-  }
-  mbar_wait(&ctrl.wbar, 0);
 
   uint32_t phase = 0;
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
 #pragma unroll
   for (int q = 0; q < NHEAD; ++q) db3_acc[q] = 0.0f;
-  const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
-  bool first = true;
-  int it = 0;
-  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
-    const int row0 = tile * TM;
-    const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
-    MAVA_STAMP(0);
-#ifdef MAVA_PROFILE_PHASES
-    if (t == 0 && blockIdx.x == gridDim.x - 1 && it < 16) g_phase_clock2[128 + it] = clock64();
-#endif
-    // the next tile's env-step indices: requested now, needed after GEMM 1 has been issued
-    const bool has_next = prefetch && tile + n_ctas < n_tiles;
-    const bool has_next2 = prefetch && tile + 2 * n_ctas < n_tiles;
-    const int32_t next2_step = has_next2 ? load_steps(tile + 2 * n_ctas) : 0;
+  const bool any_tile = cta < n_tiles;
 
-    if (!prefetch) {
-      build_x_tile(d, p.view, xt, smem + (h1t.base - s_w), row0, M, step_at);
+  if (issue_warp) {
+    // ================================ MMA-issue warp ==========================================
+    mbar_wait(&ctrl.wbar, 0);
+    bool first = true;
+    int it = 0;
+    for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
+      const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
+      const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
+      issuer_wait();  // X built; the previous tile's dZ1 stored and its accumulator drained
+      if (elect_one()) {
+        // previous tile: [dW1^T | db1] += dZ1^T [X | 1] (A = dZ1 and B = X MN-major), then layer 1
+        if (fold && !first)
+          issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, nullptr);
+        issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
+      }
+      __syncwarp();
+      issuer_wait();  // H1 stored
+      if (elect_one())
+        issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
+      __syncwarp();
+      issuer_wait();  // H2 stored
+      if (elect_one())
+        issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
+      __syncwarp();
+      issuer_wait();  // dZ3 stored
+      if (elect_one()) {
+        // dH2 = dZ3 W3^T is what the next epilogue waits for; dW3 += H2^T dZ3 runs behind it
+        issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, &ctrl.mbar);
+        issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
+      }
+      __syncwarp();
+      issuer_wait();  // dZ2 stored
+      if (elect_one()) {
+        // dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1] behind it.  Without the prefetch pipeline
+        // the next tile's X is built over H2 / dZ2 / H1 (staging): a second commit tells the
+        // epilogue warps when the weight-gradient MMAs have stopped reading them.
+        issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
+        issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first,
+                   prefetch ? nullptr : &ctrl.mbar);
+      }
+      __syncwarp();
     }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    MAVA_STAMP(1);
-    // ---- forward
-    if (mma_issuer()) {
-      fence_after_sync();
-      issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
+    if (!first && fold) {
+      const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
+      issuer_wait();  // the last tile's dZ1
+      if (elect_one())
+        issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, &ctrl.mbar);
+      __syncwarp();
     }
-    MAVA_STAMP(13);
-    if (has_next2) publish_steps((it + 2) % 3, next2_step);  // read after several CTA barriers
-    if (has_next && L.q != 0) pf_load(tile + n_ctas, (it + 1) % 3);
-    MAVA_STAMP(14);
-    // loss inputs of this row: in flight during the forward pass instead of after it
-    LossIn li{};
-    if (L.q == 0) {
-      const int row = row0 + L.r;
-      li.valid = row < M;
-      const int j = li.valid ? row / rows_per_step : 0;
-      const int ag = row - j * rows_per_step;
-      const int64_t sidx = !li.valid ? 0
-                           : prefetch ? (int64_t)ctrl.steps[it % 3][j - row0 / rows_per_step]
-                                      : (int64_t)__ldg(p.rows + j);
-      li.j = j;
-      li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
-      if (li.valid) {
-        if (is_actor) {
-          li.mk = p.mask[li.flat];
-          li.act = p.action[li.flat];
-          li.f0[0] = p.old_logp[li.flat];
-          li.f1[0] = p.adv[li.flat];
+  } else {
+    // ================================ epilogue warps ==========================================
+    // Prefetch pipeline (fold mode): while tile i is in its loss epilogue (four warps busy), the
+    // other twelve warps expand the raw rows of tile i+1 -- requested during tile i's first GEMM --
+    // into the other X buffer.  Prologue: tile 0 is built by everybody.
+    if (prefetch && any_tile) {
+      publish_steps(0, load_steps(cta));
+      if (cta + n_ctas < n_tiles) publish_steps(1, load_steps(cta + n_ctas));
+      // tile-invariant bytes of the padded rows (aligned tiles: the agent of a row is r % A)
+      for (int i = t; i < TM * (d.k1p >> 2); i += NT) reinterpret_cast<uint32_t*>(pf_stage)[i] = 0u;
+      epi_sync();
+      if (t < TM) {
+        if (id_cols) pf_stage[t * d.k1p + r_a] = 1;
+        pf_stage[t * d.k1p + d.in_dim] = 1;
+      }
+      {
+        int j0, nsteps;
+        tile_span(cta, j0, nsteps);
+        const int halves = step_bytes >> 1, total = nsteps * halves;
+        for (int idx = t; idx < total; idx += NT) {
+          const int js = idx / halves, hw = idx - js * halves;
+          int row = js, b0 = 2 * hw;
+          if (d.mode != MAVA_IN_GLOBAL) {
+            const int a0 = b0 / d.FR;
+            b0 -= a0 * d.FR;
+            row = js * d.A + a0;
+          }
+          *reinterpret_cast<uint16_t*>(pf_stage + row * d.k1p + id_cols + b0) = __ldg(
+              reinterpret_cast<const uint16_t*>(p.view + (size_t)ctrl.steps[0][js] * (size_t)step_bytes) + hw);
+        }
+      }
+      epi_sync();
+      expand_rows(cta, Tile{s_x0, 128u, 2048u}, L.q, 4, pf_stage);
+      epi_sync();
+    }
+    mbar_wait(&ctrl.wbar, 0);
+    const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
+    bool first = true;
+    int32_t next_step = 0;
+    // plain path, joint-observation rows: padded staging rows in the H1 region (see below)
+    const bool padded_global = !prefetch && d.mode == MAVA_IN_GLOBAL && (step_bytes & 7) == 0 &&
+                               TM * d.k1p <= (int)tile_bytes(TM, HCOLS);
+    int it = 0, sb = 0;  // sb = it % 3: slot of ctrl.steps holding this tile's index list
+    for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it, sb = sb == 2 ? 0 : sb + 1) {
+      const int row0 = tile * TM;
+      const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
+      const int sb1 = sb == 2 ? 0 : sb + 1, sb2 = sb1 == 2 ? 0 : sb1 + 1;
+      MAVA_STAMP(0);
+#ifdef MAVA_PROFILE_PHASES
+      if (t == 0 && blockIdx.x == gridDim.x - 1 && it < 16) g_phase_clock2[128 + it] = clock64();
+#endif
+      const bool has_next = prefetch && tile + n_ctas < n_tiles;
+      const bool has_next2 = prefetch && tile + 2 * n_ctas < n_tiles;
+      // the index list of the tile after the next: requested now, published below
+      const int32_t next2_step = has_next2 ? load_steps(tile + 2 * n_ctas) : 0;
+      if (!prefetch) {
+        // the previous tile's weight-gradient MMAs still read the buffers X is built over
+        if (!first) wait_acc(&ctrl.mbar, phase);
+        unsigned char* stg = smem + (h1t.base - s_w);  // H1 is not live before layer 1
+        if (padded_global) {
+          // joint-observation rows (centralised critic): a row is one whole env-step, so the padded
+          // staging row is the step's bytes + [1 | 0...] -- asynchronous 8-byte copies straight
+          // into place, then the uniform expansion.  The index list was requested a tile ago.
+          int j0, nsteps;
+          tile_span(tile, j0, nsteps);
+          if (t < TM) ctrl.steps[0][t] = first ? load_steps(tile) : next_step;
+          epi_sync();
+          if (tile + n_ctas < n_tiles) next_step = load_steps(tile + n_ctas);
+          if (t < TM) {
+            for (int k = d.in_dim; k < d.k1p; ++k) stg[t * d.k1p + k] = k == d.in_dim ? 1 : 0;
+          }
+          const int units = step_bytes >> 3;
+          for (int js = warp; js < nsteps; js += NWARPS) {
+            const int8_t* src = p.view + (size_t)ctrl.steps[0][js] * (size_t)step_bytes;
+            const uint32_t dst = smem_u32(stg) + (uint32_t)(js * d.k1p);
+            for (int i = lane; i < units; i += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 8), "l"(src + i * 8)
+                           : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          epi_sync();
+          expand_rows(tile, xt, L.q, 4, stg);
         } else {
-          const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
+          build_x_tile<BAR_EPI>(d, p.view, xt, stg, row0, M,
+                                [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
+        }
+      }
+      epi_arrive();  // -> layer 1 (and the previous tile's first-layer gradient)
+      MAVA_STAMP(1);
+      if (has_next2) publish_steps(sb2, next2_step);
+      if (prefetch) epi_sync();  // orders the index lists (written a tile ahead of their readers)
+      if (has_next && L.q != 0) pf_load(tile + n_ctas, sb1);
+      MAVA_STAMP(14);
+      // loss inputs of this row: in flight during the forward pass instead of after it
+      LossIn li{};
+      if (L.q == 0) {
+        const int row = row0 + L.r;
+        li.valid = row < M;
+        int j, ag;
+        if (aligned) {
+          j = tile * spt + r_j;
+          ag = r_a;
+        } else {
+          j = row / rps;
+          ag = row - j * rps;
+        }
+        if (!li.valid) j = 0;
+        const int j0 = aligned ? tile * spt : row0 / rps;
+        const int64_t sidx = !li.valid ? 0
+                             : prefetch ? (int64_t)ctrl.steps[sb][j - j0]
+                                        : (int64_t)__ldg(p.rows + j);
+        li.j = j;
+        li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
+        if (li.valid) {
+          if (is_actor) {
+            li.mk = p.mask[li.flat];
+            li.act = p.action[li.flat];
+            li.f0[0] = p.old_logp[li.flat];
+            li.f1[0] = p.adv[li.flat];
+          } else {
+            const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
 #pragma unroll
-          for (int a = 0; a < kMaxReps; ++a) {
-            if (a < reps) {
-              li.f0[a] = p.old_value[li.flat + a];
-              li.f1[a] = p.targets[li.flat + a];
+            for (int a = 0; a < kMaxReps; ++a) {
+              if (a < reps) {
+                li.f0[a] = p.old_value[li.flat + a];
+                li.f1[a] = p.targets[li.flat + a];
+              }
             }
           }
         }
       }
-    }
-    MAVA_STAMP(2);
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-    MAVA_STAMP(3);
-    hidden_epilogue(L, tmem + COL_ACC, h1t);
-    MAVA_STAMP(4);
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    MAVA_STAMP(5);
-    if (mma_issuer()) {
-      fence_after_sync();
-      issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
-    }
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-    hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead: H2 replaces it
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    MAVA_STAMP(6);
-    if (mma_issuer()) {
-      fence_after_sync();
-      issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
-    }
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-    MAVA_STAMP(7);
-    // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output);
-    //      the other twelve warps start the next tile's observation copies meanwhile (the staging
-    //      buffer has been free since this tile's X was built)
-    if (L.q != 0) {
-      MAVA_STAMP2(0);
-      if (has_next) {
-        pf_store();                                     // raw rows of tile i+1 (loaded since GEMM 1)
-        asm volatile("bar.sync 1, 384;" ::: "memory");  // ... and those of the other eleven warps
-        MAVA_STAMP2(1);
-        const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-        gather_expand(d, xn, pf_stage, (tile + n_ctas) * TM, M, L.q - 1, 3);
-        MAVA_STAMP2(2);
-        fence_proxy_async();
-        MAVA_STAMP2(3);
-        MAVA_STAMP2(4);
-      }
-    } else {
-      const bool valid = li.valid;
-      float dz[NHEAD];
-#pragma unroll
-      for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
-      if (!is_actor) {
-        // _critic_loss_fn, ff_mappo.py:190-201
-        float out[8];
-        ld8(tmem + L.tmem_lane() + COL_HEAD, out);
-        if (valid) {
-          const float v = out[0];
-          const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
-          float dv = 0.0f;
-#pragma unroll
-          for (int a = 0; a < kMaxReps; ++a) {
-            if (a >= reps) break;
-            const float vo = li.f0[a], tg = li.f1[a];
-            const float diff = v - vo;
-            const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
-            const float e1 = v - tg, e2 = vc - tg;
-            const float a1 = e1 * e1, a2 = e2 * e2;
-            const bool inside = diff > -p.clip_eps && diff < p.clip_eps;
-            float g;
-            if (a1 > a2) g = e1;
-            else if (a2 > a1) g = inside ? e2 : 0.0f;
-            else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
-            dv += g;
-            l0f += 0.5f * fmaxf(a1, a2);
-          }
-          dz[0] = dv * wrow * p.vf_coef;
+      MAVA_STAMP(2);
+      // ---- forward
+      wait_acc(&ctrl.mbar, phase);
+      MAVA_STAMP(3);
+      hidden_epilogue(L, tmem + COL_ACC, h1t);
+      MAVA_STAMP(4);
+      epi_arrive();  // -> layer 2
+      MAVA_STAMP(5);
+      wait_acc(&ctrl.mbar, phase);
+      hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead (not folded): H2 replaces it
+      epi_arrive();  // -> head
+      MAVA_STAMP(6);
+      wait_acc(&ctrl.mbar, phase);
+      MAVA_STAMP(7);
+      // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output);
+      //      the other twelve warps build the next tile's X meanwhile
+      if (L.q != 0) {
+        MAVA_STAMP2(0);
+        if (has_next) {
+          pf_store();  // raw rows of tile i+1 (requested since GEMM 1)
+          asm volatile("bar.sync %0, 384;" ::"n"(BAR_EXPAND) : "memory");  // ... of all twelve warps
+          MAVA_STAMP2(1);
+          const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
+          expand_rows(tile + n_ctas, xn, L.q - 1, 3, pf_stage);
+          MAVA_STAMP2(2);
         }
       } else {
-        const int u = li.j / p.mb_size;  // replica of this minibatch position
-        const float g = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
-        if (d.out <= 8)
-          actor_loss_row<8>(tmem + L.tmem_lane() + COL_HEAD, valid, d.out, li.mk, li.act, li.f0[0],
-                            g, p.clip_eps, p.ent_coef, wrow, dz, l0f, l1f);
-        else
-          actor_loss_row<16>(tmem + L.tmem_lane() + COL_HEAD, valid, d.out, li.mk, li.act, li.f0[0],
-                             g, p.clip_eps, p.ent_coef, wrow, dz, l0f, l1f);
-      }
-      st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 0), pack_bf16(dz[0], dz[1]),
-                   pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
-      st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 1), pack_bf16(dz[8], dz[9]),
-                   pack_bf16(dz[10], dz[11]), pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
-      MAVA_STAMP(15);
-      // head bias gradient: column sums of dZ3, kept per thread across tiles (reduced at the end)
+        const bool valid = li.valid;
+        float dz[NHEAD];
 #pragma unroll
-      for (int q = 0; q < NHEAD; ++q) db3_acc[q] += dz[q];
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    MAVA_STAMP(8);
-    // ---- backward through the head: dH2 = dZ3 W3^T ; dW3 += H2^T dZ3
-    if (mma_issuer()) {
-      fence_after_sync();
-#ifdef MAVA_EARLY_COMMIT
-      issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, &ctrl.mbar);
-      issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
-#else
-      issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, nullptr);
-      issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, &ctrl.mbar);
-#endif
-    }
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-    MAVA_STAMP(9);
-    grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    MAVA_STAMP(10);
-    // ---- dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1]
-    if (mma_issuer()) {
-      fence_after_sync();
-#ifdef MAVA_EARLY_COMMIT
-      issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
-      issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, nullptr);
-#else
-      issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, nullptr);
-      issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first, &ctrl.mbar);
-#endif
-    }
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-    MAVA_STAMP(11);
-    if (fold) {
-      // dZ1 stays on chip (H2 is dead): [dW1^T | db1] += dZ1^T [X | 1], A = dZ1 and B = X MN-major.
-      // Not waited for here: the MMAs run under the next tile's gather (other X buffer, H1 as the
-      // staging area) and complete, in issue order, before that tile's second hidden epilogue
-      // writes this region again.
-      grad_epilogue<false>(L, tmem + COL_ACC, h1t, dz1t, nullptr);
-      fence_proxy_async();
-      fence_before_sync();
-      __syncthreads();
-      if (mma_issuer()) {
-        fence_after_sync();
-        issue_gemm(tmem + COL_DW1, dz1t, true, xt, true, d.k1p, TM, !first, nullptr);
+        for (int q = 0; q < NHEAD; ++q) dz[q] = 0.0f;
+        if (!is_actor) {
+          // _critic_loss_fn, ff_mappo.py:190-201
+          float out[8];
+          ld8(tmem + L.tmem_lane() + COL_HEAD, out);
+          if (valid) {
+            const float v = out[0];
+            const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
+            float dv = 0.0f;
+#pragma unroll
+            for (int a = 0; a < kMaxReps; ++a) {
+              if (a >= reps) break;
+              const float vo = li.f0[a], tg = li.f1[a];
+              const float diff = v - vo;
+              const float vc = vo + fminf(fmaxf(diff, -p.clip_eps), p.clip_eps);
+              const float e1 = v - tg, e2 = vc - tg;
+              const float a1 = e1 * e1, a2 = e2 * e2;
+              const bool inside = diff > -p.clip_eps && diff < p.clip_eps;
+              float g;
+              if (a1 > a2) g = e1;
+              else if (a2 > a1) g = inside ? e2 : 0.0f;
+              else g = 0.5f * e1 + (inside ? 0.5f * e2 : 0.0f);
+              dv += g;
+              l0f += 0.5f * fmaxf(a1, a2);
+            }
+            dz[0] = dv * wrow * p.vf_coef;
+            db3_acc[0] += dz[0];
+          }
+        } else {
+          const int u = li.j / p.mb_size;  // replica of this minibatch position
+          const float g = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
+          const uint32_t th = tmem + L.tmem_lane() + COL_HEAD;
+#define MAVA_LOSS_ARGS th, valid, d.out, li.mk, li.act, li.f0[0], g, p.clip_eps, p.ent_coef, wrow, dz, db3_acc, l0f, l1f
+          if (d.out == 5) actor_loss_row<8, 5, true>(MAVA_LOSS_ARGS);        // RobotWarehouse
+          else if (d.out == 6) actor_loss_row<8, 6, true>(MAVA_LOSS_ARGS);   // LevelBasedForaging
+          else if (d.out <= 8) actor_loss_row<8, 8, false>(MAVA_LOSS_ARGS);
+          else actor_loss_row<16, 16, false>(MAVA_LOSS_ARGS);
+#undef MAVA_LOSS_ARGS
+        }
+        st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 0), pack_bf16(dz[0], dz[1]),
+                     pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
+        st_shared_v4(dz3t.base + chunk_off(dz3t, L.r, 1), pack_bf16(dz[8], dz[9]),
+                     pack_bf16(dz[10], dz[11]), pack_bf16(dz[12], dz[13]), pack_bf16(dz[14], dz[15]));
+        MAVA_STAMP(15);
+        // (head bias gradient: column sums of dZ3, kept per thread across tiles, reduced at the end)
+      }
+      epi_arrive();  // -> backward through the head
+      MAVA_STAMP(8);
+      wait_acc(&ctrl.mbar, phase);
+      MAVA_STAMP(9);
+      grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
+      epi_arrive();  // -> dH1, dW2
+      MAVA_STAMP(10);
+      wait_acc(&ctrl.mbar, phase);
+      MAVA_STAMP(11);
+      if (fold) {
+        // dZ1 stays on chip (H2 is dead: the dW3 MMAs completed before dH1): the first-layer gradient
+        // is issued with the next tile's layer 1
+        grad_epilogue<false>(L, tmem + COL_ACC, h1t, dz1t, nullptr);
+      } else {
+        unsigned char* gdst = p.dz1_critic + (size_t)tile * tile_bytes(TM, HID);
+        if (is_actor) gdst = p.dz1_actor + (size_t)tile * tile_bytes(TM, HID);
+        const Tile gimg{0u, 128u, 2048u};
+        grad_epilogue<true>(L, tmem + COL_ACC, h1t, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
       }
       MAVA_STAMP(12);
-    } else {
-      unsigned char* gdst = p.dz1_critic + (size_t)tile * tile_bytes(TM, HID);
-      if (is_actor) gdst = p.dz1_actor + (size_t)tile * tile_bytes(TM, HID);
-      const Tile gimg{0u, 128u, 2048u};
-      grad_epilogue<true>(L, tmem + COL_ACC, h1t, gimg, gdst);  // dZ1 tile image for the wgrad1 kernel
-      fence_before_sync();
-      __syncthreads();
+    }
+    if (!first) {
+      // everything still in the tensor pipe: the last tile's weight-gradient MMAs
+      if (!prefetch) wait_acc(&ctrl.mbar, phase);  // dW2 / dW3
+      if (fold) {                                  // dW1
+        epi_arrive();
+        wait_acc(&ctrl.mbar, phase);
+      }
     }
   }
-  if (fold && !first) {  // the last tile's dW1 MMAs
-    if (mma_issuer()) commit(&ctrl.mbar);
-    wait_mma(&ctrl.mbar, phase);
-    phase ^= 1;
-  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
 
   // head bias gradient: one reduction per CTA
-  if (L.q == 0) {
+  if (!issue_warp && L.q == 0) {
 #pragma unroll
     for (int q = 0; q < NHEAD; ++q) {
       if (q < d.out) {
@@ -542,8 +697,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
   float* gb2 = gw2 + (size_t)HID * HID;
   float* gw3 = gb2 + HID;
   float* gb3 = gw3 + (size_t)HID * d.out;
-  if (!first) {
-    fence_after_sync();
+  if (any_tile && !issue_warp) {
     // dW2^T: TMEM lane = output unit n, columns = input unit k (column HID = bias gradient)
     {
       float v[32];
@@ -583,7 +737,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_fused_kernel(const TrainArgs p) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, o);
     l1 += __shfl_xor_sync(0xffffffffu, l1, o);
   }
-  if (lane == 0 && L.q == 0) {
+  if (lane == 0 && L.q == 0 && !issue_warp) {
     if (is_actor) {
       atomicAdd(p.loss_acc + 0, l0);
       atomicAdd(p.loss_acc + 1, l1);
@@ -794,9 +948,13 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
                            kRegionMin + tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
   a.fold_actor_w1 = a.actor.k1p <= 208 && smem_fold <= 227 * 1024;
   if (a.fold_actor_w1 && smem_fold > smem_fused) smem_fused = smem_fold;
-  const size_t smem_pf = smem_fold + stage_bytes(a.actor.A, a.actor.FR, a.actor.A);
-  a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && ((a.actor.A * a.actor.FR) & 3) == 0 &&
-                     (TM / a.actor.A + 2) * ((a.actor.A * a.actor.FR) >> 2) <= 8 * (NT - TM);
+  // prefetch pipeline: padded staging rows (TM x k1p bytes); whole env-steps per tile, even rows,
+  // word-sized steps, and the tile's words must fit the register slots of the twelve idle warps
+  const size_t smem_pf = smem_fold + (size_t)TM * a.actor.k1p + 16;
+  a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && (TM % a.actor.A) == 0 &&
+                     (a.actor.FR & 1) == 0 && ((a.actor.A * a.actor.FR) & 3) == 0 &&
+                     (a.actor.A * a.actor.FR) / 4 <= 255 && TM * a.actor.k1p / 2 < 8192 &&
+                     (TM / a.actor.A) * ((a.actor.A * a.actor.FR) >> 2) <= kPfSlots * (NT - TM);
   if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
   // split the SMs between actor and critic tiles in proportion to their measured cost per tile
@@ -804,8 +962,8 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   // the prefetch pipeline ~13.8 K at k1p = 80, a tile on the plain path ~13.8 K + 30 per input
   // column (22 K for the 272-wide MAPPO critic)
   {
-    const double tile_a = (a.prefetch_actor ? 11400.0 : 13800.0) + 30.0 * a.actor.k1p;
-    const double tile_c = 13800.0 + 30.0 * a.critic.k1p;
+    const double tile_a = (a.prefetch_actor ? 7700.0 : 10750.0) + 30.0 * a.actor.k1p;
+    const double tile_c = 10750.0 + 30.0 * a.critic.k1p;
     const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
     int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
     n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
@@ -828,7 +986,7 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
     if (e != cudaSuccess) return (int)e;
     conf_wg1 = smem_wg1;
   }
-  ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_fused, s>>>(a);
+  ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT_F, smem_fused, s>>>(a);
   rc = launch_status();
   if (rc) return rc;
   if (a.fold_actor_w1) {  // only the critic's first layer is left: give it every SM
