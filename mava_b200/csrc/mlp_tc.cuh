@@ -274,6 +274,78 @@ __device__ __forceinline__ void gather_expand(const NetDesc& d, const Tile& xt,
   expand_x_row(d, xt, L, mine, valid, a, cg0, cg_step);
 }
 
+// ---- padded int8 staging rows ---------------------------------------------------------------------
+// The int8 image of an X row, k1p bytes: [onehot(agent) | observation bytes | 1 | 0...].  With the
+// rows staged like this the bf16 expansion is the same for every 8-column chunk: one 8-byte load,
+// eight conversions, one 16-byte store.
+
+// two int8 (bytes 0 and 1 of h) -> packed bf16 pair, exactly, without the conversion pipe:
+// v = u7 - 128 s (u7 = low seven bits, s = sign bit); 0x4300 | u7 is the bf16 128 + u7 and
+// 0x4300 | s << 7 the bf16 128 + 128 s; their difference v has at most 8 significant bits.
+__device__ __forceinline__ uint32_t s8x2_bf16x2(uint32_t h) {
+  const uint32_t x = __byte_perm(h, 0u, 0x4140);  // [b0, 0, b1, 0]
+  uint32_t m = (x & 0x007f007fu) | 0x43004300u, c = (x & 0x00800080u) | 0x43004300u;
+  __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&m), *reinterpret_cast<__nv_bfloat162*>(&c));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Thread (row L.r) expands chunks cg0, cg0 + cg_step, ... of its padded staging row into the bf16
+// tile; rows that are not valid become zero rows.  Four chunks' loads are in flight at a time.
+__device__ __forceinline__ void expand_padded_row(const Tile& xt, const Lane& L, uint32_t stage_row,
+                                                  bool valid, int nchunks, int cg0, int cg_step) {
+  for (int cgb = cg0; cgb < nchunks; cgb += 4 * cg_step) {
+    uint32_t w[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cg = cgb + i * cg_step;
+      w[i][0] = w[i][1] = 0u;
+      if (valid && cg < nchunks)
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                     : "=r"(w[i][0]), "=r"(w[i][1])
+                     : "r"(stage_row + 8u * cg));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cg = cgb + i * cg_step;
+      if (cg < nchunks)
+        st_shared_v4(xt.base + chunk_off(xt, L.r, cg), s8x2_bf16x2(w[i][0]),
+                     s8x2_bf16x2(w[i][0] >> 16), s8x2_bf16x2(w[i][1]), s8x2_bf16x2(w[i][1] >> 16));
+    }
+  }
+}
+
+// Joint-observation rows (centralised critic: one env-step = one tile row of in_dim = A * FR bytes, a
+// multiple of 8) are staged by bulk (TMA) copies, one per row, issued by the row's thread: no
+// registers, no LSU queue, completion on an mbarrier initialised with TM arrivals -- so the gather of
+// the NEXT tile can be in flight while this tile computes.  A bulk copy needs 16-byte aligned
+// addresses and sizes and the rows are only 8-byte aligned: the copy takes the enclosing aligned
+// range, which puts the row at offset `skew` (0 or 8) of its staging slot and drags up to 16
+// foreign bytes along (they stay inside the rollout buffer: a minibatch never indexes its last time
+// slot).  Staging slot = k1p + 16 bytes; after the copy has landed the row's thread writes the
+// [1 | 0...] tail behind the observation bytes.
+__host__ __device__ inline uint32_t grow_stride(int k1p) { return (uint32_t)k1p + 16u; }
+__device__ __forceinline__ uint32_t grow_skew(const NetDesc& d, int step) {
+  return (uint32_t)(((size_t)step * (size_t)d.in_dim) & 15u);
+}
+// thread t < TM: start the copy of row t (step index `step`, ignored when !active) and arrive
+__device__ __forceinline__ void grow_issue(const NetDesc& d, const int8_t* __restrict__ view, int step,
+                                           bool active, unsigned char* stg, int row, uint64_t* bar) {
+  if (active) {
+    const uint32_t skew = grow_skew(d, step);
+    const uint32_t bytes = (skew + (uint32_t)d.in_dim + 15u) & ~15u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(stg) + (uint32_t)row * grow_stride(d.k1p),
+             view + (size_t)step * (size_t)d.in_dim - skew, bytes, bar);
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  }
+}
+// after the copies have landed: thread t < TM completes row t
+__device__ __forceinline__ void grow_tail(const NetDesc& d, unsigned char* stg, int row, int step) {
+  unsigned char* tail = stg + (size_t)row * grow_stride(d.k1p) + grow_skew(d, step) + d.in_dim;
+  for (int k = 0; k < d.k1p - d.in_dim; ++k) tail[k] = k == 0 ? 1 : 0;
+}
+
 // One thread issues the K/16 MMAs of a GEMM (M = 128) and optionally commits to `bar`.
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool a_mn, const Tile& b,
                                            bool b_mn, int N, int K, bool accumulate,

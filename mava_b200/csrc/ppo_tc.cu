@@ -18,6 +18,8 @@
 // Every activation / gradient tile is stored once in shared memory and consumed by up to three GEMMs
 // (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.  Thread
 // mapping: 512 threads per CTA, thread (row r, column quarter q) - see mlp_tc.cuh.
+#include <cstdlib>
+
 #include "mlp_tc.cuh"
 
 namespace mava {
@@ -42,18 +44,29 @@ __device__ long long g_phase_clock2[16 * 8 + 32];
   do {                                                                             \
     if (t == 128 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock2[(it - 2) * 8 + (k)] = clock64(); \
   } while (0)
+#ifdef MAVA_STAMP_CRITIC
+#define MAVA_STAMP_CTA (gridDim.x - 1)
+#else
+#define MAVA_STAMP_CTA 0
+#endif
+#define MAVA_STAMP3(k)                                                             \
+  do {                                                                             \
+    if (t == 0 && blockIdx.x == MAVA_STAMP_CTA && it >= 2 && it < 18) g_phase_clock2[(it - 2) * 8 + 3 + (k)] = clock64(); \
+  } while (0)
 #define MAVA_STAMP(k)                                                              \
   do {                                                                             \
-    if (t == 0 && blockIdx.x == 0 && it >= 2 && it < 18) g_phase_clock[(it - 2) * 16 + (k)] = clock64(); \
+    if (t == 0 && blockIdx.x == MAVA_STAMP_CTA && it >= 2 && it < 18) g_phase_clock[(it - 2) * 16 + (k)] = clock64(); \
   } while (0)
 #else
 #define MAVA_STAMP(k) do { } while (0)
 #define MAVA_STAMP2(k) do { } while (0)
+#define MAVA_STAMP3(k) do { } while (0)
 #endif
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t COL_ACC = 0, COL_HEAD = 128, COL_DW3 = 144, COL_DW2 = 160;  // dW2: 144 columns
 constexpr uint32_t COL_DW1 = 304;  // folded first-layer gradient of the actor: up to 208 columns
+constexpr uint32_t COL_ACC1 = 384;  // layer-1 accumulator of the NEXT tile when k1p <= 80 leaves room
 constexpr uint32_t kRegionMin = tile_bytes(TM, HCOLS) + tile_bytes(TM, HID);   // H2 + dZ2
 
 struct TrainArgs {
@@ -70,13 +83,14 @@ struct TrainArgs {
   int actor_ctas, critic_ctas;
   int fold_actor_w1;  // the actor's [dW1^T | db1] accumulates in TMEM inside the fused kernel
   int prefetch_actor; // fold mode: next tile's observation rows are gathered one tile ahead
+  int pipe_layer1;    // prefetch mode: next tile's layer-1 GEMM issued behind this tile's backward pass
   float *grad_actor, *grad_critic;
   double* loss_acc;
   unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
 };
 
 struct Ctrl {
-  uint64_t wbar, mbar;
+  uint64_t wbar, mbar, mbar1, gbar;  // weights landed | MMA chain | layer-1 accumulator | gathered rows
   uint32_t tmem;
   float db3[NHEAD];
   float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
@@ -216,11 +230,6 @@ __device__ __forceinline__ bool elect_one() {
 
 constexpr int kPfSlots = 6;  // 6 x 384 words >= one aligned tile of 66-byte rows (32 * FR words)
 
-// two int8 (low half word) -> packed bf16 pair (exact: |x| <= 128)
-__device__ __forceinline__ uint32_t s8x2_bf16x2(uint32_t h) {
-  return pack_bf16((float)(int)(signed char)(h & 0xffu), (float)(int)(signed char)((h >> 8) & 0xffu));
-}
-
 __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ Ctrl ctrl;
@@ -257,6 +266,10 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   // staging buffer while this tile runs, so the two dependent HBM latencies of the gather (row
   // index -> observation bytes) leave the critical path
   const bool prefetch = fold && p.prefetch_actor != 0;
+  // Layer 1 of the next tile is issued behind this tile's last backward GEMM, into its own
+  // accumulator, when TMEM has 128 columns left: a tile then starts with its layer-1 result ready.
+  const bool pipe1 = prefetch && p.pipe_layer1 != 0 && d.k1p <= (int)(COL_ACC1 - COL_DW1);
+  const uint32_t col_acc1 = pipe1 ? COL_ACC1 : COL_ACC;
   unsigned char* pf_stage = smem + (dz3t.base - s_w) + tile_bytes(TM, NHEAD);
 
   // Tile geometry without divisions on the per-tile path: when a tile holds whole env-steps (rps
@@ -351,20 +364,15 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
                          const unsigned char* stage) {
     const bool valid = tile_idx * TM + L.r < M;
     const uint32_t src = smem_u32(stage) + (uint32_t)(L.r * d.k1p);
-    const int nchunks = d.k1p >> 3;
-    for (int cg = cg0; cg < nchunks; cg += cg_step) {
-      uint32_t w0 = 0u, w1 = 0u;
-      if (valid)
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src + 8u * cg));
-      st_shared_v4(xn.base + chunk_off(xn, L.r, cg), s8x2_bf16x2(w0), s8x2_bf16x2(w0 >> 16),
-                   s8x2_bf16x2(w1), s8x2_bf16x2(w1 >> 16));
-    }
+    expand_padded_row(xn, L, src, valid, d.k1p >> 3, cg0, cg_step);
   };
 
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
     mbar_init(&ctrl.wbar, 1);
     mbar_init(&ctrl.mbar, 1);
+    mbar_init(&ctrl.mbar1, 1);
+    mbar_init(&ctrl.gbar, TM);
     fence_mbar_init();
   }
   if (t < NHEAD) ctrl.db3[t] = 0.0f;
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
 
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase1 = 0;
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
 #pragma unroll
@@ -401,7 +409,8 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         // previous tile: [dW1^T | db1] += dZ1^T [X | 1] (A = dZ1 and B = X MN-major), then layer 1
         if (fold && !first)
           issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, nullptr);
-        issue_gemm(tmem + COL_ACC, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar);
+        if (!pipe1 || first)
+          issue_gemm(tmem + col_acc1, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
       __syncwarp();
       issuer_wait();  // H1 stored
@@ -427,6 +436,8 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
         issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first,
                    prefetch ? nullptr : &ctrl.mbar);
+        if (pipe1 && tile + n_ctas < n_tiles)  // the next tile's layer 1 (its X was built in the loss phase)
+          issue_gemm(tmem + col_acc1, xprev, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
       __syncwarp();
     }
@@ -477,8 +488,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     bool first = true;
     int32_t next_step = 0;
     // plain path, joint-observation rows: padded staging rows in the H1 region (see below)
-    const bool padded_global = !prefetch && d.mode == MAVA_IN_GLOBAL && (step_bytes & 7) == 0 &&
-                               TM * d.k1p <= (int)tile_bytes(TM, HCOLS);
+    const bool padded_global = !prefetch && !fold && d.mode == MAVA_IN_GLOBAL && (step_bytes & 7) == 0 &&
+                               TM * grow_stride(d.k1p) <= tile_bytes(TM, HCOLS) &&
+                               d.k1p <= 288 && (reinterpret_cast<size_t>(p.view) & 15) == 0;
+    uint32_t gphase = 0;
+    // bulk copies are issued one lane at a time: eight rows per warp, spread over all 16 warps
+    const bool grow_thread = lane < TM / NWARPS;
+    const int grow_r = warp * (TM / NWARPS) + lane;
     int it = 0, sb = 0;  // sb = it % 3: slot of ctrl.steps holding this tile's index list
     for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it, sb = sb == 2 ? 0 : sb + 1) {
       const int row0 = tile * TM;
@@ -495,33 +511,60 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       if (!prefetch) {
         // the previous tile's weight-gradient MMAs still read the buffers X is built over
         if (!first) wait_acc(&ctrl.mbar, phase);
-        unsigned char* stg = smem + (h1t.base - s_w);  // H1 is not live before layer 1
+        MAVA_STAMP3(0);
         if (padded_global) {
-          // joint-observation rows (centralised critic): a row is one whole env-step, so the padded
-          // staging row is the step's bytes + [1 | 0...] -- asynchronous 8-byte copies straight
-          // into place, then the uniform expansion.  The index list was requested a tile ago.
+          // joint-observation rows (centralised critic): a row is one whole env-step.  Its bytes were
+          // fetched by bulk copies started during the previous tile's backward pass (first tile:
+          // here) into the H2 part of the region X is built over, so the expansion goes through
+          // registers: every thread reads its chunks, then all of them write.
+          unsigned char* gstg = smem + (h2t.base - s_w);
           int j0, nsteps;
           tile_span(tile, j0, nsteps);
-          if (t < TM) ctrl.steps[0][t] = first ? load_steps(tile) : next_step;
-          epi_sync();
-          if (tile + n_ctas < n_tiles) next_step = load_steps(tile + n_ctas);
-          if (t < TM) {
-            for (int k = d.in_dim; k < d.k1p; ++k) stg[t * d.k1p + k] = k == d.in_dim ? 1 : 0;
+          if (first && grow_thread) {
+            const int32_t st = grow_r < nsteps ? __ldg(p.rows + j0 + grow_r) : 0;
+            ctrl.steps[0][grow_r] = st;
+            grow_issue(d, p.view, st, grow_r < nsteps, gstg, grow_r, &ctrl.gbar);
           }
-          const int units = step_bytes >> 3;
-          for (int js = warp; js < nsteps; js += NWARPS) {
-            const int8_t* src = p.view + (size_t)ctrl.steps[0][js] * (size_t)step_bytes;
-            const uint32_t dst = smem_u32(stg) + (uint32_t)(js * d.k1p);
-            for (int i = lane; i < units; i += 32)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 8), "l"(src + i * 8)
-                           : "memory");
+          if (tile + n_ctas < n_tiles && grow_thread) {
+            int j0n, nstepsn;
+            tile_span(tile + n_ctas, j0n, nstepsn);
+            next_step = grow_r < nstepsn ? __ldg(p.rows + j0n + grow_r) : 0;
           }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          mbar_wait(&ctrl.gbar, gphase);
+          gphase ^= 1u;
+          MAVA_STAMP3(1);
+          if (t < nsteps) grow_tail(d, gstg, t, ctrl.steps[it & 1][t]);
           epi_sync();
-          expand_rows(tile, xt, L.q, 4, stg);
+          MAVA_STAMP3(2);
+          constexpr int kMaxChunks = 9;  // per thread: k1p <= 288
+          uint32_t w[kMaxChunks][2];
+          const bool valid = row0 + L.r < M;
+          const uint32_t src = smem_u32(gstg) + (uint32_t)L.r * grow_stride(d.k1p) +
+                               (valid ? grow_skew(d, ctrl.steps[it & 1][L.r]) : 0u);
+          const int nchunks = d.k1p >> 3;
+          // chunk residue rotated with the row so that the 8-byte loads of a half warp (rows 288 bytes
+          // apart) fall into sixteen different bank pairs
+          const int q_rot = (L.q + (L.r >> 2)) & 3;
+#pragma unroll
+          for (int i = 0; i < kMaxChunks; ++i) {
+            const int cg = q_rot + 4 * i;
+            w[i][0] = w[i][1] = 0u;
+            if (valid && cg < nchunks)
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[i][0]), "=r"(w[i][1]) : "r"(src + 8u * cg));
+          }
+          epi_sync();  // staging has been read: X may overwrite it
+          MAVA_STAMP3(3);
+#pragma unroll
+          for (int i = 0; i < kMaxChunks; ++i) {
+            const int cg = q_rot + 4 * i;
+            if (cg < nchunks)
+              st_shared_v4(xt.base + chunk_off(xt, L.r, cg), s8x2_bf16x2(w[i][0]),
+                           s8x2_bf16x2(w[i][0] >> 16), s8x2_bf16x2(w[i][1]), s8x2_bf16x2(w[i][1] >> 16));
+          }
+          MAVA_STAMP3(4);
         } else {
-          build_x_tile<BAR_EPI>(d, p.view, xt, stg, row0, M,
+          // (H1 is not live before layer 1: it doubles as the staging area)
+          build_x_tile<BAR_EPI>(d, p.view, xt, smem + (h1t.base - s_w), row0, M,
                                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
         }
       }
@@ -546,9 +589,11 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         }
         if (!li.valid) j = 0;
         const int j0 = aligned ? tile * spt : row0 / rps;
-        const int64_t sidx = !li.valid ? 0
-                             : prefetch ? (int64_t)ctrl.steps[sb][j - j0]
-                                        : (int64_t)__ldg(p.rows + j);
+        // (both staged paths keep the tile's index list in shared memory: no dependent HBM access)
+        const int64_t sidx = !li.valid      ? 0
+                             : prefetch      ? (int64_t)ctrl.steps[sb][j - j0]
+                             : padded_global ? (int64_t)ctrl.steps[it & 1][L.r]
+                                             : (int64_t)__ldg(p.rows + j);
         li.j = j;
         li.flat = sidx * d.A + (d.mode == MAVA_IN_GLOBAL ? 0 : ag);
         if (li.valid) {
@@ -571,9 +616,9 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       }
       MAVA_STAMP(2);
       // ---- forward
-      wait_acc(&ctrl.mbar, phase);
+      wait_acc(&ctrl.mbar1, phase1);
       MAVA_STAMP(3);
-      hidden_epilogue(L, tmem + COL_ACC, h1t);
+      hidden_epilogue(L, tmem + col_acc1, h1t);
       MAVA_STAMP(4);
       epi_arrive();  // -> layer 2
       MAVA_STAMP(5);
@@ -654,6 +699,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       MAVA_STAMP(10);
       wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(11);
+      if (padded_global && tile + n_ctas < n_tiles && grow_thread) {
+        // H2 is dead (dW3 completed before dH1): the next tile's rows start arriving there now
+        int j0n, nstepsn;
+        tile_span(tile + n_ctas, j0n, nstepsn);
+        ctrl.steps[(it + 1) & 1][grow_r] = next_step;
+        grow_issue(d, p.view, next_step, grow_r < nstepsn, smem + (h2t.base - s_w), grow_r, &ctrl.gbar);
+      }
       if (fold) {
         // dZ1 stays on chip (H2 is dead: the dW3 MMAs completed before dH1): the first-layer gradient
         // is issued with the next tile's layer 1
@@ -754,8 +806,9 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
 // first-layer weight gradient: [dW1^T | db1] += dZ1^T [X | 1]
 // ------------------------------------------------------------------------------------------------
 struct Wg1Ctrl {
-  uint64_t lbar, mbar;
+  uint64_t lbar[2], mbar, gbar;  // dZ1 tile images landed | MMAs done | gathered rows landed
   uint32_t tmem;
+  int32_t steps[2][TM];  // env-step index of each row of the tile being built / being fetched
 };
 
 __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
@@ -772,15 +825,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   const int n_tiles = ceil_div(M, TM);
   const unsigned char* dz1 = is_actor ? p.dz1_actor : p.dz1_critic;
 
-  // shared memory: [dZ1 tile][X tile][gather staging]
+  // shared memory: [dZ1 tile x 2][X tile][gather staging]
   const uint32_t s0 = smem_u32(smem);
-  const Tile dzt{s0, 128u, 2048u};
-  const Tile xt{s0 + tile_bytes(TM, HID), 128u, 2048u};
-  unsigned char* stage = smem + tile_bytes(TM, HID) + tile_bytes(TM, d.k1p);
+  const uint32_t dz_bytes = tile_bytes(TM, HID);
+  const Tile xt{s0 + 2 * dz_bytes, 128u, 2048u};
+  unsigned char* stage = smem + 2 * dz_bytes + tile_bytes(TM, d.k1p);
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
-    mbar_init(&ctrl.lbar, 1);
+    mbar_init(&ctrl.lbar[0], 1);
+    mbar_init(&ctrl.lbar[1], 1);
     mbar_init(&ctrl.mbar, 1);
+    mbar_init(&ctrl.gbar, TM);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -788,18 +843,65 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   const int n_lo = d.k1p > 256 ? 256 : d.k1p, n_hi = d.k1p - n_lo;
-  uint32_t phase = 0;
+  uint32_t phase = 0, gphase = 0;
   bool first = true;
-  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false) {
-    const int row0 = tile * TM;
-    if (t == 0) {
-      mbar_expect_tx(&ctrl.lbar, tile_bytes(TM, HID));
-      bulk_g2s(dzt.base, dz1 + (size_t)tile * tile_bytes(TM, HID), tile_bytes(TM, HID), &ctrl.lbar);
+  int32_t next_step = 0;
+  // one env-step per row (centralised critic): rows fetched by bulk copies one tile ahead, padded
+  // staging rows, uniform expansion (mlp_tc.cuh)
+  const bool padded_global = d.mode == MAVA_IN_GLOBAL && (d.in_dim & 7) == 0 &&
+                             (reinterpret_cast<size_t>(p.view) & 15) == 0;
+  auto load_dz1 = [&](int tile_idx, int buf) {  // one thread: tile image -> buffer `buf`
+    mbar_expect_tx(&ctrl.lbar[buf], dz_bytes);
+    bulk_g2s(s0 + (uint32_t)buf * dz_bytes, dz1 + (size_t)tile_idx * dz_bytes, dz_bytes, &ctrl.lbar[buf]);
+  };
+  // bulk copies are issued one lane at a time: eight rows per warp, spread over all 16 warps
+  const bool grow_thread = L.lane < TM / NWARPS;
+  const int grow_r = warp * (TM / NWARPS) + L.lane;
+  auto step_of = [&](int tile_idx) -> int32_t {
+    const int r = tile_idx * TM + grow_r;
+    return (grow_thread && r < M) ? __ldg(p.rows + r) : 0;
+  };
+  if (padded_global && cta < n_tiles) {
+    const int32_t st = step_of(cta);
+    if (grow_thread) {
+      ctrl.steps[0][grow_r] = st;
+      grow_issue(d, p.view, st, cta * TM + grow_r < M, stage, grow_r, &ctrl.gbar);
     }
-    build_x_tile(d, p.view, xt, stage, row0, M,
-                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
-    fence_proxy_async();
-    mbar_wait(&ctrl.lbar, phase);
+    if (t == 0) load_dz1(cta, 0);
+  }
+  int it = 0;
+  for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
+    const int row0 = tile * TM;
+    const int buf = padded_global ? (it & 1) : 0;
+    const Tile dzt{s0 + (uint32_t)buf * dz_bytes, 128u, 2048u};
+    if (padded_global) {
+      const int nxt = tile + n_ctas;
+      const bool has_next = nxt < n_tiles;
+      if (t == 0 && has_next) load_dz1(nxt, buf ^ 1);  // free: the MMAs of tile it-1 were waited for
+      if (has_next) next_step = step_of(nxt);
+      mbar_wait(&ctrl.gbar, gphase);
+      gphase ^= 1u;
+      if (t < TM && row0 + t < M) grow_tail(d, stage, t, ctrl.steps[it & 1][t]);
+      __syncthreads();
+      const bool valid = row0 + L.r < M;
+      expand_padded_row(xt, L,
+                        smem_u32(stage) + (uint32_t)L.r * grow_stride(d.k1p) +
+                            (valid ? grow_skew(d, ctrl.steps[it & 1][L.r]) : 0u),
+                        valid, d.k1p >> 3, (L.q + (L.r >> 2)) & 3, 4);  // rotation: bank spread
+      fence_proxy_async();
+      __syncthreads();  // staging has been read: the next tile's rows may land
+      if (has_next && grow_thread) {
+        ctrl.steps[(it + 1) & 1][grow_r] = next_step;
+        grow_issue(d, p.view, next_step, nxt * TM + grow_r < M, stage, grow_r, &ctrl.gbar);
+      }
+      mbar_wait(&ctrl.lbar[buf], (uint32_t)(it >> 1) & 1u);
+    } else {
+      if (t == 0) load_dz1(tile, 0);
+      build_x_tile(d, p.view, xt, stage, row0, M,
+                   [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
+      fence_proxy_async();
+      mbar_wait(&ctrl.lbar[0], phase);
+    }
     fence_before_sync();
     __syncthreads();
     if (mma_issuer()) {
@@ -956,23 +1058,30 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
                      (a.actor.A * a.actor.FR) / 4 <= 255 && TM * a.actor.k1p / 2 < 8192 &&
                      (TM / a.actor.A) * ((a.actor.A * a.actor.FR) >> 2) <= kPfSlots * (NT - TM);
   if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
+  {
+    static const int pipe_env = getenv("MAVA_NO_PIPE1") ? 0 : 1;  // development switch
+    a.pipe_layer1 = pipe_env;
+  }
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
   // split the SMs between actor and critic tiles in proportion to their measured cost per tile
   // (cycles, scripts/exp_phase_clock.sh): an actor tile with the folded first-layer gradient and
   // the prefetch pipeline ~13.8 K at k1p = 80, a tile on the plain path ~13.8 K + 30 per input
   // column (22 K for the 272-wide MAPPO critic)
   {
-    const double tile_a = (a.prefetch_actor ? 7700.0 : 10750.0) + 30.0 * a.actor.k1p;
-    const double tile_c = 10750.0 + 30.0 * a.critic.k1p;
+    const double tile_a = (a.prefetch_actor ? 7400.0 : 9050.0) + 30.0 * a.actor.k1p;
+    const double tile_c = 9050.0 + 30.0 * a.critic.k1p;
     const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
     int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
+    if (const char* ov = getenv("MAVA_ACTOR_CTAS")) n_actor = atoi(ov);  // development switch
     n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
     a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
     a.critic_ctas = (int)(tcn < sms - n_actor ? tcn : sms - n_actor);
   }
 
-  const size_t smem_wg1 = (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
-                          tile_bytes(TM, HCOLS) + 128;  // dZ1 tile, X tile, staging
+  const size_t stage_rows = (size_t)TM * grow_stride(k1p_max);
+  const size_t stage_wg1 = stage_rows > tile_bytes(TM, HCOLS) ? stage_rows : tile_bytes(TM, HCOLS);
+  const size_t smem_wg1 = 2 * (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) + stage_wg1 +
+                          128;  // two dZ1 tile images, X tile, staging
   static size_t conf_fused = 0, conf_wg1 = 0;
   if (smem_fused > conf_fused) {
     e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -I include"
-nvcc $FLAGS -DMAVA_PROFILE_PHASES -c mava_b200/csrc/ppo_tc.cu -o mava_b200/build/ppo_tc.o
+nvcc $FLAGS -DMAVA_PROFILE_PHASES $MAVA_STAMP_FLAGS -c mava_b200/csrc/ppo_tc.cu -o mava_b200/build/ppo_tc.o
 nvcc $FLAGS -DMAVA_PROFILE_PHASES -c mava_b200/csrc/rollout_tc.cu -o mava_b200/build/rollout_tc.o
 nvcc -shared -o mava_b200/libmava_b200.so mava_b200/build/*.o -lcudart
 python - <<'PY'
@@ -42,6 +42,7 @@ assert lib.mava_debug_phases2(buf2) == 0
 b = np.array(buf2[:128]).reshape(16, 8)
 print("idle-warp branch of the loss phase (warp 4): wait+bar %.0f, expand %.0f, fence+bar %.0f, issue copies %.0f" %
       tuple(np.diff(b[:, :5], axis=1).mean(0)))
+print("critic build (with -DMAVA_STAMP_CRITIC): wait dW2 -> %s" % np.diff(np.concatenate([a[:, :1], b[:, 3:8]], axis=1), axis=1).mean(0))
 c = np.array(buf2[128:144])
 print("critic tile (last CTA), start->start: %.0f cycles" % np.diff(c[2:]).mean())
 print("gemm3_done -> dz3 stored:", (a[:, 15] - a[:, 7]).mean(), " -> db3 reduced + sync:", (a[:, 8] - a[:, 15]).mean())
