@@ -90,7 +90,10 @@ struct TrainArgs {
 };
 
 struct Ctrl {
-  uint64_t wbar, mbar, mbar1, gbar;  // weights landed | MMA chain | layer-1 accumulator | gathered rows
+  // weights landed | MMA chain | layer-1 accumulator | weight-gradient MMAs drained | gathered rows.
+  // One barrier per kind of event: two commits in a row on ONE barrier would let a late thread miss
+  // a phase (the parity it waits for comes round again).
+  uint64_t wbar, mbar, mbar1, mbar2, gbar;
   uint32_t tmem;
   float db3[NHEAD];
   float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     mbar_init(&ctrl.wbar, 1);
     mbar_init(&ctrl.mbar, 1);
     mbar_init(&ctrl.mbar1, 1);
+    mbar_init(&ctrl.mbar2, 1);
     mbar_init(&ctrl.gbar, TM);
     fence_mbar_init();
   }
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
 
-  uint32_t phase = 0, phase1 = 0;
+  uint32_t phase = 0, phase1 = 0, phase2 = 0;
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
 #pragma unroll
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         // epilogue warps when the weight-gradient MMAs have stopped reading them.
         issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
         issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first,
-                   prefetch ? nullptr : &ctrl.mbar);
+                   prefetch ? nullptr : &ctrl.mbar2);
         if (pipe1 && tile + n_ctas < n_tiles)  // the next tile's layer 1 (its X was built in the loss phase)
           issue_gemm(tmem + col_acc1, xprev, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       const int32_t next2_step = has_next2 ? load_steps(tile + 2 * n_ctas) : 0;
       if (!prefetch) {
         // the previous tile's weight-gradient MMAs still read the buffers X is built over
-        if (!first) wait_acc(&ctrl.mbar, phase);
+        if (!first) wait_acc(&ctrl.mbar2, phase2);
         MAVA_STAMP3(0);
         if (padded_global) {
           // joint-observation rows (centralised critic): a row is one whole env-step.  Its bytes were
@@ -720,7 +724,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     if (!first) {
       // everything still in the tensor pipe: the last tile's weight-gradient MMAs
-      if (!prefetch) wait_acc(&ctrl.mbar, phase);  // dW2 / dW3
+      if (!prefetch) wait_acc(&ctrl.mbar2, phase2);  // dW2 / dW3
       if (fold) {                                  // dW1
         epi_arrive();
         wait_acc(&ctrl.mbar, phase);
@@ -1063,13 +1067,14 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
     a.pipe_layer1 = pipe_env;
   }
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
-  // split the SMs between actor and critic tiles in proportion to their measured cost per tile
-  // (cycles, scripts/exp_phase_clock.sh): an actor tile with the folded first-layer gradient and
-  // the prefetch pipeline ~13.8 K at k1p = 80, a tile on the plain path ~13.8 K + 30 per input
-  // column (22 K for the 272-wide MAPPO critic)
+  // split the SMs between actor and critic tiles in proportion to their cost per tile (cycles:
+  // scripts/exp_phase_clock.sh, and a sweep of the split with MAVA_ACTOR_CTAS): an actor tile with
+  // the folded first-layer gradient and the prefetch pipeline ~9.8 K at k1p = 80; a tile on the
+  // plain path ~6.4 K + 30 per input column (14.5 K for the 272-wide MAPPO critic, whose rows
+  // arrive by bulk copies)
   {
     const double tile_a = (a.prefetch_actor ? 7400.0 : 9050.0) + 30.0 * a.actor.k1p;
-    const double tile_c = 9050.0 + 30.0 * a.critic.k1p;
+    const double tile_c = 6360.0 + 30.0 * a.critic.k1p;
     const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
     int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
     if (const char* ov = getenv("MAVA_ACTOR_CTAS")) n_actor = atoi(ov);  // development switch
