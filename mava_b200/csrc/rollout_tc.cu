@@ -65,6 +65,17 @@ struct RCtrl {
   uint32_t tmem;
   int rcount;
   uint16_t rlist[TM];
+  // Speculative regeneration.  What a finished env is regenerated from is its State.key, which only
+  // deliveries change, and a regeneration is a long dependent threefry chain -- so the warps that
+  // idle during the env step generate every env's NEXT initial state ahead of time into a spare
+  // record (tagged with the key it was generated from).  A reset whose key still matches copies the
+  // spare in; otherwise (a delivery since) it regenerates on the spot as before.  Same bits either
+  // way.
+  int bgcount;              // envs whose spare is missing or stale (found while emitting rows)
+  uint16_t bglist[TM];
+  uint32_t bgkey[TM][2];    // State.key snapshot of the listed env
+  uint32_t skey[TM][2];     // key the spare of env el was generated from
+  uint8_t sok[TM];          // spare of env el is valid
 };
 
 // Staged block -> HBM: one bulk store when size and address allow it, else a CTA-wide copy.
@@ -101,6 +112,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   uint8_t* srec = smem + wi.total() + tile_bytes(TM, d.k1p) + tile_bytes(TM, HCOLS);
   uint8_t* sobs = srec + EPC * c.stride;
   float* snoise = reinterpret_cast<float*>(sobs + round_up(EPC * G * c.FR, 16));  // [2][TM][NHEAD]
+  uint8_t* sspare = reinterpret_cast<uint8_t*>(snoise + 2 * TM * NHEAD);           // [EPC][stride]
 
   const int env0 = blockIdx.x * p.epc;
   const int nenv = min(p.epc, p.num_envs - env0);
@@ -118,7 +130,9 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     mbar_init(&ctrl.rbar, 1);
     fence_mbar_init();
     ctrl.rcount = 0;
+    ctrl.bgcount = 0;
   }
+  if (t < TM) ctrl.sok[t] = 0;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -158,6 +172,17 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   make_noise(0, t, NT);
   mbar_wait(&ctrl.wbar, 0);
   mbar_wait(&ctrl.rbar, 0);
+  // every env starts without a spare
+  auto want_spare = [&]() {
+    const uint32_t* k = reinterpret_cast<const uint32_t*>(rec + c.off_key);
+    if (!ctrl.sok[el] || ctrl.skey[el][0] != k[0] || ctrl.skey[el][1] != k[1]) {
+      const int i = atomicAdd(&ctrl.bgcount, 1);
+      ctrl.bglist[i] = (uint16_t)el;
+      ctrl.bgkey[i][0] = k[0];
+      ctrl.bgkey[i][1] = k[1];
+    }
+  };
+  if (agent && g == 0) want_spare();
   __syncthreads();
 
   uint32_t phase = 0;
@@ -253,8 +278,23 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
                              p.ep_return + (size_t)step * p.num_envs,
                              p.ep_length + (size_t)step * p.num_envs, needs_reset, replay, opk);
       if (needs_reset && g == 0) ctrl.rlist[atomicAdd(&ctrl.rcount, 1)] = (uint16_t)el;
-    } else if (step + 1 < p.T) {
-      make_noise(step + 1, t - TM, NT - TM);  // warps 4..15: next step's noise
+    } else {
+      if (step + 1 < p.T) make_noise(step + 1, t - TM, NT - TM);  // warps 4..15: next step's noise
+      // ... and one spare record per warp (the list is stable during this phase; half-warp
+      // generators were tried and are slower)
+      const int i = warp - TM / 32;
+      if (i < ctrl.bgcount) {
+        const int bel = ctrl.bglist[i];
+        const Key bk{ctrl.bgkey[i][0], ctrl.bgkey[i][1]};
+        Key nk, unused;
+        split2(bk, nk, unused);
+        rware::generate<32>(c, sspare + bel * c.stride, nk, L.lane, 0xffffffffu);
+        if (L.lane == 0) {
+          ctrl.skey[bel][0] = bk.k0;
+          ctrl.skey[bel][1] = bk.k1;
+          ctrl.sok[bel] = 1;
+        }
+      }
     }
     // the previous step's observation block must have left shared memory before it is rewritten
     if (t == 0 && pending_store) rware::bulk_commit_wait_read();
@@ -264,13 +304,29 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     // ---- finished envs: one regeneration per warp at a time, all 16 warps take part
     {
       const int nreset = ctrl.rcount;
+      if (t == 0) ctrl.bgcount = 0;  // consumed in the phase above; refilled after the barrier below
       for (int i = warp; i < nreset; i += NWARPS) {
-        uint8_t* rrec = srec + (int)ctrl.rlist[i] * c.stride;
+        const int rel = (int)ctrl.rlist[i];
+        uint8_t* rrec = srec + rel * c.stride;
         const uint32_t* k = reinterpret_cast<const uint32_t*>(rrec + c.off_key);
-        Key nk, unused;
-        split2(Key{k[0], k[1]}, nk, unused);
+        const uint32_t k0 = k[0], k1 = k[1];
+        const bool hit = ctrl.sok[rel] && ctrl.skey[rel][0] == k0 && ctrl.skey[rel][1] == k1;
         __syncwarp();
-        rware::generate<32>(c, rrec, nk, L.lane, 0xffffffffu);
+        if (hit) {
+          // the inner-env part of the record: [agents | queue | request bits | step | key] and the
+          // shelf grid; the episode-metrics words in between stay
+          const uint32_t* sp = reinterpret_cast<const uint32_t*>(sspare + rel * c.stride);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(rrec);
+          for (int w = L.lane; w < (c.off_mkey >> 2); w += 32) dst[w] = sp[w];
+          for (int w = L.lane; w < c.cells_words; w += 32)
+            dst[(c.off_cells >> 2) + w] = sp[(c.off_cells >> 2) + w];
+        } else {
+          Key nk, unused;
+          split2(Key{k0, k1}, nk, unused);
+          rware::generate<32>(c, rrec, nk, L.lane, 0xffffffffu);
+        }
+        __syncwarp();
+        if (L.lane == 0) ctrl.sok[rel] = 0;
       }
     }
     __syncthreads();
@@ -280,6 +336,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     if (agent) {
       mk = rware::emit_row<G, R>(c, rec, g, sobs + L.r * c.FR, L.r & 1, replay, opk);
       p.mask[(size_t)(step + 1) * ea_slot + (size_t)env * G + g] = (uint8_t)mk;
+      if (g == 0) want_spare();
     }
     fence_proxy_async();
     __syncthreads();
@@ -306,7 +363,8 @@ int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
   constexpr int EPC = TM / G;
   const size_t smem = (size_t)WImage{a.actor.k1p}.total() + tile_bytes(TM, a.actor.k1p) +
                       tile_bytes(TM, HCOLS) + (size_t)EPC * a.c.stride +
-                      (size_t)round_up(EPC * G * a.c.FR, 16) + 2 * TM * NHEAD * 4 + 128;
+                      (size_t)round_up(EPC * G * a.c.FR, 16) + 2 * TM * NHEAD * 4 +
+                      (size_t)EPC * a.c.stride + 128;  // ... noise, spare records
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rware_rollout_kernel<G, 1>,
