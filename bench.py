@@ -187,7 +187,7 @@ def run_ours(args) -> None:
 
     from mava_b200.systems.ppo import _runner
     from mava_b200.utils import make_env
-    from mava_b200.utils.logger import get_final_step_metrics
+    from mava_b200.systems.ppo.anakin import episode_summary
 
     device = _runner.init_distributed()
     rank = int(os.environ.get("RANK", "0"))
@@ -238,12 +238,9 @@ def run_ours(args) -> None:
     host_opt[: L.params.numel()].copy_(L.mu)
     host_opt[L.params.numel():].copy_(L.nu)
     host_key.copy_(L.key)
-    pin = {k: torch.empty(1, L.U, L.T, L.E, dtype=dt).pin_memory() for k, dt in
-           (("episode_return", torch.float32), ("episode_length", torch.int32),
-            ("is_terminal_step", torch.bool))}
     pin_loss = torch.empty(4, 1, L.epochs, L.nmb).pin_memory()
     h2d = (host_params.numel() + host_opt.numel()) * 4 + 8
-    d2h = sum(v.numel() * v.element_size() for v in pin.values()) + pin_loss.numel() * 4
+    d2h = 10 * 8 + pin_loss.numel() * 4  # finished-episode statistics (device reduction) + losses
     def e2e_step():
         # host -> device: the replicated learner inputs (params, optimiser moments, key)
         L.params.copy_(host_params, non_blocking=True)
@@ -251,17 +248,16 @@ def run_ours(args) -> None:
         L.nu.copy_(host_opt[L.params.numel():], non_blocking=True)
         L.key.copy_(host_key, non_blocking=True)
         out = learn(state)
-        # device -> host: what run_experiment consumes (episode + train metrics), then params back
-        for k2, buf in pin.items():
-            buf.copy_(out.episode_metrics[k2], non_blocking=True)
+        # device -> host: what run_experiment consumes (episode statistics + train metrics), then the
+        # parameters back
         for i, k2 in enumerate(("total_loss", "value_loss", "actor_loss", "entropy")):
             pin_loss[i].copy_(out.train_metrics[k2], non_blocking=True)
         host_params.copy_(L.params, non_blocking=True)
         host_opt[: L.params.numel()].copy_(L.mu, non_blocking=True)
         host_opt[L.params.numel():].copy_(L.nu, non_blocking=True)
         host_key.copy_(L.key, non_blocking=True)
+        episode_summary(L)  # 80 bytes, synchronises the stream
         torch.cuda.synchronize(device)
-        get_final_step_metrics({k2: v for k2, v in pin.items()})
 
     for _ in range(3):  # warm-up of the host path (first pinned copies, allocator, metric code)
         e2e_step()

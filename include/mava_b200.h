@@ -171,6 +171,18 @@ typedef struct mava_ppo_hyper {
   float clip_eps, ent_coef, vf_coef;
 } mava_ppo_hyper;
 
+/* Episode metrics of the finished episodes, reduced on the device.
+ * Replaces get_final_step_metrics (mava/wrappers/episode_metrics.py:114-132) followed by the
+ * logger's describe() (mava/utils/logger.py:44-58: mean / std / min / max) for the run loop
+ * (mava/systems/ppo/ff_mappo.py:499-505): instead of moving the three [T][NE] arrays of
+ * ExperimentOutput.episode_metrics to the host, the loop moves stats[10] (f64):
+ *   {count, sum_return, sumsq_return, min_return, max_return,
+ *    sum_length, sumsq_length, min_length, max_length, 0}
+ * over the n env-steps with done != 0.  reset != 0 re-initialises stats first; otherwise the
+ * call accumulates (one call per update of an evaluation interval). */
+int mava_episode_stats(const uint8_t* done, const float* ep_return, const int32_t* ep_length,
+                       int64_t n, int reset, double* stats, mava_stream_t s);
+
 /* Row index list of one minibatch from a permutation (ff_mappo.py:272-280): for replica u and
  * position j, rows[u*mb + j] = t*NE + u*E + e with (t,e) = divmod(perm[mb_index*mb + j], E). */
 int mava_ppo_minibatch_rows(const int32_t* perm, int mb_index, int mb_size, int num_replicas,

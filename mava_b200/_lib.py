@@ -75,6 +75,7 @@ SIGNATURES = {
     "mava_ff_value": (c_int, [P(MlpDesc), c_void, c_void, c_int, c_void, c_void]),
     "mava_gae": (c_int, [c_void] * 5 + [c_f32, c_f32, c_int, c_int, c_int, c_int, c_void, c_void,
                                         c_void]),
+    "mava_episode_stats": (c_int, [c_void, c_void, c_void, c_i64, c_int, c_void, c_void]),
     "mava_ppo_minibatch_rows": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
     "mava_ppo_workspace_bytes": (c_i64, [P(MlpDesc), P(MlpDesc), c_int]),
     "mava_ppo_loss_grad": (c_int, [P(MlpDesc), c_void, P(MlpDesc), c_void, P(PpoHyper)] +

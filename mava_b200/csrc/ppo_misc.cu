@@ -193,6 +193,82 @@ __global__ void __launch_bounds__(256) clip_adam_pair_kernel(const AdamPairArgs 
   }
 }
 
+
+// get_final_step_metrics (mava/wrappers/episode_metrics.py:114-132) + describe()
+// (mava/utils/logger.py:44-58) on the device: count, sum, sum of squares, min and max of the return
+// and the length of the episodes that END in this block of env-steps, accumulated into
+// stats[10] = {count, sum_r, sumsq_r, min_r, max_r, sum_l, sumsq_l, min_l, max_l, unused}.
+// The run loop then moves 80 bytes to the host instead of three [T][NE] arrays.
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) > v) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) < v) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+episode_stats_kernel(const uint8_t* __restrict__ done, const float* __restrict__ ep_return,
+                     const int32_t* __restrict__ ep_length, int64_t n, double* __restrict__ stats) {
+  // per-thread partial sums in fp32 would lose the small returns of long runs: the terminal steps
+  // are few (one per episode), so fp64 only runs on them
+  double cnt = 0.0, sr = 0.0, qr = 0.0, sl = 0.0, ql = 0.0;
+  float mnr = INFINITY, mxr = -INFINITY, mnl = INFINITY, mxl = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (__ldg(done + i)) {
+      const float r = __ldg(ep_return + i), l = (float)__ldg(ep_length + i);
+      cnt += 1.0;
+      sr += (double)r;
+      qr += (double)r * (double)r;
+      sl += (double)l;
+      ql += (double)l * (double)l;
+      mnr = fminf(mnr, r);
+      mxr = fmaxf(mxr, r);
+      mnl = fminf(mnl, l);
+      mxl = fmaxf(mxl, l);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    qr += __shfl_xor_sync(0xffffffffu, qr, o);
+    sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    ql += __shfl_xor_sync(0xffffffffu, ql, o);
+    mnr = fminf(mnr, __shfl_xor_sync(0xffffffffu, mnr, o));
+    mxr = fmaxf(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
+    mnl = fminf(mnl, __shfl_xor_sync(0xffffffffu, mnl, o));
+    mxl = fmaxf(mxl, __shfl_xor_sync(0xffffffffu, mxl, o));
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+    atomicAdd(stats + 0, cnt);
+    atomicAdd(stats + 1, sr);
+    atomicAdd(stats + 2, qr);
+    atomic_min_f64(stats + 3, (double)mnr);
+    atomic_max_f64(stats + 4, (double)mxr);
+    atomicAdd(stats + 5, sl);
+    atomicAdd(stats + 6, ql);
+    atomic_min_f64(stats + 7, (double)mnl);
+    atomic_max_f64(stats + 8, (double)mxl);
+  }
+}
+
+__global__ void episode_stats_init_kernel(double* stats) {
+  const int i = threadIdx.x;
+  if (i < 10) stats[i] = (i == 3 || i == 7) ? INFINITY : (i == 4 || i == 8) ? -INFINITY : 0.0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -267,6 +343,21 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
   MAVA_CHECK_ARG(n > 0 && steps_per_update > 0);
   clip_adam_kernel<<<1, 1024, 0, as_stream(s)>>>(params, mu, nu, count, grad, n, grad_scale, lr,
                                                  max_norm, lr_decay_num_updates, steps_per_update);
+  return launch_status();
+}
+
+int mava_episode_stats(const uint8_t* done, const float* ep_return, const int32_t* ep_length,
+                       int64_t n, int reset, double* stats, mava_stream_t s) {
+  MAVA_CHECK_PTR(stats);
+  MAVA_CHECK_ARG(n >= 0);
+  if (reset) episode_stats_init_kernel<<<1, 32, 0, as_stream(s)>>>(stats);
+  if (n > 0) {
+    MAVA_CHECK_PTR(done);
+    MAVA_CHECK_PTR(ep_return);
+    MAVA_CHECK_PTR(ep_length);
+    const int blocks = (int)min((int64_t)4 * sm_count(), ceil_div64(n, 256));
+    episode_stats_kernel<<<blocks, 256, 0, as_stream(s)>>>(done, ep_return, ep_length, n, stats);
+  }
   return launch_status();
 }
 

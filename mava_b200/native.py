@@ -224,6 +224,15 @@ def gae(reward, value, done, last_val, gamma: float, gae_lambda: float, T: int, 
         _p(targets, torch.float32, n, "targets"), _stream()), "mava_gae")
 
 
+def episode_stats(done, ep_return, ep_length, n: int, reset: bool, stats) -> None:
+    """Accumulate the finished-episode statistics of n env-steps into stats[10] (float64)."""
+    _count(1 + int(reset))
+    check(_lib.load().mava_episode_stats(
+        _p(done, torch.uint8, n, "done"), _p(ep_return, torch.float32, n, "ep_return"),
+        _p(ep_length, torch.int32, n, "ep_length"), n, int(reset),
+        _p(stats, torch.float64, 10, "stats"), _stream()), "mava_episode_stats")
+
+
 def ppo_minibatch_rows(perm, mb_index: int, mb_size: int, num_replicas: int, envs_per_replica: int,
                        rows) -> None:
     _count(1)

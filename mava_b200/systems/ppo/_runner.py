@@ -16,7 +16,7 @@ from ...evaluator import get_eval_fn
 from ...utils import make_env as environments
 from ...utils.logger import LogEvent, MavaLogger, get_final_step_metrics
 from ...utils.total_timestep_checker import check_total_timesteps
-from .anakin import world
+from .anakin import episode_summary, world
 
 
 def init_distributed() -> torch.device:
@@ -81,11 +81,14 @@ def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
         elapsed_time = time.time() - start_time
 
         t = int(steps_per_rollout * (eval_step + 1))
-        episode_metrics, ep_completed = get_final_step_metrics(learner_output.episode_metrics)
-        episode_metrics["steps_per_second"] = torch.tensor(steps_per_rollout / elapsed_time)
+        # the finished-episode statistics were reduced on the device (mava_episode_stats): 80 bytes
+        # cross the bus instead of ExperimentOutput.episode_metrics (three [updates][T][envs] arrays,
+        # still returned for callers that want them -- get_final_step_metrics works on them)
+        summary, ep_completed = episode_summary(learner)
         logger.log({"timestep": t}, t, eval_step, LogEvent.MISC)
         if ep_completed:
-            logger.log(episode_metrics, t, eval_step, LogEvent.ACT)
+            logger.log_summary(summary, {"steps_per_second": steps_per_rollout / elapsed_time}, t,
+                               eval_step, LogEvent.ACT)
         logger.log(learner_output.train_metrics, t, eval_step, LogEvent.TRAIN)
 
         ks = prng.split(key_e, n_devices + 1)

@@ -84,6 +84,9 @@ class FFLearner:
         self.ep_ret = z(T, NE)
         self.ep_len = z(T, NE, dtype=torch.int32)
         self.adv, self.targets = z(T, NE, A), z(T, NE, A)
+        # finished-episode statistics of the current learn() call, reduced on the device
+        self.ep_stats = z(10, dtype=torch.float64)
+        self._stats_host = None
         # scratch
         self.policy_keys = z(T, 2, dtype=torch.uint32)
         self.key3 = z(3, 2, dtype=torch.uint32)
@@ -148,11 +151,15 @@ class FFLearner:
         opt = OptStates({"mu": self.mu[:na], "nu": self.nu[:na], "count": self.counts[0:1]},
                         {"mu": self.mu[na:], "nu": self.nu[na:], "count": self.counts[1:2]})
         env_state = EnvState(self.env_buf, self.view[0], self.mask[0])
-        steps = self.env.step_count(env_state)
-        obs = self.env.decode_observation(self.view[0], self.mask[0], steps)
-        ts = TimeStep(torch.full((self.NE,), StepType.MID, dtype=torch.int8, device=self.device),
-                      self.reward[-1], torch.ones(self.NE, self.A, device=self.device), obs, {})
-        return LearnerState(params, opt, self.key, env_state, ts)
+
+        def make_timestep() -> TimeStep:
+            steps = self.env.step_count(env_state)
+            obs = self.env.decode_observation(self.view[0], self.mask[0], steps)
+            return TimeStep(
+                torch.full((self.NE,), StepType.MID, dtype=torch.int8, device=self.device),
+                self.reward[-1], torch.ones(self.NE, self.A, device=self.device), obs, {})
+
+        return LearnerState(params, opt, self.key, env_state, LazyTimeStep(make_timestep))
 
     # -- kernels --------------------------------------------------------------------------------
     def _rollout(self) -> None:
@@ -276,6 +283,8 @@ class FFLearner:
         native.gae(self.reward, self.value, self.done, self.last_val, float(self.config.system.gamma),
                    float(self.config.system.gae_lambda), self.T, self.NE, self.A, self.adv,
                    self.targets)
+        native.episode_stats(self.done, self.ep_ret, self.ep_len, self.T * self.NE, False,
+                             self.ep_stats)
         main.wait_stream(self._side)
         self._update_epochs(perms)
         self.view[0].copy_(self.view[self.T])
@@ -321,27 +330,82 @@ class FFLearner:
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
         dev, T, NE = self.device, self.T, self.NE
-        ep_ret = torch.empty(num_updates, T, NE, device=dev)
-        ep_len = torch.empty(num_updates, T, NE, dtype=torch.int32, device=dev)
-        term = torch.empty(num_updates, T, NE, dtype=torch.bool, device=dev)
-        losses = torch.empty(num_updates, self.epochs, self.nmb, 5, device=dev)
         if self.use_graph and self._graph is None:
             self._capture()
+        native.episode_stats(None, None, None, 0, True, self.ep_stats)  # re-initialise
+        single = num_updates == 1  # the rollout buffers themselves are the metrics: no copies
+        if not single:
+            ep_ret = torch.empty(num_updates, T, NE, device=dev)
+            ep_len = torch.empty(num_updates, T, NE, dtype=torch.int32, device=dev)
+            term = torch.empty(num_updates, T, NE, dtype=torch.bool, device=dev)
+            losses = torch.empty(num_updates, self.epochs, self.nmb, 5, device=dev)
         for u in range(num_updates):
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._update_step()
-            ep_ret[u].copy_(self.ep_ret)
-            ep_len[u].copy_(self.ep_len)
-            term[u].copy_(self.done)
-            losses[u].copy_(self.loss_buf)
+            if not single:
+                ep_ret[u].copy_(self.ep_ret)
+                ep_len[u].copy_(self.ep_len)
+                term[u].copy_(self.done)
+                losses[u].copy_(self.loss_buf)
+        if single:
+            ep_ret, ep_len = self.ep_ret.unsqueeze(0), self.ep_len.unsqueeze(0)
+            term, losses = self.done.view(torch.bool).unsqueeze(0), self.loss_buf.unsqueeze(0)
         shape = lambda x: x.reshape(num_updates, T, self.U, self.E).permute(0, 2, 1, 3)
         episode_metrics = {"episode_return": shape(ep_ret), "episode_length": shape(ep_len),
                            "is_terminal_step": shape(term)}
         train_metrics = {"total_loss": losses[..., 0] + losses[..., 3], "value_loss": losses[..., 4],
                          "actor_loss": losses[..., 1], "entropy": losses[..., 2]}
         return episode_metrics, train_metrics
+
+
+def episode_summary(learner) -> Tuple[Dict[str, Dict[str, float]], bool]:
+    """What the run loop logs about finished episodes (get_final_step_metrics + the logger's
+    describe(), mava/wrappers/episode_metrics.py:114-132, mava/utils/logger.py:44-58) from the
+    80-byte device reduction of the last learn() call: {metric: {mean, std, min, max}}, and whether
+    any episode finished."""
+    if learner._stats_host is None:
+        learner._stats_host = torch.zeros(10, dtype=torch.float64).pin_memory()
+    learner._stats_host.copy_(learner.ep_stats, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    n, sr, qr, mnr, mxr, sl, ql, mnl, mxl, _ = learner._stats_host.tolist()
+    if n == 0:
+        zero = {"mean": 0.0, "std": 0.0, "min": 0.0, "max": 0.0}
+        return {"episode_return": dict(zero), "episode_length": dict(zero)}, False
+
+    def desc(s1, s2, mn, mx):
+        mean = s1 / n
+        return {"mean": mean, "std": math.sqrt(max(s2 / n - mean * mean, 0.0)), "min": mn, "max": mx}
+
+    return {"episode_return": desc(sr, qr, mnr, mxr), "episode_length": desc(sl, ql, mnl, mxl),
+            "count": n}, True
+
+
+class LazyTimeStep:
+    """The TimeStep of a learner state, decoded from the packed device buffers on first access.
+    The run loop only threads the state back into ``learn`` (ff_mappo.py:497-536), so the float32
+    observation tensors of the reference layout are normally never built."""
+
+    def __init__(self, make):
+        self._make, self._ts = make, None
+
+    def _get(self) -> TimeStep:
+        if self._ts is None:
+            self._ts = self._make()
+        return self._ts
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def last(self):
+        return self._get().last()
 
 
 def get_learner_fn(learner: FFLearner, config):

@@ -104,6 +104,8 @@ class RecLearner:
         self.logp, self.value, self.reward = z(T, NE, A), z(T, NE, A), z(T, NE, A)
         self.ep_ret = z(T, NE)
         self.ep_len = z(T, NE, dtype=torch.int32)
+        self.ep_stats = z(10, dtype=torch.float64)  # finished-episode statistics (device reduction)
+        self._stats_host = None
         self.last_val = z(NE, A)
         self.adv, self.targets = z(T, NE, A), z(T, NE, A)
         self.hs_actor = z(self.nc, NE * A, self.H)
@@ -253,6 +255,9 @@ class RecLearner:
         """One ``_update_step`` of the reference (rec_mappo.py:68-402) for all U replicas."""
         n0 = native.LAUNCHES
         self._rollout()
+        # is_terminal_step of transition t is the flag entering step t + 1
+        native.episode_stats(self.done_in[1:], self.ep_ret, self.ep_len, self.T * self.NE, False,
+                             self.ep_stats)
         native.gae(self.reward, self.value, self.done_in, self.last_val,
                    float(self.config.system.gamma), float(self.config.system.gae_lambda), self.T,
                    self.NE, self.A, self.adv, self.targets, last_done=self.done_in[self.T])
@@ -312,6 +317,7 @@ class RecLearner:
         losses = torch.empty(num_updates, self.epochs, self.nmb, 5, device=dev)
         if self.use_graph and self._graph is None:
             self._capture()
+        native.episode_stats(None, None, None, 0, True, self.ep_stats)  # re-initialise
         for u in range(num_updates):
             if self._graph is not None:
                 self._graph.replay()

@@ -61,6 +61,9 @@ class MavaLogger:
             for k, v in metrics.items():
                 for stat, val in describe(v).items():
                     flat[f"{k}/{stat}" if v.size > 1 else k] = val
+        self._emit(flat, t, t_eval, event)
+
+    def _emit(self, flat: Dict[str, float], t: int, t_eval: int, event: LogEvent) -> None:
         if self.cfg.use_console:
             body = " | ".join(f"{k.replace('_', ' ').capitalize()}: {v:.3f}" for k, v in
                               flat.items() if k.endswith("mean") or "/" not in k)
@@ -68,6 +71,20 @@ class MavaLogger:
         if self._json is not None:
             self._json.write(json.dumps({"event": event.value, "t": t, "eval": t_eval, **flat}) + "\n")
             self._json.flush()
+
+    def log_summary(self, summary: Dict[str, Dict[str, float]], scalars: Dict[str, float], t: int,
+                    t_eval: int, event: LogEvent) -> None:
+        """Log metrics that arrive already described ({name: {mean, std, min, max}}, the device-side
+        reduction of the finished episodes) next to plain scalars; same keys as ``log``."""
+        if self.rank != 0:
+            return
+        flat = {}
+        for k, v in summary.items():
+            if isinstance(v, dict):
+                for stat, val in v.items():
+                    flat[f"{k}/{stat}"] = float(val)
+        flat.update({k: float(v) for k, v in scalars.items()})
+        self._emit(flat, t, t_eval, event)
 
     def stop(self) -> None:
         if self._json is not None:

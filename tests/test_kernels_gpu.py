@@ -155,3 +155,39 @@ def test_sort_by_key_matches_stable_sort(lib_built, n):
     order = torch.sort(keys, stable=True).indices
     assert int(ovf.item()) == 0
     assert torch.equal(out, vals[order])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p_done", [(1, 1.0), (1000, 0.0), (4096, 0.05), (262144, 0.3)])
+def test_episode_stats_matches_get_final_step_metrics(lib_built, n, p_done):
+    """mava_episode_stats against get_final_step_metrics + describe() on the same arrays
+    (mava/wrappers/episode_metrics.py:114-132, mava/utils/logger.py:44-58): counts and min / max
+    exact, sums to fp64 round-off; empty selections leave the initial values."""
+    import numpy as np
+
+    from mava_b200 import native
+
+    rng = np.random.default_rng(n)
+    done = (rng.random(n) < p_done).astype(np.uint8)
+    ret = rng.normal(size=n).astype(np.float32) * 3
+    length = rng.integers(1, 500, size=n).astype(np.int32)
+    stats = torch.zeros(10, dtype=torch.float64, device="cuda")
+    dev = lambda x: torch.from_numpy(x).cuda()
+    native.episode_stats(None, None, None, 0, True, stats)
+    half = n // 2  # two accumulating calls, like two updates of one evaluation interval
+    d, r, l = dev(done), dev(ret), dev(length)
+    if half:
+        native.episode_stats(d[:half].contiguous(), r[:half].contiguous(), l[:half].contiguous(), half,
+                             False, stats)
+    native.episode_stats(d[half:].contiguous(), r[half:].contiguous(), l[half:].contiguous(), n - half,
+                         False, stats)
+    got = stats.cpu().numpy()
+    sel = done.astype(bool)
+    assert got[0] == sel.sum()
+    if sel.any():
+        rs, ls = ret[sel].astype(np.float64), length[sel].astype(np.float64)
+        np.testing.assert_allclose(got[1:3], [rs.sum(), (rs * rs).sum()], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(got[5:7], [ls.sum(), (ls * ls).sum()], rtol=1e-12)
+        assert got[3] == rs.min() and got[4] == rs.max() and got[7] == ls.min() and got[8] == ls.max()
+    else:
+        assert got[1] == 0 and np.isposinf(got[3]) and np.isneginf(got[4])

@@ -220,6 +220,22 @@ def test_one_update_matches_oracle(lib_built, system, use_graph, precision):
     em = out.episode_metrics
     assert em["episode_return"].shape == (1, U, T, E)
     assert bool(em["is_terminal_step"].any())
+    # the device-side reduction the run loop logs == get_final_step_metrics + describe() on the
+    # reference-shaped arrays (episode_metrics.py:114-132, logger.py:44-58)
+    from mava_b200.systems.ppo.anakin import episode_summary
+    from mava_b200.utils.logger import describe, get_final_step_metrics
+
+    summary, completed = episode_summary(L)
+    final, completed_ref = get_final_step_metrics(em)
+    assert completed and completed_ref
+    for key in ("episode_return", "episode_length"):
+        ref = describe(final[key].float().cpu().numpy().astype(np.float64))
+        for stat in ("mean", "std", "min", "max"):
+            np.testing.assert_allclose(summary[key][stat], ref[stat], rtol=1e-6, atol=1e-6)
+    assert summary["count"] == int(em["is_terminal_step"].sum())
+    # the lazily decoded TimeStep of the returned state is the reference-shaped observation
+    ts = out.learner_state.timestep
+    assert ts.observation.agents_view.shape[:2] == (L.NE, L.A) and ts.reward.shape == (L.NE, L.A)
 
 
 def test_run_experiment_smoke(lib_built):
