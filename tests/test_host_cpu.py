@@ -153,3 +153,29 @@ def test_two_rank_gloo_partitioning(tmp_path):
                         "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
                         "29611", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_checkpoint_roundtrip_flax_naming(tmp_path):
+    """Parameters leave and re-enter through the reference's pytree naming in both containers
+    (npz, flax msgpack wire format) bit for bit."""
+    from mava_b200.networks import (DiscreteActionHead, FeedForwardActor, FeedForwardValueNet,
+                                    MLPTorso)
+    from mava_b200.utils import checkpointing as ck
+
+    actor = FeedForwardActor(MLPTorso([128, 128]), DiscreteActionHead(5))
+    critic = FeedForwardValueNet(MLPTorso([128, 128]), centralised_critic=True)
+    key = np.array([0, 42], np.uint32)
+    ap, cp = actor.init(key, 70), critic.init(key, 264)
+    opt = {"actor_opt_state": {"mu": ap * 0, "nu": ap * 0, "count": np.int32(3)}}
+    tree = ck.learner_tree(actor, critic, ap, cp, 70, 264, opt)
+    names = set(ck.flatten_tree(tree))
+    assert "learner_state/params/actor_params/params/torso/Dense_0/kernel" in names
+    assert "learner_state/params/critic_params/params/torso/Dense_1/bias" in names
+    for ext in ("npz", "msgpack"):
+        path = str(tmp_path / f"ckpt.{ext}")
+        ck.save(path, tree)
+        back = ck.load(path)
+        ap2, cp2 = ck.restore_params(back, actor, critic)
+        np.testing.assert_array_equal(ap2, ap)
+        np.testing.assert_array_equal(cp2, cp)
+        assert int(back["learner_state"]["opt_states"]["actor_opt_state"]["count"]) == 3
