@@ -219,6 +219,16 @@ int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, co
                         float lr_critic, float max_norm, int lr_decay_num_updates,
                         int steps_per_update, mava_stream_t s);
 
+/* Same step for networks that also live as packed bf16 operand images (mava_mlp_pack_bf16): the
+ * thread that updates a parameter refreshes its bf16 copy, so no packing launch follows the
+ * optimiser (optax.apply_updates, ff_mappo.py:243-250, then the next minibatch's forward pass).
+ * Both networks must be [128, 128] torsos; the images must have been packed once before. */
+int mava_clip_adam_pair_pack(float* params, float* mu, float* nu, int32_t* counts, const float* grad,
+                             const mava_mlp_desc* actor, void* actor_image,
+                             const mava_mlp_desc* critic, void* critic_image, float grad_scale,
+                             float lr_actor, float lr_critic, float max_norm,
+                             int lr_decay_num_updates, int steps_per_update, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMEM).  Same regions as mava_ff_act / mava_ppo_loss_grad with
  * bf16 operands and fp32 accumulation (tolerance 2e-2, BASELINE.json).  Requires h1 == h2 == 128.

@@ -82,6 +82,9 @@ SIGNATURES = {
                            [c_void] * 8 + [c_int, c_int, c_void, c_void, c_void]),
     "mava_clip_adam_pair": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_f32,
                                     c_f32, c_f32, c_f32, c_int, c_int, c_void]),
+    "mava_clip_adam_pair_pack": (c_int, [c_void, c_void, c_void, c_void, c_void, P(MlpDesc), c_void,
+                                         P(MlpDesc), c_void, c_f32, c_f32, c_f32, c_f32, c_int,
+                                         c_int, c_void]),
     "mava_mlp_pack_bytes": (c_i64, [P(MlpDesc)]),
     "mava_mlp_pack_bf16": (c_int, [P(MlpDesc), c_void, c_void, c_void]),
     "mava_ff_act_bf16": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void, c_void,

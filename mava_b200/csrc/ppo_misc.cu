@@ -1,5 +1,6 @@
 // GAE reverse scan, minibatch row lists and the fused clip-by-global-norm + Adam step.
 #include "common.cuh"
+#include "mlp_tc.cuh"  // layout of the packed bf16 weight images (clip_adam_pair_pack)
 
 using namespace mava;
 
@@ -119,7 +120,41 @@ struct AdamPairArgs {
   float lr[2];
   float grad_scale, max_norm;
   int lr_decay_num_updates, steps_per_update;
+  // optional: the bf16 operand images of the tensor-core kernels (mlp_tc.cuh), refreshed by the
+  // thread that updates a parameter instead of by separate packing launches
+  unsigned char* image[2];
+  int in_dim[2], k1p[2], out[2];
 };
+
+// Byte offset, in a network's packed image, of the bf16 copy of flat parameter i (flax order
+// W1 (in,H) | b1 | W2 (H,H) | b2 | W3 (H,out) | b3; biases are the extra input row of their matrix;
+// tiles are grids of 8x8 core matrices, see tc.cuh / pack_kernel in mlp_tc.cu).
+__device__ __forceinline__ size_t image_offset(int64_t i, int in_dim, int k1p, int out) {
+  using namespace tcmlp;
+  int r, c, rows;
+  size_t base;
+  const int64_t n_w1 = (int64_t)in_dim * HID;
+  if (i < n_w1 + HID) {
+    rows = k1p;
+    base = 0;
+    if (i < n_w1) { r = (int)(i / HID); c = (int)(i % HID); }
+    else { r = in_dim; c = (int)(i - n_w1); }
+  } else {
+    const int64_t i2 = i - n_w1 - HID;
+    rows = HCOLS;
+    if (i2 < HID * HID + HID) {
+      base = (size_t)k1p * HID * 2;
+      if (i2 < HID * HID) { r = (int)(i2 / HID); c = (int)(i2 % HID); }
+      else { r = HID; c = (int)(i2 - HID * HID); }
+    } else {
+      const int64_t i3 = i2 - HID * HID - HID;
+      base = (size_t)k1p * HID * 2 + (size_t)HCOLS * HID * 2;
+      if (i3 < (int64_t)HID * out) { r = (int)(i3 / out); c = (int)(i3 % out); }
+      else { r = HID; c = (int)(i3 - (int64_t)HID * out); }
+    }
+  }
+  return base + (size_t)(r >> 3) * 128 + (size_t)(c >> 3) * (rows / 8) * 128 + (r & 7) * 16 + (c & 7) * 2;
+}
 
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const AdamPairArgs a) {
   const int net = blockIdx.y;
@@ -189,7 +224,12 @@ __global__ void __launch_bounds__(256) clip_adam_pair_kernel(const AdamPairArgs 
     const float v = (1.0f - b2) * g * g + b2 * nu[i];
     mu[i] = m;
     nu[i] = v;
-    params[i] += -step_lr * ((m / bc1) / (sqrtf(v / bc2) + eps));
+    const float pnew = params[i] - step_lr * ((m / bc1) / (sqrtf(v / bc2) + eps));
+    params[i] = pnew;
+    if (a.image[net])
+      *reinterpret_cast<__nv_bfloat16*>(a.image[net] +
+                                        image_offset(i, a.in_dim[net], a.k1p[net], a.out[net])) =
+          __float2bfloat16_rn(pnew);
   }
 }
 
@@ -289,7 +329,45 @@ int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, co
   a.lr[0] = lr_actor; a.lr[1] = lr_critic;
   a.grad_scale = grad_scale; a.max_norm = max_norm;
   a.lr_decay_num_updates = lr_decay_num_updates; a.steps_per_update = steps_per_update;
+  a.image[0] = a.image[1] = nullptr;
   const unsigned ctas = (unsigned)max((int64_t)1, min((int64_t)64, ceil_div64(max(n_actor, n_critic), 1024)));
+  grad_sqnorm_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
+  clip_adam_pair_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
+  return launch_status();
+}
+
+int mava_clip_adam_pair_pack(float* params, float* mu, float* nu, int32_t* counts, const float* grad,
+                             const mava_mlp_desc* actor, void* actor_image,
+                             const mava_mlp_desc* critic, void* critic_image, float grad_scale,
+                             float lr_actor, float lr_critic, float max_norm,
+                             int lr_decay_num_updates, int steps_per_update, mava_stream_t s) {
+  MAVA_CHECK_PTR(params);
+  MAVA_CHECK_PTR(mu);
+  MAVA_CHECK_PTR(nu);
+  MAVA_CHECK_PTR(counts);
+  MAVA_CHECK_PTR(grad);
+  MAVA_CHECK_PTR(actor);
+  MAVA_CHECK_PTR(critic);
+  MAVA_CHECK_PTR(actor_image);
+  MAVA_CHECK_PTR(critic_image);
+  MAVA_CHECK_ARG(steps_per_update > 0);
+  const mava_mlp_desc* nets[2] = {actor, critic};
+  AdamPairArgs a;
+  a.params = params; a.mu = mu; a.nu = nu; a.counts = counts; a.grad = grad;
+  a.lr[0] = lr_actor; a.lr[1] = lr_critic;
+  a.grad_scale = grad_scale; a.max_norm = max_norm;
+  a.lr_decay_num_updates = lr_decay_num_updates; a.steps_per_update = steps_per_update;
+  a.image[0] = static_cast<unsigned char*>(actor_image);
+  a.image[1] = static_cast<unsigned char*>(critic_image);
+  for (int k = 0; k < 2; ++k) {
+    const mava_mlp_desc* d = nets[k];
+    MAVA_CHECK_ARG(d->h1 == tcmlp::HID && d->h2 == tcmlp::HID && d->out_dim <= tcmlp::NHEAD);
+    a.n[k] = mava_mlp_param_count(d);
+    a.in_dim[k] = d->in_dim;
+    a.k1p[k] = tcmlp::pad16(d->in_dim + 1);
+    a.out[k] = d->out_dim;
+  }
+  const unsigned ctas = (unsigned)max((int64_t)1, min((int64_t)64, ceil_div64(max(a.n[0], a.n[1]), 1024)));
   grad_sqnorm_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
   clip_adam_pair_kernel<<<dim3(ctas, 2), 256, 0, as_stream(s)>>>(a);
   return launch_status();

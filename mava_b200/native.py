@@ -388,6 +388,23 @@ def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, gr
         max_norm, lr_decay_num_updates, steps_per_update, _stream()), "mava_clip_adam_pair")
 
 
+def clip_adam_pair_pack(params, mu, nu, counts, grad, actor: MlpDesc, actor_image,
+                        critic: MlpDesc, critic_image, grad_scale: float, lr_actor: float,
+                        lr_critic: float, max_norm: float, lr_decay_num_updates: int = 0,
+                        steps_per_update: int = 1) -> None:
+    """clip_by_global_norm -> adam -> apply_updates that also refreshes the packed bf16 images."""
+    n = mlp_param_count(actor) + mlp_param_count(critic)
+    _count(2)
+    check(_lib.load().mava_clip_adam_pair_pack(
+        _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
+        _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
+        _p(grad, torch.float32, n, "grad"), C.byref(actor),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"), C.byref(critic),
+        _p(critic_image, torch.uint8, mlp_pack_bytes(critic), "critic_image"), grad_scale, lr_actor,
+        lr_critic, max_norm, lr_decay_num_updates, steps_per_update, _stream()),
+        "mava_clip_adam_pair_pack")
+
+
 # ---------------------------------------------------------------------------------------------
 # recurrent systems (rec_ippo / rec_mappo)
 # ---------------------------------------------------------------------------------------------

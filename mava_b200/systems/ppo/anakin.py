@@ -260,13 +260,18 @@ class FFLearner:
                     self.time_loss_grad.append((e0, e1))
                 if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
                     dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
-                native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na, nc,
-                                      scale, float(s.actor_lr), float(s.critic_lr),
-                                      float(s.max_grad_norm), self.lr_decay_updates,
-                                      steps_per_update)
+                if self.bf16:  # the optimiser refreshes the bf16 operand images itself
+                    native.clip_adam_pair_pack(
+                        self.params, self.mu, self.nu, self.counts, self.grad, self.actor_desc,
+                        self.actor_img, self.critic_desc, self.critic_img, scale, float(s.actor_lr),
+                        float(s.critic_lr), float(s.max_grad_norm), self.lr_decay_updates,
+                        steps_per_update)
+                else:
+                    native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na,
+                                          nc, scale, float(s.actor_lr), float(s.critic_lr),
+                                          float(s.max_grad_norm), self.lr_decay_updates,
+                                          steps_per_update)
                 self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
-                if self.bf16:
-                    self._pack()
         self.key.copy_(self.key3_ep[self.epochs - 1][0])
         if self.world > 1:
             self.loss_buf.mul_(scale)

@@ -150,3 +150,41 @@ def test_ppo_loss_grad_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode
             print(f"{net}.{name}: fro {err_fro:.4f} max {err_max:.4f}")
             assert err_fro < 5e-2 and err_max < 1e-1, (
                 f"{net}.{name}: fro err {err_fro:.4f}, max err {err_max:.4f} of scale {scale:.3e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("A,FR,N,critic_mode", [(4, 66, 5, "global"), (2, 12, 6, "agent")])
+def test_clip_adam_pair_pack_refreshes_images(lib_built, A, FR, N, critic_mode):
+    """The optimiser step that also refreshes the packed bf16 operand images: parameters and
+    moments identical to mava_clip_adam_pair, images identical to packing the new parameters."""
+    from mava_b200 import native
+
+    actor = native.mlp_desc(native.IN_AGENT_VIEW, True, A, FR, 128, 128, N)
+    cmode = native.IN_GLOBAL if critic_mode == "global" else native.IN_AGENT_VIEW
+    critic = native.mlp_desc(cmode, True, A, FR, 128, 128, 1)
+    na, nc = native.mlp_param_count(actor), native.mlp_param_count(critic)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    p0 = (torch.randn(na + nc, generator=g) * 0.1).to(DEV)
+    grad = torch.cat([torch.randn(na + nc, generator=g) * 0.3, torch.zeros(8)]).to(DEV)
+
+    def fresh():
+        return (p0.clone(), torch.zeros(na + nc, device=DEV), torch.zeros(na + nc, device=DEV),
+                torch.zeros(2, dtype=torch.int32, device=DEV))
+
+    pa, mua, nua, ca = fresh()
+    pb, mub, nub, cb = fresh()
+    ai = torch.zeros(native.mlp_pack_bytes(actor), dtype=torch.uint8, device=DEV)
+    ci = torch.zeros(native.mlp_pack_bytes(critic), dtype=torch.uint8, device=DEV)
+    native.mlp_pack_bf16(actor, pb[:na], ai)
+    native.mlp_pack_bf16(critic, pb[na:], ci)
+    for _ in range(3):
+        native.clip_adam_pair(pa, mua, nua, ca, grad, na, nc, 0.5, 2.5e-4, 2.5e-4, 0.5, 10, 4)
+        native.clip_adam_pair_pack(pb, mub, nub, cb, grad, actor, ai, critic, ci, 0.5, 2.5e-4, 2.5e-4,
+                                   0.5, 10, 4)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb) and torch.equal(mua, mub) and torch.equal(nua, nub)
+    assert torch.equal(ca, cb)
+    ai_ref, ci_ref = torch.zeros_like(ai), torch.zeros_like(ci)
+    native.mlp_pack_bf16(actor, pa[:na], ai_ref)
+    native.mlp_pack_bf16(critic, pa[na:], ci_ref)
+    assert torch.equal(ai, ai_ref) and torch.equal(ci, ci_ref)
