@@ -98,6 +98,7 @@ struct Ctrl {
   float db3[NHEAD];
   float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
   int32_t steps[3][TM + 2];      // env-step index of each minibatch position of the tiles in flight
+  uint32_t lin[2][TM][3];        // actor loss inputs of a tile's rows: mask | action << 8, old log-prob, advantage
 };
 
 constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava: num_agents <= 8)
@@ -200,18 +201,21 @@ __device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, i
 // also finish rows: the issue warp waits on a named barrier for "operands ready", issues the GEMM the
 // next epilogue needs, commits, and then issues the weight-gradient GEMMs of the phase behind the
 // commit, so that they run while the epilogue warps are already working on the accumulator.
-constexpr int NT_F = NT + 32;
-constexpr int BAR_EXPAND = 1, BAR_READY = 2, BAR_EPI = 3;
+constexpr int NLOAD = 96;             // three loader warps (20 warps x 96 registers fill the file)
+constexpr int NT_F = NT + 32 + NLOAD;  // 16 epilogue warps + the MMA-issue warp + the loader warps
+constexpr int NT_RDY = NT + 32;        // threads on the operands-ready barrier
+constexpr int BAR_EXPAND = 1, BAR_READY = 2, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 5, BAR_LOAD = 6;
+constexpr int kLdSlots = 22;           // words per loader thread: 22 x 96 = 2112 = 128 rows x 66 bytes / 4
 
 // epilogue side: my shared-memory / TMEM accesses of this phase are done
 __device__ __forceinline__ void epi_arrive() {
   fence_proxy_async();
   fence_before_sync();
-  asm volatile("bar.arrive %0, %1;" ::"n"(BAR_READY), "n"(NT_F) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"n"(BAR_READY), "n"(NT_RDY) : "memory");
 }
 // issue side: all 512 epilogue threads have arrived
 __device__ __forceinline__ void issuer_wait() {
-  asm volatile("bar.sync %0, %1;" ::"n"(BAR_READY), "n"(NT_F) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR_READY), "n"(NT_RDY) : "memory");
   fence_after_sync();
 }
 // barrier among the 16 epilogue warps only
@@ -231,7 +235,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-constexpr int kPfSlots = 6;  // 6 x 384 words >= one aligned tile of 66-byte rows (32 * FR words)
 
 __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -239,7 +242,9 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   const Lane L;
   const int t = L.t, warp = L.warp, lane = L.lane;
   // warp-uniform role (the shuffle tells the compiler so: descriptors stay in uniform registers)
-  const bool issue_warp = __shfl_sync(0xffffffffu, warp, 0) == NWARPS;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const bool issue_warp = warp_u == NWARPS;
+  const bool load_warp = warp_u > NWARPS;  // loader warps: every global load of the actor's tile loop
   const bool is_actor = (int)blockIdx.x < p.actor_ctas;
   const NetDesc& d = is_actor ? p.actor : p.critic;
   const int cta = is_actor ? blockIdx.x : blockIdx.x - p.actor_ctas;
@@ -299,68 +304,20 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   auto publish_steps = [&](int buf, int32_t my_step) {
     if (t < TM + 2) ctrl.steps[buf][t] = my_step;
   };
-  // Register-staged prefetch by the twelve warps that idle during the loss epilogue: the raw
-  // observation rows of the next tile are REQUESTED (plain loads, 4 bytes per thread and slot)
-  // while GEMM 1 runs and only consumed -- stored to the staging buffer and expanded into the
-  // other X buffer -- during the loss epilogue, so neither the HBM latency nor the copy issue is
-  // on the tile's critical path.  Slot k of thread t is word u of step js of the tile, the same
-  // (js, u) for every tile.
+  // Prefetch by the loader warps: the raw observation rows of the next tile and its per-row loss
+  // inputs are fetched with plain loads by three warps that do nothing else -- they never execute a
+  // proxy fence (fence.proxy.async is a MEMBAR that waits for the thread's outstanding loads, and a
+  // random row costs ~3 K cycles under this kernel), so a whole tile time hides the latency.
   // Staging layout: one padded byte row per tile row, [onehot(agent) | view bytes | 1 | 0...] of k1p
   // bytes -- the int8 image of the X row.  Agent-id, ones and padding bytes do not depend on the
-  // tile and are written once; the prefetch only replaces the view bytes (two 16-bit stores per
+  // tile and are written once; the loaders only replace the view bytes (two 16-bit stores per
   // 32-bit word: FR is even, so a half word never straddles two rows).  The expansion is then the
   // same for every 8-column chunk: one 8-byte load, eight conversions, one 16-byte store.
   // Slot metadata, one register: bit 0 = the word straddles two rows, bits 1..13 = destination half
   // word, bits 14..21 = word u of the step, bits 22..27 = step js of the tile.
-  uint32_t pf_reg[kPfSlots], pf_meta[kPfSlots];
   const int pf_units = step_bytes >> 2;
   const int id_cols = (d.mode == MAVA_IN_AGENT_VIEW && d.add_id) ? d.A : 0;
   const uint32_t pf_gap = d.mode == MAVA_IN_GLOBAL ? 0u : (uint32_t)(d.k1p - d.FR) >> 1;
-  int pf_total = 0;
-  if (prefetch && !issue_warp && L.q != 0) {
-#pragma unroll
-    for (int k = 0; k < kPfSlots; ++k) {
-      const int idx = k * (NT - TM) + (t - TM);
-      const int js = idx / pf_units, u = idx - js * pf_units;
-      const int sbyte = 4 * u;
-      int row = js, b0 = sbyte;
-      if (d.mode != MAVA_IN_GLOBAL) {
-        const int a0 = sbyte / d.FR;
-        b0 = sbyte - a0 * d.FR;
-        row = js * d.A + a0;
-      }
-      const uint32_t dst0 = (uint32_t)(row * d.k1p + id_cols + b0) >> 1;
-      const uint32_t straddle = (d.mode != MAVA_IN_GLOBAL && b0 + 2 >= d.FR) ? 1u : 0u;
-      pf_meta[k] = straddle | (dst0 << 1) | ((uint32_t)u << 14) | ((uint32_t)js << 22);
-    }
-  }
-  auto pf_load = [&](int tile_idx, int buf) {
-    int j0, nsteps;
-    tile_span(tile_idx, j0, nsteps);
-    const int total = nsteps * pf_units;
-#pragma unroll
-    for (int k = 0; k < kPfSlots; ++k) {
-      const int idx = k * (NT - TM) + (t - TM);
-      if (idx < total)
-        pf_reg[k] = __ldg(reinterpret_cast<const uint32_t*>(
-                              p.view + (size_t)ctrl.steps[buf][pf_meta[k] >> 22] * (size_t)step_bytes) +
-                          ((pf_meta[k] >> 14) & 0xffu));
-    }
-    pf_total = total;
-  };
-  auto pf_store = [&]() {
-    const uint32_t base = smem_u32(pf_stage);
-#pragma unroll
-    for (int k = 0; k < kPfSlots; ++k) {
-      const int idx = k * (NT - TM) + (t - TM);
-      if (idx < pf_total) {
-        const uint32_t h0 = (pf_meta[k] >> 1) & 0x1fffu;
-        const uint32_t h1 = h0 + 1u + (pf_meta[k] & 1u) * pf_gap;
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + 2u * h0), "r"(pf_reg[k] & 0xffffu) : "memory");
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + 2u * h1), "r"(pf_reg[k] >> 16) : "memory");
-      }
-    }
-  };
   // bf16 X rows of tile `tile_idx` from the padded staging rows (thread: row L.r, chunks cg0,
   // cg0 + cg_step, ...)
   auto expand_rows = [&](int tile_idx, const Tile& xn, int cg0, int cg_step,
@@ -452,6 +409,114 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, &ctrl.mbar);
       __syncwarp();
     }
+  } else if (load_warp) {
+    // ================================ loader warps ============================================
+    if (prefetch && cta + n_ctas < n_tiles) {
+      const int lt = t - NT_RDY;  // 0 .. NLOAD-1
+      // Thread lt walks words [lt * kLdSlots, (lt + 1) * kLdSlots) of the tile's observation bytes
+      // (steps back to back, pf_units words each).  Source (step js, word u) and destination (padded
+      // row, byte b) both advance incrementally -- a step is A rows of FR bytes, rows are numbered
+      // js * A + a -- so the walk needs two divisions per kernel, not per word.
+      uint32_t data[kLdSlots];
+      const int w0 = lt * kLdSlots;
+      const int js0 = w0 / pf_units, u0 = w0 - js0 * pf_units;
+      int row0w = js0, b0w = 4 * u0;
+      if (d.mode != MAVA_IN_GLOBAL) {
+        const int a0 = b0w / d.FR;
+        b0w -= a0 * d.FR;
+        row0w = js0 * d.A + a0;
+      }
+      const int row_bytes = d.mode == MAVA_IN_GLOBAL ? step_bytes : d.FR;
+      // index lists: ctrl.steps[1] / [2] belong to the loaders (slot 0 is the prologue's)
+      {
+        int j0, nsteps;
+        tile_span(cta + n_ctas, j0, nsteps);
+        if (lt < nsteps) ctrl.steps[1][lt] = __ldg(p.rows + j0 + lt);
+      }
+      asm volatile("bar.sync %0, %1;" ::"n"(BAR_LOAD), "n"(NLOAD) : "memory");
+      int itl = 0;
+      for (int tile = cta; tile + n_ctas < n_tiles; tile += n_ctas, ++itl) {
+        const int nt = tile + n_ctas;  // the tile being fetched
+        const int cur = 1 + (itl & 1), nxt = 1 + ((itl + 1) & 1);
+        int j0, nsteps;
+        tile_span(nt, j0, nsteps);
+        // the index list of the tile after it: requested first, stored last
+        int32_t idx_next = 0;
+        if (nt + n_ctas < n_tiles) {
+          int j0n, nstepsn;
+          tile_span(nt + n_ctas, j0n, nstepsn);
+          if (lt < nstepsn) idx_next = __ldg(p.rows + j0n + lt);
+        }
+        const int total = nsteps * pf_units;
+        {
+          int js = js0, u = u0;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(
+              p.view + (size_t)ctrl.steps[cur][js] * (size_t)step_bytes);
+#pragma unroll
+          for (int k = 0; k < kLdSlots; ++k) {
+            if (w0 + k < total) data[k] = __ldg(src + u);
+            if (++u == pf_units) {
+              u = 0;
+              ++js;
+              src = reinterpret_cast<const uint32_t*>(
+                  p.view + (size_t)ctrl.steps[cur][js < TM ? js : TM - 1] * (size_t)step_bytes);
+            }
+          }
+        }
+        // loss inputs of rows lt and lt + NLOAD
+        uint32_t lm[2] = {0u, 0u}, la[2] = {0u, 0u};
+        float lp[2] = {0.0f, 0.0f}, ladv[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lt + h * NLOAD;
+          if (r < TM && nt * TM + r < M) {
+            const int rj = r / rps, ra = r - rj * rps;
+            const size_t flat = (size_t)ctrl.steps[cur][rj] * d.A + ra;
+            lm[h] = p.mask[flat];
+            la[h] = (uint32_t)(uint8_t)p.action[flat];
+            lp[h] = p.old_logp[flat];
+            ladv[h] = p.adv[flat];
+          }
+        }
+        // the staging rows and this parity's loss-input buffer have been consumed
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
+        {
+          // two 16-bit stores per word: the second half word may belong to the next row
+          int b = b0w;
+          uint32_t dst = smem_u32(pf_stage) + (uint32_t)(row0w * d.k1p + id_cols + b0w);
+#pragma unroll
+          for (int k = 0; k < kLdSlots; ++k) {
+            const bool on = w0 + k < total;
+            if (on) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "r"(data[k] & 0xffffu) : "memory");
+            b += 2;
+            dst += 2;
+            if (b == row_bytes) {
+              b = 0;
+              dst += (uint32_t)(d.k1p - row_bytes);
+            }
+            if (on) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "r"(data[k] >> 16) : "memory");
+            b += 2;
+            dst += 2;
+            if (b == row_bytes) {
+              b = 0;
+              dst += (uint32_t)(d.k1p - row_bytes);
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lt + h * NLOAD;
+          if (r < TM) {
+            ctrl.lin[(itl + 1) & 1][r][0] = lm[h] | (la[h] << 8);
+            ctrl.lin[(itl + 1) & 1][r][1] = __float_as_uint(lp[h]);
+            ctrl.lin[(itl + 1) & 1][r][2] = __float_as_uint(ladv[h]);
+          }
+        }
+        if (lt < TM + 2) ctrl.steps[nxt][lt] = idx_next;
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_LOAD), "n"(NLOAD) : "memory");
+      }
+    }
   } else {
     // ================================ epilogue warps ==========================================
     // Prefetch pipeline (fold mode): while tile i is in its loss epilogue (four warps busy), the
@@ -459,7 +524,6 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     // into the other X buffer.  Prologue: tile 0 is built by everybody.
     if (prefetch && any_tile) {
       publish_steps(0, load_steps(cta));
-      if (cta + n_ctas < n_tiles) publish_steps(1, load_steps(cta + n_ctas));
       // tile-invariant bytes of the padded rows (aligned tiles: the agent of a row is r % A)
       for (int i = t; i < TM * (d.k1p >> 2); i += NT) reinterpret_cast<uint32_t*>(pf_stage)[i] = 0u;
       epi_sync();
@@ -485,7 +549,16 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       }
       epi_sync();
       expand_rows(cta, Tile{s_x0, 128u, 2048u}, L.q, 4, pf_stage);
+      if (L.q == 0 && cta * TM + L.r < M) {  // tile 0's loss inputs (later tiles: the loader warps)
+        const size_t flat = (size_t)ctrl.steps[0][r_j] * d.A + r_a;
+        ctrl.lin[0][L.r][0] = (uint32_t)p.mask[flat] | ((uint32_t)(uint8_t)p.action[flat] << 8);
+        ctrl.lin[0][L.r][1] = __float_as_uint(p.old_logp[flat]);
+        ctrl.lin[0][L.r][2] = __float_as_uint(p.adv[flat]);
+      }
       epi_sync();
+      // the staging rows are free: the loaders may bring in tile 1
+      if (cta + n_ctas < n_tiles)
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
     }
     mbar_wait(&ctrl.wbar, 0);
     const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
@@ -503,15 +576,12 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it, sb = sb == 2 ? 0 : sb + 1) {
       const int row0 = tile * TM;
       const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
-      const int sb1 = sb == 2 ? 0 : sb + 1, sb2 = sb1 == 2 ? 0 : sb1 + 1;
       MAVA_STAMP(0);
 #ifdef MAVA_PROFILE_PHASES
       if (t == 0 && blockIdx.x == gridDim.x - 1 && it < 16) g_phase_clock2[128 + it] = clock64();
 #endif
       const bool has_next = prefetch && tile + n_ctas < n_tiles;
       const bool has_next2 = prefetch && tile + 2 * n_ctas < n_tiles;
-      // the index list of the tile after the next: requested now, published below
-      const int32_t next2_step = has_next2 ? load_steps(tile + 2 * n_ctas) : 0;
       if (!prefetch) {
         // the previous tile's weight-gradient MMAs still read the buffers X is built over
         if (!first) wait_acc(&ctrl.mbar2, phase2);
@@ -574,13 +644,14 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       }
       epi_arrive();  // -> layer 1 (and the previous tile's first-layer gradient)
       MAVA_STAMP(1);
-      if (has_next2) publish_steps(sb2, next2_step);
-      if (prefetch) epi_sync();  // orders the index lists (written a tile ahead of their readers)
-      if (has_next && L.q != 0) pf_load(tile + n_ctas, sb1);
       MAVA_STAMP(14);
-      // loss inputs of this row: in flight during the forward pass instead of after it
+      // loss inputs of this row.  Prefetch path: the loader warps put them into ctrl.lin; plain
+      // paths: fetched here, in flight during the forward pass
       LossIn li{};
-      if (L.q == 0) {
+      if (L.q == 0 && prefetch) {
+        li.valid = row0 + L.r < M;
+        li.j = li.valid ? tile * spt + r_j : 0;
+      } else if (L.q == 0) {
         const int row = row0 + L.r;
         li.valid = row < M;
         int j, ag;
@@ -634,11 +705,11 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       MAVA_STAMP(7);
       // ---- loss epilogue (first four warps, one thread per row): d(total loss)/d(head output);
       //      the other twelve warps build the next tile's X meanwhile
+      // the loaders have filled the staging rows (tile i+1) and the loss inputs (tile i+1)
+      if (has_next) asm volatile("bar.sync %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");
       if (L.q != 0) {
         MAVA_STAMP2(0);
         if (has_next) {
-          pf_store();  // raw rows of tile i+1 (requested since GEMM 1)
-          asm volatile("bar.sync %0, 384;" ::"n"(BAR_EXPAND) : "memory");  // ... of all twelve warps
           MAVA_STAMP2(1);
           const Tile xn{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
           expand_rows(tile + n_ctas, xn, L.q - 1, 3, pf_stage);
@@ -677,6 +748,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
             db3_acc[0] += dz[0];
           }
         } else {
+          if (prefetch) {
+            const uint32_t w0 = ctrl.lin[it & 1][L.r][0];
+            li.mk = w0 & 0xffu;
+            li.act = (int)(signed char)(w0 >> 8);
+            li.f0[0] = __uint_as_float(ctrl.lin[it & 1][L.r][1]);
+            li.f1[0] = __uint_as_float(ctrl.lin[it & 1][L.r][2]);
+          }
           const int u = li.j / p.mb_size;  // replica of this minibatch position
           const float g = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
           const uint32_t th = tmem + L.tmem_lane() + COL_HEAD;
@@ -694,6 +772,8 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         MAVA_STAMP(15);
         // (head bias gradient: column sums of dZ3, kept per thread across tiles, reduced at the end)
       }
+      // staging rows expanded, loss inputs read: the loaders may bring in tile i+2
+      if (has_next2) asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
       epi_arrive();  // -> backward through the head
       MAVA_STAMP(8);
       wait_acc(&ctrl.mbar, phase);
@@ -753,7 +833,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   float* gb2 = gw2 + (size_t)HID * HID;
   float* gw3 = gb2 + HID;
   float* gb3 = gw3 + (size_t)HID * d.out;
-  if (any_tile && !issue_warp) {
+  if (any_tile && warp_u < NWARPS) {  // the sixteen epilogue warps
     // dW2^T: TMEM lane = output unit n, columns = input unit k (column HID = bias gradient)
     {
       float v[32];
@@ -1060,7 +1140,8 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   a.prefetch_actor = a.fold_actor_w1 && smem_pf <= 227 * 1024 && (TM % a.actor.A) == 0 &&
                      (a.actor.FR & 1) == 0 && ((a.actor.A * a.actor.FR) & 3) == 0 &&
                      (a.actor.A * a.actor.FR) / 4 <= 255 && TM * a.actor.k1p / 2 < 8192 &&
-                     (TM / a.actor.A) * ((a.actor.A * a.actor.FR) >> 2) <= kPfSlots * (NT - TM);
+                     (TM / a.actor.A) * ((a.actor.A * a.actor.FR) >> 2) <= kLdSlots * NLOAD &&
+                     TM / a.actor.A + 2 <= NLOAD;
   if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
   {
     static const int pipe_env = getenv("MAVA_NO_PIPE1") ? 0 : 1;  // development switch
