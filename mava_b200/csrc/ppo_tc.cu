@@ -1148,16 +1148,25 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
     a.pipe_layer1 = pipe_env;
   }
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
-  // split the SMs between actor and critic tiles in proportion to their cost per tile (cycles:
-  // scripts/exp_phase_clock.sh, and a sweep of the split with MAVA_ACTOR_CTAS): an actor tile with
-  // the folded first-layer gradient and the prefetch pipeline ~9.8 K at k1p = 80; a tile on the
-  // plain path ~6.4 K + 30 per input column (14.5 K for the 272-wide MAPPO critic, whose rows
-  // arrive by bulk copies)
+  // Split the SMs between actor and critic tiles: the split that minimises the slower side's
+  // whole-tile count x cost per tile (cycles: scripts/exp_phase_clock.sh, checked by a sweep of the
+  // split with MAVA_ACTOR_CTAS).  An actor tile with the folded first-layer gradient and the
+  // loader-warp pipeline ~8.8 K at k1p = 80; a tile on the plain path ~6.4 K + 30 per input column
+  // (14.5 K for the 272-wide MAPPO critic, whose rows arrive by bulk copies).
   {
-    const double tile_a = (a.prefetch_actor ? 7400.0 : 9050.0) + 30.0 * a.actor.k1p;
+    const double tile_a = (a.prefetch_actor ? 6420.0 : 9050.0) + 30.0 * a.actor.k1p;
     const double tile_c = 6360.0 + 30.0 * a.critic.k1p;
-    const double ca = (double)ta * tile_a, cc = (double)tcn * tile_c;
-    int n_actor = (int)(sms * ca / (ca + cc) + 0.5);
+    int n_actor = 1;
+    double best = 1e300;
+    for (int na = 1; na < sms; ++na) {
+      const int64_t ca = ta < na ? ta : na, cc = tcn < sms - na ? tcn : sms - na;
+      const double t_a = (double)ceil_div64(ta, ca) * tile_a, t_c = (double)ceil_div64(tcn, cc) * tile_c;
+      const double worst = t_a > t_c ? t_a : t_c;
+      if (worst < best) {
+        best = worst;
+        n_actor = na;
+      }
+    }
     if (const char* ov = getenv("MAVA_ACTOR_CTAS")) n_actor = atoi(ov);  // development switch
     n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
     a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
