@@ -98,7 +98,10 @@ struct Ctrl {
   float db3[NHEAD];
   float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
   int32_t steps[3][TM + 2];      // env-step index of each minibatch position of the tiles in flight
-  uint32_t lin[2][TM][3];        // actor loss inputs of a tile's rows: mask | action << 8, old log-prob, advantage
+  // loss inputs of a tile's rows, written by the loader warps.  Actor: two buffers of
+  // {mask | action << 8, old log-prob, advantage}; centralised critic: ONE buffer of 8 floats per
+  // row, old values [0..A) and targets [4..4+A) of the env-step's agents (A <= 4)
+  uint32_t lin[2][TM][4];
 };
 
 constexpr int kMaxReps = 8;  // agents a centralised-critic row stands for (mava: num_agents <= 8)
@@ -350,6 +353,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   const uint32_t tmem = ctrl.tmem;
   if (t == 0) load_weights(s_w, is_actor ? p.actor_img : p.critic_img, wi.total(), &ctrl.wbar);
 
+  // plain path, joint-observation rows (centralised critic): rows fetched by bulk copies into padded
+  // staging rows (see the tile loop); `cl`: its index lists and loss inputs come from the loader warps
+  const bool padded_global = !prefetch && !fold && d.mode == MAVA_IN_GLOBAL && (step_bytes & 7) == 0 &&
+                             TM * grow_stride(d.k1p) <= tile_bytes(TM, HCOLS) && d.k1p <= 288 &&
+                             (reinterpret_cast<size_t>(p.view) & 15) == 0;
+  const bool cl = padded_global && d.A <= 4;
+  float* linc = reinterpret_cast<float*>(&ctrl.lin[0][0][0]);  // [TM][8]
   uint32_t phase = 0, phase1 = 0, phase2 = 0;
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
@@ -517,6 +527,61 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         asm volatile("bar.sync %0, %1;" ::"n"(BAR_LOAD), "n"(NLOAD) : "memory");
       }
     }
+    if (cl && cta + n_ctas < n_tiles) {
+      // centralised critic: index lists (list of tile k in ctrl.steps[k % 3]) and the per-row loss
+      // inputs (old values and targets of the env-step's agents) of the tiles after the first
+      const int lt = t - NT_RDY;
+      {
+        int j0, nsteps;
+        tile_span(cta + n_ctas, j0, nsteps);
+        for (int r = lt; r < TM; r += NLOAD) ctrl.steps[1][r] = r < nsteps ? __ldg(p.rows + j0 + r) : 0;
+      }
+      asm volatile("bar.sync %0, %1;" ::"n"(BAR_LOAD), "n"(NLOAD) : "memory");
+      asm volatile("bar.arrive %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");  // list of tile 1
+      int itl = 0, cur = 1;
+      for (int tile = cta; tile + n_ctas < n_tiles; tile += n_ctas, ++itl, cur = cur == 2 ? 0 : cur + 1) {
+        const int nt = tile + n_ctas;  // the tile whose loss inputs are fetched; its list is in `cur`
+        const int nxt = cur == 2 ? 0 : cur + 1;
+        int32_t idx_next[2] = {0, 0};
+        if (nt + n_ctas < n_tiles) {
+          int j0n, nstepsn;
+          tile_span(nt + n_ctas, j0n, nstepsn);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = lt + h * NLOAD;
+            if (r < nstepsn) idx_next[h] = __ldg(p.rows + j0n + r);
+          }
+        }
+        float f0[2][4], f1[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lt + h * NLOAD;
+          const bool on = r < TM && nt * TM + r < M;
+          const size_t flat = on ? (size_t)ctrl.steps[cur][r] * d.A : 0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            f0[h][a] = (on && a < d.A) ? p.old_value[flat + a] : 0.0f;
+            f1[h][a] = (on && a < d.A) ? p.targets[flat + a] : 0.0f;
+          }
+        }
+        // the previous tile's loss inputs have been read
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lt + h * NLOAD;
+          if (r < TM) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              linc[r * 8 + a] = f0[h][a];
+              linc[r * 8 + 4 + a] = f1[h][a];
+            }
+            ctrl.steps[nxt][r] = idx_next[h];
+          }
+        }
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_LOAD), "n"(NLOAD) : "memory");
+      }
+    }
   } else {
     // ================================ epilogue warps ==========================================
     // Prefetch pipeline (fold mode): while tile i is in its loss epilogue (four warps busy), the
@@ -560,14 +625,22 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       if (cta + n_ctas < n_tiles)
         asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
     }
+    if (cl && any_tile) {
+      publish_steps(0, load_steps(cta));
+      epi_sync();
+      if (L.q == 0 && cta * TM + L.r < M) {  // tile 0's loss inputs (later tiles: the loader warps)
+        const size_t flat = (size_t)ctrl.steps[0][L.r] * d.A;
+        for (int a = 0; a < d.A; ++a) {
+          linc[L.r * 8 + a] = p.old_value[flat + a];
+          linc[L.r * 8 + 4 + a] = p.targets[flat + a];
+        }
+      }
+      epi_sync();
+    }
     mbar_wait(&ctrl.wbar, 0);
     const float wrow = 1.0f / ((float)p.R * (float)d.A);  // mean over rows, replicas and agents
     bool first = true;
     int32_t next_step = 0;
-    // plain path, joint-observation rows: padded staging rows in the H1 region (see below)
-    const bool padded_global = !prefetch && !fold && d.mode == MAVA_IN_GLOBAL && (step_bytes & 7) == 0 &&
-                               TM * grow_stride(d.k1p) <= tile_bytes(TM, HCOLS) &&
-                               d.k1p <= 288 && (reinterpret_cast<size_t>(p.view) & 15) == 0;
     uint32_t gphase = 0;
     // bulk copies are issued one lane at a time: eight rows per warp, spread over all 16 warps
     const bool grow_thread = lane < TM / NWARPS;
@@ -594,12 +667,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           unsigned char* gstg = smem + (h2t.base - s_w);
           int j0, nsteps;
           tile_span(tile, j0, nsteps);
+          const int ls = cl ? sb : (it & 1);  // slot of this tile's index list
           if (first && grow_thread) {
-            const int32_t st = grow_r < nsteps ? __ldg(p.rows + j0 + grow_r) : 0;
-            ctrl.steps[0][grow_r] = st;
+            const int32_t st = cl ? ctrl.steps[0][grow_r] : (grow_r < nsteps ? __ldg(p.rows + j0 + grow_r) : 0);
+            if (!cl) ctrl.steps[0][grow_r] = st;
             grow_issue(d, p.view, st, grow_r < nsteps, gstg, grow_r, &ctrl.gbar);
           }
-          if (tile + n_ctas < n_tiles && grow_thread) {
+          if (!cl && tile + n_ctas < n_tiles && grow_thread) {
             int j0n, nstepsn;
             tile_span(tile + n_ctas, j0n, nstepsn);
             next_step = grow_r < nstepsn ? __ldg(p.rows + j0n + grow_r) : 0;
@@ -607,14 +681,14 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           mbar_wait(&ctrl.gbar, gphase);
           gphase ^= 1u;
           MAVA_STAMP3(1);
-          if (t < nsteps) grow_tail(d, gstg, t, ctrl.steps[it & 1][t]);
+          if (t < nsteps) grow_tail(d, gstg, t, ctrl.steps[ls][t]);
           epi_sync();
           MAVA_STAMP3(2);
           constexpr int kMaxChunks = 9;  // per thread: k1p <= 288
           uint32_t w[kMaxChunks][2];
           const bool valid = row0 + L.r < M;
           const uint32_t src = smem_u32(gstg) + (uint32_t)L.r * grow_stride(d.k1p) +
-                               (valid ? grow_skew(d, ctrl.steps[it & 1][L.r]) : 0u);
+                               (valid ? grow_skew(d, ctrl.steps[ls][L.r]) : 0u);
           const int nchunks = d.k1p >> 3;
           // chunk residue rotated with the row so that the 8-byte loads of a half warp (rows 288 bytes
           // apart) fall into sixteen different bank pairs
@@ -651,6 +725,9 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       if (L.q == 0 && prefetch) {
         li.valid = row0 + L.r < M;
         li.j = li.valid ? tile * spt + r_j : 0;
+      } else if (L.q == 0 && cl) {
+        li.valid = row0 + L.r < M;
+        li.j = li.valid ? row0 + L.r : 0;
       } else if (L.q == 0) {
         const int row = row0 + L.r;
         li.valid = row < M;
@@ -707,6 +784,11 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       //      the other twelve warps build the next tile's X meanwhile
       // the loaders have filled the staging rows (tile i+1) and the loss inputs (tile i+1)
       if (has_next) asm volatile("bar.sync %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");
+      // centralised critic: the loaders' previous round (this tile's loss inputs, the next tile's
+      // index list); the round before the first tile only carries the list of tile 1
+      const bool c_next = cl && tile + n_ctas < n_tiles;
+      if (cl && (it > 0 || c_next))
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_FULL), "n"(NT + NLOAD) : "memory");
       if (L.q != 0) {
         MAVA_STAMP2(0);
         if (has_next) {
@@ -728,6 +810,13 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
             const float v = out[0];
             const int reps = d.mode == MAVA_IN_GLOBAL ? d.A : 1;
             float dv = 0.0f;
+            if (cl) {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                li.f0[a] = linc[L.r * 8 + a];
+                li.f1[a] = linc[L.r * 8 + 4 + a];
+              }
+            }
 #pragma unroll
             for (int a = 0; a < kMaxReps; ++a) {
               if (a >= reps) break;
@@ -773,7 +862,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         // (head bias gradient: column sums of dZ3, kept per thread across tiles, reduced at the end)
       }
       // staging rows expanded, loss inputs read: the loaders may bring in tile i+2
-      if (has_next2) asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
+      if (has_next2 || c_next) asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
       epi_arrive();  // -> backward through the head
       MAVA_STAMP(8);
       wait_acc(&ctrl.mbar, phase);
@@ -787,8 +876,10 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
         // H2 is dead (dW3 completed before dH1): the next tile's rows start arriving there now
         int j0n, nstepsn;
         tile_span(tile + n_ctas, j0n, nstepsn);
-        ctrl.steps[(it + 1) & 1][grow_r] = next_step;
-        grow_issue(d, p.view, next_step, grow_r < nstepsn, smem + (h2t.base - s_w), grow_r, &ctrl.gbar);
+        const int sb1 = sb == 2 ? 0 : sb + 1;
+        if (!cl) ctrl.steps[(it + 1) & 1][grow_r] = next_step;
+        const int32_t st_next = cl ? ctrl.steps[sb1][grow_r] : next_step;
+        grow_issue(d, p.view, st_next, grow_r < nstepsn, smem + (h2t.base - s_w), grow_r, &ctrl.gbar);
       }
       if (fold) {
         // dZ1 stays on chip (H2 is dead: the dW3 MMAs completed before dH1): the first-layer gradient
