@@ -222,6 +222,149 @@ __global__ void __launch_bounds__(NT, 1) act_kernel(const ActArgs p) {
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// batched critic pass on joint observations (centralised critic, all T + 1 slots of a rollout)
+// ------------------------------------------------------------------------------------------------
+// The rows of a tile are 128 consecutive env-steps of in_dim = A * FR bytes: ONE bulk (TMA) copy per
+// tile.  Persistent CTAs: the weight image is loaded once per CTA (the one-tile-per-CTA acting
+// kernel reloads 111 KB per 128 rows), and the next tile's bytes are requested as soon as layer 1
+// has consumed X -- into the upper half of the X region, which is why the expansion goes through
+// registers (every thread reads its chunks, then all of them write).
+struct ValueCtrl {
+  uint64_t wbar, mbar, xbar;  // weights landed | MMA chain | observation bytes landed
+  uint32_t tmem;
+};
+
+__global__ void __launch_bounds__(NT, 1) value_batch_kernel(const ActArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ ValueCtrl ctrl;
+  const Lane L;
+  const int t = L.t, warp = L.warp;
+  const NetDesc& d = p.critic;
+  const int M = p.num_envs;  // one row per env-step
+  const int n_tiles = ceil_div(M, TM);
+  const WImage wi{d.k1p};
+  const uint32_t s_w = smem_u32(smem);
+  const uint32_t x_bytes = tile_bytes(TM, d.k1p);
+  const Tile xt{s_w + wi.total(), 128u, (uint32_t)(TM / 8) * 128u};
+  const Tile ht{xt.base + x_bytes, 128u, (uint32_t)(TM / 8) * 128u};
+  const uint32_t row_bytes = (uint32_t)d.in_dim;
+  const uint32_t stage_off = (x_bytes - TM * row_bytes) & ~15u;  // upper part of the X region
+  unsigned char* stage = smem + wi.total() + stage_off;
+
+  if (warp == 0) tmem_alloc<256>(&ctrl.tmem);
+  if (t == 0) {
+    mbar_init(&ctrl.wbar, 1);
+    mbar_init(&ctrl.mbar, 1);
+    mbar_init(&ctrl.xbar, 1);
+    fence_mbar_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = ctrl.tmem;
+  // a tile whose byte count is a multiple of 16 arrives by one bulk copy; the (partial) last tile
+  // may not be: it is copied with plain loads
+  auto tile_rows = [&](int tile) { return M - tile * TM < TM ? M - tile * TM : TM; };
+  auto bulk_ok = [&](int tile) { return (((uint32_t)tile_rows(tile) * row_bytes) & 15u) == 0u; };
+  auto request = [&](int tile) {  // one thread
+    const uint32_t bytes = (uint32_t)tile_rows(tile) * row_bytes;
+    if (bulk_ok(tile)) {
+      mbar_expect_tx(&ctrl.xbar, bytes);
+      bulk_g2s(smem_u32(stage), p.view + (size_t)tile * TM * row_bytes, bytes, &ctrl.xbar);
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ctrl.xbar)) : "memory");
+    }
+  };
+  if (t == 0) {
+    load_weights(s_w, p.critic_img, wi.total(), &ctrl.wbar);
+    if ((int)blockIdx.x < n_tiles) request(blockIdx.x);
+  }
+  mbar_wait(&ctrl.wbar, 0);
+  uint32_t phase = 0, xphase = 0;
+  const int nchunks = d.in_dim >> 3;  // chunks of observation bytes; chunk nchunks is [1 | 0...]
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row0 = tile * TM;
+    mbar_wait(&ctrl.xbar, xphase);
+    xphase ^= 1u;
+    if (!bulk_ok(tile)) {  // plain copy of the last tile (8-byte units)
+      const int units = tile_rows(tile) * (int)(row_bytes >> 3);
+      const uint2* src = reinterpret_cast<const uint2*>(p.view + (size_t)tile * TM * row_bytes);
+      for (int i = t; i < units; i += NT) reinterpret_cast<uint2*>(stage)[i] = __ldg(src + i);
+      __syncthreads();
+    }
+    // ---- X tile: observation bytes -> registers -> bf16 chunks (the staging bytes live in the
+    //      region the chunks are written to)
+    constexpr int kMaxChunks = 9;  // per thread: in_dim <= 288
+    uint32_t w[kMaxChunks][2];
+    const bool valid = row0 + L.r < M;
+    const uint32_t src = smem_u32(stage) + (uint32_t)L.r * row_bytes;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+      const int cg = L.q + 4 * i;
+      w[i][0] = w[i][1] = 0u;
+      if (valid && cg < nchunks)
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[i][0]), "=r"(w[i][1]) : "r"(src + 8u * cg));
+    }
+    __syncthreads();  // staging has been read: X may overwrite it
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+      const int cg = L.q + 4 * i;
+      if (cg < nchunks)
+        st_shared_v4(xt.base + chunk_off(xt, L.r, cg), s8x2_bf16x2(w[i][0]), s8x2_bf16x2(w[i][0] >> 16),
+                     s8x2_bf16x2(w[i][1]), s8x2_bf16x2(w[i][1] >> 16));
+    }
+    for (int cg = nchunks + L.q; cg < d.k1p / 8; cg += 4)  // ones column, padding
+      st_shared_v4(xt.base + chunk_off(xt, L.r, cg), (valid && cg == nchunks) ? 0x00003F80u : 0u, 0u,
+                   0u, 0u);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    // ---- layer 1
+    if (mma_issuer()) {
+      fence_after_sync();
+      issue_gemm(tmem, xt, false, w1_tile(s_w, d.k1p), true, HID, d.k1p, false, &ctrl.mbar);
+    }
+    wait_mma(&ctrl.mbar, phase);
+    phase ^= 1;
+    // X is dead: the next tile's bytes may land in its upper half
+    if (t == 0 && tile + (int)gridDim.x < n_tiles) request(tile + gridDim.x);
+    hidden_epilogue(L, tmem, ht);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    // ---- layer 2
+    if (mma_issuer()) {
+      fence_after_sync();
+      issue_gemm(tmem, ht, false, w2_tile(s_w, d.k1p), true, HID, HCOLS, false, &ctrl.mbar);
+    }
+    wait_mma(&ctrl.mbar, phase);
+    phase ^= 1;
+    hidden_epilogue(L, tmem, ht);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    // ---- head
+    if (mma_issuer()) {
+      fence_after_sync();
+      issue_gemm(tmem + HID, ht, false, w3_tile(s_w, d.k1p), true, NHEAD, HCOLS, false, &ctrl.mbar);
+    }
+    wait_mma(&ctrl.mbar, phase);
+    phase ^= 1;
+    if (L.q == 0) {
+      float out[8];
+      ld8(tmem + L.tmem_lane() + (uint32_t)HID, out);
+      if (valid)
+        for (int a = 0; a < d.A; ++a) p.value[(size_t)(row0 + L.r) * d.A + a] = out[0];
+    }
+    fence_before_sync();
+    __syncthreads();  // the head accumulator has been read before the next tile's chain writes
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 }  // namespace
 
 int make_net(const mava_mlp_desc* d, const float* params, NetDesc* n) {
@@ -317,6 +460,22 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, cons
   a.greedy = greedy;
   const size_t smem = (size_t)WImage{k1p_max}.total() + tile_bytes(TM, k1p_max) +
                       tile_bytes(TM, HCOLS) + 128;
+  // critic only, joint observations: the persistent batched kernel (one bulk copy per tile)
+  if (!actor && critic->input_mode == MAVA_IN_GLOBAL && (a.critic.in_dim & 7) == 0 &&
+      a.critic.in_dim <= 288 && a.critic.k1p > a.critic.in_dim &&
+      (size_t)TM * a.critic.in_dim + 16 <= tile_bytes(TM, a.critic.k1p) &&
+      (reinterpret_cast<size_t>(view) & 15) == 0) {
+    static size_t configured_v = 0;
+    if (smem > configured_v) {
+      cudaError_t e = cudaFuncSetAttribute(value_batch_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured_v = smem;
+    }
+    const int ctas = a.critic_ctas < sm_count() ? a.critic_ctas : sm_count();
+    value_batch_kernel<<<ctas, NT, smem, as_stream(s)>>>(a);
+    return launch_status();
+  }
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

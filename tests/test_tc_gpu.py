@@ -188,3 +188,37 @@ def test_clip_adam_pair_pack_refreshes_images(lib_built, A, FR, N, critic_mode):
     native.mlp_pack_bf16(actor, pa[:na], ai_ref)
     native.mlp_pack_bf16(critic, pa[na:], ci_ref)
     assert torch.equal(ai, ai_ref) and torch.equal(ci, ci_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NE", [129, 300, 301, 4133])
+def test_value_batch_matches_acting_kernel(lib_built, NE):
+    """The persistent batched critic pass (bulk-copied joint observations, weights loaded once per
+    CTA) against the critic half of the acting kernel on the same rows: same operands, same MMA
+    order -- identical values.  NE covers full tiles, a last tile that arrives by bulk copy and one
+    that does not (odd row count: byte count not a multiple of 16)."""
+    import numpy as np
+
+    from mava_b200 import native
+    from tests.test_mlp_gpu import flat, make_params, random_batch
+
+    A, FR, N = 4, 66, 5
+    rng = np.random.default_rng(NE)
+    view, mask_bool, mask = random_batch(rng, NE, A, FR, N)
+    actor = native.mlp_desc(native.IN_AGENT_VIEW, True, A, FR, 128, 128, N)
+    critic = native.mlp_desc(native.IN_GLOBAL, True, A, FR, 128, 128, 1)
+    ap = torch.from_numpy(flat(make_params(rng, actor.in_dim, 128, 128, N))).to(DEV)
+    cp = torch.from_numpy(flat(make_params(rng, critic.in_dim, 128, 128, 1))).to(DEV)
+    ai = torch.zeros(native.mlp_pack_bytes(actor), dtype=torch.uint8, device=DEV)
+    ci = torch.zeros(native.mlp_pack_bytes(critic), dtype=torch.uint8, device=DEV)
+    native.mlp_pack_bf16(actor, ap, ai)
+    native.mlp_pack_bf16(critic, cp, ci)
+    tv, tm = torch.from_numpy(view).to(DEV), torch.from_numpy(mask).to(DEV)
+    key = torch.tensor([1, 2], dtype=torch.uint32, device=DEV)
+    act = torch.zeros(NE, A, dtype=torch.int8, device=DEV)
+    logp, v_act = torch.zeros(NE, A, device=DEV), torch.zeros(NE, A, device=DEV)
+    native.ff_act_bf16(actor, ap, ai, critic, cp, ci, tv, tm, key, NE, NE, act, logp, v_act)
+    v_batch = torch.full((NE, A), float("nan"), device=DEV)
+    native.ff_act_bf16(None, None, None, critic, cp, ci, tv, None, None, NE, NE, None, None, v_batch)
+    torch.cuda.synchronize()
+    assert torch.equal(v_batch, v_act)
