@@ -285,11 +285,14 @@ class FFLearner:
         with torch.cuda.stream(self._side):
             perms = self._epoch_permutations()
         self._rollout()
+        # finished-episode statistics: off the critical path, next to GAE (a graph branch)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            native.episode_stats(self.done, self.ep_ret, self.ep_len, self.T * self.NE, False,
+                                 self.ep_stats)
         native.gae(self.reward, self.value, self.done, self.last_val, float(self.config.system.gamma),
                    float(self.config.system.gae_lambda), self.T, self.NE, self.A, self.adv,
                    self.targets)
-        native.episode_stats(self.done, self.ep_ret, self.ep_len, self.T * self.NE, False,
-                             self.ep_stats)
         main.wait_stream(self._side)
         self._update_epochs(perms)
         self.view[0].copy_(self.view[self.T])
