@@ -259,6 +259,24 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor_host, const float* actor_
                             const int32_t* rows, int num_replicas, int mb_size, float* grad_out,
                             void* workspace, mava_stream_t s);
 
+/* The per-replica advantage statistics of a minibatch (sum and sum of squares over its rows and
+ * agents: the mean / std of `gae` in _actor_loss_fn, ff_mappo.py:164) depend only on the rollout and
+ * the row list, not on the parameters: mava_ppo_adv_stats computes them ahead of time (stats: 16
+ * doubles, [2 * replica] = sum, [2 * replica + 1] = sum of squares) and
+ * mava_ppo_loss_grad_bf16_stats takes them instead of recomputing them, so that the row lists and
+ * statistics of all minibatches of an update can be prepared off the critical path. */
+int mava_ppo_adv_stats(const float* adv, const int32_t* rows, int num_replicas, int mb_size,
+                       int num_agents, double* stats, mava_stream_t stream);
+int mava_ppo_loss_grad_bf16_stats(const mava_mlp_desc* actor, const float* actor_params,
+                                  const void* actor_image, const mava_mlp_desc* critic,
+                                  const float* critic_params, const void* critic_image,
+                                  const mava_ppo_hyper* hyper, const int8_t* view,
+                                  const uint8_t* mask, const int8_t* action, const float* old_logp,
+                                  const float* old_value, const float* adv, const float* targets,
+                                  const int32_t* rows, int num_replicas, int mb_size,
+                                  const double* adv_stats, float* grad_out, void* workspace,
+                                  mava_stream_t stream);
+
 /* The whole rollout scan of ff_ippo / ff_mappo (ff_mappo.py:76-106) in one persistent kernel:
  * rollout_length x (actor forward + masked categorical sample + env step through the wrapper
  * stack), env records, observation rows and the actor weights resident in shared memory for the

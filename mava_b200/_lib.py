@@ -94,6 +94,10 @@ SIGNATURES = {
     "mava_ppo_loss_grad_bf16": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void,
                                         P(PpoHyper)] + [c_void] * 8 +
                                 [c_int, c_int, c_void, c_void, c_void]),
+    "mava_ppo_adv_stats": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void]),
+    "mava_ppo_loss_grad_bf16_stats": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void,
+                                              P(PpoHyper)] + [c_void] * 8 +
+                                      [c_int, c_int, c_void, c_void, c_void, c_void]),
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
     "mava_ff_rollout_bf16": (c_int, [c_void, P(MlpDesc)] + [c_void] * 6 + [c_int] * 3 +
                              [c_void] * 7),

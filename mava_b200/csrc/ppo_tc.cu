@@ -1146,14 +1146,15 @@ int64_t mava_ppo_workspace_bytes_bf16(const mava_mlp_desc* actor, const mava_mlp
                    (int64_t)tile_bytes(TM, HID);
 }
 
-int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_params,
-                            const void* actor_image, const mava_mlp_desc* critic,
-                            const float* critic_params, const void* critic_image,
-                            const mava_ppo_hyper* hyper, const int8_t* view, const uint8_t* mask,
-                            const int8_t* action, const float* old_logp, const float* old_value,
-                            const float* adv, const float* targets, const int32_t* rows,
-                            int num_replicas, int mb_size, float* grad_out, void* workspace,
-                            mava_stream_t stream) {
+static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* actor_params,
+                                   const void* actor_image, const mava_mlp_desc* critic,
+                                   const float* critic_params, const void* critic_image,
+                                   const mava_ppo_hyper* hyper, const int8_t* view,
+                                   const uint8_t* mask, const int8_t* action, const float* old_logp,
+                                   const float* old_value, const float* adv, const float* targets,
+                                   const int32_t* rows, int num_replicas, int mb_size,
+                                   float* grad_out, void* workspace, const double* adv_stats,
+                                   mava_stream_t stream) {
   TrainArgs a{};
   int rc = make_net(actor, actor_params, &a.actor);
   if (rc) return rc;
@@ -1195,7 +1196,7 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   a.adv = adv;
   a.targets = targets;
   a.rows = rows;
-  a.adv_stats = stats;
+  a.adv_stats = adv_stats ? adv_stats : stats;
   a.R = R;
   a.mb_size = mb_size;
   a.num_replicas = num_replicas;
@@ -1213,8 +1214,10 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(grad_out, 0, (size_t)(na + nc + 8) * sizeof(float), s);
   if (e != cudaSuccess) return (int)e;
-  rc = launch_adv_stats(adv, rows, mb_size, actor->num_agents, num_replicas, stats, s);
-  if (rc) return rc;
+  if (!adv_stats) {
+    rc = launch_adv_stats(adv, rows, mb_size, actor->num_agents, num_replicas, stats, s);
+    if (rc) return rc;
+  }
 
   const int k1p_max = a.actor.k1p > a.critic.k1p ? a.actor.k1p : a.critic.k1p;
   size_t smem_fused = (size_t)WImage{k1p_max}.total() + region_bytes(k1p_max) +
@@ -1293,6 +1296,47 @@ int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_param
   if (rc) return rc;
   return launch_finalize_loss(loss_acc, (double)R * actor->num_agents, hyper->ent_coef,
                               hyper->vf_coef, grad_out + na + nc, s);
+}
+
+int mava_ppo_loss_grad_bf16(const mava_mlp_desc* actor, const float* actor_params,
+                            const void* actor_image, const mava_mlp_desc* critic,
+                            const float* critic_params, const void* critic_image,
+                            const mava_ppo_hyper* hyper, const int8_t* view, const uint8_t* mask,
+                            const int8_t* action, const float* old_logp, const float* old_value,
+                            const float* adv, const float* targets, const int32_t* rows,
+                            int num_replicas, int mb_size, float* grad_out, void* workspace,
+                            mava_stream_t stream) {
+  return ppo_loss_grad_bf16_impl(actor, actor_params, actor_image, critic, critic_params,
+                                 critic_image, hyper, view, mask, action, old_logp, old_value, adv,
+                                 targets, rows, num_replicas, mb_size, grad_out, workspace, nullptr,
+                                 stream);
+}
+
+int mava_ppo_adv_stats(const float* adv, const int32_t* rows, int num_replicas, int mb_size,
+                       int num_agents, double* stats, mava_stream_t stream) {
+  MAVA_CHECK_PTR(adv);
+  MAVA_CHECK_PTR(rows);
+  MAVA_CHECK_PTR(stats);
+  MAVA_CHECK_ARG(num_replicas > 0 && num_replicas <= 8 && mb_size > 0 && num_agents > 0);
+  cudaError_t e = cudaMemsetAsync(stats, 0, 16 * sizeof(double), as_stream(stream));
+  if (e != cudaSuccess) return (int)e;
+  return launch_adv_stats(adv, rows, mb_size, num_agents, num_replicas, stats, as_stream(stream));
+}
+
+int mava_ppo_loss_grad_bf16_stats(const mava_mlp_desc* actor, const float* actor_params,
+                                  const void* actor_image, const mava_mlp_desc* critic,
+                                  const float* critic_params, const void* critic_image,
+                                  const mava_ppo_hyper* hyper, const int8_t* view,
+                                  const uint8_t* mask, const int8_t* action, const float* old_logp,
+                                  const float* old_value, const float* adv, const float* targets,
+                                  const int32_t* rows, int num_replicas, int mb_size,
+                                  const double* adv_stats, float* grad_out, void* workspace,
+                                  mava_stream_t stream) {
+  MAVA_CHECK_PTR(adv_stats);
+  return ppo_loss_grad_bf16_impl(actor, actor_params, actor_image, critic, critic_params,
+                                 critic_image, hyper, view, mask, action, old_logp, old_value, adv,
+                                 targets, rows, num_replicas, mb_size, grad_out, workspace, adv_stats,
+                                 stream);
 }
 
 }  // extern "C"

@@ -376,6 +376,38 @@ def ppo_loss_grad_bf16(actor: MlpDesc, actor_params, actor_image, critic: MlpDes
         _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16")
 
 
+def ppo_adv_stats(adv, rows, num_replicas: int, mb_size: int, num_agents: int, stats) -> None:
+    """Per-replica advantage sums of one minibatch (16 doubles), ahead of the loss kernels."""
+    _count(1)
+    check(_lib.load().mava_ppo_adv_stats(
+        _p(adv, torch.float32, None, "adv"), _p(rows, torch.int32, num_replicas * mb_size, "rows"),
+        num_replicas, mb_size, num_agents, _p(stats, torch.float64, 16, "stats"), _stream()),
+        "mava_ppo_adv_stats")
+
+
+def ppo_loss_grad_bf16_stats(actor: MlpDesc, actor_params, actor_image, critic: MlpDesc,
+                             critic_params, critic_image, hyper: PpoHyper, view, mask, action,
+                             old_logp, old_value, adv, targets, rows, num_replicas: int,
+                             mb_size: int, adv_stats, grad_out, workspace) -> None:
+    """ppo_loss_grad_bf16 with the advantage statistics computed beforehand (ppo_adv_stats)."""
+    na, nc = mlp_param_count(actor), mlp_param_count(critic)
+    need = ppo_workspace_bytes_bf16(actor, critic, num_replicas * mb_size)
+    _count(3)  # fused fwd+bwd, first-layer wgrad, loss finalize
+    check(_lib.load().mava_ppo_loss_grad_bf16_stats(
+        C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"), C.byref(critic),
+        _p(critic_params, torch.float32, nc, "critic_params"),
+        _p(critic_image, torch.uint8, mlp_pack_bytes(critic), "critic_image"), C.byref(hyper),
+        _p(view, torch.int8, None, "view"), _p(mask, torch.uint8, None, "mask"),
+        _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
+        _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
+        _p(targets, torch.float32, None, "targets"),
+        _p(rows, torch.int32, num_replicas * mb_size, "rows"), num_replicas, mb_size,
+        _p(adv_stats, torch.float64, 16, "adv_stats"),
+        _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
+        _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16_stats")
+
+
 def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, grad_scale: float,
                    lr_actor: float, lr_critic: float, max_norm: float,
                    lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:

@@ -103,6 +103,10 @@ class FFLearner:
         self.key2 = z(2, 2, dtype=torch.uint32)
         self.bits = z(T * self.E, dtype=torch.uint32)
         self.rows = z(self.U * self.mb, dtype=torch.int32)
+        # bf16 path: row lists and advantage statistics of ALL minibatches of an update, prepared off
+        # the critical path (side stream) -- they depend on the permutations and on GAE only
+        self.rows_all = z(int(s.ppo_epochs), self.nmb, self.U * self.mb, dtype=torch.int32)
+        self.adv_stats_all = z(int(s.ppo_epochs), self.nmb, 16, dtype=torch.float64)
         self.grad = z(self.na + self.nc + 8)
         self.loss_buf = z(self.epochs, self.nmb, 5)
         # precision: the bf16 tensor-core kernels need two hidden layers of width 128
@@ -228,6 +232,10 @@ class FFLearner:
             native.prng_split(k, self.key3_ep[ep], 3)  # key, shuffle_key, entropy_key (:269)
             k = self.key3_ep[ep][0]
             perms.append(self._permutation(self.key3_ep[ep][1], ep))
+            if self.bf16:
+                for m in range(self.nmb):
+                    native.ppo_minibatch_rows(perms[ep], m, self.mb, self.U, self.E,
+                                              self.rows_all[ep, m])
         return perms
 
     def _update_epochs(self, perms) -> None:
@@ -236,19 +244,39 @@ class FFLearner:
         na, nc = self.na, self.nc
         scale = 1.0 / self.world
         steps_per_update = self.epochs * self.nmb
+        main = torch.cuda.current_stream()
+        stats_done = []
+        if self.bf16:
+            # advantage statistics of every minibatch on the side stream (GAE is done on `main`);
+            # minibatch (ep, m) waits for its own event only
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                for ep in range(self.epochs):
+                    evs = []
+                    for m in range(self.nmb):
+                        native.ppo_adv_stats(self.adv, self.rows_all[ep, m], self.U, self.mb, self.A,
+                                             self.adv_stats_all[ep, m])
+                        ev = torch.cuda.Event()
+                        ev.record(self._side)
+                        evs.append(ev)
+                    stats_done.append(evs)
         for ep in range(self.epochs):
             perm = perms[ep]
             for m in range(self.nmb):
-                native.ppo_minibatch_rows(perm, m, self.mb, self.U, self.E, self.rows)
+                if self.bf16:
+                    main.wait_event(stats_done[ep][m])
+                else:
+                    native.ppo_minibatch_rows(perm, m, self.mb, self.U, self.E, self.rows)
                 if self.time_loss_grad is not None:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
                 if self.bf16:
-                    native.ppo_loss_grad_bf16(self.actor_desc, self.actor_params, self.actor_img,
-                                              self.critic_desc, self.critic_params, self.critic_img,
-                                              self.hyper, self.view, self.mask, self.action,
-                                              self.logp, self.value, self.adv, self.targets,
-                                              self.rows, self.U, self.mb, self.grad, self.workspace)
+                    native.ppo_loss_grad_bf16_stats(
+                        self.actor_desc, self.actor_params, self.actor_img, self.critic_desc,
+                        self.critic_params, self.critic_img, self.hyper, self.view, self.mask,
+                        self.action, self.logp, self.value, self.adv, self.targets,
+                        self.rows_all[ep, m], self.U, self.mb, self.adv_stats_all[ep, m], self.grad,
+                        self.workspace)
                 else:
                     native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
                                          self.critic_params, self.hyper, self.view, self.mask,
