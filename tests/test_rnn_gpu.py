@@ -127,7 +127,10 @@ def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, preci
     action = torch.from_numpy(rng.integers(0, N, (T, NE, A)).astype(np.int8))
     action = torch.where(torch.from_numpy(np.take_along_axis(mask_b, action.numpy()[..., None].astype(np.int64), -1)[..., 0]),
                          action, torch.zeros_like(action))
-    old_logp = -torch.rand(T, NE, A) * 2 - 0.3
+    # (own seeded generator: the global torch generator differs from process to process, and with it
+    # which ratios sit next to a clip boundary -- the bf16 cases then flipped a few clip decisions
+    # in some runs and not in others)
+    old_logp = -torch.rand(T, NE, A, generator=torch.Generator().manual_seed(7)) * 2 - 0.3
     old_value, adv, targets = f32(T, NE, A), f32(T, NE, A), f32(T, NE, A)
     done = rng.random((T, NE)) < 0.25
     hs_a, hs_c = f32(T, NE * A, H), f32(T, NE * rpc, H)  # hidden entering every step (oracle view)
