@@ -207,18 +207,26 @@ __device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, i
 constexpr int NLOAD = 96;             // three loader warps (20 warps x 96 registers fill the file)
 constexpr int NT_F = NT + 32 + NLOAD;  // 16 epilogue warps + the MMA-issue warp + the loader warps
 constexpr int NT_RDY = NT + 32;        // threads on the operands-ready barrier
-constexpr int BAR_EXPAND = 1, BAR_READY = 2, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 5, BAR_LOAD = 6;
+constexpr int BAR_READY = 2, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 5, BAR_LOAD = 6, BAR_READY2 = 7;
 constexpr int kLdSlots = 22;           // words per loader thread: 22 x 96 = 2112 = 128 rows x 66 bytes / 4
 
+// The operands-ready handshake alternates between two named barriers.  A named barrier cannot tell
+// generations apart: with the next tile's layer 1 already in TMEM an epilogue warp passes from
+// "X ready" to "H1 stored" without waiting for anything the issue warp does, so on ONE barrier its
+// second arrival could complete the first generation while a slow warp is still storing.  Between
+// two arrivals on the SAME barrier there is always a wait for an MMA the issue warp issued after the
+// generation in between.
 // epilogue side: my shared-memory / TMEM accesses of this phase are done
-__device__ __forceinline__ void epi_arrive() {
+__device__ __forceinline__ void epi_arrive(uint32_t& rb) {
   fence_proxy_async();
   fence_before_sync();
-  asm volatile("bar.arrive %0, %1;" ::"n"(BAR_READY), "n"(NT_RDY) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"r"(rb ? BAR_READY2 : BAR_READY), "n"(NT_RDY) : "memory");
+  rb ^= 1u;
 }
 // issue side: all 512 epilogue threads have arrived
-__device__ __forceinline__ void issuer_wait() {
-  asm volatile("bar.sync %0, %1;" ::"n"(BAR_READY), "n"(NT_RDY) : "memory");
+__device__ __forceinline__ void issuer_wait(uint32_t& rb) {
+  asm volatile("bar.sync %0, %1;" ::"r"(rb ? BAR_READY2 : BAR_READY), "n"(NT_RDY) : "memory");
+  rb ^= 1u;
   fence_after_sync();
 }
 // barrier among the 16 epilogue warps only
@@ -361,6 +369,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   const bool cl = padded_global && d.A <= 4;
   float* linc = reinterpret_cast<float*>(&ctrl.lin[0][0][0]);  // [TM][8]
   uint32_t phase = 0, phase1 = 0, phase2 = 0;
+  uint32_t rb = 0;  // which of the two operands-ready barriers comes next (both sides alternate)
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
 #pragma unroll
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
       const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
       const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-      issuer_wait();  // X built; the previous tile's dZ1 stored and its accumulator drained
+      issuer_wait(rb);  // X built; the previous tile's dZ1 stored and its accumulator drained
       if (elect_one()) {
         // previous tile: [dW1^T | db1] += dZ1^T [X | 1] (A = dZ1 and B = X MN-major), then layer 1
         if (fold && !first)
@@ -384,22 +393,22 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           issue_gemm(tmem + col_acc1, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
       __syncwarp();
-      issuer_wait();  // H1 stored
+      issuer_wait(rb);  // H1 stored
       if (elect_one())
         issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
       __syncwarp();
-      issuer_wait();  // H2 stored
+      issuer_wait(rb);  // H2 stored
       if (elect_one())
         issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
       __syncwarp();
-      issuer_wait();  // dZ3 stored
+      issuer_wait(rb);  // dZ3 stored
       if (elect_one()) {
         // dH2 = dZ3 W3^T is what the next epilogue waits for; dW3 += H2^T dZ3 runs behind it
         issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, &ctrl.mbar);
         issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
       }
       __syncwarp();
-      issuer_wait();  // dZ2 stored
+      issuer_wait(rb);  // dZ2 stored
       if (elect_one()) {
         // dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1] behind it.  Without the prefetch pipeline
         // the next tile's X is built over H2 / dZ2 / H1 (staging): a second commit tells the
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     }
     if (!first && fold) {
       const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-      issuer_wait();  // the last tile's dZ1
+      issuer_wait(rb);  // the last tile's dZ1
       if (elect_one())
         issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, &ctrl.mbar);
       __syncwarp();
@@ -716,7 +725,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
                                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
         }
       }
-      epi_arrive();  // -> layer 1 (and the previous tile's first-layer gradient)
+      epi_arrive(rb);  // -> layer 1 (and the previous tile's first-layer gradient)
       MAVA_STAMP(1);
       MAVA_STAMP(14);
       // loss inputs of this row.  Prefetch path: the loader warps put them into ctrl.lin; plain
@@ -772,11 +781,11 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       MAVA_STAMP(3);
       hidden_epilogue(L, tmem + col_acc1, h1t);
       MAVA_STAMP(4);
-      epi_arrive();  // -> layer 2
+      epi_arrive(rb);  // -> layer 2
       MAVA_STAMP(5);
       wait_acc(&ctrl.mbar, phase);
       hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead (not folded): H2 replaces it
-      epi_arrive();  // -> head
+      epi_arrive(rb);  // -> head
       MAVA_STAMP(6);
       wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(7);
@@ -863,12 +872,12 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       }
       // staging rows expanded, loss inputs read: the loaders may bring in tile i+2
       if (has_next2 || c_next) asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
-      epi_arrive();  // -> backward through the head
+      epi_arrive(rb);  // -> backward through the head
       MAVA_STAMP(8);
       wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(9);
       grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
-      epi_arrive();  // -> dH1, dW2
+      epi_arrive(rb);  // -> dH1, dW2
       MAVA_STAMP(10);
       wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(11);
@@ -897,7 +906,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       // everything still in the tensor pipe: the last tile's weight-gradient MMAs
       if (!prefetch) wait_acc(&ctrl.mbar2, phase2);  // dW2 / dW3
       if (fold) {                                  // dW1
-        epi_arrive();
+        epi_arrive(rb);
         wait_acc(&ctrl.mbar, phase);
       }
     }
