@@ -16,8 +16,20 @@
 //                      dZ1 tile images brought in by bulk (TMA) copies and X rebuilt from the int8 obs.
 //
 // Every activation / gradient tile is stored once in shared memory and consumed by up to three GEMMs
-// (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.  Thread
-// mapping: 512 threads per CTA, thread (row r, column quarter q) - see mlp_tc.cuh.
+// (forward or backward as K-major A, weight gradient as MN-major A or B) - see tc.cuh.
+//
+// Roles inside a CTA of ppo_fused_kernel (640 threads, 20 warps x 96 registers):
+//   warps 0-15   epilogue warps: thread (row r, column quarter q) of the tile, see mlp_tc.cuh.  They
+//                turn accumulators into the next GEMM's operand (TMEM -> registers -> bf16 -> shared
+//                memory) and finish the loss rows; they issue no MMA and (on the staged paths) no
+//                global load.
+//   warp 16      MMA-issue warp: waits on a named barrier for "operands ready", issues the GEMM the
+//                next epilogue needs, commits, then issues the weight-gradient GEMMs behind the commit.
+//   warps 17-19  loader warps: the next tile's observation bytes, loss inputs and index lists (plain
+//                loads; they never execute a proxy fence, which would wait for their loads).
+// Handshakes: epilogue -> issue: two alternating named barriers (bar.arrive / bar.sync);
+// issue -> epilogue: tcgen05.commit on one mbarrier per kind of event; loaders <-> epilogue: FULL /
+// EMPTY named barriers around the staging rows; bulk (TMA) copies complete on an mbarrier.
 #include <cstdlib>
 
 #include "mlp_tc.cuh"
@@ -1270,7 +1282,8 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
         n_actor = na;
       }
     }
-    if (const char* ov = getenv("MAVA_ACTOR_CTAS")) n_actor = atoi(ov);  // development switch
+    static const char* const split_override = getenv("MAVA_ACTOR_CTAS");  // development switch
+    if (split_override) n_actor = atoi(split_override);
     n_actor = n_actor < 1 ? 1 : (n_actor > sms - 1 ? sms - 1 : n_actor);
     a.actor_ctas = (int)(ta < n_actor ? ta : n_actor);
     a.critic_ctas = (int)(tcn < sms - n_actor ? tcn : sms - n_actor);
