@@ -319,7 +319,7 @@ def run_ours(args) -> None:
     e2e_value = world * steps_per_update * args.steps / (e2e_ms * 1e-3)
 
     cpu_baseline = None
-    if not args.no_cpu_baseline and args.workload == "ff_mappo_rware":
+    if world == 1 and not args.no_cpu_baseline and args.workload == "ff_mappo_rware":  # N = 1 only
         from oracle import cpu_baseline as cb
 
         res = cb.run(TASK, num_envs=512, updates=1, warmup=0)
