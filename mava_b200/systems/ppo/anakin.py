@@ -35,6 +35,11 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def _nccl_allreduce(grad: torch.Tensor) -> None:
+    """pmean("device") as a sum over ranks (1/world is folded into the optimiser kernel)."""
+    dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+
+
 def _u32(a: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32)).to(device)
 
@@ -43,10 +48,14 @@ class FFLearner:
     """Device buffers + the kernel schedule of one GPU's share of the Anakin learner."""
 
     def __init__(self, env: NativeMarlEnv, actor: FeedForwardActor, critic: FeedForwardValueNet,
-                 config, centralised_critic: bool, device: torch.device):
+                 config, centralised_critic: bool, device: torch.device,
+                 rank_world: Optional[Tuple[int, int]] = None):
         s = config.system
         self.env, self.config, self.device = env, config, device
-        self.rank, self.world = world()
+        # rank_world overrides the process group: a test can build the learners of several ranks in
+        # one process and do pmean("device") by hand (tests/test_multirank_gpu.py)
+        self.rank, self.world = rank_world if rank_world is not None else world()
+        self.allreduce = _nccl_allreduce if rank_world is None else None
         self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
             config.arch.num_envs)
         self.NE = self.U * self.E
@@ -137,8 +146,15 @@ class FFLearner:
         self.compute_dtype = "bf16" if self.bf16 else "f32"
         self.dominant_kernel = ("ppo_fused_kernel + ppo_wgrad1_kernel (tcgen05, bf16)" if self.bf16
                                 else "ppo_loss_grad (fp32 mlp_fwd/mlp_bwd/mlp_wgrad kernels)")
-        lr_decay = bool(s.decay_learning_rates)
-        self.lr_decay_updates = int(s.num_updates) if lr_decay else 0
+
+    @property
+    def lr_decay_updates(self) -> int:
+        """num_updates of the linear schedule (mava/utils/training.py:38-47), read when the update
+        is issued / captured: run_experiment replaces ``self.config`` after check_total_timesteps
+        has rewritten ``system.num_updates``, like the reference's schedule closes over the mutated
+        config and is traced on the first learn() call."""
+        s = self.config.system
+        return int(s.num_updates) if bool(s.decay_learning_rates) else 0
 
     # -- views of the state ---------------------------------------------------------------------
     @property
@@ -238,75 +254,91 @@ class FFLearner:
                                               self.rows_all[ep, m])
         return perms
 
-    def _update_epochs(self, perms) -> None:
-        """ff_mappo.py:141-295."""
+    def _epochs_begin(self) -> None:
+        """Before the first minibatch: the advantage statistics of every minibatch of the update on
+        the side stream (GAE is done on `main`); minibatch (ep, m) waits for its own event only."""
+        self._stats_done = []
+        if not self.bf16:
+            return
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            for ep in range(self.epochs):
+                evs = []
+                for m in range(self.nmb):
+                    native.ppo_adv_stats(self.adv, self.rows_all[ep, m], self.U, self.mb, self.A,
+                                         self.adv_stats_all[ep, m])
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                    evs.append(ev)
+                self._stats_done.append(evs)
+
+    def _minibatch_grad(self, ep: int, m: int, perms) -> None:
+        """value_and_grad of both losses on minibatch m of epoch ep, averaged over the replicas
+        (ff_mappo.py:150-226) -> self.grad = [actor grads | critic grads | 5 loss scalars]."""
+        if self.bf16:
+            torch.cuda.current_stream().wait_event(self._stats_done[ep][m])
+        else:
+            native.ppo_minibatch_rows(perms[ep], m, self.mb, self.U, self.E, self.rows)
+        if self.time_loss_grad is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if self.bf16:
+            native.ppo_loss_grad_bf16_stats(
+                self.actor_desc, self.actor_params, self.actor_img, self.critic_desc,
+                self.critic_params, self.critic_img, self.hyper, self.view, self.mask,
+                self.action, self.logp, self.value, self.adv, self.targets,
+                self.rows_all[ep, m], self.U, self.mb, self.adv_stats_all[ep, m], self.grad,
+                self.workspace)
+        else:
+            native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
+                                 self.critic_params, self.hyper, self.view, self.mask,
+                                 self.action, self.logp, self.value, self.adv, self.targets,
+                                 self.rows, self.U, self.mb, self.grad, self.workspace)
+        if self.time_loss_grad is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.time_loss_grad.append((e0, e1))
+
+    def _minibatch_apply(self, ep: int, m: int) -> None:
+        """clip_by_global_norm -> adam -> apply_updates on the device-summed gradients
+        (ff_mappo.py:240-250); 1/world of pmean("device") is folded into the kernel."""
         s = self.config.system
         na, nc = self.na, self.nc
         scale = 1.0 / self.world
         steps_per_update = self.epochs * self.nmb
-        main = torch.cuda.current_stream()
-        stats_done = []
-        if self.bf16:
-            # advantage statistics of every minibatch on the side stream (GAE is done on `main`);
-            # minibatch (ep, m) waits for its own event only
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                for ep in range(self.epochs):
-                    evs = []
-                    for m in range(self.nmb):
-                        native.ppo_adv_stats(self.adv, self.rows_all[ep, m], self.U, self.mb, self.A,
-                                             self.adv_stats_all[ep, m])
-                        ev = torch.cuda.Event()
-                        ev.record(self._side)
-                        evs.append(ev)
-                    stats_done.append(evs)
-        for ep in range(self.epochs):
-            perm = perms[ep]
-            for m in range(self.nmb):
-                if self.bf16:
-                    main.wait_event(stats_done[ep][m])
-                else:
-                    native.ppo_minibatch_rows(perm, m, self.mb, self.U, self.E, self.rows)
-                if self.time_loss_grad is not None:
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                if self.bf16:
-                    native.ppo_loss_grad_bf16_stats(
-                        self.actor_desc, self.actor_params, self.actor_img, self.critic_desc,
-                        self.critic_params, self.critic_img, self.hyper, self.view, self.mask,
-                        self.action, self.logp, self.value, self.adv, self.targets,
-                        self.rows_all[ep, m], self.U, self.mb, self.adv_stats_all[ep, m], self.grad,
-                        self.workspace)
-                else:
-                    native.ppo_loss_grad(self.actor_desc, self.actor_params, self.critic_desc,
-                                         self.critic_params, self.hyper, self.view, self.mask,
-                                         self.action, self.logp, self.value, self.adv, self.targets,
-                                         self.rows, self.U, self.mb, self.grad, self.workspace)
-                if self.time_loss_grad is not None:
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    e1.record()
-                    self.time_loss_grad.append((e0, e1))
-                if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
-                    dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
-                if self.bf16:  # the optimiser refreshes the bf16 operand images itself
-                    native.clip_adam_pair_pack(
-                        self.params, self.mu, self.nu, self.counts, self.grad, self.actor_desc,
-                        self.actor_img, self.critic_desc, self.critic_img, scale, float(s.actor_lr),
-                        float(s.critic_lr), float(s.max_grad_norm), self.lr_decay_updates,
-                        steps_per_update)
-                else:
-                    native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na,
-                                          nc, scale, float(s.actor_lr), float(s.critic_lr),
-                                          float(s.max_grad_norm), self.lr_decay_updates,
-                                          steps_per_update)
-                self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
+        if self.bf16:  # the optimiser refreshes the bf16 operand images itself
+            native.clip_adam_pair_pack(
+                self.params, self.mu, self.nu, self.counts, self.grad, self.actor_desc,
+                self.actor_img, self.critic_desc, self.critic_img, scale, float(s.actor_lr),
+                float(s.critic_lr), float(s.max_grad_norm), self.lr_decay_updates,
+                steps_per_update)
+        else:
+            native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na,
+                                  nc, scale, float(s.actor_lr), float(s.critic_lr),
+                                  float(s.max_grad_norm), self.lr_decay_updates,
+                                  steps_per_update)
+        self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
+
+    def _epochs_end(self) -> None:
         self.key.copy_(self.key3_ep[self.epochs - 1][0])
         if self.world > 1:
-            self.loss_buf.mul_(scale)
+            self.loss_buf.mul_(1.0 / self.world)
 
-    def _update_step(self) -> None:
-        """One ``_update_step`` of the reference (ff_mappo.py:56-300) for all U replicas."""
-        n0 = native.LAUNCHES
+    def _update_epochs(self, perms) -> None:
+        """ff_mappo.py:141-295."""
+        self._epochs_begin()
+        for ep in range(self.epochs):
+            for m in range(self.nmb):
+                self._minibatch_grad(ep, m, perms)
+                if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
+                    self.allreduce(self.grad)
+                self._minibatch_apply(ep, m)
+        self._epochs_end()
+
+    def _rollout_and_gae(self):
+        """ff_mappo.py:76-139 for all U replicas; returns the epoch permutations (prepared on the
+        side stream next to the rollout)."""
         native.prng_split_chain(self.key, self.policy_keys, self.T)  # key, policy_key per step (:81)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
@@ -322,9 +354,19 @@ class FFLearner:
                    float(self.config.system.gae_lambda), self.T, self.NE, self.A, self.adv,
                    self.targets)
         main.wait_stream(self._side)
-        self._update_epochs(perms)
+        return perms
+
+    def _carry_over(self) -> None:
+        """The bootstrap observation becomes slot 0 of the next update."""
         self.view[0].copy_(self.view[self.T])
         self.mask[0].copy_(self.mask[self.T])
+
+    def _update_step(self) -> None:
+        """One ``_update_step`` of the reference (ff_mappo.py:56-300) for all U replicas."""
+        n0 = native.LAUNCHES
+        perms = self._rollout_and_gae()
+        self._update_epochs(perms)
+        self._carry_over()
         self.launches_per_update = native.LAUNCHES - n0
 
     # -- CUDA graph -----------------------------------------------------------------------------
@@ -350,18 +392,15 @@ class FFLearner:
         self._graph = g
 
     def check_sort(self) -> None:
-        """The permutation sort assumes uniform keys; a bucket overflow is reported here.  The flag
-        is read without stalling the stream: the copy issued by the previous call is checked, then
-        a new one is issued."""
+        """The permutation sort assumes uniform keys; a bucket overflow is raised by the learn()
+        call that produced it (the flag is read after that call's work has drained)."""
         if self._ovf_host is None:
             self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._ovf_event = torch.cuda.Event()
-        else:
-            self._ovf_event.synchronize()
-            if int(self._ovf_host[0]) != 0:
-                raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys)")
         self._ovf_host.copy_(self.sort_overflow, non_blocking=True)
-        self._ovf_event.record()
+        torch.cuda.current_stream().synchronize()
+        if int(self._ovf_host[0]) != 0:
+            raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
+                               "parameters of this learn() call are not to be trusted")
 
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
@@ -403,7 +442,16 @@ def episode_summary(learner) -> Tuple[Dict[str, Dict[str, float]], bool]:
     any episode finished."""
     if learner._stats_host is None:
         learner._stats_host = torch.zeros(10, dtype=torch.float64).pin_memory()
-    learner._stats_host.copy_(learner.ep_stats, non_blocking=True)
+    stats = learner.ep_stats
+    if learner.world > 1 and learner.allreduce is not None:
+        # the reference reduces over the pmap output of all devices: sums add, extrema combine
+        stats = stats.clone()
+        sums, mins, maxs = stats[[0, 1, 2, 5, 6]], stats[[3, 7]], stats[[4, 8]]
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mins, op=dist.ReduceOp.MIN)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+        stats[[0, 1, 2, 5, 6]], stats[[3, 7]], stats[[4, 8]] = sums, mins, maxs
+    learner._stats_host.copy_(stats, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     n, sr, qr, mnr, mxr, sl, ql, mnl, mxl, _ = learner._stats_host.tolist()
     if n == 0:
@@ -470,12 +518,14 @@ def _adopt(learner: FFLearner, st: LearnerState) -> None:
 
 
 def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
-                  device: Optional[torch.device] = None):
-    """ff_mappo.py:333-432: networks, optimiser state, env reset, replicated learner state."""
+                  device: Optional[torch.device] = None,
+                  rank_world: Optional[Tuple[int, int]] = None):
+    """ff_mappo.py:333-432: networks, optimiser state, env reset, replicated learner state.
+    ``rank_world`` builds the learner of one rank of a larger job without a process group."""
     from ...networks import instantiate
 
     device = device or env.device
-    rank, n_devices = world()
+    rank, n_devices = rank_world if rank_world is not None else world()
     config.system.num_agents = env.num_agents
     key, actor_net_key, critic_net_key = keys
 
@@ -485,7 +535,8 @@ def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
     actor_network = FeedForwardActor(torso=actor_torso, action_head=action_head)
     critic_network = FeedForwardValueNet(torso=critic_torso, centralised_critic=centralised_critic)
 
-    learner = FFLearner(env, actor_network, critic_network, config, centralised_critic, device)
+    learner = FFLearner(env, actor_network, critic_network, config, centralised_critic, device,
+                        rank_world)
     ap = actor_network.init(actor_net_key, learner.actor_desc.in_dim)
     cp = critic_network.init(critic_net_key, learner.critic_desc.in_dim)
     learner.params.copy_(torch.from_numpy(np.concatenate([ap, cp])).to(device))

@@ -28,17 +28,19 @@ from ...networks import RecurrentActor, RecurrentValueNet
 from ...types import (ExperimentOutput, HiddenStates, OptStates, Params, RNNLearnerState, StepType,
                       TimeStep)
 from ...wrappers import EnvState, NativeMarlEnv
-from .anakin import _u32, world
+from .anakin import _nccl_allreduce, _u32, world
 
 
 class RecLearner:
     """Device buffers + the kernel schedule of one GPU's share of the recurrent learner."""
 
     def __init__(self, env: NativeMarlEnv, actor: RecurrentActor, critic: RecurrentValueNet,
-                 config, centralised_critic: bool, device: torch.device):
+                 config, centralised_critic: bool, device: torch.device,
+                 rank_world: Optional[Tuple[int, int]] = None):
         s = config.system
         self.env, self.config, self.device = env, config, device
-        self.rank, self.world = world()
+        self.rank, self.world = rank_world if rank_world is not None else world()
+        self.allreduce = _nccl_allreduce if rank_world is None else None
         self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
             config.arch.num_envs)
         self.NE = self.U * self.E
@@ -137,7 +139,12 @@ class RecLearner:
         self.compute_dtype = "bf16" if self.bf16 else "f32"
         self.dominant_kernel = ("tc_gemm_kernel (tcgen05 bf16 GRU scan + dense layers)" if self.bf16
                                 else "sgemm_kernel (fp32 GRU scan + dense layers)")
-        self.lr_decay_updates = int(s.num_updates) if bool(s.decay_learning_rates) else 0
+
+    @property
+    def lr_decay_updates(self) -> int:
+        """Read when the update is issued / captured (see FFLearner.lr_decay_updates)."""
+        s = self.config.system
+        return int(s.num_updates) if bool(s.decay_learning_rates) else 0
 
     # -- views of the state ---------------------------------------------------------------------
     @property
@@ -242,7 +249,7 @@ class RecLearner:
                     e1.record()
                     self.time_loss_grad.append((e0, e1))
                 if self.world > 1:  # pmean("device"), rec_mappo.py:283-293
-                    dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+                    self.allreduce(self.grad)
                 native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na, nc,
                                       scale, float(s.actor_lr), float(s.critic_lr),
                                       float(s.max_grad_norm), self.lr_decay_updates,
@@ -297,16 +304,14 @@ class RecLearner:
         self._graph = g
 
     def check_sort(self) -> None:
-        """Bucket overflow of the permutation sort, read one call late (no stream stall)."""
+        """Bucket overflow of the permutation sort, raised by the learn() call that produced it."""
         if self._ovf_host is None:
             self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._ovf_event = torch.cuda.Event()
-        else:
-            self._ovf_event.synchronize()
-            if int(self._ovf_host[0]) != 0:
-                raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys)")
         self._ovf_host.copy_(self.sort_overflow, non_blocking=True)
-        self._ovf_event.record()
+        torch.cuda.current_stream().synchronize()
+        if int(self._ovf_host[0]) != 0:
+            raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
+                               "parameters of this learn() call are not to be trusted")
 
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
@@ -365,12 +370,13 @@ def _adopt(learner: RecLearner, st: RNNLearnerState) -> None:
 
 
 def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
-                  device: Optional[torch.device] = None):
+                  device: Optional[torch.device] = None,
+                  rank_world: Optional[Tuple[int, int]] = None):
     """rec_mappo.py:435-560: networks, optimiser state, env reset, replicated learner state."""
     from ...networks import instantiate
 
     device = device or env.device
-    rank, n_devices = world()
+    rank, n_devices = rank_world if rank_world is not None else world()
     config.system.num_agents = env.num_agents
     key, actor_net_key, critic_net_key = keys
     if config.system.get("recurrent_chunk_size", None) is None:
@@ -387,7 +393,8 @@ def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
         post_torso=instantiate(config.network.critic_network.post_torso),
         centralised_critic=centralised_critic, hidden_state_dim=hsd)
 
-    learner = RecLearner(env, actor_network, critic_network, config, centralised_critic, device)
+    learner = RecLearner(env, actor_network, critic_network, config, centralised_critic, device,
+                         rank_world)
     ap = actor_network.init(actor_net_key, learner.actor_desc.in_dim)
     cp = critic_network.init(critic_net_key, learner.critic_desc.in_dim)
     learner.params.copy_(torch.from_numpy(np.concatenate([ap, cp])).to(device))

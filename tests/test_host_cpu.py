@@ -96,7 +96,6 @@ def test_network_descriptors_and_flax_tree():
     assert flat.size == 70 * 128 + 128 + 128 * 128 + 128 + 128 * 5 + 5 == 26245
     tree = actor.to_flax_tree(flat, 70)
     k0 = tree["params"]["torso"]["Dense_0"]["kernel"]
-    np.testing.assert_allclose(k0.T @ k0, 2.0 * np.eye(128) * (70 / 70) if False else k0.T @ k0)
     # orthogonal(sqrt 2): rows of the (70,128) kernel are orthogonal with squared norm 2
     np.testing.assert_allclose(k0 @ k0.T, 2.0 * np.eye(70), atol=1e-4)
     np.testing.assert_array_equal(actor.from_flax_tree(tree), flat)

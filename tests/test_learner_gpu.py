@@ -13,6 +13,10 @@ from oracle import threefry as tf
 
 pytestmark = pytest.mark.gpu
 
+# relative L2 error of the parameter movement of one whole bf16 update against the float64 oracle
+# update: 1.5x the largest value measured on B200 (profiles/bf16_grad_errors_r2.json)
+BF16_UPDATE_REL_L2 = 0.5
+
 
 def _layers(flat, shapes, dtype=torch.float64):
     out, off = [], 0
@@ -144,21 +148,6 @@ def test_one_update_matches_oracle(lib_built, system, use_graph, precision):
     np.testing.assert_allclose(L.adv.cpu().numpy(), adv, rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(L.targets.cpu().numpy(), tgt, rtol=1e-5, atol=2e-5)
 
-    if bf16:
-        # the bf16 update is checked kernel by kernel against the fp32 kernels (test_tc_gpu.py);
-        # here: the key schedule is the reference's, the parameters moved, the losses are sane
-        kk = k
-        for _ in range(2):
-            kk = tf.split(kk, 3)[0]
-        np.testing.assert_array_equal(L.key.cpu().numpy(), kk)
-        moved = np.abs(L.params.cpu().numpy() - p0).max()
-        assert 1e-4 < moved < 1e-2
-        for name in ("total_loss", "value_loss", "actor_loss", "entropy"):
-            assert torch.isfinite(out.train_metrics[name]).all()
-        ent = out.train_metrics["entropy"][0].cpu().numpy()
-        assert (ent > 0.5).all() and (ent < np.log(5) + 1e-3).all()
-        return
-
     # ---- PPO epochs with the reference's key schedule and permutation
     params = p0.copy()
     mu = np.zeros_like(params)
@@ -204,19 +193,37 @@ def test_one_update_matches_oracle(lib_built, system, use_graph, precision):
             losses.append(info)
     np.testing.assert_array_equal(L.key.cpu().numpy(), k)
     got = L.params.cpu().numpy()
-    # each Adam step moves a weight by at most ~lr = 2.5e-4; fp32 noise in near-zero gradients can
-    # flip a tiny fraction of those steps, so compare on the scale of the total movement
     moved = np.abs(params - p0).max()
     assert moved > 1e-4
-    np.testing.assert_allclose(got, params, rtol=0, atol=0.02 * moved)
-    assert np.mean(np.abs(got - params) < 1e-3 * moved) > 0.99
     losses = np.array(losses).reshape(2, 2, 5)
     tm = out.train_metrics
-    np.testing.assert_allclose(tm["actor_loss"][0].cpu().numpy(), losses[..., 1], rtol=2e-4, atol=1e-6)
-    np.testing.assert_allclose(tm["entropy"][0].cpu().numpy(), losses[..., 2], rtol=2e-4, atol=1e-6)
-    np.testing.assert_allclose(tm["value_loss"][0].cpu().numpy(), losses[..., 4], rtol=2e-4, atol=1e-6)
+    if bf16:
+        # The oracle update above runs in float64 on the rollout the GPU recorded, so what differs
+        # is the bf16 rounding of the loss / gradient GEMMs (BASELINE.json: 2e-2), seen through
+        # four Adam steps.  Adam normalises every gradient element by its own magnitude, so an
+        # element whose gradient is below the bf16 noise can step the other way: the parameters are
+        # compared as a movement vector (relative L2 error of `params - p0`) and element-wise on the
+        # scale of the largest movement.  Measured on B200: see profiles/bf16_grad_errors_r2.json.
+        delta_ref, delta_got = params - p0, got - p0
+        rel = np.linalg.norm(delta_got - delta_ref) / np.linalg.norm(delta_ref)
+        frac_close = np.mean(np.abs(got - params) < 0.1 * moved)
+        print(f"bf16 whole update [{system}]: movement rel-L2 error {rel:.4f}, "
+              f"within 10% of max movement: {frac_close:.4f}")
+        assert rel < BF16_UPDATE_REL_L2, rel
+        assert frac_close > 0.97, frac_close
+        np.testing.assert_allclose(got, params, rtol=0, atol=2.0 * moved)
+        ltol = dict(rtol=2e-2, atol=2e-3)
+    else:
+        # each Adam step moves a weight by at most ~lr = 2.5e-4; fp32 noise in near-zero gradients
+        # can flip a tiny fraction of those steps, so compare on the scale of the total movement
+        np.testing.assert_allclose(got, params, rtol=0, atol=0.02 * moved)
+        assert np.mean(np.abs(got - params) < 1e-3 * moved) > 0.99
+        ltol = dict(rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(tm["actor_loss"][0].cpu().numpy(), losses[..., 1], **ltol)
+    np.testing.assert_allclose(tm["entropy"][0].cpu().numpy(), losses[..., 2], **ltol)
+    np.testing.assert_allclose(tm["value_loss"][0].cpu().numpy(), losses[..., 4], **ltol)
     np.testing.assert_allclose(tm["total_loss"][0].cpu().numpy(), losses[..., 0] + losses[..., 3],
-                               rtol=2e-4, atol=1e-6)
+                               **ltol)
     em = out.episode_metrics
     assert em["episode_return"].shape == (1, U, T, E)
     assert bool(em["is_terminal_step"].any())
