@@ -90,11 +90,12 @@ def run_reference(args) -> None:
         return
     from oracle import cpu_baseline as cb
 
-    sample_envs = 512
+    sample_envs = WORKLOADS["ff_mappo_rware"]["envs_per_gpu"]  # one GPU's full share: 2048 envs
     res = cb.run(TASK, num_envs=sample_envs, updates=max(1, args.steps), warmup=min(args.warmup, 1))
     value = res["env_steps_per_s"]
     sample = (f"{max(1, args.steps)} update(s) of {sample_envs} envs x 128 steps, 4 epochs x 2 "
-              "minibatches (1/4 of one GPU's share of the workload)")
+              "minibatches = one GPU's whole share of the workload per step (oracle port: C/OpenMP "
+              "env + torch-CPU networks, every host core)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * res["seconds"] / max(1, args.steps),
@@ -109,47 +110,79 @@ def run_reference(args) -> None:
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event reasons of one GPU, sampled through NVML every `period_ms` (a thread
+    in this process: nvidia-smi's own loop cannot go below ~100 ms, which is longer than the timed
+    region of the headline).  start() before the warm-up, mark() at the start of the timed region,
+    stop() after it: `sm_mhz` is the median over the timed region (`samples` of them), reasons are
+    collected over warm-up + timed region."""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def __init__(self, gpu_index: int, period_ms: float = 4.0):
+        self.gpu, self.period = gpu_index, period_ms * 1e-3
+        self.rows, self._stop, self._t_mark, self._thread, self._h = [], False, None, None, None
+        self._nv = None
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def _handle(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        self._nv = nv
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() \
+                else self.gpu
+            return nv.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            self._h = self._handle()
+            self._max = float(self._nv.nvmlDeviceGetMaxClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self._h, self._err = None, repr(e)
+            return self
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        self._t_mark = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                    "reasons": ["nvml unavailable: " + getattr(self, "_err", "?")]}
+        time.sleep(2 * self.period)
+        self._stop = True
+        self._thread.join(timeout=1.0)
+        nv = self._nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        timed = [r for r in self.rows if self._t_mark is None or r[0] >= self._t_mark]
+        use = timed or self.rows
+        sm = sorted(r[1] for r in use)
+        reasons = sorted({n for r in self.rows for bit, n in names.items() if r[2] & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None,
+                "sm_max_mhz": self._max, "reasons": reasons, "samples": len(timed),
+                "samples_incl_warmup": len(self.rows), "period_ms": self.period * 1e3,
+                "source": "nvml"}
 
 
 def loss_grad_flops(L) -> float:
@@ -184,17 +217,168 @@ def _finish(world: int, device) -> None:
     os._exit(0)
 
 
+def _peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _setup(name: str, precision: str, device):
+    """Learner of one BASELINE.json workload on this rank's GPU (synthetic data, seeded init)."""
+    import importlib
+
+    from mava_b200 import prng
+    from mava_b200.config import compose
+    from mava_b200.utils import make_env
+
+    wl = WORKLOADS[name]
+    system = importlib.import_module(f"mava_b200.systems.ppo.{wl['system']}")
+    cfg = compose(system.CONFIG_NAME, wl["overrides"] + [f"+arch.precision={precision}"])
+    env, _ = make_env.make(cfg, add_global_state=system.CENTRALISED_CRITIC, device=device)
+    key, _, ak, ck = prng.split(prng.PRNGKey(cfg.system.seed), 4)
+    learn, _, state = system.learner_setup(env, (key, ak, ck), cfg)
+    cfg.system.num_updates_per_eval = 1
+    return learn, state, learn.learner
+
+
+def _time_updates(L, steps: int, warmup: int, flush, barrier, learn=None, state=None):
+    """W untimed + K timed updates (graph replays), CUDA events per update; returns total ms."""
+    import torch
+
+    for _ in range(warmup):
+        learn(state) if learn is not None else L.learn(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        flush.fill_(k & 0xFF)  # evict L2 between timed steps
+        ev[k][0].record()
+        L.learn(1)
+        ev[k][1].record()
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
+def other_workloads(args, device, world, flush, barrier) -> dict:
+    """The other single-GPU-share configurations of BASELINE.json (configs[2], configs[3]) in the same
+    run: value (whole job, env-steps/s) and ms per update, device-timed like the headline."""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    out = {}
+    for name in ("ff_ippo_lbf", "rec_mappo_smax"):
+        learn, state, L = _setup(name, args.precision, device)
+        steps = max(2, min(args.steps, 5))
+        ms = _time_updates(L, steps, 3, flush, barrier, learn, state)
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[name] = {"metric": WORKLOADS[name]["metric"],
+                     "value": world * L.T * L.NE * steps / (ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms / steps, "steps": steps, "warmup": 3, "n_gpus": world,
+                     "dtype": L.compute_dtype, "envs_per_gpu": L.NE,
+                     "workload": WORKLOADS[name]["text"]}
+        if hasattr(L, "release"):
+            L.release()
+        del learn, state, L
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
+def roofline_extra(device) -> list:
+    """north_star's HBM-bound kernels against the measured copy bandwidth, each with its own NVML
+    clock record over warm-up + timed region: the env-step kernels at 2^20 envs (state + outputs =
+    0.6-0.9 GB per step, far beyond the 126 MB L2, so every step streams from HBM) and GAE at 64 M
+    elements (1.1 GB).  achieved = algorithmic bytes / CUDA-event time."""
+    import torch
+
+    from mava_b200 import native, prng
+    from sweep_rollout import SCENARIOS
+
+    peak = float(_peaks().get("hbm_gbs", 6548.8))
+    dev_index = torch.cuda.current_device()
+    rows = []
+    E = 1 << 20
+    for scen, kernel in (("small-4ag", "rware_step_kernel"), ("tiny-4ag", "rware_step_kernel"),
+                         ("lbf-8x8-2p-2f-coop", "lbf_step_kernel")):
+        sc = dict(SCENARIOS[scen])
+        kind = sc.pop("kind")
+        env = native.Env.rware(**sc) if kind == "rware" else native.Env.lbf(**sc)
+        A, FR, N = env.num_agents, env.view_dim, env.num_actions
+        keys = torch.from_numpy(prng.split(prng.PRNGKey(0), E).copy()).to(device)
+        state = env.alloc_state(E, device)
+        view = torch.zeros(E, A, FR, dtype=torch.int8, device=device)
+        mask = torch.zeros(E, A, dtype=torch.uint8, device=device)
+        reward = torch.zeros(E, A, device=device)
+        done = torch.zeros(E, dtype=torch.uint8, device=device)
+        ep_ret = torch.zeros(E, device=device)
+        ep_len = torch.zeros(E, dtype=torch.int32, device=device)
+        env.reset(keys, state, view, mask, E)
+        g = torch.Generator(device=device).manual_seed(0)
+        acts = [torch.randint(0, N, (E, A), generator=g, device=device, dtype=torch.int8)
+                for _ in range(8)]
+        sampler = ClockSampler(dev_index).start()
+        for i in range(50):
+            env.step(state, acts[i % 8], view, mask, reward, done, ep_ret, ep_len, E, True)
+        torch.cuda.synchronize(device)
+        steps = 300
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark()
+        e0.record()
+        for i in range(steps):
+            env.step(state, acts[i % 8], view, mask, reward, done, ep_ret, ep_len, E, True)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / steps
+        algo = int(env.dims.algo_bytes_per_step) * E
+        gbs = algo / (ms * 1e-3) / 1e9
+        rows.append({"kernel": kernel, "workload": f"{scen}, 2^20 envs, random actions, auto-reset",
+                     "bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
+                     "algo_bytes": algo, "algo_bytes_per_env_step": int(env.dims.algo_bytes_per_step),
+                     "ms": ms, "env_steps_per_s": E / (ms * 1e-3), "launches_timed": steps,
+                     "clocks": sampler.stop()})
+        del state, view, mask, reward, done, ep_ret, ep_len, acts, keys
+        torch.cuda.empty_cache()
+    # GAE: 64 Mi elements (T = 128 x 2^19 env-agents), 17 B per element
+    T, A, n = 128, 4, 1 << 19
+    NE = n // A
+    reward = torch.randn(T, NE, A, device=device)
+    value = torch.randn(T, NE, A, device=device)
+    done = (torch.rand(T, NE, device=device) < 0.01).to(torch.uint8)
+    last_val = torch.randn(NE, A, device=device)
+    adv, tgt = torch.empty_like(reward), torch.empty_like(reward)
+    sampler = ClockSampler(dev_index).start()
+    for _ in range(5):
+        native.gae(reward, value, done, last_val, 0.99, 0.95, T, NE, A, adv, tgt)
+    torch.cuda.synchronize(device)
+    iters = 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
+    e0.record()
+    for _ in range(iters):
+        native.gae(reward, value, done, last_val, 0.99, 0.95, T, NE, A, adv, tgt)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / iters
+    algo = 16 * T * n + T * NE + 4 * n
+    gbs = algo / (ms * 1e-3) / 1e9
+    rows.append({"kernel": "gae_kernel", "workload": "T=128 x 2^19 env-agents = 64 Mi elements",
+                 "bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
+                 "algo_bytes": algo, "ms": ms, "launches_timed": iters, "clocks": sampler.stop()})
+    return rows
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from mava_b200 import native, prng
-    from mava_b200.config import compose
-    import importlib
-
     from mava_b200.systems.ppo import _runner
-    from mava_b200.utils import make_env
     from mava_b200.systems.ppo.anakin import episode_summary
 
     device = _runner.init_distributed()
@@ -203,13 +387,7 @@ def run_ours(args) -> None:
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
     wl = WORKLOADS[args.workload]
-    system = importlib.import_module(f"mava_b200.systems.ppo.{wl['system']}")
-    cfg = compose(system.CONFIG_NAME, wl["overrides"] + [f"+arch.precision={args.precision}"])
-    env, _ = make_env.make(cfg, add_global_state=system.CENTRALISED_CRITIC, device=device)
-    key, _, ak, ck = prng.split(prng.PRNGKey(cfg.system.seed), 4)
-    learn, _, state = system.learner_setup(env, (key, ak, ck), cfg)
-    L = learn.learner
-    cfg.system.num_updates_per_eval = 1
+    learn, state, L = _setup(args.workload, args.precision, device)
     steps_per_update = L.T * L.NE  # per GPU
 
     def barrier():
@@ -218,17 +396,17 @@ def run_ours(args) -> None:
         torch.cuda.synchronize(device)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    sampler = ClockSampler(torch.cuda.current_device()).start()  # covers warm-up + timed region
     for _ in range(max(args.warmup, 3)):
         learn(state)
     torch.cuda.synchronize(device)
     launches_per_update = L.launches_per_update
 
     # ---- device-timed region: K updates, inputs resident in HBM -------------------------------
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    sampler.mark()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # evict L2 between timed steps
         ev[k][0].record()
@@ -281,29 +459,43 @@ def run_ours(args) -> None:
     L.use_graph_saved, L._graph_saved = L.use_graph, L._graph
     L.use_graph, L._graph = False, None
     L.time_loss_grad = []
+    L.time_reduce_apply = []
     roof_steps = min(args.steps, 3)
     for _ in range(roof_steps):
         L.learn(1)
     torch.cuda.synchronize(device)
     lg_ms = [a.elapsed_time(b) for a, b in L.time_loss_grad]
+    ra_ms = [a.elapsed_time(b) for a, b in L.time_reduce_apply]
     L.time_loss_grad = None
+    L.time_reduce_apply = None
     L.use_graph, L._graph = L.use_graph_saved, L._graph_saved
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1000.0, float(np.mean(lg_ms))], device=device,
-                     dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, float(np.mean(lg_ms)),
+                      float(np.mean(ra_ms)) if ra_ms else 0.0], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, lg_mean_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms, lg_mean_ms, ra_mean_ms = (float(x) for x in t.tolist())
+
+    extras = not args.no_extras and args.workload == "ff_mappo_rware"
+    flops = loss_grad_flops(L)
+    dominant, dtype_name = L.dominant_kernel, L.compute_dtype
+    collective = getattr(L, "collective", "none" if world == 1 else "nccl all_reduce")
+    if extras:  # free the headline learner before the other workloads are set up
+        import gc
+
+        if hasattr(L, "release"):
+            L.release()
+        del learn, state, L
+        gc.collect()
+        torch.cuda.empty_cache()
+    workloads = other_workloads(args, device, world, flush, barrier) if extras else None
     if rank != 0:
         _finish(world, device)
         return
+    extra = roofline_extra(device) if extras and world == 1 else None
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
@@ -313,7 +505,6 @@ def run_ours(args) -> None:
         traffic = int(tr["dram_read_bytes"]) + int(tr["dram_write_bytes"])
     except Exception:
         pass
-    flops = loss_grad_flops(L)
     achieved = flops / (lg_mean_ms * 1e-3) / 1e12
     value = world * steps_per_update * args.steps / (dev_ms * 1e-3)
     e2e_value = world * steps_per_update * args.steps / (e2e_ms * 1e-3)
@@ -322,28 +513,37 @@ def run_ours(args) -> None:
     if world == 1 and not args.no_cpu_baseline and args.workload == "ff_mappo_rware":  # N = 1 only
         from oracle import cpu_baseline as cb
 
-        res = cb.run(TASK, num_envs=512, updates=1, warmup=0)
+        envs = wl["envs_per_gpu"]
+        res = cb.run(TASK, num_envs=envs, updates=1, warmup=0)
         cpu_baseline = {"value": res["env_steps_per_s"], "unit": UNIT, "cores": res["cores"],
                         "kind": "port",
-                        "sample": "1 update of 512 envs x 128 steps, 4 epochs x 2 minibatches "
-                                  "(1/4 of one GPU's share), oracle port on all host cores"}
+                        "sample": f"1 update of {envs} envs x 128 steps, 4 epochs x 2 minibatches "
+                                  "(one GPU's whole share), oracle port on all host cores"}
 
     line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": L.compute_dtype, "data": "synthetic",
+            "dtype": dtype_name, "data": "synthetic",
             "config": workload_config(world, args.workload),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_update * args.steps),
-            "roofline": {"kernel": L.dominant_kernel, "bound": "tensor", "achieved": achieved,
+            "roofline": {"kernel": dominant, "bound": "tensor", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "peak_source": peak_src,
                          "flops_per_launch": flops, "ms_per_launch": lg_mean_ms,
                          "launches_timed": len(lg_ms)},
+            "collective": {"kind": collective, "reduce_clip_adam_us": ra_mean_ms * 1e3,
+                           "per_update": len(ra_ms) // max(1, roof_steps),
+                           "note": "gradient mean over ranks + clip + Adam + bf16 repack per "
+                                   "minibatch, CUDA events, eager launches, max over ranks"},
             "cpu_baseline": cpu_baseline}
+    if extra is not None:
+        line["roofline_extra"] = extra
+    if workloads is not None:
+        line["workloads"] = workloads
     print(json.dumps(line), flush=True)
     _finish(world, device)
 
@@ -356,6 +556,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip roofline_extra and the other BASELINE.json workloads")
     ap.add_argument("--workload", default="ff_mappo_rware", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     if os.environ.get("MAVA_BENCH_DEBUG"):  # dump every thread's stack if the run gets stuck

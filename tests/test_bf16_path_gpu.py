@@ -30,9 +30,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# Bars per gradient block (relative Frobenius error vs the fp64 gradient), 1.5x the errors measured
-# on B200 (profiles/bf16_grad_errors_r2.json).  No block may exceed north_star's 2e-2.
-FRO_BAR = 2e-2
+# Bars per gradient block: (relative Frobenius error, max element error / block scale) against the
+# fp64 gradient, 1.5x the largest errors measured on B200 (profiles/bf16_grad_errors_r2.json: actor
+# blocks <= 0.0043 / 0.0042, critic blocks <= 0.0108 / 0.0131 -- the critic's mean of dL/dv is a
+# small difference of large terms on this random data, which amplifies its relative error).  Every
+# bar is below north_star's 2e-2 for bf16 GEMMs.
+BARS = {"actor": (0.0065, 0.0065), "critic": (0.0165, 0.02)}
 
 
 def _blocks(d, off):
@@ -128,8 +131,8 @@ def test_bf16_stats_kernels_vs_fp64_autograd(lib_built, T, E, U, nmb, m):
     got = grad.cpu().numpy()
     assert np.isfinite(got[:na + nc + 5]).all()
 
-    # losses: 2e-2 of the value (bf16 GEMM tolerance of BASELINE.json)
-    np.testing.assert_allclose(got[na + nc:na + nc + 5], infos, rtol=2e-2, atol=2e-4)
+    # losses: measured <= 3.6e-3 relative (profiles/bf16_grad_errors_r2.json); bar 6e-3
+    np.testing.assert_allclose(got[na + nc:na + nc + 5], infos, rtol=6e-3, atol=1e-6)
     report = {}
     for net, d, off, ref in (("actor", actor, 0, ga), ("critic", critic, na, gc)):
         for name, sl in _blocks(d, off):
@@ -146,8 +149,9 @@ def test_bf16_stats_kernels_vs_fp64_autograd(lib_built, T, E, U, nmb, m):
                        "losses_rel": (np.abs(got[na + nc:na + nc + 5] - infos)
                                       / (np.abs(infos) + 1e-30)).tolist(),
                        "blocks": report}, f, indent=1)
-    bad = {k: v for k, v in report.items() if v["fro"] > FRO_BAR or v["max"] > 2 * FRO_BAR}
-    assert not bad, f"gradient blocks above the bf16 bar ({FRO_BAR} Frobenius): {bad}"
+    bad = {k: v for k, v in report.items()
+           if v["fro"] > BARS[k.split(".")[0]][0] or v["max"] > BARS[k.split(".")[0]][1]}
+    assert not bad, f"gradient blocks above the measured bf16 bars {BARS}: {bad}"
 
 
 def test_fused_rollout_vs_c_oracle_at_config2_shape(lib_built):

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 # relative L2 error of the parameter movement of one whole bf16 update against the float64 oracle
 # update: 1.5x the largest value measured on B200 (profiles/bf16_grad_errors_r2.json)
-BF16_UPDATE_REL_L2 = 0.5
+BF16_UPDATE_REL_L2 = 0.06  # measured 0.038 (ff_mappo), 0.035 (ff_ippo)
 
 
 def _layers(flat, shapes, dtype=torch.float64):
@@ -210,7 +210,7 @@ def test_one_update_matches_oracle(lib_built, system, use_graph, precision):
         print(f"bf16 whole update [{system}]: movement rel-L2 error {rel:.4f}, "
               f"within 10% of max movement: {frac_close:.4f}")
         assert rel < BF16_UPDATE_REL_L2, rel
-        assert frac_close > 0.97, frac_close
+        assert frac_close > 0.99, frac_close  # measured 0.9959 / 0.9978
         np.testing.assert_allclose(got, params, rtol=0, atol=2.0 * moved)
         ltol = dict(rtol=2e-2, atol=2e-3)
     else:

@@ -137,6 +137,7 @@ def test_ppo_loss_grad_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode
             yield n_, slice(off, off + s_)
             off += s_
 
+    worst = [0.0, 0.0]
     for net, d, off in (("actor", actor, 0), ("critic", critic, na)):
         for name, sl in blocks(d, off):
             ref, got = g32[sl], g16[sl]
@@ -148,8 +149,10 @@ def test_ppo_loss_grad_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode
             err_max = np.abs(got - ref).max() / scale
             err_fro = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12)
             print(f"{net}.{name}: fro {err_fro:.4f} max {err_max:.4f}")
+            worst[0], worst[1] = max(worst[0], err_fro), max(worst[1], err_max)
             assert err_fro < 5e-2 and err_max < 1e-1, (
                 f"{net}.{name}: fro err {err_fro:.4f}, max err {err_max:.4f} of scale {scale:.3e}")
+    print(f"WORST mb={mb} U={U}: fro {worst[0]:.4f} max {worst[1]:.4f}")
 
 
 @pytest.mark.gpu
