@@ -205,16 +205,18 @@ def loss_grad_flops(L) -> float:
 
 
 def _finish(world: int, device) -> None:
-    """Leave a multi-rank run without tearing NCCL down: destroy_process_group blocks while CUDA
-    graphs that captured collectives are alive, so drain the device and exit the process."""
+    """Leave a multi-rank run: the update graphs hold no NCCL collective (the gradient mean runs
+    inside the optimiser kernel over peer-mapped buffers), so the group tears down normally."""
     if world <= 1:
         return
     import torch
+    import torch.distributed as dist
 
     torch.cuda.synchronize(device)
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def _peaks() -> dict:
@@ -480,15 +482,15 @@ def run_ours(args) -> None:
     extras = not args.no_extras and args.workload == "ff_mappo_rware"
     flops = loss_grad_flops(L)
     dominant, dtype_name = L.dominant_kernel, L.compute_dtype
-    collective = getattr(L, "collective", "none" if world == 1 else "nccl all_reduce")
-    if extras:  # free the headline learner before the other workloads are set up
-        import gc
+    collective = {"peer": "one-shot all-reduce over peer-mapped buffers (NVLink) inside the "
+                          "optimiser kernel (csrc/peer.cu)",
+                  "nccl": "nccl all_reduce + optimiser kernel", "none": "none (1 rank)"}[L.collective]
+    import gc
 
-        if hasattr(L, "release"):
-            L.release()
-        del learn, state, L
-        gc.collect()
-        torch.cuda.empty_cache()
+    L.release()  # drop the graph and the peer mappings before the next learner / the teardown
+    del learn, state, L
+    gc.collect()
+    torch.cuda.empty_cache()
     workloads = other_workloads(args, device, world, flush, barrier) if extras else None
     if rank != 0:
         _finish(world, device)

@@ -230,6 +230,46 @@ int mava_clip_adam_pair_pack(float* params, float* mu, float* nu, int32_t* count
                              int lr_decay_num_updates, int steps_per_update, mava_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * pmean("device") fused with the optimiser step (ff_mappo.py:224-250; rec_mappo.py:283-305):
+ * one launch = all-reduce(sum) of the ranks' gradient buffers over peer-mapped memory (NVLink /
+ * NVSwitch) -> clip_by_global_norm -> adam -> apply_updates -> bf16 image refresh -> loss metrics.
+ *
+ * Every rank of the node owns ONE exchange buffer: [n_grad floats: actor grads | critic grads |
+ * 8 loss scalars][flag block].  mava_peer_alloc creates it (cudaMalloc, zeroed) and returns the
+ * 64-byte CUDA IPC handle the host layer sends to the other ranks (torch.distributed /
+ * MPI / a pipe - not this library's business); mava_peer_open maps a peer's buffer.  The loss kernels
+ * write their gradients straight into the rank's own buffer (grad_out = buf), so nothing is copied.
+ * Each rank adds the W vectors in rank order: all ranks obtain bit-identical sums, like the
+ * reference's psum.  Flag handshakes inside the kernel order "gradients complete" before the reads
+ * and "everybody has read" before the kernel ends (the buffer may be overwritten right after it).
+ * A handshake that does not complete within 2 s raises the buffer's error word (mava_peer_status)
+ * instead of hanging the device.  world == 1 degenerates to clip + Adam on buf[0] (any 16-byte
+ * aligned device buffer of n_grad floats; no flag block is touched). */
+#define MAVA_PEER_MAX_RANKS 8
+typedef struct mava_peer_group {
+  int32_t rank, world;
+  void* buf[MAVA_PEER_MAX_RANKS]; /* this process's mapping of every rank's exchange buffer */
+} mava_peer_group;
+int64_t mava_peer_buffer_bytes(int64_t n_grad);
+int mava_peer_alloc(int64_t bytes, void** buf_out, void* ipc_handle64_host);
+int mava_peer_open(const void* ipc_handle64_host, void** buf_out);
+int mava_peer_close(void* buf);
+int mava_peer_free(void* buf);
+/* Calls completed on this rank's buffer and its error word (synchronises the stream). */
+int mava_peer_status(const void* buf, int64_t n_grad, uint32_t* seq_out_host, uint32_t* err_out_host,
+                     mava_stream_t s);
+/* gsum: local scratch of n_actor + n_critic floats.  actor/critic + images: optional (both NULL for
+ * networks without packed bf16 images, e.g. the recurrent ones).  grad_scale = 1/world_size.
+ * loss_out5 (optional) receives the 5 loss scalars behind the gradients, averaged over the ranks. */
+int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts,
+                               const mava_peer_group* group_host, float* gsum, int64_t n_actor,
+                               int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
+                               const mava_mlp_desc* critic, void* critic_image, float grad_scale,
+                               float lr_actor, float lr_critic, float max_norm,
+                               int lr_decay_num_updates, int steps_per_update, float* loss_out5,
+                               mava_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMEM).  Same regions as mava_ff_act / mava_ppo_loss_grad with
  * bf16 operands and fp32 accumulation (tolerance 2e-2, BASELINE.json).  Requires h1 == h2 == 128.
  * The fp32 parameters are first packed into a bf16 image in the shared-memory operand format;

@@ -48,6 +48,10 @@ class SynthConfig(C.Structure):
         ("done_prob", C.c_float), ("reward_std", C.c_float)]
 
 
+class PeerGroup(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("buf", C.c_void_p * 8)]
+
+
 class PpoHyper(C.Structure):
     _fields_ = [("clip_eps", c_f32), ("ent_coef", c_f32), ("vf_coef", c_f32)]
 
@@ -112,6 +116,15 @@ SIGNATURES = {
     "mava_rec_ppo_workspace_bytes": (c_i64, [P(RnnDesc), P(RnnDesc), c_int, c_int]),
     "mava_rec_ppo_loss_grad": (c_int, [P(RnnDesc), c_void, P(RnnDesc), c_void, P(PpoHyper)] +
                                [c_void] * 13 + [c_int] * 5 + [c_void] * 3),
+    "mava_peer_buffer_bytes": (c_i64, [c_i64]),
+    "mava_peer_alloc": (c_int, [c_i64, P(c_void), c_void]),
+    "mava_peer_open": (c_int, [c_void, P(c_void)]),
+    "mava_peer_close": (c_int, [c_void]),
+    "mava_peer_free": (c_int, [c_void]),
+    "mava_peer_status": (c_int, [c_void, c_i64, P(C.c_uint32), P(C.c_uint32), c_void]),
+    "mava_reduce_clip_adam_pair": (c_int, [c_void, c_void, c_void, c_void, P(PeerGroup), c_void,
+                                           c_i64, c_i64, P(MlpDesc), c_void, P(MlpDesc), c_void,
+                                           c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_void, c_void]),
     "mava_clip_adam": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32,
                                c_int, c_int, c_void]),
 }

@@ -49,6 +49,35 @@ __device__ __forceinline__ Tile w3_tile(uint32_t base, int k1p) {
   return Tile{base + (uint32_t)k1p * HID * 2 + HCOLS * HID * 2, 128u, (uint32_t)(HCOLS / 8) * 128u};
 }
 
+// Byte offset, in a network's packed image, of the bf16 copy of flat parameter i (flax order
+// W1 (in,H) | b1 | W2 (H,H) | b2 | W3 (H,out) | b3; biases are the extra input row of their matrix;
+// tiles are grids of 8x8 core matrices, see tc.cuh / pack_kernel in mlp_tc.cu).
+__device__ __forceinline__ size_t image_offset(int64_t i, int in_dim, int k1p, int out) {
+  int r, c, rows;
+  size_t base;
+  const int64_t n_w1 = (int64_t)in_dim * HID;
+  if (i < n_w1 + HID) {
+    rows = k1p;
+    base = 0;
+    if (i < n_w1) { r = (int)(i / HID); c = (int)(i % HID); }
+    else { r = in_dim; c = (int)(i - n_w1); }
+  } else {
+    const int64_t i2 = i - n_w1 - HID;
+    rows = HCOLS;
+    if (i2 < HID * HID + HID) {
+      base = (size_t)k1p * HID * 2;
+      if (i2 < HID * HID) { r = (int)(i2 / HID); c = (int)(i2 % HID); }
+      else { r = HID; c = (int)(i2 - HID * HID); }
+    } else {
+      const int64_t i3 = i2 - HID * HID - HID;
+      base = (size_t)k1p * HID * 2 + (size_t)HCOLS * HID * 2;
+      if (i3 < (int64_t)HID * out) { r = (int)(i3 / out); c = (int)(i3 % out); }
+      else { r = HID; c = (int)(i3 - (int64_t)HID * out); }
+    }
+  }
+  return base + (size_t)(r >> 3) * 128 + (size_t)(c >> 3) * (rows / 8) * 128 + (r & 7) * 16 + (c & 7) * 2;
+}
+
 struct NetDesc {
   int mode, add_id, A, FR, in_dim, k1p, out;  // k1p = pad16(in_dim + 1): room for the ones column
 };

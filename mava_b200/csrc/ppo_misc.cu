@@ -126,36 +126,6 @@ struct AdamPairArgs {
   int in_dim[2], k1p[2], out[2];
 };
 
-// Byte offset, in a network's packed image, of the bf16 copy of flat parameter i (flax order
-// W1 (in,H) | b1 | W2 (H,H) | b2 | W3 (H,out) | b3; biases are the extra input row of their matrix;
-// tiles are grids of 8x8 core matrices, see tc.cuh / pack_kernel in mlp_tc.cu).
-__device__ __forceinline__ size_t image_offset(int64_t i, int in_dim, int k1p, int out) {
-  using namespace tcmlp;
-  int r, c, rows;
-  size_t base;
-  const int64_t n_w1 = (int64_t)in_dim * HID;
-  if (i < n_w1 + HID) {
-    rows = k1p;
-    base = 0;
-    if (i < n_w1) { r = (int)(i / HID); c = (int)(i % HID); }
-    else { r = in_dim; c = (int)(i - n_w1); }
-  } else {
-    const int64_t i2 = i - n_w1 - HID;
-    rows = HCOLS;
-    if (i2 < HID * HID + HID) {
-      base = (size_t)k1p * HID * 2;
-      if (i2 < HID * HID) { r = (int)(i2 / HID); c = (int)(i2 % HID); }
-      else { r = HID; c = (int)(i2 - HID * HID); }
-    } else {
-      const int64_t i3 = i2 - HID * HID - HID;
-      base = (size_t)k1p * HID * 2 + (size_t)HCOLS * HID * 2;
-      if (i3 < (int64_t)HID * out) { r = (int)(i3 / out); c = (int)(i3 % out); }
-      else { r = HID; c = (int)(i3 - (int64_t)HID * out); }
-    }
-  }
-  return base + (size_t)(r >> 3) * 128 + (size_t)(c >> 3) * (rows / 8) * 128 + (r & 7) * 16 + (c & 7) * 2;
-}
-
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const AdamPairArgs a) {
   const int net = blockIdx.y;
   const float* grad = a.grad + (net == 0 ? 0 : a.n[0]);
@@ -228,7 +198,7 @@ __global__ void __launch_bounds__(256) clip_adam_pair_kernel(const AdamPairArgs 
     params[i] = pnew;
     if (a.image[net])
       *reinterpret_cast<__nv_bfloat16*>(a.image[net] +
-                                        image_offset(i, a.in_dim[net], a.k1p[net], a.out[net])) =
+                                        tcmlp::image_offset(i, a.in_dim[net], a.k1p[net], a.out[net])) =
           __float2bfloat16_rn(pnew);
   }
 }

@@ -580,3 +580,27 @@ def rec_ppo_loss_grad(actor: RnnDesc, actor_params, critic: RnnDesc, critic_para
         _p(cols, torch.int32, mb_cols, "cols"), num_replicas, envs_per_replica, mb_cols, chunk,
         num_chunks, _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
         _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_rec_ppo_loss_grad")
+
+
+# ---------------------------------------------------------------------------------------------
+# pmean("device") fused with the optimiser step (csrc/peer.cu)
+# ---------------------------------------------------------------------------------------------
+def reduce_clip_adam_pair(params, mu, nu, counts, group, gsum, n_actor: int, n_critic: int,
+                          actor: Optional[MlpDesc], actor_image, critic: Optional[MlpDesc],
+                          critic_image, grad_scale: float, lr_actor: float, lr_critic: float,
+                          max_norm: float, lr_decay_num_updates: int = 0, steps_per_update: int = 1,
+                          loss_out=None) -> None:
+    """all-reduce(sum) over the ranks' exchange buffers of ``group`` (a ``peer.PeerGroup``) ->
+    clip_by_global_norm -> adam -> apply_updates (+ bf16 image refresh, + loss metrics): one launch."""
+    n = n_actor + n_critic
+    _count(1)
+    check(_lib.load().mava_reduce_clip_adam_pair(
+        _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
+        _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
+        C.byref(group.struct), _p(gsum, torch.float32, n, "gsum"), n_actor, n_critic,
+        C.byref(actor) if actor is not None else None,
+        _p(actor_image, torch.uint8, None, "actor_image"),
+        C.byref(critic) if critic is not None else None,
+        _p(critic_image, torch.uint8, None, "critic_image"), grad_scale, lr_actor, lr_critic,
+        max_norm, lr_decay_num_updates, steps_per_update,
+        _p(loss_out, torch.float32, 5, "loss_out"), _stream()), "mava_reduce_clip_adam_pair")

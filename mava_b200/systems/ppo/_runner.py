@@ -68,6 +68,13 @@ def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
                          * config.arch.num_envs)
 
     logger = MavaLogger(config, rank)
+    # Set up checkpointer (ff_mappo.py:482-489); rank 0 writes, the state is replicated
+    save_checkpoint = bool(config.logger.checkpointing.save_model)
+    if save_checkpoint:
+        from ...utils.checkpointing import Checkpointer
+
+        checkpointer = Checkpointer(metadata=config, model_name=config.logger.system_name,
+                                    **dict(config.logger.checkpointing.save_args))
     max_episode_return = -np.inf
     best_params = None
     eval_metrics = {}
@@ -98,6 +105,10 @@ def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
         logger.log(eval_metrics, t, eval_step, LogEvent.EVAL)
         episode_return = float(eval_metrics["episode_return"].float().mean().item())
 
+        if save_checkpoint and rank == 0:  # ff_mappo.py:522-528
+            checkpointer.save(timestep=t, unreplicated_learner_state=_checkpoint_tree(learner),
+                              episode_return=episode_return)
+
         if config.arch.absolute_metric and max_episode_return <= episode_return:
             best_params = trained_params.clone()
             max_episode_return = episode_return
@@ -112,7 +123,26 @@ def run_experiment(_config, learner_setup: Callable, make_eval_act_fn: Callable,
         t = int(steps_per_rollout * (eval_step + 1))
         logger.log(abs_metrics, t, eval_step, LogEvent.ABSOLUTE)
     logger.stop()
+    learner.release()
     return eval_performance
+
+
+def _checkpoint_tree(learner):
+    """The unreplicated learner state as the reference's checkpoint tree (params in flax naming,
+    optimiser moments in optax naming)."""
+    from ...utils.checkpointing import learner_tree
+
+    actor_net, critic_net = learner.networks
+    na = learner.na
+    p = learner.params.cpu().numpy()
+    mu, nu = learner.mu.cpu().numpy(), learner.nu.cpu().numpy()
+    cnt = learner.counts.cpu().numpy()
+    ain, cin = learner.actor_desc.in_dim, learner.critic_desc.in_dim
+    opt = {"actor_opt_state": {"count": cnt[0], "mu": actor_net.to_flax_tree(mu[:na], ain),
+                               "nu": actor_net.to_flax_tree(nu[:na], ain)},
+           "critic_opt_state": {"count": cnt[1], "mu": critic_net.to_flax_tree(mu[na:], cin),
+                                "nu": critic_net.to_flax_tree(nu[na:], cin)}}
+    return learner_tree(actor_net, critic_net, p[:na], p[na:], ain, cin, opt)
 
 
 def _gather_metrics(metrics, n_devices: int):

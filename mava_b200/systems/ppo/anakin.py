@@ -23,6 +23,7 @@ import torch.distributed as dist
 
 from ... import native, prng
 from ..._lib import PpoHyper
+from ...peer import PeerGroup
 from ...networks import FeedForwardActor, FeedForwardValueNet
 from ...types import (ExperimentOutput, LearnerState, OptStates, Params, StepType, TimeStep)
 from ...wrappers import EnvState, NativeMarlEnv
@@ -56,6 +57,13 @@ class FFLearner:
         # one process and do pmean("device") by hand (tests/test_multirank_gpu.py)
         self.rank, self.world = rank_world if rank_world is not None else world()
         self.allreduce = _nccl_allreduce if rank_world is None else None
+        # pmean("device"): "peer" = inside the optimiser kernel over peer-mapped buffers (csrc/peer.cu),
+        # "nccl" = dist.all_reduce before it (kept as the checker of the peer path)
+        self.collective = str(config.arch.get("collective", "peer"))
+        if self.collective not in ("peer", "nccl"):
+            raise ValueError(f"arch.collective must be peer or nccl, got {self.collective}")
+        if self.world == 1 or rank_world is not None:
+            self.collective = "none"
         self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
             config.arch.num_envs)
         self.NE = self.U * self.E
@@ -116,7 +124,15 @@ class FFLearner:
         # the critical path (side stream) -- they depend on the permutations and on GAE only
         self.rows_all = z(int(s.ppo_epochs), self.nmb, self.U * self.mb, dtype=torch.int32)
         self.adv_stats_all = z(int(s.ppo_epochs), self.nmb, 16, dtype=torch.float64)
-        self.grad = z(self.na + self.nc + 8)
+        # gradients live in this rank's exchange buffer [actor | critic | 8 loss scalars]; with
+        # collective == "peer" the other ranks read it over NVLink inside the optimiser kernel
+        n_grad = self.na + self.nc + 8
+        self.peer = PeerGroup(n_grad, dev, self.rank, self.world) if self.collective == "peer" \
+            else PeerGroup(n_grad, dev, 0, 1)
+        self.peer_local = self.peer if self.peer.world == 1 else \
+            PeerGroup(n_grad, dev, 0, 1, local_bufs=[self.peer.struct.buf[self.rank]])
+        self.grad = self.peer.grad
+        self.gsum = z(self.na + self.nc)
         self.loss_buf = z(self.epochs, self.nmb, 5)
         # precision: the bf16 tensor-core kernels need two hidden layers of width 128
         tc_ok = all(d.h1 == 128 and d.h2 == 128 and d.out_dim <= 16
@@ -143,6 +159,7 @@ class FFLearner:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0  # mava_b200 kernels per update (counted on the first run)
         self.time_loss_grad = None  # list of (start, end) CUDA events when profiling (bench.py)
+        self.time_reduce_apply = None
         self.compute_dtype = "bf16" if self.bf16 else "f32"
         self.dominant_kernel = ("ppo_fused_kernel + ppo_wgrad1_kernel (tcgen05, bf16)" if self.bf16
                                 else "ppo_loss_grad (fp32 mlp_fwd/mlp_bwd/mlp_wgrad kernels)")
@@ -301,29 +318,31 @@ class FFLearner:
             self.time_loss_grad.append((e0, e1))
 
     def _minibatch_apply(self, ep: int, m: int) -> None:
-        """clip_by_global_norm -> adam -> apply_updates on the device-summed gradients
-        (ff_mappo.py:240-250); 1/world of pmean("device") is folded into the kernel."""
+        """pmean("device") of the gradient buffers -> clip_by_global_norm -> adam -> apply_updates
+        -> refreshed bf16 operand images -> the minibatch's loss metrics (ff_mappo.py:228-250,
+        260-265): ONE launch (csrc/peer.cu).  With collective == "nccl" (or gradients already summed
+        by the caller) the kernel runs on the local buffer and only applies 1/world."""
         s = self.config.system
-        na, nc = self.na, self.nc
-        scale = 1.0 / self.world
         steps_per_update = self.epochs * self.nmb
-        if self.bf16:  # the optimiser refreshes the bf16 operand images itself
-            native.clip_adam_pair_pack(
-                self.params, self.mu, self.nu, self.counts, self.grad, self.actor_desc,
-                self.actor_img, self.critic_desc, self.critic_img, scale, float(s.actor_lr),
-                float(s.critic_lr), float(s.max_grad_norm), self.lr_decay_updates,
-                steps_per_update)
-        else:
-            native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na,
-                                  nc, scale, float(s.actor_lr), float(s.critic_lr),
-                                  float(s.max_grad_norm), self.lr_decay_updates,
-                                  steps_per_update)
-        self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
+        group = self.peer if self.collective == "peer" else self.peer_local
+        if self.time_reduce_apply is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if self.collective == "nccl":
+            self.allreduce(self.grad)
+        native.reduce_clip_adam_pair(
+            self.params, self.mu, self.nu, self.counts, group, self.gsum, self.na, self.nc,
+            self.actor_desc if self.bf16 else None, self.actor_img if self.bf16 else None,
+            self.critic_desc if self.bf16 else None, self.critic_img if self.bf16 else None,
+            1.0 / self.world, float(s.actor_lr), float(s.critic_lr), float(s.max_grad_norm),
+            self.lr_decay_updates, steps_per_update, self.loss_buf[ep, m])
+        if self.time_reduce_apply is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.time_reduce_apply.append((e0, e1))
 
     def _epochs_end(self) -> None:
         self.key.copy_(self.key3_ep[self.epochs - 1][0])
-        if self.world > 1:
-            self.loss_buf.mul_(1.0 / self.world)
 
     def _update_epochs(self, perms) -> None:
         """ff_mappo.py:141-295."""
@@ -331,8 +350,6 @@ class FFLearner:
         for ep in range(self.epochs):
             for m in range(self.nmb):
                 self._minibatch_grad(ep, m, perms)
-                if self.world > 1:  # pmean("device"), ff_mappo.py:228-238
-                    self.allreduce(self.grad)
                 self._minibatch_apply(ep, m)
         self._epochs_end()
 
@@ -401,6 +418,17 @@ class FFLearner:
         if int(self._ovf_host[0]) != 0:
             raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
                                "parameters of this learn() call are not to be trusted")
+        self.peer.check()  # a peer handshake of the fused all-reduce timed out
+
+    def release(self) -> None:
+        """Drop the CUDA graph and the peer mappings (before the process group is destroyed)."""
+        self._graph = None
+        if self.peer is not None:
+            if self.peer_local is not self.peer:
+                self.peer_local.release()
+            self.peer.release()
+            self.peer = self.peer_local = None
+            self.grad = None
 
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
@@ -539,7 +567,15 @@ def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
                         rank_world)
     ap = actor_network.init(actor_net_key, learner.actor_desc.in_dim)
     cp = critic_network.init(critic_net_key, learner.critic_desc.in_dim)
+    # Load model from checkpoint if specified (ff_mappo.py:405-414, rec_mappo.py:527-536).
+    if config.logger.checkpointing.load_model:
+        from ...utils.checkpointing import Checkpointer
+
+        loaded = Checkpointer(model_name=config.logger.system_name,
+                              **dict(config.logger.checkpointing.load_args))
+        ap, cp = loaded.restore_params(actor_network, critic_network)
     learner.params.copy_(torch.from_numpy(np.concatenate([ap, cp])).to(device))
+    learner.networks = (actor_network, critic_network)
 
     # env keys: one per (device, replica, env), this rank takes its block (ff_mappo.py:392-403)
     per_dev = learner.U * learner.E

@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from ... import native, prng
 from ..._lib import PpoHyper
+from ...peer import PeerGroup
 from ...networks import RecurrentActor, RecurrentValueNet
 from ...types import (ExperimentOutput, HiddenStates, OptStates, Params, RNNLearnerState, StepType,
                       TimeStep)
@@ -41,6 +42,11 @@ class RecLearner:
         self.env, self.config, self.device = env, config, device
         self.rank, self.world = rank_world if rank_world is not None else world()
         self.allreduce = _nccl_allreduce if rank_world is None else None
+        self.collective = str(config.arch.get("collective", "peer"))  # see FFLearner
+        if self.collective not in ("peer", "nccl"):
+            raise ValueError(f"arch.collective must be peer or nccl, got {self.collective}")
+        if self.world == 1 or rank_world is not None:
+            self.collective = "none"
         self.T, self.U, self.E = int(s.rollout_length), int(s.update_batch_size), int(
             config.arch.num_envs)
         self.NE = self.U * self.E
@@ -118,7 +124,12 @@ class RecLearner:
         self.key2 = z(2, 2, dtype=torch.uint32)
         self.ncols = self.E * self.nc
         self.bits = z(self.ncols, dtype=torch.uint32)
-        self.grad = z(n_all + 8)
+        self.peer = PeerGroup(n_all + 8, dev, self.rank, self.world) if self.collective == "peer" \
+            else PeerGroup(n_all + 8, dev, 0, 1)
+        self.peer_local = self.peer if self.peer.world == 1 else \
+            PeerGroup(n_all + 8, dev, 0, 1, local_bufs=[self.peer.struct.buf[self.rank]])
+        self.grad = self.peer.grad  # this rank's exchange buffer (csrc/peer.cu)
+        self.gsum = z(n_all)
         self.loss_buf = z(self.epochs, self.nmb, 5)
         self.act_ws = z(native.rec_act_workspace_bytes(self.actor_desc, self.critic_desc, NE),
                         dtype=torch.uint8)
@@ -136,6 +147,7 @@ class RecLearner:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_update = 0
         self.time_loss_grad = None
+        self.time_reduce_apply = None
         self.compute_dtype = "bf16" if self.bf16 else "f32"
         self.dominant_kernel = ("tc_gemm_kernel (tcgen05 bf16 GRU scan + dense layers)" if self.bf16
                                 else "sgemm_kernel (fp32 GRU scan + dense layers)")
@@ -248,15 +260,22 @@ class RecLearner:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
                     self.time_loss_grad.append((e0, e1))
-                if self.world > 1:  # pmean("device"), rec_mappo.py:283-293
+                # pmean("device") + clip + Adam + loss metrics in one launch (rec_mappo.py:283-305)
+                if self.time_reduce_apply is not None:
+                    r0 = torch.cuda.Event(enable_timing=True)
+                    r0.record()
+                if self.collective == "nccl":
                     self.allreduce(self.grad)
-                native.clip_adam_pair(self.params, self.mu, self.nu, self.counts, self.grad, na, nc,
-                                      scale, float(s.actor_lr), float(s.critic_lr),
-                                      float(s.max_grad_norm), self.lr_decay_updates,
-                                      steps_per_update)
-                self.loss_buf[ep, m].copy_(self.grad[na + nc:na + nc + 5])
-        if self.world > 1:
-            self.loss_buf.mul_(scale)
+                native.reduce_clip_adam_pair(
+                    self.params, self.mu, self.nu, self.counts,
+                    self.peer if self.collective == "peer" else self.peer_local, self.gsum, na, nc,
+                    None, None, None, None, scale, float(s.actor_lr), float(s.critic_lr),
+                    float(s.max_grad_norm), self.lr_decay_updates, steps_per_update,
+                    self.loss_buf[ep, m])
+                if self.time_reduce_apply is not None:
+                    r1 = torch.cuda.Event(enable_timing=True)
+                    r1.record()
+                    self.time_reduce_apply.append((r0, r1))
 
     def _update_step(self) -> None:
         """One ``_update_step`` of the reference (rec_mappo.py:68-402) for all U replicas."""
@@ -312,6 +331,17 @@ class RecLearner:
         if int(self._ovf_host[0]) != 0:
             raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
                                "parameters of this learn() call are not to be trusted")
+        self.peer.check()
+
+    def release(self) -> None:
+        """Drop the CUDA graph and the peer mappings (before the process group is destroyed)."""
+        self._graph = None
+        if self.peer is not None:
+            if self.peer_local is not self.peer:
+                self.peer_local.release()
+            self.peer.release()
+            self.peer = self.peer_local = None
+            self.grad = None
 
     # -- public -----------------------------------------------------------------------------------
     def learn(self, num_updates: int) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
@@ -397,7 +427,15 @@ def learner_setup(env: NativeMarlEnv, keys, config, centralised_critic: bool,
                          rank_world)
     ap = actor_network.init(actor_net_key, learner.actor_desc.in_dim)
     cp = critic_network.init(critic_net_key, learner.critic_desc.in_dim)
+    # Load model from checkpoint if specified (ff_mappo.py:405-414, rec_mappo.py:527-536).
+    if config.logger.checkpointing.load_model:
+        from ...utils.checkpointing import Checkpointer
+
+        loaded = Checkpointer(model_name=config.logger.system_name,
+                              **dict(config.logger.checkpointing.load_args))
+        ap, cp = loaded.restore_params(actor_network, critic_network)
     learner.params.copy_(torch.from_numpy(np.concatenate([ap, cp])).to(device))
+    learner.networks = (actor_network, critic_network)
 
     per_dev = learner.U * learner.E
     all_keys = prng.split(key, n_devices * per_dev + 1)

@@ -108,3 +108,84 @@ def restore_params(tree: Dict[str, Any], actor_network, critic_network):
     p = tree["learner_state"]["params"]
     return (actor_network.from_flax_tree(p["actor_params"]),
             critic_network.from_flax_tree(p["critic_params"]))
+
+
+CHECKPOINTER_VERSION = 1.0
+
+
+class Checkpointer:
+    """The reference's ``Checkpointer`` surface (mava/utils/checkpointing.py:36-207: same constructor
+    arguments, ``save`` and ``restore_params``) on the tree containers above.  Directory layout
+    ``<cwd>/<rel_dir>/<model_name>/<checkpoint_uid>/<timestep>/checkpoint.msgpack`` like the
+    reference's Orbax manager; the files hold the same *tree* but are NOT Orbax directories
+    (orbax / jax are not installable here)."""
+
+    def __init__(self, model_name: str, metadata: Any = None, rel_dir: str = "checkpoints",
+                 checkpoint_uid: str | None = None, save_interval_steps: int = 1,
+                 max_to_keep: int | None = 1, keep_period: int | None = None):
+        import os
+        from datetime import datetime
+
+        uid = checkpoint_uid if checkpoint_uid else datetime.now().strftime("%Y%m%d%H%M%S")
+        self.directory = os.path.join(os.getcwd(), rel_dir, model_name, uid)
+        self.save_interval_steps = max(1, int(save_interval_steps))
+        self.max_to_keep, self.keep_period = max_to_keep, keep_period
+        self.metadata = {"checkpointer_version": CHECKPOINTER_VERSION}
+        if metadata is not None:
+            self.metadata["config"] = _json_ready(metadata)
+        self._saved: Dict[int, float] = {}  # timestep -> episode_return (best_fn of the reference)
+        self._n_calls = 0
+
+    def _path(self, timestep: int) -> str:
+        import os
+
+        return os.path.join(self.directory, str(int(timestep)), "checkpoint.msgpack")
+
+    def save(self, timestep: int, unreplicated_learner_state: Dict[str, Any],
+             episode_return: float = 0.0) -> bool:
+        """``unreplicated_learner_state`` is a checkpoint tree (``learner_tree``)."""
+        import json
+        import os
+        import shutil
+
+        self._n_calls += 1
+        if (self._n_calls - 1) % self.save_interval_steps != 0:
+            return False
+        path = self._path(timestep)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        save(path, unreplicated_learner_state)
+        with open(os.path.join(self.directory, "metadata.json"), "w") as f:
+            json.dump(self.metadata, f)
+        self._saved[int(timestep)] = float(episode_return)
+        if self.max_to_keep is not None:
+            keep_always = {t for t in self._saved if self.keep_period and t % self.keep_period == 0}
+            ranked = sorted((t for t in self._saved if t not in keep_always),
+                            key=lambda t: (self._saved[t], t), reverse=True)
+            for t in ranked[self.max_to_keep:]:
+                shutil.rmtree(os.path.dirname(self._path(t)), ignore_errors=True)
+                del self._saved[t]
+        return True
+
+    def restore_tree(self, timestep: int | None = None) -> Dict[str, Any]:
+        import os
+
+        if timestep is None:
+            steps = [int(d) for d in os.listdir(self.directory) if d.isdigit()]
+            if not steps:
+                raise FileNotFoundError(f"no checkpoint under {self.directory}")
+            timestep = max(steps)
+        return load(self._path(timestep))
+
+    def restore_params(self, actor_network, critic_network, timestep: int | None = None):
+        """(actor_flat, critic_flat) of the latest (or the given) checkpoint."""
+        return restore_params(self.restore_tree(timestep), actor_network, critic_network)
+
+
+def _json_ready(obj: Any) -> Any:
+    if isinstance(obj, dict) or hasattr(obj, "items"):
+        return {str(k): _json_ready(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_json_ready(v) for v in obj]
+    if isinstance(obj, (bool, str, int, float, type(None))):
+        return obj
+    return str(obj)

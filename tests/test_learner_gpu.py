@@ -259,3 +259,78 @@ def test_run_experiment_smoke(lib_built):
             "logger.use_console=False"])
         perf = mod.run_experiment(cfg)
         assert isinstance(perf, float) and np.isfinite(perf)
+
+
+def test_lr_decay_horizon_follows_total_timesteps(lib_built):
+    """run_experiment order (ff_mappo.py:445-466): learner_setup, THEN check_total_timesteps rewrites
+    system.num_updates.  The linear LR schedule (mava/utils/training.py:38-47) must decay against the
+    rewritten value, like the reference's schedule that closes over the mutated config."""
+    from mava_b200 import prng
+    from mava_b200.config import compose
+    from mava_b200.systems.ppo import ff_ippo
+    from mava_b200.utils import make_env
+    from mava_b200.utils.total_timestep_checker import check_total_timesteps
+
+    torch.cuda.set_device(0)
+    base = ["env/scenario=tiny-2ag", "arch.num_envs=8", "system.rollout_length=8",
+            "system.update_batch_size=1", "system.decay_learning_rates=True",
+            "logger.use_console=False"]
+
+    def run(extra, via_checker):
+        cfg = compose(ff_ippo.CONFIG_NAME, base + extra)
+        env, _ = make_env.make(cfg, add_global_state=False)
+        key, _, ak, ck = prng.split(prng.PRNGKey(1), 4)
+        learn, _, state = ff_ippo.learner_setup(env, (key, ak, ck), cfg)
+        if via_checker:
+            cfg = check_total_timesteps(cfg, 1)
+            learn.learner.config = cfg
+        cfg.system.num_updates_per_eval = 3
+        assert learn.learner.lr_decay_updates == 4
+        learn(state)
+        torch.cuda.synchronize()
+        return learn.learner.params.clone()
+
+    direct = run(["system.num_updates=4"], False)
+    checked = run([f"system.total_timesteps={4 * 8 * 1 * 8}"], True)  # default num_updates is 1000
+    assert torch.equal(direct, checked)
+    # and the horizon matters: the default (1000 updates) decays much more slowly
+    cfg = compose(ff_ippo.CONFIG_NAME, base)
+    env, _ = make_env.make(cfg, add_global_state=False)
+    key, _, ak, ck = prng.split(prng.PRNGKey(1), 4)
+    learn, _, state = ff_ippo.learner_setup(env, (key, ak, ck), cfg)
+    cfg.system.num_updates_per_eval = 3
+    learn(state)
+    assert not torch.equal(learn.learner.params, direct)
+
+
+def test_checkpoint_save_then_load(lib_built, tmp_path, monkeypatch):
+    """logger.checkpointing.save_model / load_model are honoured by run_experiment / learner_setup
+    (ff_mappo.py:405-414,482-528): a run that loads starts from the saved parameters."""
+    from mava_b200 import prng
+    from mava_b200.config import compose
+    from mava_b200.systems.ppo import ff_mappo
+    from mava_b200.utils import make_env
+    from mava_b200.utils.checkpointing import Checkpointer
+
+    monkeypatch.chdir(tmp_path)
+    common = ["env/scenario=tiny-2ag", "arch.num_envs=4", "system.rollout_length=8",
+              "system.num_updates=4", "arch.num_evaluation=2", "arch.num_eval_episodes=4",
+              "arch.num_absolute_metric_eval_episodes=4", "env.kwargs.time_limit=12",
+              "logger.use_console=False"]
+    cfg = compose(ff_mappo.CONFIG_NAME, common + [
+        "logger.checkpointing.save_model=True",
+        "logger.checkpointing.save_args.checkpoint_uid=unit"])
+    ff_mappo.run_experiment(cfg)
+    ck = Checkpointer(model_name=cfg.logger.system_name, checkpoint_uid="unit")
+    cfg2 = compose(ff_mappo.CONFIG_NAME, common + [
+        "logger.checkpointing.load_model=True",
+        "logger.checkpointing.load_args.checkpoint_uid=unit"])
+    env, _ = make_env.make(cfg2, add_global_state=True)
+    key, _, ak, ck_key = prng.split(prng.PRNGKey(99), 4)  # a different seed: init must not matter
+    learn, actor_net, _ = ff_mappo.learner_setup(env, (key, ak, ck_key), cfg2)
+    L = learn.learner
+    a, c = ck.restore_params(*L.networks)
+    np.testing.assert_array_equal(L.params[:L.na].cpu().numpy(), a)
+    np.testing.assert_array_equal(L.params[L.na:].cpu().numpy(), c)
+    tree = ck.restore_tree()
+    assert int(tree["learner_state"]["opt_states"]["actor_opt_state"]["count"]) > 0
