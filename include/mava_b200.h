@@ -73,7 +73,7 @@ int mava_sort_by_key(const uint32_t* keys, const int32_t* val_in, int32_t* val_o
 /* ------------------------------------------------------------------------------------------
  * Environments - replaces jax.vmap(env.step) / jax.vmap(env.reset) through the whole wrapper
  * stack RecordEpisodeMetrics(AutoResetWrapper(AgentIDWrapper(RwareWrapper|LbfWrapper(env))))
- * (ff_mappo.py:88,395; mava/utils/make_env.py:69-83; mava/wrappers/*.py).
+ * (ff_mappo.py:88,395; mava/utils/make_env.py:69-83; mava/wrappers/ *.py).
  * ---------------------------------------------------------------------------------------- */
 #define MAVA_ENV_RWARE 1
 #define MAVA_ENV_LBF 2
@@ -243,8 +243,10 @@ int mava_clip_adam_pair_pack(float* params, float* mu, float* nu, int32_t* count
  * reference's psum.  Flag handshakes inside the kernel order "gradients complete" before the reads
  * and "everybody has read" before the kernel ends (the buffer may be overwritten right after it).
  * A handshake that does not complete within 2 s raises the buffer's error word (mava_peer_status)
- * instead of hanging the device.  world == 1 degenerates to clip + Adam on buf[0] (any 16-byte
- * aligned device buffer of n_grad floats; no flag block is touched). */
+ * instead of hanging the device.  world == 1 degenerates to clip + Adam on buf[0], which must still
+ * be a mava_peer_alloc buffer: the kernel keeps its call counter, its grid-barrier word and the two
+ * squared-norm accumulators in the flag block (no device-global scratch: re-entrant across learners
+ * and streams). */
 #define MAVA_PEER_MAX_RANKS 8
 typedef struct mava_peer_group {
   int32_t rank, world;
@@ -332,6 +334,22 @@ int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor_host, const 
                          const uint32_t* policy_keys, int envs_per_replica, int num_envs,
                          int rollout_length, int8_t* action, float* logp, float* reward,
                          uint8_t* done, float* ep_return, int32_t* ep_length, mava_stream_t s);
+/* The same kernel as the evaluator runs it (mava/evaluator.py:80-172): auto_reset = 0 is the
+ * evaluation env (no AutoResetWrapper, make_env.py:79-81), greedy != 0 takes pi.mode()
+ * (evaluator.py:183), record = 0 keeps only done / ep_return / ep_length per step ([T][NE]) and
+ * writes observation, mask, action, log-prob and reward of every step into slot 0 of their
+ * buffers, which then need one time slot only. */
+int mava_ff_rollout_bf16_ex(mava_env_t env, const mava_mlp_desc* actor_host, const float* actor_params,
+                            const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,
+                            const uint32_t* policy_keys, int envs_per_replica, int num_envs,
+                            int rollout_length, int auto_reset, int greedy, int record,
+                            int8_t* action, float* logp, float* reward, uint8_t* done,
+                            float* ep_return, int32_t* ep_length, mava_stream_t s);
+/* The evaluator's metric pick (evaluator.py:143-150): per env, episode return and length at the
+ * FIRST terminal step of done[T][NE] (argmax of the flag; step 0 if the episode never ended). */
+int mava_episode_first_terminal(const uint8_t* done, const float* ep_return,
+                                const int32_t* ep_length, int T, int num_envs, float* out_return,
+                                int32_t* out_length, mava_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Recurrent systems - RecurrentActor / RecurrentValueNet / ScannedRNN (mava/networks.py:238-331)

@@ -105,6 +105,10 @@ SIGNATURES = {
     "mava_tc_selftest": (c_int, [c_int, c_void, c_void, c_void, c_int, c_int, c_void]),
     "mava_ff_rollout_bf16": (c_int, [c_void, P(MlpDesc)] + [c_void] * 6 + [c_int] * 3 +
                              [c_void] * 7),
+    "mava_ff_rollout_bf16_ex": (c_int, [c_void, P(MlpDesc)] + [c_void] * 6 + [c_int] * 6 +
+                                [c_void] * 7),
+    "mava_episode_first_terminal": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_void,
+                                            c_void]),
     "mava_synth_reset": (c_int, [P(SynthConfig)] + [c_void] * 5 + [c_int, c_void]),
     "mava_synth_step": (c_int, [P(SynthConfig)] + [c_void] * 10 + [c_int, c_void]),
     "mava_gemm": (c_int, [c_int, c_void, c_int, c_i64, c_void, c_int, c_i64, c_void, c_i64, c_int,

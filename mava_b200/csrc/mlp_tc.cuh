@@ -52,30 +52,30 @@ __device__ __forceinline__ Tile w3_tile(uint32_t base, int k1p) {
 // Byte offset, in a network's packed image, of the bf16 copy of flat parameter i (flax order
 // W1 (in,H) | b1 | W2 (H,H) | b2 | W3 (H,out) | b3; biases are the extra input row of their matrix;
 // tiles are grids of 8x8 core matrices, see tc.cuh / pack_kernel in mlp_tc.cu).
-__device__ __forceinline__ size_t image_offset(int64_t i, int in_dim, int k1p, int out) {
+__device__ __forceinline__ uint32_t image_offset(int i, int in_dim, int k1p, int out) {
   int r, c, rows;
-  size_t base;
-  const int64_t n_w1 = (int64_t)in_dim * HID;
+  uint32_t base;
+  const int n_w1 = in_dim * HID;
   if (i < n_w1 + HID) {
     rows = k1p;
     base = 0;
-    if (i < n_w1) { r = (int)(i / HID); c = (int)(i % HID); }
-    else { r = in_dim; c = (int)(i - n_w1); }
+    if (i < n_w1) { r = i / HID; c = i % HID; }
+    else { r = in_dim; c = i - n_w1; }
   } else {
-    const int64_t i2 = i - n_w1 - HID;
+    const int i2 = i - n_w1 - HID;
     rows = HCOLS;
     if (i2 < HID * HID + HID) {
-      base = (size_t)k1p * HID * 2;
-      if (i2 < HID * HID) { r = (int)(i2 / HID); c = (int)(i2 % HID); }
-      else { r = HID; c = (int)(i2 - HID * HID); }
+      base = (uint32_t)k1p * HID * 2;
+      if (i2 < HID * HID) { r = i2 / HID; c = i2 % HID; }
+      else { r = HID; c = i2 - HID * HID; }
     } else {
-      const int64_t i3 = i2 - HID * HID - HID;
-      base = (size_t)k1p * HID * 2 + (size_t)HCOLS * HID * 2;
-      if (i3 < (int64_t)HID * out) { r = (int)(i3 / out); c = (int)(i3 % out); }
-      else { r = HID; c = (int)(i3 - (int64_t)HID * out); }
+      const int i3 = i2 - HID * HID - HID;
+      base = (uint32_t)k1p * HID * 2 + (uint32_t)HCOLS * HID * 2;
+      if (i3 < HID * out) { r = i3 / out; c = i3 % out; }
+      else { r = HID; c = i3 - HID * out; }
     }
   }
-  return base + (size_t)(r >> 3) * 128 + (size_t)(c >> 3) * (rows / 8) * 128 + (r & 7) * 16 + (c & 7) * 2;
+  return base + (uint32_t)(r >> 3) * 128 + (uint32_t)(c >> 3) * (rows / 8) * 128 + (r & 7) * 16 + (c & 7) * 2;
 }
 
 struct NetDesc {

@@ -13,31 +13,30 @@
 // the end of the kernel ("I have read yours") lets a rank overwrite its buffer as soon as the
 // kernel is done: one buffer, no parity games with the host-side schedule.
 //
-// The kernel is one thread-block cluster (8 CTAs x 1024 threads): the squared global norms are
-// combined through distributed shared memory and a cluster barrier -- the hardware co-schedules a
-// cluster, so no grid-wide barrier or device-global scratch is needed and the kernel is re-entrant
-// across learners and streams.  Spin loops give up after 2 s and raise the buffer's error word
-// instead of hanging the device (a rank that died, a mismatched call sequence).
-#include <cooperative_groups.h>
-
+// The kernel is a cooperative launch of up to 128 small CTAs (all co-resident): the squared global
+// norms are combined through two fp64 accumulators and one grid barrier, both kept in the rank's own
+// flag block, so the kernel is re-entrant across learners and streams (no device-global scratch).
+// Peer handshakes give up after 2 s and raise the buffer's error word instead of hanging the
+// device (a rank that died, a mismatched call sequence).
 #include <cstring>
 
 #include "common.cuh"
 #include "mlp_tc.cuh"
 
-namespace cg = cooperative_groups;
 using namespace mava;
 
 namespace {
 
 constexpr int kMaxRanks = MAVA_PEER_MAX_RANKS;
-constexpr int kCluster = 8;
-constexpr int kThreads = 1024;
+constexpr int kThreads = 256;
+constexpr int kMaxCtas = 128;
 // flag block (uint32 words) behind the gradient vector of an exchange buffer
 constexpr int F_READY = 0;            // [kMaxRanks] written by rank p: "p's gradients of call #seq are complete"
 constexpr int F_DONE = kMaxRanks;     // [kMaxRanks] written by rank p: "p has read this buffer in call #seq"
 constexpr int F_SEQ = 2 * kMaxRanks;  // calls completed on this buffer (local)
 constexpr int F_ERR = 2 * kMaxRanks + 1;  // != 0: a handshake timed out (local)
+constexpr int F_GRID = 2 * kMaxRanks + 2;  // arrivals at the kernel's grid barrier, ever growing (local)
+constexpr int F_NORM = 2 * kMaxRanks + 4;  // 2 x 2 doubles: squared norms of call parity 0 / 1 (local)
 constexpr int F_WORDS = 32;
 
 __host__ __device__ inline int64_t grad_bytes_padded(int64_t n_grad) {
@@ -85,7 +84,8 @@ struct ReduceAdamArgs {
   float *params, *mu, *nu;
   int32_t* counts;
   const float* grad[kMaxRanks];  // this rank's mapping of every rank's gradient vector
-  uint32_t* flags[kMaxRanks];    // ... and of every rank's flag block
+  uint32_t* flags[kMaxRanks];    // ... and of every rank's flag block (world > 1)
+  uint32_t* local_flags;         // this rank's flag block (world == 1: a block owned by the library)
   int rank, world;
   float* gsum;  // local scratch, n[0] + n[1] floats: the reduced, scaled gradients
   int64_t n[2];
@@ -97,41 +97,57 @@ struct ReduceAdamArgs {
   float* loss_out;  // [5] or null: mean over ranks of the loss scalars behind the gradients
 };
 
-__device__ __forceinline__ void adam_one(const ReduceAdamArgs& a, int64_t i, float g, float g_norm,
-                                         bool keep, int net, int64_t off, float step_lr, float bc1,
-                                         float bc2) {
+struct AdamStep {  // per network: what every element of one call shares
+  float g_norm, step_lr, bc1, bc2;
+  bool keep;
+};
+
+// optax.clip_by_global_norm -> optax.adam(eps=1e-5) -> apply_updates on one element (registers)
+__device__ __forceinline__ float adam_math(float g, float& m, float& v, float p, const AdamStep& st,
+                                           float max_norm) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-5f;
-  if (!keep) g = (g / g_norm) * a.max_norm;
-  const float m = (1.0f - b1) * g + b1 * a.mu[i];
-  const float v = (1.0f - b2) * g * g + b2 * a.nu[i];
-  a.mu[i] = m;
-  a.nu[i] = v;
-  const float pnew = a.params[i] - step_lr * ((m / bc1) / (sqrtf(v / bc2) + eps));
-  a.params[i] = pnew;
-  if (a.image[net])
-    *reinterpret_cast<__nv_bfloat16*>(
-        a.image[net] + tcmlp::image_offset(i - off, a.in_dim[net], a.k1p[net], a.out[net])) =
-        __float2bfloat16_rn(pnew);
+  if (!st.keep) g = (g / st.g_norm) * max_norm;
+  m = (1.0f - b1) * g + b1 * m;
+  v = (1.0f - b2) * g * g + b2 * v;
+  return p - st.step_lr * ((m / st.bc1) / (sqrtf(v / st.bc2) + eps));
 }
 
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
-reduce_clip_adam_kernel(const ReduceAdamArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned crank = cluster.block_rank();
+__device__ __forceinline__ void store_image(const ReduceAdamArgs& a, int net, int i_local, float p) {
+  if (a.image[net])
+    *reinterpret_cast<__nv_bfloat16*>(
+        a.image[net] + tcmlp::image_offset(i_local, a.in_dim[net], a.k1p[net], a.out[net])) =
+        __float2bfloat16_rn(p);
+}
+
+// Grid barrier of a cooperative launch (all CTAs co-resident): arrivals are counted in a word of the
+// rank's flag block that only ever grows; generation k of a kernel that runs `per_call` barriers is
+// complete at (calls_before * per_call + k) * gridDim.x arrivals.
+__device__ __forceinline__ void grid_arrive_wait(uint32_t* counter, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while ((int32_t)(ld_acquire_sys(counter) - target) < 0) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const ReduceAdamArgs a) {
   const int t = threadIdx.x;
-  const int64_t tid = (int64_t)crank * kThreads + t;
-  constexpr int64_t nthreads = (int64_t)kCluster * kThreads;
-  uint32_t* my_flags = a.flags[a.rank];
-  __shared__ double s_part[kCluster][2];  // CTA 0's copy collects every CTA's partial norms
+  const int64_t tid = (int64_t)blockIdx.x * kThreads + t;
+  const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+  uint32_t* my_flags = a.local_flags;
   __shared__ double s_red[kThreads / 32][2];
-  __shared__ float s_norm[2];
 
   const int c0[2] = {a.counts[0], a.counts[1]};
-  const uint32_t seq = (a.world > 1 ? my_flags[F_SEQ] : 0u) + 1u;
+  const uint32_t calls = my_flags[F_SEQ];  // calls completed on this flag block
+  const uint32_t seq = calls + 1u;
+  double* norm2 = reinterpret_cast<double*>(my_flags + F_NORM) + 2 * (seq & 1u);
 
   // ---- handshake 1: every rank's gradients of this call are complete ---------------------------
   if (a.world > 1) {
-    if (crank == 0 && t < a.world && t != a.rank) {
+    if (blockIdx.x == 0 && t < a.world && t != a.rank) {
       __threadfence_system();
       st_release_sys(a.flags[t] + F_READY + a.rank, seq);
     }
@@ -161,11 +177,12 @@ reduce_clip_adam_kernel(const ReduceAdamArgs a) {
       s = *reinterpret_cast<const float4*>(a.grad[0] + 4 * c);
     }
     float g[4] = {s.x * a.grad_scale, s.y * a.grad_scale, s.z * a.grad_scale, s.w * a.grad_scale};
+    if (4 * c + 4 <= n01) *reinterpret_cast<float4*>(a.gsum + 4 * c) = make_float4(g[0], g[1], g[2], g[3]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t i = 4 * c + j;
       if (i < n01) {
-        a.gsum[i] = g[j];
+        if (4 * c + 4 > n01) a.gsum[i] = g[j];
         const int net = i < n0 ? 0 : 1;
         ss[net] = fmaf(g[j], g[j], ss[net]);
       } else if (i < n01 + 5 && a.loss_out != nullptr) {
@@ -185,14 +202,14 @@ reduce_clip_adam_kernel(const ReduceAdamArgs a) {
       a.loss_out[i - n01] = g;
     }
   }
-  double d0 = (double)ss[0], d1 = (double)ss[1];
+  // fp32 partial sums per thread (a handful of elements), combined in fp64
   for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+    ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
   }
   if ((t & 31) == 0) {
-    s_red[t >> 5][0] = d0;
-    s_red[t >> 5][1] = d1;
+    s_red[t >> 5][0] = (double)ss[0];
+    s_red[t >> 5][1] = (double)ss[1];
   }
   __syncthreads();
   if (t == 0) {
@@ -201,68 +218,94 @@ reduce_clip_adam_kernel(const ReduceAdamArgs a) {
       v0 += s_red[w][0];
       v1 += s_red[w][1];
     }
-    double* dst = cluster.map_shared_rank(&s_part[0][0], 0);  // CTA 0 collects
-    dst[2 * crank + 0] = v0;
-    dst[2 * crank + 1] = v1;
+    atomicAdd(norm2 + 0, v0);
+    atomicAdd(norm2 + 1, v1);
   }
-  cluster.sync();  // every CTA has consumed its share of the peers' buffers and posted its norms
+  // every CTA of this rank has consumed its share of the peers' buffers and posted its norms
+  grid_arrive_wait(my_flags + F_GRID, seq * gridDim.x);
 
   // ---- handshake 2, first half: tell the peers their buffers have been read ---------------------
-  if (a.world > 1 && crank == 0 && t < a.world && t != a.rank)
+  if (a.world > 1 && blockIdx.x == 0 && t < a.world && t != a.rank)
     st_release_sys(a.flags[t] + F_DONE + a.rank, seq);
 
-  if (t == 0) {
-    const double* src = cluster.map_shared_rank(&s_part[0][0], 0);
-    double v0 = 0.0, v1 = 0.0;
-    for (int c = 0; c < kCluster; ++c) {  // fixed order: every CTA computes the same norms
-      v0 += src[2 * c + 0];
-      v1 += src[2 * c + 1];
-    }
-    s_norm[0] = (float)sqrt(v0);
-    s_norm[1] = (float)sqrt(v1);
-  }
-  __syncthreads();
-
   // ---- clip + Adam + apply (+ bf16 image refresh); every thread re-reads what it wrote ----------
-  float g_norm[2], step_lr[2], bc1[2], bc2[2];
-  bool keep[2];
+  AdamStep st[2];
 #pragma unroll
   for (int net = 0; net < 2; ++net) {
-    g_norm[net] = s_norm[net];
-    keep[net] = g_norm[net] < a.max_norm;
+    st[net].g_norm = (float)sqrt(*reinterpret_cast<volatile double*>(norm2 + net));
+    st[net].keep = st[net].g_norm < a.max_norm;
     const int c = c0[net] + 1;
-    bc1[net] = 1.0f - powf(0.9f, (float)c);
-    bc2[net] = 1.0f - powf(0.999f, (float)c);
-    step_lr[net] = a.lr[net];
+    st[net].bc1 = 1.0f - powf(0.9f, (float)c);
+    st[net].bc2 = 1.0f - powf(0.999f, (float)c);
+    st[net].step_lr = a.lr[net];
     if (a.lr_decay_num_updates > 0)
-      step_lr[net] *= 1.0f - (float)(c0[net] / a.steps_per_update) / (float)a.lr_decay_num_updates;
+      st[net].step_lr *=
+          1.0f - (float)(c0[net] / a.steps_per_update) / (float)a.lr_decay_num_updates;
   }
+  // Whole 16-byte chunks: the four moments / parameters of a chunk are loaded together (no store
+  // sits between the loads of a thread's elements), updated in registers and stored together.
+  const int n0i = (int)n0, n01i = (int)n01;
   for (int64_t c = tid; c < chunks; c += nthreads) {
+    const int i0 = (int)(4 * c);
+    if (i0 + 4 <= n01i) {
+      const float4 g4 = *reinterpret_cast<const float4*>(a.gsum + i0);
+      float4 m4 = *reinterpret_cast<const float4*>(a.mu + i0);
+      float4 v4 = *reinterpret_cast<const float4*>(a.nu + i0);
+      float4 p4 = *reinterpret_cast<const float4*>(a.params + i0);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float pn[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t i = 4 * c + j;
-      if (i < n01) {
-        const int net = i < n0 ? 0 : 1;
-        adam_one(a, i, a.gsum[i], g_norm[net], keep[net], net, net ? n0 : 0, step_lr[net], bc1[net],
-                 bc2[net]);
+      for (int j = 0; j < 4; ++j) {
+        const int net = i0 + j < n0i ? 0 : 1;
+        pn[j] = adam_math(g[j], m[j], v[j], pn[j], st[net], a.max_norm);
+      }
+      *reinterpret_cast<float4*>(a.mu + i0) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(a.nu + i0) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(a.params + i0) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int net = i0 + j < n0i ? 0 : 1;
+        store_image(a, net, i0 + j - (net ? n0i : 0), pn[j]);
+      }
+    } else {
+      for (int i = i0; i < n01i; ++i) {  // the chunk that holds the end of the vector
+        const int net = i < n0i ? 0 : 1;
+        float m = a.mu[i], v = a.nu[i];
+        const float pn = adam_math(a.gsum[i], m, v, a.params[i], st[net], a.max_norm);
+        a.mu[i] = m;
+        a.nu[i] = v;
+        a.params[i] = pn;
+        store_image(a, net, i - (net ? n0i : 0), pn);
       }
     }
   }
-  for (int64_t i = 4 * chunks + tid; i < n01; i += nthreads) {
-    const int net = i < n0 ? 0 : 1;
-    adam_one(a, i, a.gsum[i], g_norm[net], keep[net], net, net ? n0 : 0, step_lr[net], bc1[net],
-             bc2[net]);
+  for (int64_t i64 = 4 * chunks + tid; i64 < n01; i64 += nthreads) {
+    const int i = (int)i64;
+    const int net = i < n0i ? 0 : 1;
+    float m = a.mu[i], v = a.nu[i];
+    const float pn = adam_math(a.gsum[i], m, v, a.params[i], st[net], a.max_norm);
+    a.mu[i] = m;
+    a.nu[i] = v;
+    a.params[i] = pn;
+    store_image(a, net, i - (net ? n0i : 0), pn);
   }
 
   // ---- handshake 2, second half: nobody reads this rank's buffer any more -----------------------
-  if (a.world > 1 && crank == 0 && t < a.world && t != a.rank) {
-    if (!wait_flag(my_flags + F_DONE + t, seq)) my_flags[F_ERR] = 1u;
-  }
-  cluster.sync();  // CTA 0's shared memory stays alive until every CTA has read the norms
-  if (crank == 0 && t == 0) {
-    a.counts[0] = c0[0] + 1;
-    a.counts[1] = c0[1] + 1;
-    if (a.world > 1) my_flags[F_SEQ] = seq;
+  if (blockIdx.x == 0) {
+    if (a.world > 1 && t < a.world && t != a.rank) {
+      if (!wait_flag(my_flags + F_DONE + t, seq)) my_flags[F_ERR] = 1u;
+    }
+    __syncthreads();
+    if (t == 0) {
+      // every CTA has passed the grid barrier, i.e. has read counts, F_SEQ and the norms of this call
+      a.counts[0] = c0[0] + 1;
+      a.counts[1] = c0[1] + 1;
+      double* other = reinterpret_cast<double*>(my_flags + F_NORM) + 2 * ((seq + 1u) & 1u);
+      other[0] = 0.0;  // the next call's accumulators (this call's are zeroed by the call after it)
+      other[1] = 0.0;
+      my_flags[F_SEQ] = seq;
+    }
   }
 }
 
@@ -342,7 +385,10 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
   MAVA_CHECK_PTR(counts);
   MAVA_CHECK_PTR(group_host);
   MAVA_CHECK_PTR(gsum);
-  MAVA_CHECK_ARG(n_actor > 0 && n_critic > 0 && steps_per_update > 0);
+  MAVA_CHECK_ARG(n_actor > 0 && n_critic > 0 && steps_per_update > 0 &&
+                 n_actor + n_critic < ((int64_t)1 << 31));
+  MAVA_CHECK_ARG(((reinterpret_cast<size_t>(params) | reinterpret_cast<size_t>(mu) |
+                   reinterpret_cast<size_t>(nu) | reinterpret_cast<size_t>(gsum)) & 15) == 0);
   MAVA_CHECK_ARG(group_host->world >= 1 && group_host->world <= kMaxRanks &&
                  group_host->rank >= 0 && group_host->rank < group_host->world);
   ReduceAdamArgs a{};
@@ -356,6 +402,7 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
     a.flags[r] = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(group_host->buf[r]) +
                                              grad_bytes_padded(n_grad));
   }
+  a.local_flags = a.flags[a.rank];
   a.gsum = gsum;
   a.n[0] = n_actor; a.n[1] = n_critic;
   a.lr[0] = lr_actor; a.lr[1] = lr_critic;
@@ -376,7 +423,21 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
       a.out[k] = d->out_dim;
     }
   }
-  reduce_clip_adam_kernel<<<kCluster, kThreads, 0, as_stream(s)>>>(a);
+  const int64_t chunks = (n_grad + 3) / 4;
+  int ctas = (int)ceil_div64(chunks, kThreads);
+  ctas = ctas < 1 ? 1 : (ctas > kMaxCtas ? kMaxCtas : ctas);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = as_stream(s);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // the grid barrier needs every CTA resident
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_clip_adam_kernel, a);
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
 

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) clip_adam_pair_kernel(const AdamPairArgs 
     params[i] = pnew;
     if (a.image[net])
       *reinterpret_cast<__nv_bfloat16*>(a.image[net] +
-                                        tcmlp::image_offset(i, a.in_dim[net], a.k1p[net], a.out[net])) =
+                                        tcmlp::image_offset((int)i, a.in_dim[net], a.k1p[net], a.out[net])) =
           __float2bfloat16_rn(pnew);
   }
 }
@@ -272,6 +272,24 @@ episode_stats_kernel(const uint8_t* __restrict__ done, const float* __restrict__
     atomic_min_f64(stats + 7, (double)mnl);
     atomic_max_f64(stats + 8, (double)mxl);
   }
+}
+
+// evaluator.py:143-150: metrics at the first terminal step of every env (argmax of the done flag)
+__global__ void first_terminal_kernel(const uint8_t* __restrict__ done,
+                                      const float* __restrict__ ep_return,
+                                      const int32_t* __restrict__ ep_length, int T, int num_envs,
+                                      float* __restrict__ out_return, int32_t* __restrict__ out_length) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= num_envs) return;
+  int first = 0;
+  for (int t = 0; t < T; ++t) {
+    if (__ldg(done + (size_t)t * num_envs + e)) {
+      first = t;
+      break;
+    }
+  }
+  out_return[e] = ep_return[(size_t)first * num_envs + e];
+  out_length[e] = ep_length[(size_t)first * num_envs + e];
 }
 
 __global__ void episode_stats_init_kernel(double* stats) {
@@ -391,6 +409,20 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
   MAVA_CHECK_ARG(n > 0 && steps_per_update > 0);
   clip_adam_kernel<<<1, 1024, 0, as_stream(s)>>>(params, mu, nu, count, grad, n, grad_scale, lr,
                                                  max_norm, lr_decay_num_updates, steps_per_update);
+  return launch_status();
+}
+
+int mava_episode_first_terminal(const uint8_t* done, const float* ep_return,
+                                const int32_t* ep_length, int T, int num_envs, float* out_return,
+                                int32_t* out_length, mava_stream_t s) {
+  MAVA_CHECK_PTR(done);
+  MAVA_CHECK_PTR(ep_return);
+  MAVA_CHECK_PTR(ep_length);
+  MAVA_CHECK_PTR(out_return);
+  MAVA_CHECK_PTR(out_length);
+  MAVA_CHECK_ARG(T > 0 && num_envs > 0);
+  first_terminal_kernel<<<ceil_div(num_envs, 128), 128, 0, as_stream(s)>>>(
+      done, ep_return, ep_length, T, num_envs, out_return, out_length);
   return launch_status();
 }
 

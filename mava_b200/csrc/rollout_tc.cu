@@ -58,6 +58,10 @@ struct RolloutArgs {
   int32_t* ep_length;           // [T][NE]
   int num_envs, envs_per_replica, T;
   int epc;  // envs per CTA (<= TM / A): fewer than a full tile when that fills more SMs
+  // evaluator flavour (mava/evaluator.py:80-172): no AutoResetWrapper, pi.mode() instead of a
+  // sample, and -- record == 0 -- only done / episode metrics are kept per step: observation, mask,
+  // action, log-prob and reward of every step go to slot 0 of their buffers
+  int auto_reset, greedy, record;
 };
 
 struct RCtrl {
@@ -169,7 +173,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
       dst[row * NHEAD + j] = bits_to_gumbel(random_bits_at(key, base + j, size));
     }
   };
-  make_noise(0, t, NT);
+  if (!p.greedy) make_noise(0, t, NT);
   mbar_wait(&ctrl.wbar, 0);
   mbar_wait(&ctrl.rbar, 0);
   // every env starts without a spare
@@ -182,7 +186,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
       ctrl.bgkey[i][1] = k[1];
     }
   };
-  if (agent && g == 0) want_spare();
+  if (agent && g == 0 && p.auto_reset) want_spare();
   __syncthreads();
 
   uint32_t phase = 0;
@@ -191,6 +195,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
   // reads are 64 B/clk per SM: half a tile of dead rows would cost as much as the live half)
   const bool live = (warp & 3) * 32 < rows_valid;
   for (int step = 0; step < p.T; ++step) {
+    const int so = p.record ? step : 0, so1 = p.record ? step + 1 : 0;  // output slots of this step
     MAVA_RSTAMP(0);
     // ---- 1. X tile from the observation rows in shared memory
     expand_x_row(d, xt, L, reinterpret_cast<const signed char*>(sobs) + L.r * c.FR,
@@ -260,7 +265,7 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
 #pragma unroll
         for (int j = 0; j < NHEAD; ++j) {
           if (j < d.out) {
-            const float z = nz[j] + out[j];
+            const float z = (p.greedy ? 0.0f : nz[j]) + out[j];
             if (j == 0 || z > best) { best = z; act = j; }
           }
         }
@@ -268,18 +273,20 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
 #pragma unroll
         for (int j = 0; j < NHEAD; ++j)
           if (j == act) la = out[j] - lse;
-        const size_t o = (size_t)step * ea_slot + (size_t)env * G + g;
+        const size_t o = (size_t)so * ea_slot + (size_t)env * G + g;
         p.action[o] = (int8_t)act;
         p.logp[o] = la;
       }
       if (el < nenv)
-        rware::step_group<G>(c, rec, g, gmask, agent, act, env, 1, p.reward + (size_t)step * ea_slot,
+        rware::step_group<G>(c, rec, g, gmask, agent, act, env, p.auto_reset,
+                             p.reward + (size_t)so * ea_slot,
                              p.done + (size_t)step * p.num_envs,
                              p.ep_return + (size_t)step * p.num_envs,
                              p.ep_length + (size_t)step * p.num_envs, needs_reset, replay, opk);
       if (needs_reset && g == 0) ctrl.rlist[atomicAdd(&ctrl.rcount, 1)] = (uint16_t)el;
     } else {
-      if (step + 1 < p.T) make_noise(step + 1, t - TM, NT - TM);  // warps 4..15: next step's noise
+      if (step + 1 < p.T && !p.greedy)
+        make_noise(step + 1, t - TM, NT - TM);  // warps 4..15: next step's noise
       // ... and one spare record per warp (the list is stable during this phase; half-warp
       // generators were tried and are slower)
       const int i = warp - TM / 32;
@@ -335,14 +342,14 @@ rware_rollout_kernel(const __grid_constant__ RolloutArgs p) {
     // ---- next observation rows and masks
     if (agent) {
       mk = rware::emit_row<G, R>(c, rec, g, sobs + L.r * c.FR, L.r & 1, replay, opk);
-      p.mask[(size_t)(step + 1) * ea_slot + (size_t)env * G + g] = (uint8_t)mk;
-      if (g == 0) want_spare();
+      p.mask[(size_t)so1 * ea_slot + (size_t)env * G + g] = (uint8_t)mk;
+      if (g == 0 && p.auto_reset) want_spare();
     }
     fence_proxy_async();
     __syncthreads();
     MAVA_RSTAMP(9);
     pending_store = store_block(
-        sobs, reinterpret_cast<uint8_t*>(p.view) + (size_t)(step + 1) * obs_slot +
+        sobs, reinterpret_cast<uint8_t*>(p.view) + (size_t)so1 * obs_slot +
                   (size_t)env0 * G * c.FR,
         obs_bytes);
     if (t == 0 && pending_store) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -396,11 +403,12 @@ int mava_debug_rollout_phases(long long* out_host) {
 }
 #endif
 
-int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor, const float* actor_params,
-                         const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,
-                         const uint32_t* policy_keys, int envs_per_replica, int num_envs,
-                         int rollout_length, int8_t* action, float* logp, float* reward,
-                         uint8_t* done, float* ep_return, int32_t* ep_length, mava_stream_t s) {
+int mava_ff_rollout_bf16_ex(mava_env_t env, const mava_mlp_desc* actor, const float* actor_params,
+                            const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,
+                            const uint32_t* policy_keys, int envs_per_replica, int num_envs,
+                            int rollout_length, int auto_reset, int greedy, int record,
+                            int8_t* action, float* logp, float* reward, uint8_t* done,
+                            float* ep_return, int32_t* ep_length, mava_stream_t s) {
   MAVA_CHECK_PTR(env);
   RolloutArgs a{};
   int rc = make_net(actor, actor_params, &a.actor);
@@ -437,9 +445,23 @@ int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor, const float
   a.num_envs = num_envs;
   a.envs_per_replica = envs_per_replica;
   a.T = rollout_length;
+  a.auto_reset = auto_reset != 0;
+  a.greedy = greedy != 0;
+  a.record = record != 0;
   if (c.A == 2) return launch_rollout<2>(a, as_stream(s));
   if (c.A == 4) return launch_rollout<4>(a, as_stream(s));
   return launch_rollout<8>(a, as_stream(s));
+}
+
+int mava_ff_rollout_bf16(mava_env_t env, const mava_mlp_desc* actor, const float* actor_params,
+                         const void* actor_image, uint8_t* state, int8_t* view, uint8_t* mask,
+                         const uint32_t* policy_keys, int envs_per_replica, int num_envs,
+                         int rollout_length, int8_t* action, float* logp, float* reward,
+                         uint8_t* done, float* ep_return, int32_t* ep_length, mava_stream_t s) {
+  return mava_ff_rollout_bf16_ex(env, actor, actor_params, actor_image, state, view, mask,
+                                 policy_keys, envs_per_replica, num_envs, rollout_length,
+                                 /*auto_reset=*/1, /*greedy=*/0, /*record=*/1, action, logp, reward,
+                                 done, ep_return, ep_length, s);
 }
 
 }  // extern "C"

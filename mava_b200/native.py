@@ -351,6 +351,42 @@ def ff_rollout_bf16(env: "Env", actor: MlpDesc, actor_params, actor_image, state
         _p(ep_length, torch.int32, T * num_envs, "ep_length"), _stream()), "mava_ff_rollout_bf16")
 
 
+def ff_rollout_bf16_ex(env: "Env", actor: MlpDesc, actor_params, actor_image, state, view, mask,
+                       policy_keys, envs_per_replica: int, num_envs: int, T: int, auto_reset: bool,
+                       greedy: bool, record: bool, action, logp, reward, done, ep_return,
+                       ep_length) -> None:
+    """The fused rollout kernel as the evaluator runs it (no auto-reset, optional pi.mode(), and --
+    record=False -- per-step outputs other than done / episode metrics folded into slot 0)."""
+    A, F = actor.num_agents, actor.view_dim
+    slots, slots1 = (T, T + 1) if record else (1, 1)
+    _count(1)
+    check(_lib.load().mava_ff_rollout_bf16_ex(
+        env._h, C.byref(actor), _p(actor_params, torch.float32, mlp_param_count(actor), "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"),
+        _p(state, torch.uint8, num_envs * env.state_stride, "state"),
+        _p(view, torch.int8, slots1 * num_envs * A * F, "view"),
+        _p(mask, torch.uint8, slots1 * num_envs * A, "mask"),
+        _p(policy_keys, torch.uint32, 2 * T, "policy_keys"), envs_per_replica, num_envs, T,
+        int(auto_reset), int(greedy), int(record),
+        _p(action, torch.int8, slots * num_envs * A, "action"),
+        _p(logp, torch.float32, slots * num_envs * A, "logp"),
+        _p(reward, torch.float32, slots * num_envs * A, "reward"),
+        _p(done, torch.uint8, T * num_envs, "done"),
+        _p(ep_return, torch.float32, T * num_envs, "ep_return"),
+        _p(ep_length, torch.int32, T * num_envs, "ep_length"), _stream()), "mava_ff_rollout_bf16_ex")
+
+
+def episode_first_terminal(done, ep_return, ep_length, T: int, num_envs: int, out_return,
+                           out_length) -> None:
+    """Per env: episode return / length at the first terminal step (evaluator.py:143-150)."""
+    _count(1)
+    check(_lib.load().mava_episode_first_terminal(
+        _p(done, torch.uint8, T * num_envs, "done"), _p(ep_return, torch.float32, T * num_envs, "ep_return"),
+        _p(ep_length, torch.int32, T * num_envs, "ep_length"), T, num_envs,
+        _p(out_return, torch.float32, num_envs, "out_return"),
+        _p(out_length, torch.int32, num_envs, "out_length"), _stream()), "mava_episode_first_terminal")
+
+
 def ppo_workspace_bytes_bf16(actor: MlpDesc, critic: MlpDesc, rows_total: int) -> int:
     return int(_lib.load().mava_ppo_workspace_bytes_bf16(C.byref(actor), C.byref(critic),
                                                          rows_total))

@@ -16,15 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from oracle import rware as orw  # noqa: E402
 from oracle import threefry as tf  # noqa: E402
 
-SCENARIOS = {
-    "tiny-2ag": dict(column_height=8, shelf_rows=1, shelf_columns=3, num_agents=2, sensor_range=1,
-                     request_queue_size=2),
-    "tiny-4ag": dict(column_height=8, shelf_rows=1, shelf_columns=3, num_agents=4, sensor_range=1,
-                     request_queue_size=4),
-    "small-4ag": dict(column_height=8, shelf_rows=2, shelf_columns=3, num_agents=4, sensor_range=1,
-                      request_queue_size=4),
-}
-
+from tests.golden.golden_inputs import RWARE_SCENARIOS as SCENARIOS  # noqa: E402
 
 def main():
     out = {}

@@ -152,3 +152,91 @@ def test_clip_adam_first_step():
     np.testing.assert_allclose(mu, 0.1 * gc, rtol=1e-6)
     expect = -1e-3 * gc / (np.abs(gc) + 1e-5)
     np.testing.assert_allclose(p1[:2], expect[:2], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["8x8-2p-2f-coop", "2s-10x10-3p-3f"])
+def test_lbf_oracle_reproduces_golden(name):
+    """tests/golden/lbf_golden.npz (make_oracle_golden.py, or make_reference_golden.py where the real
+    jumanji exists) against the numpy LBF restatement."""
+    from oracle import lbf as olbf
+    from tests.golden import golden_inputs as gi
+
+    g = np.load(os.path.join(GOLD, "lbf_golden.npz"))
+    spec = olbf.make_spec(time_limit=gi.LBF_TIME_LIMIT, **gi.LBF_SCENARIOS[name])
+    env = olbf.MavaLbf(spec, add_global_state=False, add_agent_id=False)
+    keys, actions = g[f"{name}/keys"], g[f"{name}/actions"]
+    states, ts = zip(*[env.reset(k) for k in keys])
+    states = list(states)
+    np.testing.assert_array_equal(np.stack([t["obs"]["agents_view"] for t in ts]).astype(np.int8),
+                                  g[f"{name}/views"][0])
+    np.testing.assert_array_equal(np.stack([t["obs"]["action_mask"] for t in ts]),
+                                  g[f"{name}/masks"][0])
+    for t in range(actions.shape[0]):
+        res = [env.step(states[e], actions[t, e]) for e in range(len(keys))]
+        states = [r[0] for r in res]
+        np.testing.assert_array_equal(
+            np.stack([r[1]["obs"]["agents_view"] for r in res]).astype(np.int8),
+            g[f"{name}/views"][t + 1], err_msg=f"t={t}")
+        np.testing.assert_array_equal(np.stack([r[1]["obs"]["action_mask"] for r in res]),
+                                      g[f"{name}/masks"][t + 1])
+        np.testing.assert_array_equal(np.stack([r[1]["reward"] for r in res]), g[f"{name}/rewards"][t])
+        np.testing.assert_array_equal(np.array([r[1]["done"] for r in res]), g[f"{name}/dones"][t])
+        np.testing.assert_array_equal(
+            np.array([r[1]["metrics"]["episode_return"] for r in res], np.float32),
+            g[f"{name}/ep_returns"][t])
+
+
+def test_ppo_oracle_reproduces_golden():
+    """tests/golden/ppo_golden.npz: jax.random.permutation, both GAE flavours, the losses and
+    gradients of one ff_mappo minibatch and three optax steps, against oracle/ppo.py and
+    oracle/threefry.py (float tolerances: the file may come from XLA, see make_reference_golden.py)."""
+    import torch
+
+    from oracle import ppo as oppo
+    from tests.golden import golden_inputs as gi
+
+    g = np.load(os.path.join(GOLD, "ppo_golden.npz"))
+    for n in gi.PERM_SIZES:
+        np.testing.assert_array_equal(tf.permutation(tf.prng_key(gi.PERM_SEED + n), n), g[f"perm/{n}"])
+    x = gi.gae_inputs()
+    A = x["reward"].shape[2]
+    done_a = np.repeat(x["done"][:, :, None], A, 2)
+    adv, tgt = oppo.gae_ff(x["reward"], x["value"], done_a, x["last_val"], x["gamma"], x["gae_lambda"])
+    np.testing.assert_allclose(adv, g["gae/ff_adv"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(tgt, g["gae/ff_targets"], rtol=1e-5, atol=1e-6)
+    adv, tgt = oppo.gae_rec(x["reward"], x["value"], done_a, x["last_val"],
+                            np.repeat(x["last_done"][:, None], A, 1), x["gamma"], x["gae_lambda"])
+    np.testing.assert_allclose(adv, g["gae/rec_adv"], rtol=1e-5, atol=1e-6)
+
+    li = gi.loss_inputs()
+    S, A, FR = li["view"].shape
+    mk = lambda ps: [torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in ps]  # noqa: E731
+    at, ct = mk(li["actor"]), mk(li["critic"])
+    lay = lambda t: [(t[0], t[1]), (t[2], t[3]), (t[4], t[5])]  # noqa: E731
+    v = li["view"].astype(np.float64)
+    xa = torch.tensor(np.concatenate([np.broadcast_to(np.eye(A), (S, A, A)), v], -1))
+    xg = torch.tensor(np.repeat(v.reshape(S, 1, A * FR), A, 1))
+    logits = oppo.actor_logits(lay(at), xa, torch.tensor(li["mask"]))
+    ta, la, ent = oppo.actor_loss(logits, torch.tensor(li["action"]),
+                                  torch.tensor(li["old_logp"], dtype=torch.float64),
+                                  torch.tensor(li["adv"], dtype=torch.float64), 0.2, 0.01)
+    val = oppo.critic_value(lay(ct), xg)
+    tc, vl = oppo.critic_loss(val, torch.tensor(li["old_value"], dtype=torch.float64),
+                              torch.tensor(li["targets"], dtype=torch.float64), 0.2, 0.5)
+    ta.backward()
+    tc.backward()
+    legal = li["mask"]
+    np.testing.assert_allclose(logits.detach().numpy()[legal], g["loss/logits"][legal], rtol=1e-4,
+                               atol=1e-5)
+    np.testing.assert_allclose(val.detach().numpy(), g["loss/value"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose([ta.item(), la.item(), ent.item(), tc.item(), vl.item()],
+                               g["loss/scalars"], rtol=1e-4, atol=1e-6)
+    for ts, key in ((at, "loss/actor_grad"), (ct, "loss/critic_grad")):
+        got = np.concatenate([p.grad.numpy().ravel() for p in ts])
+        np.testing.assert_allclose(got, g[key], rtol=1e-3, atol=1e-4 * np.abs(g[key]).max())
+    ai = gi.adam_inputs()
+    p, mu, nu = ai["params"].copy(), np.zeros_like(ai["params"]), np.zeros_like(ai["params"])
+    for c, gr in enumerate(ai["grads"]):
+        p, mu, nu = oppo.clip_adam(p, gr, mu, nu, c, float(ai["lr"]), float(ai["max_norm"]))
+    np.testing.assert_allclose(p, g["adam/params"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(nu, g["adam/nu"], rtol=1e-5, atol=1e-12)
