@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kMaxRanks = MAVA_PEER_MAX_RANKS;
 constexpr int kThreads = 256;
-constexpr int kMaxCtas = 128;
+constexpr int kMaxCtas = 128;  // x 256 threads, one 16-byte chunk per thread for the headline networks
 // flag block (uint32 words) behind the gradient vector of an exchange buffer
 constexpr int F_READY = 0;            // [kMaxRanks] written by rank p: "p's gradients of call #seq are complete"
 constexpr int F_DONE = kMaxRanks;     // [kMaxRanks] written by rank p: "p has read this buffer in call #seq"

@@ -35,7 +35,7 @@ def exact_collective_check(device, rank, world):
     peer = PeerGroup(n + 8, device, rank, world)
     local = PeerGroup(n + 8, device)
     z = lambda k, dt=torch.float32: torch.zeros(k, dtype=dt, device=device)
-    st = {k: dict(p=p0.clone(), mu=z(n), nu=z(n), c=z(2, torch.int32), gsum=z(n), loss=z(6, 5))
+    st = {k: dict(p=p0.clone(), mu=z(n), nu=z(n), c=z(2, torch.int32), gsum=z(n), loss=torch.zeros(6, 5, device=device))
           for k in ("peer", "nccl")}
     for k, grad in enumerate(grads):
         peer.grad.copy_(grad)
