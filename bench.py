@@ -226,6 +226,9 @@ def _peaks() -> dict:
         return {}
 
 
+COLLECTIVE = "peer"  # --collective: peer (fused NVLink all-reduce, default) | nccl (the checker)
+
+
 def _setup(name: str, precision: str, device):
     """Learner of one BASELINE.json workload on this rank's GPU (synthetic data, seeded init)."""
     import importlib
@@ -236,7 +239,8 @@ def _setup(name: str, precision: str, device):
 
     wl = WORKLOADS[name]
     system = importlib.import_module(f"mava_b200.systems.ppo.{wl['system']}")
-    cfg = compose(system.CONFIG_NAME, wl["overrides"] + [f"+arch.precision={precision}"])
+    cfg = compose(system.CONFIG_NAME, wl["overrides"] + [f"+arch.precision={precision}",
+                                                         f"+arch.collective={COLLECTIVE}"])
     env, _ = make_env.make(cfg, add_global_state=system.CENTRALISED_CRITIC, device=device)
     key, _, ak, ck = prng.split(prng.PRNGKey(cfg.system.seed), 4)
     learn, _, state = system.learner_setup(env, (key, ak, ck), cfg)
@@ -561,7 +565,11 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true",
                     help="skip roofline_extra and the other BASELINE.json workloads")
     ap.add_argument("--workload", default="ff_mappo_rware", choices=sorted(WORKLOADS))
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="gradient mean over ranks: fused peer-memory all-reduce, or NCCL (checker)")
     args = ap.parse_args()
+    global COLLECTIVE
+    COLLECTIVE = args.collective
     if os.environ.get("MAVA_BENCH_DEBUG"):  # dump every thread's stack if the run gets stuck
         import faulthandler
 

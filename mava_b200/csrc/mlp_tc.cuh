@@ -397,24 +397,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const Tile& a, bool 
   if (bar) commit(bar);
 }
 
-// K steps [k0, k1) of the N columns starting at column n0 of a GEMM (M = 128): the unit the fused
-// PPO kernel pipelines with -- an accumulator is produced as two 64-column halves, each over two K
-// ranges, so that an epilogue group starts on its half while the other half is still in the pipe.
-__device__ __forceinline__ void issue_part(uint32_t d_tmem, const Tile& a, bool a_mn, const Tile& b,
-                                           bool b_mn, int n0, int N, int k0, int k1,
-                                           bool accumulate) {
-  const uint32_t idesc = instr_desc(TM, N, a_mn, b_mn);
-  uint64_t ad = a_mn ? desc_mnmajor(a, k0) : desc_kmajor(a, k0);
-  uint64_t bd = b_mn ? desc_mnmajor(b, k0, n0) : desc_kmajor(b, k0, n0);
-  const uint64_t a_inc = (uint64_t)(((a_mn ? a.s_r : a.s_c) * 2u) >> 4);
-  const uint64_t b_inc = (uint64_t)(((b_mn ? b.s_r : b.s_c) * 2u) >> 4);
-  for (int k = k0; k < k1; ++k) {
-    mma(d_tmem + (uint32_t)n0, ad, bd, idesc, accumulate || k > k0);
-    ad += a_inc;
-    bd += b_inc;
-  }
-}
-
 __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&x);
   v = __hmax2(v, __floats2bfloat162_rn(0.0f, 0.0f));

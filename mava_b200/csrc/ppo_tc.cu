@@ -96,7 +96,6 @@ struct TrainArgs {
   int fold_actor_w1;  // the actor's [dW1^T | db1] accumulates in TMEM inside the fused kernel
   int prefetch_actor; // fold mode: next tile's observation rows are gathered one tile ahead
   int pipe_layer1;    // prefetch mode: next tile's layer-1 GEMM issued behind this tile's backward pass
-  int split_n;        // GEMMs issued as two 64-column halves with their own completion barriers
   float *grad_actor, *grad_critic;
   double* loss_acc;
   unsigned char *dz1_actor, *dz1_critic;  // [tiles][TM*HID*2] tile images
@@ -107,11 +106,6 @@ struct Ctrl {
   // One barrier per kind of event: two commits in a row on ONE barrier would let a late thread miss
   // a phase (the parity it waits for comes round again).
   uint64_t wbar, mbar, mbar1, mbar2, gbar;
-  // Column halves: the epilogue warps of quarters {0, 1} (group 0) and {2, 3} (group 1) wait for
-  // their own half of an accumulator -- [0] columns 0..63, [1] columns 64..127 -- so that one group
-  // converts its half while the tensor core still produces the other (mbarc: the layer-2 / dH2 / dH1
-  // chain, mbar1h: layer 1).  `mbar` is left with the events every thread waits for (head, flush).
-  uint64_t mbarc[2], mbar1h[2];
   uint32_t tmem;
   float db3[NHEAD];
   float adv_mean[8], adv_isd[8];  // per replica: mean and 1 / (std + 1e-8), from the fp64 sums
@@ -224,9 +218,8 @@ __device__ __forceinline__ void actor_loss_row(uint32_t tmem_head, bool valid, i
 // commit, so that they run while the epilogue warps are already working on the accumulator.
 constexpr int NLOAD = 96;             // three loader warps (20 warps x 96 registers fill the file)
 constexpr int NT_F = NT + 32 + NLOAD;  // 16 epilogue warps + the MMA-issue warp + the loader warps
-constexpr int NT_RDY = NT + 32;        // epilogue threads + the MMA-issue warp (loaders start behind them)
+constexpr int NT_RDY = NT + 32;        // threads on the operands-ready barrier
 constexpr int BAR_READY = 2, BAR_EPI = 3, BAR_FULL = 4, BAR_EMPTY = 5, BAR_LOAD = 6, BAR_READY2 = 7;
-constexpr int BAR_READYB = 8, BAR_READY2B = 9;  // the same pair for the second column-half group
 constexpr int kLdSlots = 22;           // words per loader thread: 22 x 96 = 2112 = 128 rows x 66 bytes / 4
 
 // The operands-ready handshake alternates between two named barriers.  A named barrier cannot tell
@@ -235,22 +228,17 @@ constexpr int kLdSlots = 22;           // words per loader thread: 22 x 96 = 211
 // second arrival could complete the first generation while a slow warp is still storing.  Between
 // two arrivals on the SAME barrier there is always a wait for an MMA the issue warp issued after the
 // generation in between.
-// Each column-half group has its own pair of barriers (256 epilogue threads + the issue warp).
-constexpr int NT_GRP = NT / 2 + 32;
-__device__ __forceinline__ int ready_bar(int group, uint32_t rb) {
-  return group ? (rb ? BAR_READY2B : BAR_READYB) : (rb ? BAR_READY2 : BAR_READY);
-}
 // epilogue side: my shared-memory / TMEM accesses of this phase are done
-__device__ __forceinline__ void epi_arrive(int group, uint32_t& rb) {
+__device__ __forceinline__ void epi_arrive(uint32_t& rb) {
   fence_proxy_async();
   fence_before_sync();
-  asm volatile("bar.arrive %0, %1;" ::"r"(ready_bar(group, rb)), "n"(NT_GRP) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"r"(rb ? BAR_READY2 : BAR_READY), "n"(NT_RDY) : "memory");
   rb ^= 1u;
 }
-// issue side: the 256 epilogue threads of `group` have arrived (rb is toggled by the caller once both
-// groups of a phase have been waited for)
-__device__ __forceinline__ void issuer_wait(int group, uint32_t rb) {
-  asm volatile("bar.sync %0, %1;" ::"r"(ready_bar(group, rb)), "n"(NT_GRP) : "memory");
+// issue side: all 512 epilogue threads have arrived
+__device__ __forceinline__ void issuer_wait(uint32_t& rb) {
+  asm volatile("bar.sync %0, %1;" ::"r"(rb ? BAR_READY2 : BAR_READY), "n"(NT_RDY) : "memory");
+  rb ^= 1u;
   fence_after_sync();
 }
 // barrier among the 16 epilogue warps only
@@ -369,10 +357,6 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
     mbar_init(&ctrl.mbar1, 1);
     mbar_init(&ctrl.mbar2, 1);
     mbar_init(&ctrl.gbar, TM);
-    mbar_init(&ctrl.mbarc[0], 1);
-    mbar_init(&ctrl.mbarc[1], 1);
-    mbar_init(&ctrl.mbar1h[0], 1);
-    mbar_init(&ctrl.mbar1h[1], 1);
     fence_mbar_init();
   }
   if (t < NHEAD) ctrl.db3[t] = 0.0f;
@@ -396,8 +380,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
                              (reinterpret_cast<size_t>(p.view) & 15) == 0;
   const bool cl = padded_global && d.A <= 4;
   float* linc = reinterpret_cast<float*>(&ctrl.lin[0][0][0]);  // [TM][8]
-  uint32_t phase = 0, phase1 = 0, phase2 = 0, phasec = 0;
-  const int gi = L.q >> 1;  // column-half group of an epilogue thread
+  uint32_t phase = 0, phase1 = 0, phase2 = 0;
   uint32_t rb = 0;  // which of the two operands-ready barriers comes next (both sides alternate)
   float l0f = 0.0f, l1f = 0.0f;
   float db3_acc[NHEAD];
@@ -407,138 +390,52 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
 
   if (issue_warp) {
     // ================================ MMA-issue warp ==========================================
-    // An accumulator is produced as two 64-column halves, [0] = columns 0..63 for the epilogue warps
-    // of quarters {0, 1} (group 0) and [1] = columns 64..127 for group 1; its K range splits the same
-    // way, because the operand tile is written by those two groups.  Per GEMM of the chain:
-    //   group 0 has stored its half of the operand  ->  half 0 over K steps {0..3, ones column}
-    //   group 1 has stored its half                 ->  half 0 over K steps {4..7}, commit [0];
-    //                                                   half 1 over all K steps,    commit [1]
-    // Half 0 may overwrite accumulator columns 0..63 as soon as group 0 is done with them; columns
-    // 64..127 are only written once group 1 has arrived (it may still be reading them).  With
-    // split_n == 0 every GEMM is issued whole after both arrivals and both barriers get its commit.
     mbar_wait(&ctrl.wbar, 0);
     bool first = true;
     int it = 0;
-    const bool sp = p.split_n != 0;
-    constexpr int KH = HID / 32;        // K steps per operand half (64 columns)
-    constexpr int KONE = HID / 16;      // the K step of the ones column (activation tiles only)
-    // one N-half (or, unsplit, the whole width) of a forward / backward GEMM over K steps [k0, k1)
-    auto part = [&](uint32_t col, const Tile& a, const Tile& b, bool b_mn, int half, int k0, int k1,
-                    bool acc) {
-      issue_part(tmem + col, a, false, b, b_mn, sp ? half * (HID / 2) : 0, sp ? HID / 2 : HID, k0,
-                 k1, acc);
-    };
-    auto commit_half = [&](uint64_t* bars, int half) {
-      if (sp) commit(&bars[half]);
-      else { commit(&bars[0]); commit(&bars[1]); }
-    };
-    // layer 1 of a tile: the whole K range is available at once, only the N split applies
-    auto layer1 = [&](const Tile& x) {
-      if (sp) {
-        part(col_acc1, x, w1, true, 0, 0, d.k1p / 16, false);
-        commit(&ctrl.mbar1h[0]);
-        part(col_acc1, x, w1, true, 1, 0, d.k1p / 16, false);
-        commit(&ctrl.mbar1h[1]);
-      } else {
-        part(col_acc1, x, w1, true, 0, 0, d.k1p / 16, false);
-        commit_half(ctrl.mbar1h, 0);
-      }
-    };
     for (int tile = cta; tile < n_tiles; tile += n_ctas, first = false, ++it) {
       const Tile xt{fold ? s_x0 + (uint32_t)(it & 1) * x_bytes : s_x0, 128u, 2048u};
       const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-      // ---- X built; the previous tile's dZ1 stored and its accumulator drained
-      issuer_wait(0, rb);
-      issuer_wait(1, rb);
-      rb ^= 1u;
+      issuer_wait(rb);  // X built; the previous tile's dZ1 stored and its accumulator drained
       if (elect_one()) {
         // previous tile: [dW1^T | db1] += dZ1^T [X | 1] (A = dZ1 and B = X MN-major), then layer 1
         if (fold && !first)
           issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, nullptr);
-        if (!pipe1 || first) layer1(xt);
+        if (!pipe1 || first)
+          issue_gemm(tmem + col_acc1, xt, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
       __syncwarp();
-      // ---- layer 2: H1 stored (group 0: columns 0..63 and the ones column; group 1: 64..127)
-      issuer_wait(0, rb);
-      if (sp && elect_one()) {
-        part(COL_ACC, h1t, w2, true, 0, 0, KH, false);
-        part(COL_ACC, h1t, w2, true, 0, KONE, KONE + 1, true);
-      }
+      issuer_wait(rb);  // H1 stored
+      if (elect_one())
+        issue_gemm(tmem + COL_ACC, h1t, false, w2, true, HID, HCOLS, false, &ctrl.mbar);
       __syncwarp();
-      issuer_wait(1, rb);
-      rb ^= 1u;
-      if (elect_one()) {
-        if (sp) {
-          part(COL_ACC, h1t, w2, true, 0, KH, 2 * KH, true);
-          commit(&ctrl.mbarc[0]);
-          part(COL_ACC, h1t, w2, true, 1, 0, HCOLS / 16, false);
-          commit(&ctrl.mbarc[1]);
-        } else {
-          part(COL_ACC, h1t, w2, true, 0, 0, HCOLS / 16, false);
-          commit_half(ctrl.mbarc, 0);
-        }
-      }
+      issuer_wait(rb);  // H2 stored
+      if (elect_one())
+        issue_gemm(tmem + COL_HEAD, h2t, false, w3, true, NHEAD, HCOLS, false, &ctrl.mbar);
       __syncwarp();
-      // ---- head: H2 stored; one commit, every epilogue thread waits for it
-      issuer_wait(0, rb);
-      if (sp && elect_one()) {
-        issue_part(tmem + COL_HEAD, h2t, false, w3, true, 0, NHEAD, 0, KH, false);
-        issue_part(tmem + COL_HEAD, h2t, false, w3, true, 0, NHEAD, KONE, KONE + 1, true);
-      }
-      __syncwarp();
-      issuer_wait(1, rb);
-      rb ^= 1u;
-      if (elect_one()) {
-        if (sp) issue_part(tmem + COL_HEAD, h2t, false, w3, true, 0, NHEAD, KH, 2 * KH, true);
-        else issue_part(tmem + COL_HEAD, h2t, false, w3, true, 0, NHEAD, 0, HCOLS / 16, false);
-        commit(&ctrl.mbar);
-      }
-      __syncwarp();
-      // ---- dZ3 stored (the loss rows; both groups pass through this phase)
-      issuer_wait(0, rb);
-      issuer_wait(1, rb);
-      rb ^= 1u;
+      issuer_wait(rb);  // dZ3 stored
       if (elect_one()) {
         // dH2 = dZ3 W3^T is what the next epilogue waits for; dW3 += H2^T dZ3 runs behind it
-        part(COL_ACC, dz3t, w3, false, 0, 0, NHEAD / 16, false);
-        commit_half(ctrl.mbarc, 0);
-        if (sp) {
-          part(COL_ACC, dz3t, w3, false, 1, 0, NHEAD / 16, false);
-          commit(&ctrl.mbarc[1]);
-        }
+        issue_gemm(tmem + COL_ACC, dz3t, false, w3, false, HID, NHEAD, false, &ctrl.mbar);
         issue_gemm(tmem + COL_DW3, h2t, true, dz3t, true, NHEAD, TM, !first, nullptr);
       }
       __syncwarp();
-      // ---- dZ2 stored: dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1] behind it.  Without the
-      // prefetch pipeline the next tile's X is built over H2 / dZ2 / H1 (staging): a second commit
-      // tells the epilogue warps when the weight-gradient MMAs have stopped reading them.
-      issuer_wait(0, rb);
-      if (sp && elect_one()) part(COL_ACC, dz2t, w2, false, 0, 0, KH, false);
-      __syncwarp();
-      issuer_wait(1, rb);
-      rb ^= 1u;
+      issuer_wait(rb);  // dZ2 stored
       if (elect_one()) {
-        if (sp) {
-          part(COL_ACC, dz2t, w2, false, 0, KH, 2 * KH, true);
-          commit(&ctrl.mbarc[0]);
-          part(COL_ACC, dz2t, w2, false, 1, 0, HID / 16, false);
-          commit(&ctrl.mbarc[1]);
-        } else {
-          part(COL_ACC, dz2t, w2, false, 0, 0, HID / 16, false);
-          commit_half(ctrl.mbarc, 0);
-        }
+        // dH1 = dZ2 W2^T ; [dW2^T | db2] += dZ2^T [H1 | 1] behind it.  Without the prefetch pipeline
+        // the next tile's X is built over H2 / dZ2 / H1 (staging): a second commit tells the
+        // epilogue warps when the weight-gradient MMAs have stopped reading them.
+        issue_gemm(tmem + COL_ACC, dz2t, false, w2, false, HID, HID, false, &ctrl.mbar);
         issue_gemm(tmem + COL_DW2, dz2t, true, h1t, true, HCOLS, TM, !first,
                    prefetch ? nullptr : &ctrl.mbar2);
         if (pipe1 && tile + n_ctas < n_tiles)  // the next tile's layer 1 (its X was built in the loss phase)
-          layer1(xprev);
+          issue_gemm(tmem + col_acc1, xprev, false, w1, true, HID, d.k1p, false, &ctrl.mbar1);
       }
       __syncwarp();
     }
     if (!first && fold) {
       const Tile xprev{s_x0 + (uint32_t)((it + 1) & 1) * x_bytes, 128u, 2048u};
-      issuer_wait(0, rb);  // the last tile's dZ1
-      issuer_wait(1, rb);
-      rb ^= 1u;
+      issuer_wait(rb);  // the last tile's dZ1
       if (elect_one())
         issue_gemm(tmem + COL_DW1, dz1t, true, xprev, true, d.k1p, TM, it > 1, &ctrl.mbar);
       __syncwarp();
@@ -840,15 +737,23 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
                                 [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
         }
       }
-      epi_arrive(gi, rb);  // -> layer 1 (and the previous tile's first-layer gradient)
+      epi_arrive(rb);  // -> layer 1 (and the previous tile's first-layer gradient)
       MAVA_STAMP(1);
       MAVA_STAMP(14);
       // loss inputs of this row.  Prefetch path: the loader warps put them into ctrl.lin; plain
       // paths: fetched here, in flight during the forward pass
       LossIn li{};
+      float g_norm_adv = 0.0f;  // (advantage - mean) / (std + 1e-8) of this row's replica (actor)
       if (L.q == 0 && prefetch) {
         li.valid = row0 + L.r < M;
         li.j = li.valid ? tile * spt + r_j : 0;
+        // this tile's loss inputs were published by the loader warps during the previous tile (its
+        // BAR_FULL): unpack them here, off the path between the head GEMM and dZ3
+        const uint32_t w0 = ctrl.lin[it & 1][L.r][0];
+        li.mk = w0 & 0xffu;
+        li.act = (int)(signed char)(w0 >> 8);
+        li.f0[0] = __uint_as_float(ctrl.lin[it & 1][L.r][1]);
+        li.f1[0] = __uint_as_float(ctrl.lin[it & 1][L.r][2]);
       } else if (L.q == 0 && cl) {
         li.valid = row0 + L.r < M;
         li.j = li.valid ? row0 + L.r : 0;
@@ -890,17 +795,23 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           }
         }
       }
+      if (L.q == 0 && is_actor) {
+        int u = 0;  // replica of this minibatch position (at most 8: no division)
+#pragma unroll
+        for (int k = 1; k < 8; ++k) u += (k < p.num_replicas && li.j >= k * p.mb_size) ? 1 : 0;
+        g_norm_adv = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
+      }
       MAVA_STAMP(2);
       // ---- forward
-      wait_acc(&ctrl.mbar1h[gi], phase1);
+      wait_acc(&ctrl.mbar1, phase1);
       MAVA_STAMP(3);
       hidden_epilogue(L, tmem + col_acc1, h1t);
       MAVA_STAMP(4);
-      epi_arrive(gi, rb);  // -> layer 2
+      epi_arrive(rb);  // -> layer 2
       MAVA_STAMP(5);
-      wait_acc(&ctrl.mbarc[gi], phasec);
+      wait_acc(&ctrl.mbar, phase);
       hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead (not folded): H2 replaces it
-      epi_arrive(gi, rb);  // -> head
+      epi_arrive(rb);  // -> head
       MAVA_STAMP(6);
       wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(7);
@@ -961,15 +872,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
             db3_acc[0] += dz[0];
           }
         } else {
-          if (prefetch) {
-            const uint32_t w0 = ctrl.lin[it & 1][L.r][0];
-            li.mk = w0 & 0xffu;
-            li.act = (int)(signed char)(w0 >> 8);
-            li.f0[0] = __uint_as_float(ctrl.lin[it & 1][L.r][1]);
-            li.f1[0] = __uint_as_float(ctrl.lin[it & 1][L.r][2]);
-          }
-          const int u = li.j / p.mb_size;  // replica of this minibatch position
-          const float g = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
+          const float g = g_norm_adv;
           const uint32_t th = tmem + L.tmem_lane() + COL_HEAD;
 #define MAVA_LOSS_ARGS th, valid, d.out, li.mk, li.act, li.f0[0], g, p.clip_eps, p.ent_coef, wrow, dz, db3_acc, l0f, l1f
           if (d.out == 5) actor_loss_row<8, 5, true>(MAVA_LOSS_ARGS);        // RobotWarehouse
@@ -987,14 +890,14 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       }
       // staging rows expanded, loss inputs read: the loaders may bring in tile i+2
       if (has_next2 || c_next) asm volatile("bar.arrive %0, %1;" ::"n"(BAR_EMPTY), "n"(NT + NLOAD) : "memory");
-      epi_arrive(gi, rb);  // -> backward through the head
+      epi_arrive(rb);  // -> backward through the head
       MAVA_STAMP(8);
-      wait_acc(&ctrl.mbarc[gi], phasec);
+      wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(9);
       grad_epilogue<false>(L, tmem + COL_ACC, h2t, dz2t, nullptr);  // dZ2 = dH2 * relu'(layer 2)
-      epi_arrive(gi, rb);  // -> dH1, dW2
+      epi_arrive(rb);  // -> dH1, dW2
       MAVA_STAMP(10);
-      wait_acc(&ctrl.mbarc[gi], phasec);
+      wait_acc(&ctrl.mbar, phase);
       MAVA_STAMP(11);
       if (padded_global && tile + n_ctas < n_tiles && grow_thread) {
         // H2 is dead (dW3 completed before dH1): the next tile's rows start arriving there now
@@ -1021,7 +924,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       // everything still in the tensor pipe: the last tile's weight-gradient MMAs
       if (!prefetch) wait_acc(&ctrl.mbar2, phase2);  // dW2 / dW3
       if (fold) {                                  // dW1
-        epi_arrive(gi, rb);
+        epi_arrive(rb);
         wait_acc(&ctrl.mbar, phase);
       }
     }
@@ -1364,8 +1267,6 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
   {
     static const int pipe_env = getenv("MAVA_NO_PIPE1") ? 0 : 1;  // development switch
     a.pipe_layer1 = pipe_env;
-    static const int split_env = getenv("MAVA_NO_SPLIT") ? 0 : 1;  // development switch
-    a.split_n = split_env;
   }
   MAVA_CHECK_ARG(actor->num_agents <= kMaxReps);
   // Split the SMs between actor and critic tiles: the split that minimises the slower side's
