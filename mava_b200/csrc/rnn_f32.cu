@@ -17,7 +17,10 @@
 // are element-wise kernels.  A tensor-core (tcgen05) version of the scan is the next step; this
 // path is the rtol-1e-5 one the bf16 kernels will be checked against.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "gemm.cuh"
+#include "gru_scan.cuh"
 #include "prng.cuh"
 
 namespace mava {
@@ -698,8 +701,23 @@ struct SeqInput {
   int64_t Senv;  // env-sequences per position
 };
 
-// Runs pre-torso, GRU scan, post-torso and head.  k.out holds logits [R][OMAX] or values [R].
-int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
+// bf16 path, training: the whole scan in one persistent launch (W_h resident in shared memory, the
+// hidden state in registers; gru_scan.cu); the per-step schedule stays for fp32 and for acting.
+bool scan_capable(const Net& n, const SeqInput& in, const Work& k) {
+  const bool off = getenv("MAVA_NO_GRU_SCAN") != nullptr;  // development / A-B test switch
+  return !off && n.tc && n.H == 128 && in.L > 1 && in.steps != nullptr && k.gates != nullptr;
+}
+
+GruScanNet scan_net(const Net& n, const SeqInput& in, const Work& k) {
+  GruScanNet g;
+  g.Wh = n.w_h; g.b_hn = n.b_hn; g.Gx = k.Gx; g.gates = k.gates; g.Hin = k.Hin; g.Hout = k.Hout;
+  g.steps = in.steps; g.done_in = in.done_in; g.Senv = in.Senv;
+  g.S = in.Senv * n.rows_per_env; g.rpe = n.rows_per_env; g.L = in.L;
+  return g;
+}
+
+// forward, part 1: observation rows, pre-torso, x-side of the gates, reset-masked chunk-start state
+int forward_pre(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
   const int H = n.H, L = in.L;
   const int64_t S = in.Senv * n.rows_per_env, R = S * L;
   expand_obs_kernel<<<ew_blocks(R * n.in_dim), 256, 0, s>>>(
@@ -710,9 +728,16 @@ int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
   if (rc) return rc;
   mask_hidden_kernel<<<ew_blocks(S * H), 256, 0, s>>>(in.h0, in.steps, in.done_in, S,
                                                        n.rows_per_env, H, 0, in.h0_gather, k.Hin);
+  return launch_status();
+}
+
+// forward, part 2: the scan over the L positions, one GEMM + one gate kernel per position
+int forward_scan_steps(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
+  const int H = n.H, L = in.L;
+  const int64_t S = in.Senv * n.rows_per_env;
   for (int l = 0; l < L; ++l) {
     const float* hin = k.Hin + (int64_t)l * S * H;
-    rc = Gemm(hin, 0, H, n.w_h, 0, 3 * H, k.Gh, 3 * H, (int)S, 3 * H, H).tc(n.tc).run(s);
+    int rc = Gemm(hin, 0, H, n.w_h, 0, 3 * H, k.Gh, 3 * H, (int)S, 3 * H, H).tc(n.tc).run(s);
     if (rc) return rc;
     const bool more = l + 1 < L;
     gru_fwd_kernel<<<ew_blocks(S * H), 256, 0, s>>>(
@@ -721,7 +746,14 @@ int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
         more ? in.steps + (int64_t)(l + 1) * in.Senv : nullptr, in.done_in, n.rows_per_env,
         more ? k.Hin + (int64_t)(l + 1) * S * H : nullptr);
   }
-  rc = Gemm(k.Hout, 0, H, n.w_post, 0, n.Q, k.P, n.Q, (int)R, n.Q, H).bias(n.b_post).relu().tc(n.tc).run(s);
+  return launch_status();
+}
+
+// forward, part 3: post-torso and head.  k.out holds logits [R][OMAX] or values [R].
+int forward_post(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
+  const int H = n.H;
+  const int64_t S = in.Senv * n.rows_per_env, R = S * in.L;
+  int rc = Gemm(k.Hout, 0, H, n.w_post, 0, n.Q, k.P, n.Q, (int)R, n.Q, H).bias(n.b_post).relu().tc(n.tc).run(s);
   if (rc) return rc;
   const int ldo = n.out == 1 ? 1 : OMAX;
   rc = Gemm(k.P, 0, n.Q, n.w_head, 0, n.out, k.out, ldo, (int)R, n.out, n.Q).bias(n.b_head).tc(n.tc).run(s);
@@ -729,8 +761,23 @@ int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
   return launch_status();
 }
 
+// Runs pre-torso, GRU scan, post-torso and head of one network.
+int forward(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
+  int rc = forward_pre(n, in, k, s);
+  if (rc) return rc;
+  if (scan_capable(n, in, k)) {
+    const GruScanNet g = scan_net(n, in, k);
+    rc = launch_gru_scan_fwd(&g, 1, s);
+  } else {
+    rc = forward_scan_steps(n, in, k, s);
+  }
+  if (rc) return rc;
+  return forward_post(n, in, k, s);
+}
+
 // Backward from dOut (in k.out: dlogits [R][OMAX] or dvalue [R]) into the flat gradient g.
-int backward(const Net& n, const Net& g, const SeqInput& in, const Work& k, cudaStream_t s) {
+// Part 1: head and post-torso, down to dHout (in place over Hout).
+int backward_pre(const Net& n, const Net& g, const SeqInput& in, const Work& k, cudaStream_t s) {
   const int H = n.H, L = in.L, Q = n.Q;
   const int64_t S = in.Senv * n.rows_per_env, R = S * L;
   const int ldo = n.out == 1 ? 1 : OMAX;
@@ -749,9 +796,13 @@ int backward(const Net& n, const Net& g, const SeqInput& in, const Work& k, cuda
   rc = launch_colsum(k.P, Q, R, Q, G(g.b_post), s);
   if (rc) return rc;
   // dHout = dP W_post^T, in place over Hout
-  rc = Gemm(k.P, 0, Q, n.w_post, 1, Q, k.Hout, H, (int)R, H, Q).tc(n.tc).run(s);
-  if (rc) return rc;
-  // reverse scan
+  return Gemm(k.P, 0, Q, n.w_post, 1, Q, k.Hout, H, (int)R, H, Q).tc(n.tc).run(s);
+}
+
+// Part 2: the reverse scan, one gate kernel + one GEMM per position.
+int backward_scan_steps(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s) {
+  const int H = n.H, L = in.L;
+  const int64_t S = in.Senv * n.rows_per_env;
   float* dH[2] = {k.dH0, k.dH1};
   float* dT[2] = {k.dT0, k.dT1};
   for (int l = L - 1; l >= 0; --l) {
@@ -763,13 +814,21 @@ int backward(const Net& n, const Net& g, const SeqInput& in, const Work& k, cuda
         k.Hin + (int64_t)l * S * H, k.gates + (int64_t)l * S * 4 * H,
         k.Gx + (int64_t)l * S * 3 * H, dH[l & 1], S, H);
     if (l > 0) {  // dGh W_h^T (the chunk-start state carries no gradient)
-      rc = Gemm(k.gates + (int64_t)l * S * 4 * H, 0, 4 * H, n.w_h, 1, 3 * H, dT[l & 1], H, (int)S, H,
-                3 * H).tc(n.tc).run(s);
+      int rc = Gemm(k.gates + (int64_t)l * S * 4 * H, 0, 4 * H, n.w_h, 1, 3 * H, dT[l & 1], H, (int)S,
+                    H, 3 * H).tc(n.tc).run(s);
       if (rc) return rc;
     }
   }
-  // recurrent and input weights of the cell: one contraction over all (position, sequence) rows
-  rc = Gemm(k.Hin, 1, H, k.gates, 0, 4 * H, G(g.w_h), 3 * H, H, 3 * H, (int)R).split_k_atomic().tc(n.tc).run(s);
+  return launch_status();
+}
+
+// Part 3: recurrent and input weights of the cell and the pre-torso -- contractions over all
+// (position, sequence) rows.
+int backward_post(const Net& n, const Net& g, const SeqInput& in, const Work& k, cudaStream_t s) {
+  const int H = n.H, L = in.L;
+  const int64_t S = in.Senv * n.rows_per_env, R = S * L;
+  auto G = [](const float* p) { return const_cast<float*>(p); };
+  int rc = Gemm(k.Hin, 1, H, k.gates, 0, 4 * H, G(g.w_h), 3 * H, H, 3 * H, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   rc = launch_colsum(k.gates + 2 * H, 4 * H, R, H, G(g.b_hn), s);
   if (rc) return rc;
@@ -900,8 +959,9 @@ int64_t mava_rec_ppo_workspace_bytes(const mava_rnn_desc* actor, const mava_rnn_
   if (!actor || !critic || seq_envs_total <= 0 || chunk <= 0) return -1;
   const int64_t Sa = (int64_t)seq_envs_total * actor->rows_per_env;
   const int64_t Sc = (int64_t)seq_envs_total * critic->rows_per_env;
-  const int64_t f = max(work_floats(actor, Sa * chunk, Sa, true),
-                        work_floats(critic, Sc * chunk, Sc, true));
+  // both networks' work areas side by side: their scans run in one launch (gru_scan.cu)
+  const int64_t f = work_floats(actor, Sa * chunk, Sa, true) +
+                    work_floats(critic, Sc * chunk, Sc, true);
   return 1024 + align256((int64_t)seq_envs_total * chunk * 4) + f * 4 + 1024;
 }
 
@@ -963,46 +1023,74 @@ int mava_rec_ppo_loss_grad(const mava_rnn_desc* actor, const float* actor_params
     rec_adv_stats_kernel<<<grid, 256, 0, s>>>(adv, steps, L, Senv, mb_cols, A, stats);
   }
   const double cnt = (double)L * mb_cols * A;  // elements per replica the means run over
-  // ---- actor
-  {
-    const Net n = make_net(actor, actor_params);
-    const Net g = make_net(actor, grad_out);
-    const int64_t S = (int64_t)Senv * actor->rows_per_env, R = S * L;
-    Work k = carve(wf, actor, R, S, true);
-    SeqInput in{view, obs_actor, steps, done_in, hs_actor, 1, L, Senv};
-    rc = forward(n, in, k, s);
+  // Both networks advance phase by phase, so that their scans -- 128 CTAs of actor sequences and 16
+  // of critic sequences at the SMAX shapes, each bound by the latency of a time step -- share one
+  // launch per direction.
+  const Net an = make_net(actor, actor_params), ag = make_net(actor, grad_out);
+  const Net cn = make_net(critic, critic_params), cg = make_net(critic, grad_out + na);
+  const int64_t Sa = (int64_t)Senv * actor->rows_per_env, Ra = Sa * L;
+  const int64_t Sc = (int64_t)Senv * critic->rows_per_env, Rc = Sc * L;
+  const Work ka = carve(wf, actor, Ra, Sa, true);
+  const Work kc = carve(wf + work_floats(actor, Ra, Sa, true), critic, Rc, Sc, true);
+  const SeqInput ia{view, obs_actor, steps, done_in, hs_actor, 1, L, Senv};
+  const SeqInput ic{view, obs_critic, steps, done_in, hs_critic, 1, L, Senv};
+  const bool scan = scan_capable(an, ia, ka) && scan_capable(cn, ic, kc);
+  const GruScanNet sn[2] = {scan_net(an, ia, ka), scan_net(cn, ic, kc)};
+  // ---- forward
+  rc = forward_pre(an, ia, ka, s);
+  if (rc) return rc;
+  rc = forward_pre(cn, ic, kc, s);
+  if (rc) return rc;
+  if (scan) {
+    rc = launch_gru_scan_fwd(sn, 2, s);
+  } else {
+    rc = forward_scan_steps(an, ia, ka, s);
     if (rc) return rc;
+    rc = forward_scan_steps(cn, ic, kc, s);
+  }
+  if (rc) return rc;
+  rc = forward_post(an, ia, ka, s);
+  if (rc) return rc;
+  rc = forward_post(cn, ic, kc, s);
+  if (rc) return rc;
+  // ---- losses: d(loss)/d(head output) in place over the head outputs
+  {
     HeadArgs h{};
-    h.logits = k.out; h.rows = R; h.rpe = actor->rows_per_env; h.A = A; h.N = actor->out_dim;
+    h.logits = ka.out; h.rows = Ra; h.rpe = actor->rows_per_env; h.A = A; h.N = actor->out_dim;
     h.steps = steps; h.mask = mask; h.action_old = action; h.old_logp = old_logp; h.adv = adv;
-    h.adv_stats = stats; h.rows_per_replica = (int64_t)mb_cols * A; h.rows_per_pos = S;
+    h.adv_stats = stats; h.rows_per_replica = (int64_t)mb_cols * A; h.rows_per_pos = Sa;
     h.count_per_replica = cnt; h.num_replicas = U; h.clip_eps = hyper->clip_eps;
-    h.ent_coef = hyper->ent_coef; h.vf_coef = hyper->vf_coef; h.dOut = k.out;
+    h.ent_coef = hyper->ent_coef; h.vf_coef = hyper->vf_coef; h.dOut = ka.out;
     h.loss_acc = loss_acc;
-    rec_actor_loss_kernel<<<(unsigned)ceil_div64(R, 256), 256, 0, s>>>(h);
-    rc = backward(n, g, in, k, s);
-    if (rc) return rc;
+    rec_actor_loss_kernel<<<(unsigned)ceil_div64(Ra, 256), 256, 0, s>>>(h);
   }
-  // ---- critic
   {
-    const Net n = make_net(critic, critic_params);
-    const Net g = make_net(critic, grad_out + na);
-    const int64_t S = (int64_t)Senv * critic->rows_per_env, R = S * L;
-    Work k = carve(wf, critic, R, S, true);
-    SeqInput in{view, obs_critic, steps, done_in, hs_critic, 1, L, Senv};
-    rc = forward(n, in, k, s);
-    if (rc) return rc;
     HeadArgs h{};
-    h.logits = k.out; h.rows = R; h.rpe = critic->rows_per_env; h.A = A; h.steps = steps;
+    h.logits = kc.out; h.rows = Rc; h.rpe = critic->rows_per_env; h.A = A; h.steps = steps;
     h.old_value = old_value; h.targets = targets;
-    h.rows_per_replica = (int64_t)mb_cols * critic->rows_per_env; h.rows_per_pos = S;
+    h.rows_per_replica = (int64_t)mb_cols * critic->rows_per_env; h.rows_per_pos = Sc;
     h.count_per_replica = cnt; h.num_replicas = U; h.clip_eps = hyper->clip_eps;
-    h.ent_coef = hyper->ent_coef; h.vf_coef = hyper->vf_coef; h.dOut = k.out;
+    h.ent_coef = hyper->ent_coef; h.vf_coef = hyper->vf_coef; h.dOut = kc.out;
     h.loss_acc = loss_acc;
-    rec_critic_loss_kernel<<<(unsigned)ceil_div64(R, 256), 256, 0, s>>>(h);
-    rc = backward(n, g, in, k, s);
-    if (rc) return rc;
+    rec_critic_loss_kernel<<<(unsigned)ceil_div64(Rc, 256), 256, 0, s>>>(h);
   }
+  // ---- backward
+  rc = backward_pre(an, ag, ia, ka, s);
+  if (rc) return rc;
+  rc = backward_pre(cn, cg, ic, kc, s);
+  if (rc) return rc;
+  if (scan) {
+    rc = launch_gru_scan_bwd(sn, 2, s);
+  } else {
+    rc = backward_scan_steps(an, ia, ka, s);
+    if (rc) return rc;
+    rc = backward_scan_steps(cn, ic, kc, s);
+  }
+  if (rc) return rc;
+  rc = backward_post(an, ag, ia, ka, s);
+  if (rc) return rc;
+  rc = backward_post(cn, cg, ic, kc, s);
+  if (rc) return rc;
   return launch_finalize_loss(loss_acc, cnt * U, hyper->ent_coef, hyper->vf_coef,
                               grad_out + na + nc, s);
 }

@@ -470,18 +470,25 @@ def episode_summary(learner) -> Tuple[Dict[str, Dict[str, float]], bool]:
     any episode finished."""
     if learner._stats_host is None:
         learner._stats_host = torch.zeros(10, dtype=torch.float64).pin_memory()
-    stats = learner.ep_stats
     if learner.world > 1 and learner.allreduce is not None:
-        # the reference reduces over the pmap output of all devices: sums add, extrema combine
-        stats = stats.clone()
-        sums, mins, maxs = stats[[0, 1, 2, 5, 6]], stats[[3, 7]], stats[[4, 8]]
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
-        stats[[0, 1, 2, 5, 6]], stats[[3, 7]], stats[[4, 8]] = sums, mins, maxs
-    learner._stats_host.copy_(stats, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    n, sr, qr, mnr, mxr, sl, ql, mnl, mxl, _ = learner._stats_host.tolist()
+        # the reference reduces over the pmap output of all devices: ONE all_gather of the ranks'
+        # 80-byte reductions, combined on the host (sums add, extrema combine)
+        if getattr(learner, "_stats_all", None) is None:
+            learner._stats_all = torch.zeros(learner.world, 10, dtype=torch.float64,
+                                             device=learner.device)
+            learner._stats_all_host = torch.zeros(learner.world, 10, dtype=torch.float64).pin_memory()
+        dist.all_gather_into_tensor(learner._stats_all, learner.ep_stats)
+        learner._stats_all_host.copy_(learner._stats_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        a = learner._stats_all_host
+        n, sr, qr = float(a[:, 0].sum()), float(a[:, 1].sum()), float(a[:, 2].sum())
+        mnr, mxr = float(a[:, 3].min()), float(a[:, 4].max())
+        sl, ql = float(a[:, 5].sum()), float(a[:, 6].sum())
+        mnl, mxl = float(a[:, 7].min()), float(a[:, 8].max())
+    else:
+        learner._stats_host.copy_(learner.ep_stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n, sr, qr, mnr, mxr, sl, ql, mnl, mxl, _ = learner._stats_host.tolist()
     if n == 0:
         zero = {"mean": 0.0, "std": 0.0, "min": 0.0, "max": 0.0}
         return {"episode_return": dict(zero), "episode_length": dict(zero)}, False

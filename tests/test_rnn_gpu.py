@@ -35,7 +35,9 @@ def _make(rng, mode, A, FR, H, Q, out, dense_dim=0, rpe=None, precision=0):
 
     d = native.rnn_desc(mode, True, A, FR, H, Q, out, dense_dim, rpe, precision)
     n = native.rnn_param_count(d)
-    flat = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    # weight scale ~ 1 / sqrt(fan-in) relative to the H = 16 cases (0.3): keeps the pre-activations of
+    # the wide nets out of saturation, where a bf16 rounding of h flips gates
+    flat = (rng.standard_normal(n) * 0.3 * min(1.0, (16.0 / H) ** 0.5)).astype(np.float32)
     return d, flat
 
 
@@ -100,15 +102,18 @@ def test_rec_act_matches_oracle(lib_built, critic_mode):
     np.testing.assert_allclose(value.cpu().numpy(), v, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("critic_mode,chunk,precision", [
-    ("global", 8, 0), ("agent", 4, 0), ("dense", 2, 0), ("global", 8, 1), ("dense", 4, 1)])
-def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, precision):
+@pytest.mark.parametrize("critic_mode,chunk,precision,H", [
+    ("global", 8, 0, 16), ("agent", 4, 0, 16), ("dense", 2, 0, 16), ("global", 8, 1, 16),
+    ("dense", 4, 1, 16),
+    # hidden width 128 + bf16: the persistent GRU scan kernels (csrc/gru_scan.cu) carry the time loop
+    ("global", 8, 1, 128), ("dense", 4, 1, 128), ("agent", 2, 1, 128)])
+def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, precision, H):
     from mava_b200 import native
     from mava_b200._lib import PpoHyper
 
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(1)
-    T, E, U, A, FR, H, Q, N, nmb = 8, 6, 2, 3, 7, 16, 24, 5, 2
+    T, E, U, A, FR, Q, N, nmb = 8, 6, 2, 3, 7, 24, 5, 2
     NE, nc = U * E, T // chunk
     dense_dim = 10
     if critic_mode == "dense":
@@ -188,10 +193,15 @@ def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, preci
     scale_a, scale_c = float(ga.abs().max()), float(gc.abs().max())
     if precision == 1:
         # bf16 tensor-core contractions (fp32 accumulation): 2e-2 tolerance of BASELINE.json on the
-        # losses, gradient blocks within 5e-2 in Frobenius norm (chains of 3 to 5 bf16 GEMMs)
+        # losses, gradient blocks within 5e-2 in Frobenius norm (chains of 3 to 5 bf16 GEMMs).  At
+        # hidden width 128 every recurrent contraction sums 128 bf16 products per step and the chain
+        # runs through up to 8 steps: measured 0.054 ... 0.085 on these random networks (the scan
+        # kernels and the per-step schedule give bit-identical numbers), bar 0.13.
+        bar = 5e-2 if H <= 16 else 0.13
         for got, want in ((grad[:na], ga.numpy()), (grad[na:na + ncr], gc.numpy())):
             err = np.linalg.norm(got - want) / np.linalg.norm(want)
-            assert err < 5e-2, err
+            print(f"rec bf16 grad error H={H} {critic_mode}: {err:.4f}")
+            assert err < bar, err
         np.testing.assert_allclose(grad[na + ncr:na + ncr + 5],
                                    [tot_a.item(), la, ent, tot_c.item(), vl], rtol=2e-2, atol=2e-3)
         return
@@ -199,3 +209,52 @@ def test_rec_ppo_loss_grad_matches_autograd(lib_built, critic_mode, chunk, preci
     np.testing.assert_allclose(grad[na:na + ncr], gc.numpy(), rtol=2e-4, atol=2e-5 * scale_c)
     np.testing.assert_allclose(grad[na + ncr:na + ncr + 5],
                                [tot_a.item(), la, ent, tot_c.item(), vl], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("E,A,chunk,T", [(44, 3, 8, 16), (64, 4, 16, 16), (20, 8, 4, 8)])
+def test_gru_scan_matches_per_step_schedule(lib_built, E, A, chunk, T, monkeypatch):
+    """The persistent scan kernels against the per-time-step launches they replace (same bf16
+    contractions, same fp32 gate arithmetic): losses and every gradient agree to rounding.  Sizes
+    cover several CTAs and a last tile of sequences that is only partly filled; a quarter of the
+    steps reset the hidden state."""
+    from mava_b200 import native
+    from mava_b200._lib import PpoHyper
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(E + A)
+    U, FR, Hd, Q, N, nmb, dense_dim = 2, 9, 128, 128, 6, 2, 21
+    NE, nc = U * E, T // chunk
+    ad, ap = _make(rng, native.IN_DENSE, A, FR, Hd, Q, N, dense_dim, A, 1)
+    cd, cp = _make(rng, native.IN_DENSE, A, FR, Hd, Q, 1, dense_dim + 3, 1, 1)
+    f32 = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(dev)
+    oa, oc = f32(T, NE, A, dense_dim), f32(T, NE, 1, dense_dim + 3)
+    mask = torch.full((T, NE, A), (1 << N) - 1, dtype=torch.uint8, device=dev)
+    action = torch.from_numpy(rng.integers(0, N, (T, NE, A)).astype(np.int8)).to(dev)
+    old_logp = (-torch.rand(T, NE, A, generator=torch.Generator().manual_seed(3)) * 2 - 0.3).to(dev)
+    old_value, adv, targets = f32(T, NE, A), f32(T, NE, A), f32(T, NE, A)
+    done = torch.from_numpy((rng.random((T, NE)) < 0.25).astype(np.uint8)).to(dev)
+    hs_a, hs_c = f32(nc, NE * A, Hd), f32(nc, NE, Hd)
+    mb_cols = E * nc // nmb
+    cols = torch.from_numpy(rng.permutation(E * nc).astype(np.int32))[:mb_cols].contiguous().to(dev)
+    hyper = PpoHyper(0.2, 0.01, 0.5)
+    na, ncr = native.rnn_param_count(ad), native.rnn_param_count(cd)
+    tap, tcp = torch.from_numpy(ap).to(dev), torch.from_numpy(cp).to(dev)
+
+    def run():
+        grad = torch.zeros(na + ncr + 8, device=dev)
+        ws = torch.zeros(native.rec_ppo_workspace_bytes(ad, cd, U * mb_cols, chunk),
+                         dtype=torch.uint8, device=dev)
+        native.rec_ppo_loss_grad(ad, tap, cd, tcp, hyper, None, oa, oc, mask, action, old_logp,
+                                 old_value, adv, targets, done, hs_a, hs_c, cols, U, E, mb_cols, chunk,
+                                 nc, grad, ws)
+        torch.cuda.synchronize()
+        return grad.cpu().numpy()
+
+    monkeypatch.delenv("MAVA_NO_GRU_SCAN", raising=False)
+    scan = run()
+    monkeypatch.setenv("MAVA_NO_GRU_SCAN", "1")
+    steps = run()
+    np.testing.assert_allclose(scan[na + ncr:na + ncr + 5], steps[na + ncr:na + ncr + 5], rtol=1e-5)
+    for sl in (slice(0, na), slice(na, na + ncr)):
+        scale = np.abs(steps[sl]).max()
+        np.testing.assert_allclose(scan[sl], steps[sl], rtol=1e-3, atol=1e-5 * scale)
