@@ -1008,9 +1008,9 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
 // first-layer weight gradient: [dW1^T | db1] += dZ1^T [X | 1]
 // ------------------------------------------------------------------------------------------------
 struct Wg1Ctrl {
-  uint64_t lbar[2], mbar, gbar;  // dZ1 tile images landed | MMAs done | gathered rows landed
+  uint64_t lbar[2], mbar, gbar[2];  // dZ1 tile images landed | MMAs done | gathered rows landed
   uint32_t tmem;
-  int32_t steps[2][TM];  // env-step index of each row of the tile being built / being fetched
+  int32_t steps[3][TM];  // env-step index of each row of the tile being built / the two being fetched
 };
 
 __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
@@ -1027,17 +1027,19 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   const int n_tiles = ceil_div(M, TM);
   const unsigned char* dz1 = is_actor ? p.dz1_actor : p.dz1_critic;
 
-  // shared memory: [dZ1 tile x 2][X tile][gather staging]
+  // shared memory: [dZ1 tile x 2][X tile][gather staging x 2 (one when the rows are not bulk-copied)]
   const uint32_t s0 = smem_u32(smem);
   const uint32_t dz_bytes = tile_bytes(TM, HID);
   const Tile xt{s0 + 2 * dz_bytes, 128u, 2048u};
-  unsigned char* stage = smem + 2 * dz_bytes + tile_bytes(TM, d.k1p);
+  unsigned char* stage0 = smem + 2 * dz_bytes + tile_bytes(TM, d.k1p);
+  const uint32_t stage_bytes_g = (TM * grow_stride(d.k1p) + 127u) & ~127u;
   if (warp == 0) tmem_alloc<kTmemCols>(&ctrl.tmem);
   if (t == 0) {
     mbar_init(&ctrl.lbar[0], 1);
     mbar_init(&ctrl.lbar[1], 1);
     mbar_init(&ctrl.mbar, 1);
-    mbar_init(&ctrl.gbar, TM);
+    mbar_init(&ctrl.gbar[0], TM);
+    mbar_init(&ctrl.gbar[1], TM);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -1045,11 +1047,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   const int n_lo = d.k1p > 256 ? 256 : d.k1p, n_hi = d.k1p - n_lo;
-  uint32_t phase = 0, gphase = 0;
+  uint32_t phase = 0;
   bool first = true;
-  int32_t next_step = 0;
-  // one env-step per row (centralised critic): rows fetched by bulk copies one tile ahead, padded
-  // staging rows, uniform expansion (mlp_tc.cuh)
+  // one env-step per row (centralised critic): rows fetched by bulk copies TWO tiles ahead into two
+  // staging buffers (a tile's rows are requested as soon as the buffer of the tile two before it
+  // has been expanded: a whole tile time hides the HBM latency of the random rows), padded staging
+  // rows, uniform expansion (mlp_tc.cuh)
   const bool padded_global = d.mode == MAVA_IN_GLOBAL && (d.in_dim & 7) == 0 &&
                              (reinterpret_cast<size_t>(p.view) & 15) == 0;
   auto load_dz1 = [&](int tile_idx, int buf) {  // one thread: tile image -> buffer `buf`
@@ -1063,12 +1066,18 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     const int r = tile_idx * TM + grow_r;
     return (grow_thread && r < M) ? __ldg(p.rows + r) : 0;
   };
-  if (padded_global && cta < n_tiles) {
-    const int32_t st = step_of(cta);
+  // request the rows of the k-th tile of this CTA (tile index tile_idx) into staging buffer k & 1;
+  // its index list goes to ctrl.steps[k % 3]
+  auto request_rows = [&](int k, int tile_idx, int32_t st) {
     if (grow_thread) {
-      ctrl.steps[0][grow_r] = st;
-      grow_issue(d, p.view, st, cta * TM + grow_r < M, stage, grow_r, &ctrl.gbar);
+      ctrl.steps[k % 3][grow_r] = st;
+      grow_issue(d, p.view, st, tile_idx * TM + grow_r < M, stage0 + (size_t)(k & 1) * stage_bytes_g,
+                 grow_r, &ctrl.gbar[k & 1]);
     }
+  };
+  if (padded_global && cta < n_tiles) {
+    request_rows(0, cta, step_of(cta));
+    if (cta + n_ctas < n_tiles) request_rows(1, cta + n_ctas, step_of(cta + n_ctas));
     if (t == 0) load_dz1(cta, 0);
   }
   int it = 0;
@@ -1077,29 +1086,25 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     const int buf = padded_global ? (it & 1) : 0;
     const Tile dzt{s0 + (uint32_t)buf * dz_bytes, 128u, 2048u};
     if (padded_global) {
-      const int nxt = tile + n_ctas;
-      const bool has_next = nxt < n_tiles;
-      if (t == 0 && has_next) load_dz1(nxt, buf ^ 1);  // free: the MMAs of tile it-1 were waited for
-      if (has_next) next_step = step_of(nxt);
-      mbar_wait(&ctrl.gbar, gphase);
-      gphase ^= 1u;
-      if (t < TM && row0 + t < M) grow_tail(d, stage, t, ctrl.steps[it & 1][t]);
+      const int nxt = tile + n_ctas, nxt2 = tile + 2 * n_ctas;
+      unsigned char* stage = stage0 + (size_t)(it & 1) * stage_bytes_g;
+      if (t == 0 && nxt < n_tiles) load_dz1(nxt, buf ^ 1);  // free: the MMAs of tile it-1 were waited for
+      const int32_t step2 = nxt2 < n_tiles ? step_of(nxt2) : 0;  // index list two tiles ahead
+      mbar_wait(&ctrl.gbar[it & 1], (uint32_t)(it >> 1) & 1u);
+      if (t < TM && row0 + t < M) grow_tail(d, stage, t, ctrl.steps[it % 3][t]);
       __syncthreads();
       const bool valid = row0 + L.r < M;
       expand_padded_row(xt, L,
                         smem_u32(stage) + (uint32_t)L.r * grow_stride(d.k1p) +
-                            (valid ? grow_skew(d, ctrl.steps[it & 1][L.r]) : 0u),
+                            (valid ? grow_skew(d, ctrl.steps[it % 3][L.r]) : 0u),
                         valid, d.k1p >> 3, (L.q + (L.r >> 2)) & 3, 4);  // rotation: bank spread
       fence_proxy_async();
-      __syncthreads();  // staging has been read: the next tile's rows may land
-      if (has_next && grow_thread) {
-        ctrl.steps[(it + 1) & 1][grow_r] = next_step;
-        grow_issue(d, p.view, next_step, nxt * TM + grow_r < M, stage, grow_r, &ctrl.gbar);
-      }
+      __syncthreads();  // this staging buffer has been read: the rows of tile it + 2 may land in it
+      if (nxt2 < n_tiles) request_rows(it + 2, nxt2, step2);
       mbar_wait(&ctrl.lbar[buf], (uint32_t)(it >> 1) & 1u);
     } else {
       if (t == 0) load_dz1(tile, 0);
-      build_x_tile(d, p.view, xt, stage, row0, M,
+      build_x_tile(d, p.view, xt, stage0, row0, M,
                    [&](int64_t jj) { return (int64_t)__ldg(p.rows + jj); });
       fence_proxy_async();
       mbar_wait(&ctrl.lbar[0], phase);
@@ -1297,8 +1302,10 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
 
   const size_t stage_rows = (size_t)TM * grow_stride(k1p_max);
   const size_t stage_wg1 = stage_rows > tile_bytes(TM, HCOLS) ? stage_rows : tile_bytes(TM, HCOLS);
-  const size_t smem_wg1 = 2 * (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) + stage_wg1 +
-                          128;  // two dZ1 tile images, X tile, staging
+  // two dZ1 tile images, X tile, two staging buffers (rows requested two tiles ahead)
+  const size_t stage_g = ((size_t)TM * grow_stride(k1p_max) + 127) & ~(size_t)127;
+  const size_t smem_wg1 = 2 * (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
+                          (2 * stage_g > stage_wg1 ? 2 * stage_g : stage_wg1) + 128;
   static size_t conf_fused = 0, conf_wg1 = 0;
   if (smem_fused > conf_fused) {
     e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
