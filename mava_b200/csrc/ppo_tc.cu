@@ -95,6 +95,9 @@ struct TrainArgs {
   int actor_ctas, critic_ctas;
   int fold_actor_w1;  // the actor's [dW1^T | db1] accumulates in TMEM inside the fused kernel
   int prefetch_actor; // fold mode: next tile's observation rows are gathered one tile ahead
+  // the same two switches for a critic that reads the agent's own view (ff_ippo): it then runs on the
+  // actor's pipeline (loader warps, folded first-layer gradient) and needs no ppo_wgrad1_kernel pass
+  int fold_critic_w1, prefetch_critic;
   int pipe_layer1;    // prefetch mode: next tile's layer-1 GEMM issued behind this tile's backward pass
   float *grad_actor, *grad_critic;
   double* loss_acc;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   // fold mode (actor): [weights][X ping][X pong][region: H2 (later dZ1) + dZ2][H1][dZ3] -- X stays
   // alive to the end of the tile so that [dW1^T | db1] += dZ1^T [X | 1] runs here, in TMEM, while the
   // next tile is gathered into the other X buffer.
-  const bool fold = is_actor && p.fold_actor_w1 != 0;
+  const bool fold = (is_actor ? p.fold_actor_w1 : p.fold_critic_w1) != 0;
   const WImage wi{d.k1p};
   const uint32_t s_w = smem_u32(smem);
   const uint32_t x_bytes = tile_bytes(TM, d.k1p);
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
   // fold mode also prefetches: the next tile's observation rows are gathered into a dedicated
   // staging buffer while this tile runs, so the two dependent HBM latencies of the gather (row
   // index -> observation bytes) leave the critical path
-  const bool prefetch = fold && p.prefetch_actor != 0;
+  const bool prefetch = fold && (is_actor ? p.prefetch_actor : p.prefetch_critic) != 0;
   // Layer 1 of the next tile is issued behind this tile's last backward GEMM, into its own
   // accumulator, when TMEM has 128 columns left: a tile then starts with its layer-1 result ready.
   const bool pipe1 = prefetch && p.pipe_layer1 != 0 && d.k1p <= (int)(COL_ACC1 - COL_DW1);
@@ -503,10 +506,15 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           if (r < TM && nt * TM + r < M) {
             const int rj = r / rps, ra = r - rj * rps;
             const size_t flat = (size_t)ctrl.steps[cur][rj] * d.A + ra;
-            lm[h] = p.mask[flat];
-            la[h] = (uint32_t)(uint8_t)p.action[flat];
-            lp[h] = p.old_logp[flat];
-            ladv[h] = p.adv[flat];
+            if (is_actor) {
+              lm[h] = p.mask[flat];
+              la[h] = (uint32_t)(uint8_t)p.action[flat];
+              lp[h] = p.old_logp[flat];
+              ladv[h] = p.adv[flat];
+            } else {  // decentralised critic on this pipeline: old value and target of the row
+              lp[h] = p.old_value[flat];
+              ladv[h] = p.targets[flat];
+            }
           }
         }
         // the staging rows and this parity's loss-input buffer have been consumed
@@ -637,9 +645,15 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       expand_rows(cta, Tile{s_x0, 128u, 2048u}, L.q, 4, pf_stage);
       if (L.q == 0 && cta * TM + L.r < M) {  // tile 0's loss inputs (later tiles: the loader warps)
         const size_t flat = (size_t)ctrl.steps[0][r_j] * d.A + r_a;
-        ctrl.lin[0][L.r][0] = (uint32_t)p.mask[flat] | ((uint32_t)(uint8_t)p.action[flat] << 8);
-        ctrl.lin[0][L.r][1] = __float_as_uint(p.old_logp[flat]);
-        ctrl.lin[0][L.r][2] = __float_as_uint(p.adv[flat]);
+        if (is_actor) {
+          ctrl.lin[0][L.r][0] = (uint32_t)p.mask[flat] | ((uint32_t)(uint8_t)p.action[flat] << 8);
+          ctrl.lin[0][L.r][1] = __float_as_uint(p.old_logp[flat]);
+          ctrl.lin[0][L.r][2] = __float_as_uint(p.adv[flat]);
+        } else {
+          ctrl.lin[0][L.r][0] = 0u;
+          ctrl.lin[0][L.r][1] = __float_as_uint(p.old_value[flat]);
+          ctrl.lin[0][L.r][2] = __float_as_uint(p.targets[flat]);
+        }
       }
       epi_sync();
       // the staging rows are free: the loaders may bring in tile 1
@@ -1269,6 +1283,20 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
                      (TM / a.actor.A) * ((a.actor.A * a.actor.FR) >> 2) <= kLdSlots * NLOAD &&
                      TM / a.actor.A + 2 <= NLOAD;
   if (a.prefetch_actor && smem_pf > smem_fused) smem_fused = smem_pf;
+  // a critic on the agent's own view (ff_ippo) has the actor's input: same pipeline, same conditions
+  {
+    const NetDesc& c = a.critic;
+    const size_t c_fold = (size_t)WImage{c.k1p}.total() + 2 * tile_bytes(TM, c.k1p) + kRegionMin +
+                          tile_bytes(TM, HCOLS) + tile_bytes(TM, NHEAD) + 128;
+    const size_t c_pf = c_fold + (size_t)TM * c.k1p + 16;
+    const bool ok = c.mode == MAVA_IN_AGENT_VIEW && c.k1p <= 208 && c_pf <= 227 * 1024 &&
+                    (TM % c.A) == 0 && (c.FR & 1) == 0 && ((c.A * c.FR) & 3) == 0 &&
+                    (c.A * c.FR) / 4 <= 255 && TM * c.k1p / 2 < 8192 &&
+                    (TM / c.A) * ((c.A * c.FR) >> 2) <= kLdSlots * NLOAD && TM / c.A + 2 <= NLOAD &&
+                    getenv("MAVA_NO_CRITIC_FOLD") == nullptr;
+    a.fold_critic_w1 = a.prefetch_critic = ok ? 1 : 0;
+    if (ok && c_pf > smem_fused) smem_fused = c_pf;
+  }
   {
     static const int pipe_env = getenv("MAVA_NO_PIPE1") ? 0 : 1;  // development switch
     a.pipe_layer1 = pipe_env;
@@ -1281,7 +1309,7 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
   // (14.5 K for the 272-wide MAPPO critic, whose rows arrive by bulk copies).
   {
     const double tile_a = (a.prefetch_actor ? 6420.0 : 9050.0) + 30.0 * a.actor.k1p;
-    const double tile_c = 6360.0 + 30.0 * a.critic.k1p;
+    const double tile_c = (a.prefetch_critic ? 6420.0 : 6360.0) + 30.0 * a.critic.k1p;
     int n_actor = 1;
     double best = 1e300;
     for (int na = 1; na < sms; ++na) {
@@ -1322,13 +1350,21 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
   ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT_F, smem_fused, s>>>(a);
   rc = launch_status();
   if (rc) return rc;
-  if (a.fold_actor_w1) {  // only the critic's first layer is left: give it every SM
+  // first-layer gradients that were not folded into the fused kernel: every SM to what is left
+  if (a.fold_actor_w1 && a.fold_critic_w1) {
+    a.actor_ctas = a.critic_ctas = 0;
+  } else if (a.fold_actor_w1) {
     a.actor_ctas = 0;
     a.critic_ctas = (int)(tcn < sms ? tcn : sms);
+  } else if (a.fold_critic_w1) {
+    a.actor_ctas = (int)(ta < sms ? ta : sms);
+    a.critic_ctas = 0;
   }
-  ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_wg1, s>>>(a);
-  rc = launch_status();
-  if (rc) return rc;
+  if (a.actor_ctas + a.critic_ctas > 0) {
+    ppo_wgrad1_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem_wg1, s>>>(a);
+    rc = launch_status();
+    if (rc) return rc;
+  }
   return launch_finalize_loss(loss_acc, (double)R * actor->num_agents, hyper->ent_coef,
                               hyper->vf_coef, grad_out + na + nc, s);
 }

@@ -141,16 +141,19 @@ def test_ppo_loss_grad_bf16_matches_fp32_kernel(lib_built, A, FR, N, critic_mode
     for net, d, off in (("actor", actor, 0), ("critic", critic, na)):
         for name, sl in blocks(d, off):
             ref, got = g32[sl], g16[sl]
-            # tolerance: BASELINE.json allows 2e-2 per bf16 GEMM; a gradient block is the product of a
-            # chain of three to five such GEMMs (and, for the critic, of v - target where v carries
-            # the forward error), so a block may be off by 5e-2 in Frobenius norm and no single
-            # element by more than 1e-1 of the block's scale
+            # tolerance: BASELINE.json allows 2e-2 per bf16 GEMM.  Against the float64 oracle at the
+            # headline minibatch size every block is within 1.1e-2 (tests/test_bf16_path_gpu.py,
+            # profiles/bf16_grad_errors_r2.json).  Here the reference is the fp32 KERNEL and the
+            # minibatches are small, so single clip decisions that differ between the two paths show:
+            # measured worst block 0.034 / 0.041 Frobenius (0.051 / 0.094 max) at mb = 96 / 200 and
+            # 0.013 (0.015 max) at mb = 2048; bars at <= 1.5x of that.
             scale = np.abs(ref).max() + 1e-12
             err_max = np.abs(got - ref).max() / scale
             err_fro = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12)
             print(f"{net}.{name}: fro {err_fro:.4f} max {err_max:.4f}")
             worst[0], worst[1] = max(worst[0], err_fro), max(worst[1], err_max)
-            assert err_fro < 5e-2 and err_max < 1e-1, (
+            bar_fro, bar_max = (2e-2, 2.3e-2) if mb >= 2048 else (6e-2, 1.4e-1)
+            assert err_fro < bar_fro and err_max < bar_max, (
                 f"{net}.{name}: fro err {err_fro:.4f}, max err {err_max:.4f} of scale {scale:.3e}")
     print(f"WORST mb={mb} U={U}: fro {worst[0]:.4f} max {worst[1]:.4f}")
 
