@@ -213,7 +213,10 @@ int mava_clip_adam(float* params, float* mu, float* nu, int32_t* count, const fl
                    int64_t n, float grad_scale, float lr, float max_norm, int lr_decay_num_updates,
                    int steps_per_update, mava_stream_t s);
 
-/* Both networks in one launch: params/mu/nu/grad hold [actor | critic], counts[2]. */
+/* Both networks in two launches (squared norms, update): params/mu/nu/grad hold [actor | critic],
+ * counts[2].  Kept for hosts that run their own all-reduce; NOT re-entrant across streams of one
+ * device (the norm accumulator is a device global) -- mava_reduce_clip_adam_pair below is, and is what
+ * the learners of this repository call. */
 int mava_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts, const float* grad,
                         int64_t n_actor, int64_t n_critic, float grad_scale, float lr_actor,
                         float lr_critic, float max_norm, int lr_decay_num_updates,

@@ -213,14 +213,8 @@ __global__ void rware_peek_kernel(const __grid_constant__ RwareConst c,
 
 template <typename K>
 int prepare(K kernel, size_t smem) {
-  static size_t configured = 0;  // one instance per kernel type
-  if (smem > 48 * 1024 && smem > configured) {
-    configured = smem;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  return 0;
+  static size_t configured[kMaxDevices] = {};  // one instance per kernel type
+  return ensure_dyn_smem(kernel, smem, configured);
 }
 
 }  // namespace

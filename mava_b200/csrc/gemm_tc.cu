@@ -244,13 +244,8 @@ __global__ void __launch_bounds__(NT, 2) tc_gemm_kernel(const GemmArgs p) {
 template <int BN>
 int launch(const GemmArgs& a, cudaStream_t s) {
   constexpr size_t smem = 2 * (size_t)(TM * BK * 2 + BN * BK * 2) + 128;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(tc_gemm_kernel<BN>, smem, configured)) return rc;
   dim3 grid(ceil_div(a.M, TM), ceil_div(a.N, BN), ceil_div(a.K, a.kchunk));
   tc_gemm_kernel<BN><<<grid, NT, smem, s>>>(a);
   return launch_status();

@@ -389,12 +389,8 @@ int launch_gru_scan_fwd(const GruScanNet* nets, int n, cudaStream_t s) {
     tiles += (int)ceil_div64(g.S, TM);
   }
   const size_t smem = 4 * (size_t)kTile + 128;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gru_scan_fwd_kernel, smem, configured)) return rc;
   gru_scan_fwd_kernel<<<(unsigned)tiles, NT, smem, s>>>(pp);
   return launch_status();
 }
@@ -412,12 +408,8 @@ int launch_gru_scan_bwd(const GruScanNet* nets, int n, cudaStream_t s) {
     tiles += (int)ceil_div64(g.S, TM);
   }
   const size_t smem = 6 * (size_t)kTile + 128;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(gru_scan_bwd_kernel, smem, configured)) return rc;
   gru_scan_bwd_kernel<<<(unsigned)tiles, NT, smem, s>>>(pp);
   return launch_status();
 }

@@ -595,14 +595,8 @@ InputDesc make_input(const mava_mlp_desc* d, const int8_t* view, const int32_t* 
 
 template <int MODE>
 int launch_fwd(const FwdArgs& a, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(FwdSmem));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(mlp_fwd_kernel<MODE>, sizeof(FwdSmem), configured)) return rc;
   const int blocks = (int)ceil_div64(a.M, BM);
   mlp_fwd_kernel<MODE><<<blocks, NT, sizeof(FwdSmem), s>>>(a);
   return launch_status();

@@ -465,24 +465,14 @@ int mava_ff_act_bf16(const mava_mlp_desc* actor, const float* actor_params, cons
       a.critic.in_dim <= 288 && a.critic.k1p > a.critic.in_dim &&
       (size_t)TM * a.critic.in_dim + 16 <= tile_bytes(TM, a.critic.k1p) &&
       (reinterpret_cast<size_t>(view) & 15) == 0) {
-    static size_t configured_v = 0;
-    if (smem > configured_v) {
-      cudaError_t e = cudaFuncSetAttribute(value_batch_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      configured_v = smem;
-    }
+    static size_t configured_v[kMaxDevices] = {};
+    if (int rc2 = ensure_dyn_smem(value_batch_kernel, smem, configured_v)) return rc2;
     const int ctas = a.critic_ctas < sm_count() ? a.critic_ctas : sm_count();
     value_batch_kernel<<<ctas, NT, smem, as_stream(s)>>>(a);
     return launch_status();
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc2 = ensure_dyn_smem(act_kernel, smem, configured)) return rc2;
   act_kernel<<<a.actor_ctas + a.critic_ctas, NT, smem, as_stream(s)>>>(a);
   return launch_status();
 }

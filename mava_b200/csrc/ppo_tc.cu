@@ -1334,19 +1334,11 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
   const size_t stage_g = ((size_t)TM * grow_stride(k1p_max) + 127) & ~(size_t)127;
   const size_t smem_wg1 = 2 * (size_t)tile_bytes(TM, HID) + tile_bytes(TM, k1p_max) +
                           (2 * stage_g > stage_wg1 ? 2 * stage_g : stage_wg1) + 128;
-  static size_t conf_fused = 0, conf_wg1 = 0;
-  if (smem_fused > conf_fused) {
-    e = cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_fused);
-    if (e != cudaSuccess) return (int)e;
-    conf_fused = smem_fused;
-  }
-  if (smem_wg1 > conf_wg1) {
-    e = cudaFuncSetAttribute(ppo_wgrad1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_wg1);
-    if (e != cudaSuccess) return (int)e;
-    conf_wg1 = smem_wg1;
-  }
+  static size_t conf_fused[kMaxDevices] = {}, conf_wg1[kMaxDevices] = {};
+  rc = ensure_dyn_smem(ppo_fused_kernel, smem_fused, conf_fused);
+  if (rc) return rc;
+  rc = ensure_dyn_smem(ppo_wgrad1_kernel, smem_wg1, conf_wg1);
+  if (rc) return rc;
   ppo_fused_kernel<<<a.actor_ctas + a.critic_ctas, NT_F, smem_fused, s>>>(a);
   rc = launch_status();
   if (rc) return rc;

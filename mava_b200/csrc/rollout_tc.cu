@@ -372,13 +372,8 @@ int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
                       tile_bytes(TM, HCOLS) + (size_t)EPC * a.c.stride +
                       (size_t)round_up(EPC * G * a.c.FR, 16) + 2 * TM * NHEAD * 4 +
                       (size_t)EPC * a.c.stride + 128;  // ... noise, spare records
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rware_rollout_kernel<G, 1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static size_t configured[kMaxDevices] = {};
+  if (int rc = ensure_dyn_smem(rware_rollout_kernel<G, 1>, smem, configured)) return rc;
   // spread the envs over the SMs: a CTA takes whole warps of envs (32 / G each), at most a tile
   RolloutArgs b = a;
   const int per_warp = 32 / G;
