@@ -26,6 +26,21 @@ using namespace tc;
 
 constexpr int TM = 128, BK = 64, NT = 256;
 
+// Rows of the fp32 matrices are walked 32 bytes per thread, every lane of a warp on a different row:
+// an access instruction then costs one LSU wavefront per lane whatever its width, so 256-bit accesses
+// (sm_100) halve the wavefronts per byte against pairs of 128-bit ones.  The big-M contractions of the
+// recurrent path are bound by exactly that.
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y),
+               "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
 struct Ctrl {
   uint64_t bar[2];
   uint32_t tmem;
@@ -64,7 +79,9 @@ struct Stager {
       v[it][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (idx < GROUPS && gr < rmax && gc < cmax) {
         const float* p = src + (int64_t)gr * ld + gc;
-        if (gc + 8 <= cmax && vec) {
+        if (gc + 8 <= cmax && vec && ((size_t)p & 31) == 0) {
+          ldg256(p, v[it][0], v[it][1]);
+        } else if (gc + 8 <= cmax && vec) {
           v[it][0] = __ldg(reinterpret_cast<const float4*>(p));
           v[it][1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
         } else {
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(NT, 2) tc_gemm_kernel(const GemmArgs p) {
     const bool fast = i < p.M && jb + HALF <= p.N && p.mode != 2 && (((size_t)crow) & 15) == 0 &&
                       (rrow == nullptr || (((size_t)rrow) & 15) == 0);
     float4 cold[HALF / 4], rref[HALF / 4];
+    const bool wide = fast && (((size_t)crow) & 31) == 0;  // 32-byte aligned rows: 256-bit stores
     if (fast) {
 #pragma unroll
       for (int q = 0; q < HALF / 4; ++q) {
@@ -204,21 +222,32 @@ __global__ void __launch_bounds__(NT, 2) tc_gemm_kernel(const GemmArgs p) {
       const int j0 = jb + cc;
       if (fast) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 o = cold[cc / 4 + q4], rr = rref[cc / 4 + q4];
-          const float ov[4] = {o.x, o.y, o.z, o.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
-          float x[4];
+        for (int q8 = 0; q8 < 2; ++q8) {
+          float4 o4[2];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float y = p.alpha * v[q4 * 4 + q];
-            if (p.bias != nullptr && blockIdx.z == 0) y += __ldg(p.bias + j0 + q4 * 4 + q);
-            if (p.relu) y = fmaxf(y, 0.0f);
-            if (!(rv[q] > 0.0f)) y = 0.0f;
-            x[q] = y + ov[q];
+          for (int h = 0; h < 2; ++h) {
+            const int q4 = q8 * 2 + h;
+            const float4 o = cold[cc / 4 + q4], rr = rref[cc / 4 + q4];
+            const float ov[4] = {o.x, o.y, o.z, o.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+            float x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float y = p.alpha * v[q4 * 4 + q];
+              if (p.bias != nullptr && blockIdx.z == 0) y += __ldg(p.bias + j0 + q4 * 4 + q);
+              if (p.relu) y = fmaxf(y, 0.0f);
+              if (!(rv[q] > 0.0f)) y = 0.0f;
+              x[q] = y + ov[q];
+            }
+            o4[h] = make_float4(x[0], x[1], x[2], x[3]);
           }
-          *reinterpret_cast<float4*>(crow + cc + q4 * 4) = make_float4(x[0], x[1], x[2], x[3]);
+          if (wide) {
+            st256(crow + cc + q8 * 8, o4[0], o4[1]);
+          } else {
+            *reinterpret_cast<float4*>(crow + cc + q8 * 8) = o4[0];
+            *reinterpret_cast<float4*>(crow + cc + q8 * 8 + 4) = o4[1];
+          }
         }
-      } else if (i < p.M && j0 < p.N) {
+    } else if (i < p.M && j0 < p.N) {
         float* dst = crow + cc;
         const float* ref = rrow ? rrow + cc : nullptr;
 #pragma unroll

@@ -275,10 +275,12 @@ Net make_net(const mava_rnn_desc* d, T* p) {
 // ------------------------------------------------------------------------------------------------
 // X[(l*Senv + q)*rpe + a][:] = network input of env-step steps[l*Senv + q] (identity when steps is
 // null): [onehot(a) | view] (AGENT_VIEW), concat_a view (GLOBAL), or the dense f32 row.
+// Rows of X are `ldx` floats apart (in_dim rounded up to 8): 32-byte aligned rows let the contractions
+// read them with 256-bit loads; the padding columns are never read.
 __global__ void __launch_bounds__(256)
 expand_obs_kernel(const int8_t* __restrict__ view, const float* __restrict__ dense,
                   const int32_t* __restrict__ steps, int64_t rows, int rpe, int mode, int add_id,
-                  int A, int FR, int in_dim, float* __restrict__ X) {
+                  int A, int FR, int in_dim, int ldx, float* __restrict__ X) {
   const int64_t total = rows * in_dim;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -297,7 +299,7 @@ expand_obs_kernel(const int8_t* __restrict__ view, const float* __restrict__ den
     } else {
       v = (float)view[(st * A + a) * FR + (add_id ? k - A : k)];
     }
-    X[idx] = v;
+    X[row * ldx + k] = v;
   }
 }
 
@@ -664,7 +666,7 @@ struct Work {
 int64_t work_floats(const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
   const int64_t H = d->hidden, Q = d->post;
   int64_t f = 0;
-  f += align256(R * d->in_dim) + align256(R * H) + align256(R * 3 * H);  // X, E1, Gx
+  f += align256(R * round_up(d->in_dim, 8)) + align256(R * H) + align256(R * 3 * H);  // X, E1, Gx
   f += train ? align256(R * 4 * H) : 0;                                   // gates
   f += align256(R * H) * 2 + align256(R * Q) + align256(R * OMAX);        // Hin, Hout, P, out
   f += align256(S * 3 * H) + 4 * align256(S * H);                         // Gh, dH0/1, dT0/1
@@ -674,7 +676,7 @@ int64_t work_floats(const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
 Work carve(float* w, const mava_rnn_desc* d, int64_t R, int64_t S, bool train) {
   const int64_t H = d->hidden, Q = d->post;
   Work k;
-  k.X = w; w += align256(R * d->in_dim);
+  k.X = w; w += align256(R * round_up(d->in_dim, 8));
   k.E1 = w; w += align256(R * H);
   k.Gx = w; w += align256(R * 3 * H);
   k.gates = train ? w : nullptr; w += train ? align256(R * 4 * H) : 0;
@@ -721,8 +723,9 @@ int forward_pre(const Net& n, const SeqInput& in, const Work& k, cudaStream_t s)
   const int H = n.H, L = in.L;
   const int64_t S = in.Senv * n.rows_per_env, R = S * L;
   expand_obs_kernel<<<ew_blocks(R * n.in_dim), 256, 0, s>>>(
-      in.view, in.dense, in.steps, R, n.rows_per_env, n.mode, n.add_id, n.A, n.FR, n.in_dim, k.X);
-  int rc = Gemm(k.X, 0, n.in_dim, n.w_pre, 0, H, k.E1, H, (int)R, H, n.in_dim).bias(n.b_pre).relu().tc(n.tc).run(s);
+      in.view, in.dense, in.steps, R, n.rows_per_env, n.mode, n.add_id, n.A, n.FR, n.in_dim,
+      round_up(n.in_dim, 8), k.X);
+  int rc = Gemm(k.X, 0, round_up(n.in_dim, 8), n.w_pre, 0, H, k.E1, H, (int)R, H, n.in_dim).bias(n.b_pre).relu().tc(n.tc).run(s);
   if (rc) return rc;
   rc = Gemm(k.E1, 0, H, n.w_i, 0, 3 * H, k.Gx, 3 * H, (int)R, 3 * H, H).bias(n.b_i).tc(n.tc).run(s);
   if (rc) return rc;
@@ -839,7 +842,7 @@ int backward_post(const Net& n, const Net& g, const SeqInput& in, const Work& k,
   // dE1 = (dGx W_i^T) * relu'(E1), in place over E1
   rc = Gemm(k.Gx, 0, 3 * H, n.w_i, 1, 3 * H, k.E1, H, (int)R, H, 3 * H).relu_ref(k.E1, H).tc(n.tc).run(s);
   if (rc) return rc;
-  rc = Gemm(k.X, 1, n.in_dim, k.E1, 0, H, G(g.w_pre), H, n.in_dim, H, (int)R).split_k_atomic().tc(n.tc).run(s);
+  rc = Gemm(k.X, 1, round_up(n.in_dim, 8), k.E1, 0, H, G(g.w_pre), H, n.in_dim, H, (int)R).split_k_atomic().tc(n.tc).run(s);
   if (rc) return rc;
   return launch_colsum(k.E1, H, R, H, G(g.b_pre), s);
 }
