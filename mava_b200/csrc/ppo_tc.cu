@@ -50,6 +50,11 @@ namespace {
 // record clock64() at the phase boundaries of its first tiles (read back with
 // mava_debug_phases).  Compiled out by default.
 #ifdef MAVA_PROFILE_PHASES
+__device__ long long g_wg1_clock[8 * 12];  // ppo_wgrad1_kernel: CTA 0, first 8 tiles, 12 stamps
+#define MAVA_WSTAMP(k)                                                             \
+  do {                                                                             \
+    if (t == 0 && blockIdx.x == 0 && it < 8) g_wg1_clock[it * 12 + (k)] = clock64(); \
+  } while (0)
 __device__ long long g_phase_clock[16 * 16];
 __device__ long long g_phase_clock2[16 * 8 + 32];
 #define MAVA_STAMP2(k)                                                             \
@@ -71,6 +76,7 @@ __device__ long long g_phase_clock2[16 * 8 + 32];
   } while (0)
 #else
 #define MAVA_STAMP(k) do { } while (0)
+#define MAVA_WSTAMP(k) do { } while (0)
 #define MAVA_STAMP2(k) do { } while (0)
 #define MAVA_STAMP3(k) do { } while (0)
 #endif
@@ -1023,6 +1029,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
 // ------------------------------------------------------------------------------------------------
 struct Wg1Ctrl {
   uint64_t lbar[2], mbar, gbar[2];  // dZ1 tile images landed | MMAs done | gathered rows landed
+  uint64_t hbar[2];                  // MMAs of column half 0 / half 1 of X done (bulk-copied rows path)
   uint32_t tmem;
   int32_t steps[3][TM];  // env-step index of each row of the tile being built / the two being fetched
 };
@@ -1054,6 +1061,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     mbar_init(&ctrl.mbar, 1);
     mbar_init(&ctrl.gbar[0], TM);
     mbar_init(&ctrl.gbar[1], TM);
+    mbar_init(&ctrl.hbar[0], 1);
+    mbar_init(&ctrl.hbar[1], 1);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -1061,6 +1070,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   fence_after_sync();
   const uint32_t tmem = ctrl.tmem;
   const int n_lo = d.k1p > 256 ? 256 : d.k1p, n_hi = d.k1p - n_lo;
+  // bulk-copied rows path: X is expanded and multiplied in two column halves, so that the MMAs of one
+  // half run under the int8 -> bf16 expansion of the other (the expansion, 2.6 K cycles per tile, is
+  // what bounds this kernel; the MMAs, 1.5 K, used to follow it)
+  const int c_h0 = d.k1p >= 64 ? pad16(d.k1p / 2) : d.k1p, c_h1 = d.k1p - c_h0;
   uint32_t phase = 0;
   bool first = true;
   // one env-step per row (centralised critic): rows fetched by bulk copies TWO tiles ahead into two
@@ -1102,20 +1115,66 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
     if (padded_global) {
       const int nxt = tile + n_ctas, nxt2 = tile + 2 * n_ctas;
       unsigned char* stage = stage0 + (size_t)(it & 1) * stage_bytes_g;
-      if (t == 0 && nxt < n_tiles) load_dz1(nxt, buf ^ 1);  // free: the MMAs of tile it-1 were waited for
+      const uint32_t hpar = (uint32_t)(it + 1) & 1u;  // parity of the previous tile's half commits
+      // the MMAs of a column half: D[n][k] += sum_rows dZ1[row][n] * X[row][k], A = dZ1 and B = X both
+      // MN-major; called by ONE elected thread
+      auto issue_half = [&](int half) {
+        const int c0 = half ? c_h0 : 0, nc = half ? c_h1 : c_h0;
+        if (nc > 0) {
+          const uint32_t idesc = instr_desc(TM, nc, true, true);
+          for (int k = 0; k < TM / 16; ++k)
+            mma(tmem + (uint32_t)c0, desc_mnmajor(dzt, k), desc_mnmajor(xt, k, c0), idesc,
+                !first || k > 0);
+        }
+        commit(&ctrl.hbar[half]);
+      };
+      MAVA_WSTAMP(0);
+      if (t == 0 && nxt < n_tiles) {
+        // the other dZ1 buffer was read by the MMAs of tile it - 1 (both halves)
+        if (it > 0) mbar_wait(&ctrl.hbar[1], hpar);
+        load_dz1(nxt, buf ^ 1);
+      }
       const int32_t step2 = nxt2 < n_tiles ? step_of(nxt2) : 0;  // index list two tiles ahead
       mbar_wait(&ctrl.gbar[it & 1], (uint32_t)(it >> 1) & 1u);
+      MAVA_WSTAMP(1);
       if (t < TM && row0 + t < M) grow_tail(d, stage, t, ctrl.steps[it % 3][t]);
+      if (it > 0) mbar_wait(&ctrl.hbar[0], hpar);  // X columns [0, c_h0) are free again
       __syncthreads();
+      MAVA_WSTAMP(2);
       const bool valid = row0 + L.r < M;
-      expand_padded_row(xt, L,
-                        smem_u32(stage) + (uint32_t)L.r * grow_stride(d.k1p) +
-                            (valid ? grow_skew(d, ctrl.steps[it % 3][L.r]) : 0u),
-                        valid, d.k1p >> 3, (L.q + (L.r >> 2)) & 3, 4);  // rotation: bank spread
+      const uint32_t srow = smem_u32(stage) + (uint32_t)L.r * grow_stride(d.k1p) +
+                            (valid ? grow_skew(d, ctrl.steps[it % 3][L.r]) : 0u);
+      const int rot = (L.q + (L.r >> 2)) & 3;  // rotation: bank spread of the 8-byte staging reads
+      // ---- column half 0
+      expand_padded_row(xt, L, srow, valid, c_h0 >> 3, rot, 4);
+      MAVA_WSTAMP(3);
       fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (mma_issuer()) {
+        fence_after_sync();
+        mbar_wait(&ctrl.lbar[buf], (uint32_t)(it >> 1) & 1u);  // this tile's dZ1 image
+        issue_half(0);
+      }
+      MAVA_WSTAMP(4);
+      // ---- column half 1 (under the MMAs of half 0)
+      if (c_h1 > 0) {
+        if (it > 0) mbar_wait(&ctrl.hbar[1], hpar);  // X columns [c_h0, k1p) are free again
+        const Tile xh{xt.base + (uint32_t)(c_h0 >> 3) * xt.s_c, xt.s_r, xt.s_c};
+        expand_padded_row(xh, L, srow + (uint32_t)c_h0, valid, c_h1 >> 3, rot, 4);
+      }
+      MAVA_WSTAMP(5);
+      fence_proxy_async();
+      fence_before_sync();
       __syncthreads();  // this staging buffer has been read: the rows of tile it + 2 may land in it
+      MAVA_WSTAMP(6);
+      if (mma_issuer()) {
+        fence_after_sync();
+        issue_half(1);
+      }
       if (nxt2 < n_tiles) request_rows(it + 2, nxt2, step2);
-      mbar_wait(&ctrl.lbar[buf], (uint32_t)(it >> 1) & 1u);
+      MAVA_WSTAMP(7);
+      continue;
     } else {
       if (t == 0) load_dz1(tile, 0);
       build_x_tile(d, p.view, xt, stage0, row0, M,
@@ -1138,9 +1197,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
       }
       commit(&ctrl.mbar);
     }
+    MAVA_WSTAMP(7);
     wait_mma(&ctrl.mbar, phase);  // operands are free again once the MMAs have completed
+    MAVA_WSTAMP(8);
     phase ^= 1;
   }
+  if (padded_global && !first) {  // the last tile's MMAs (commits complete in issue order)
+    mbar_wait(&ctrl.hbar[1], (uint32_t)(it + 1) & 1u);
+  }
+#ifdef MAVA_PROFILE_PHASES
+  if (t == 0 && blockIdx.x == 0) g_wg1_clock[7 * 12 + 10] = clock64();
+#endif
   if (!first) {
     float* g = is_actor ? p.grad_actor : p.grad_critic;
     float* gb1 = g + (size_t)d.in_dim * HID;
@@ -1159,6 +1226,9 @@ __global__ void __launch_bounds__(NT, 1) ppo_wgrad1_kernel(const TrainArgs p) {
   }
   fence_before_sync();
   __syncthreads();
+#ifdef MAVA_PROFILE_PHASES
+  if (t == 0 && blockIdx.x == 0) g_wg1_clock[7 * 12 + 11] = clock64();
+#endif
   if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
@@ -1179,6 +1249,9 @@ extern "C" {
 #ifdef MAVA_PROFILE_PHASES
 int mava_debug_phases(long long* out_host) {
   return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 256);
+}
+int mava_debug_wg1(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_wg1_clock, sizeof(long long) * 96);
 }
 int mava_debug_phases2(long long* out_host) {
   return (int)cudaMemcpyFromSymbol(out_host, g_phase_clock2, sizeof(long long) * 160);

@@ -46,6 +46,15 @@ print("critic build (with -DMAVA_STAMP_CRITIC): wait dW2 -> %s" % np.diff(np.con
 c = np.array(buf2[128:144])
 print("critic tile (last CTA), start->start: %.0f cycles" % np.diff(c[2:]).mean())
 print("gemm3_done -> dz3 stored:", (a[:, 15] - a[:, 7]).mean(), " -> db3 reduced + sync:", (a[:, 8] - a[:, 15]).mean())
+wb = (ctypes.c_longlong * 96)()
+lib.mava_debug_wg1.restype = ctypes.c_int
+assert lib.mava_debug_wg1(wb) == 0
+w = np.array(wb[:]).reshape(8, 12)
+wn = ["wait rows", "tail+sync", "expand", "fence+sync", "request rows", "wait dZ1", "sync+MMA issue", "wait MMA"]
+print("ppo_wgrad1_kernel, cycles per phase (CTA 0, tiles 0..6):")
+for i in range(7):
+    print("  tile %d: " % i + ", ".join("%s %d" % (n_, v) for n_, v in zip(wn, np.diff(w[i, :9]))) + ", total %d" % (w[i, 8] - w[i, 0]))
+print("  flush (TMEM -> atomics): %d cycles" % (w[7, 11] - w[7, 10]))
 rb = (ctypes.c_longlong * 256)()
 lib.mava_debug_rollout_phases.restype = ctypes.c_int
 assert lib.mava_debug_rollout_phases(rb) == 0
