@@ -233,21 +233,21 @@ __device__ __forceinline__ void set5(unsigned long long (&M)[MW], int s, unsigne
   }
 }
 
-// Builds the row of agent g from the (post-step) record and writes it, with the action mask bits
-// returned.  opk[j] = old cell | new cell << 10 | moved << 20 of agent j for this step; when
-// `replay` is set the AGENTS grid is evaluated exactly as the reference's sequence of grid writes
-// leaves it (needed only for the terminal observation of a collision without auto-reset), else
-// agents are on distinct cells and the grid is simply {cell of j -> j}.
+// Builds the row of agent g from the (post-step) record as O::NW little-endian words (the upper half
+// of the last one is zero), with the action mask bits returned.  opk[j] = old cell | new cell << 10 |
+// moved << 20 of agent j for this step; when `replay` is set the AGENTS grid is evaluated exactly as
+// the reference's sequence of grid writes leaves it (needed only for the terminal observation of a
+// collision without auto-reset), else agents are on distinct cells and the grid is simply
+// {cell of j -> j}.
 template <int G, int R>
-__device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* rec, int g,
-                                            uint8_t* row, int row_parity, bool replay,
-                                            const uint32_t (&opk)[G]) {
+__device__ __forceinline__ uint8_t build_row(const RwareConst& c, const uint8_t* rec, int g,
+                                             bool replay, const uint32_t (&opk)[G],
+                                             uint32_t (&w)[ObsDims<R>::NW]) {
   using O = ObsDims<R>;
   const uint32_t* agents = reinterpret_cast<const uint32_t*>(rec + c.off_agents);
   const uint8_t* cells = rec + c.off_cells;
   const uint32_t me = agents[g];
   const int x = me & 0xff, y = (me >> 8) & 0xff, d = (me >> 16) & 0xff, carry = me >> 24;
-  uint32_t w[O::NW];
 #pragma unroll
   for (int i = 0; i < O::NW; ++i) w[i] = 0u;
   w[0] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)carry << 16) | ((uint32_t)(d == 0) << 24);
@@ -323,19 +323,36 @@ __device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* 
     const uint32_t h = present | (((word >> (s1 & 31)) & present) << 8);
     w[O::SH0 + ci / 2] |= h << (16 * (ci & 1));
   }
-  // rows are FR = 2 (mod 4) bytes long: odd rows start on a half word
-  uint32_t* wp = reinterpret_cast<uint32_t*>(row + 2 * row_parity);
-  const int sh = 16 * row_parity;
-#pragma unroll
-  for (int k = 0; k + 1 < O::NW; ++k) wp[k] = __funnelshift_r(w[k], w[k + 1], sh);
-  uint16_t* hp = reinterpret_cast<uint16_t*>(row_parity ? row : row + 4 * (O::NW - 1));
-  *hp = (uint16_t)(row_parity ? w[0] : w[O::NW - 1]);
   // utils.compute_action_mask: only FORWARD can be illegal
   int nx, ny;
   forward_cell(c, x, y, d, nx, ny);
   const bool stuck = nx == x && ny == y;
   const bool blocked = carry && cells[nx * c.W + ny] != 0;
   return (uint8_t)(0x1Du | ((stuck || blocked) ? 0u : 0x2u));
+}
+
+// The words of build_row to the int8 row at `row` (rows are FR = 2 (mod 4) bytes long: odd rows
+// start on a half word).
+template <int R>
+__device__ __forceinline__ void store_row(const uint32_t (&w)[ObsDims<R>::NW], uint8_t* row,
+                                          int row_parity) {
+  using O = ObsDims<R>;
+  uint32_t* wp = reinterpret_cast<uint32_t*>(row + 2 * row_parity);
+  const int sh = 16 * row_parity;
+#pragma unroll
+  for (int k = 0; k + 1 < O::NW; ++k) wp[k] = __funnelshift_r(w[k], w[k + 1], sh);
+  uint16_t* hp = reinterpret_cast<uint16_t*>(row_parity ? row : row + 4 * (O::NW - 1));
+  *hp = (uint16_t)(row_parity ? w[0] : w[O::NW - 1]);
+}
+
+template <int G, int R>
+__device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* rec, int g,
+                                            uint8_t* row, int row_parity, bool replay,
+                                            const uint32_t (&opk)[G]) {
+  uint32_t w[ObsDims<R>::NW];
+  const uint8_t mk = build_row<G, R>(c, rec, g, replay, opk, w);
+  store_row<R>(w, row, row_parity);
+  return mk;
 }
 
 // One env-step of the G lanes of an env on its shared-memory record (everything of env.step and the

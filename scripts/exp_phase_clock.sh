@@ -59,9 +59,10 @@ rb = (ctypes.c_longlong * 256)()
 lib.mava_debug_rollout_phases.restype = ctypes.c_int
 assert lib.mava_debug_rollout_phases(rb) == 0
 ra = np.array(rb[:]).reshape(16, 16)
-rn = ["x_expand+sync", "gemm1", "epi1+sync", "gemm2", "epi2+sync", "gemm3", "head+env_step", "resets", "emit_rows+sync", "store_issue"]
+rn = ["gemm1", "epi1+sync", "gemm2", "epi2+sync", "gemm3", "head", "env step", "reset + rows + X row", "sync"]
 print("rollout kernel, cycles per phase of a step (CTA 0, steps 16..31):")
-for n_, v in zip(rn, np.diff(ra[:, :11], axis=1).mean(0)):
-    print(f"  {n_:18s} {v:8.0f}")
+for n_, v in zip(rn, np.diff(ra[:, :10], axis=1).mean(0)):
+    print(f"  {n_:22s} {v:8.0f}")
+print(f"  {'regeneration + store':22s} {(ra[:, 12] - ra[:, 9]).mean():8.0f}")
 print("  step total (start->start):", np.diff(ra[:, 0]).mean())
 PY
