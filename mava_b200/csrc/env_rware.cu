@@ -91,9 +91,8 @@ rware_step_kernel(const __grid_constant__ RwareConst c, uint8_t* __restrict__ st
   uint32_t opk[G];
 #pragma unroll
   for (int j = 0; j < G; ++j) opk[j] = 0u;
-  if (active)
-    rware::step_group<G>(c, rec, g, gmask, agent, act, env, auto_reset, reward, done, ep_return,
-                         ep_length, needs_reset, replay, opk);
+  rware::step_group<G>(c, rec, g, gmask, active, agent, act, env, auto_reset, reward, done,
+                       ep_return, ep_length, needs_reset, replay, opk);
   // --- AutoResetWrapper: on the last step the state and observation are those of a fresh episode
   //     seeded with split(state.key)[0] (auto_reset_wrapper.py:74-75).  Episode ends are rare and a
   //     regeneration is a long dependent chain of threefry calls, so finished envs go into a CTA

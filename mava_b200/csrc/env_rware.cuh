@@ -356,17 +356,24 @@ __device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* 
 }
 
 // One env-step of the G lanes of an env on its shared-memory record (everything of env.step and the
-// wrapper stack up to, not including, the auto-reset and the next observation).  `act` is lane g's
-// action; outputs go to the per-env / per-agent slots of this step.  Returns through the
-// references whether the env must be regenerated, whether the terminal observation needs the
-// exact grid replay, and the (old cell, new cell, moved) words of all agents.
-template <int G>
+// wrapper stack up to, not including, the auto-reset and the next observation).  Called by ALL 32
+// lanes of a warp together -- lanes whose env does not exist pass active = false (and any readable
+// record) -- so that the exchanges between an env's lanes are whole-warp shuffles / votes / barriers
+// (one instruction each) instead of collectives on a run-time lane mask (a MATCH.ANY + vote +
+// divergence check each).  `act` is lane g's action; VALIDATED: it is known to respect the action
+// mask of the current state (sampled from masked logits).  Outputs go to the per-env / per-agent
+// slots of this step (index env, env * A + g).  Returns through the references whether the env must
+// be regenerated, whether the terminal observation needs the exact grid replay, and the (old cell,
+// new cell, moved) words of all agents.
+template <int G, bool VALIDATED = false>
 __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, int g, unsigned gmask,
-                                           bool agent, int act, int env, int auto_reset,
-                                           float* __restrict__ reward, uint8_t* __restrict__ done,
+                                           bool active, bool agent, int act, int env,
+                                           int auto_reset, float* __restrict__ reward,
+                                           uint8_t* __restrict__ done,
                                            float* __restrict__ ep_return,
                                            int32_t* __restrict__ ep_length, bool& needs_reset,
                                            bool& replay, uint32_t (&opk)[G]) {
+  constexpr unsigned kAll = 0xffffffffu;
   uint8_t* cells = rec + c.off_cells;
   Key key{0u, 0u};
   // --- validate the action against the mask of the current state (utils.get_valid_actions)
@@ -378,7 +385,7 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
     d = (me >> 16) & 0xff;
     carry = me >> 24;
     forward_cell(c, x, y, d, nx, ny);
-    if (act == 1) {
+    if (!VALIDATED && act == 1) {
       const bool stuck = nx == x && ny == y;
       const bool blocked = carry && cells[nx * c.W + ny] != 0;
       if (stuck || blocked) act = 0;
@@ -391,7 +398,7 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
   const int newcell = moved ? nx * c.W + ny : oldcell;
   const uint32_t pk = (uint32_t)oldcell | ((uint32_t)newcell << 10) | ((uint32_t)moved << 20);
 #pragma unroll
-  for (int j = 0; j < G; ++j) opk[j] = __shfl_sync(gmask, pk, j, G);
+  for (int j = 0; j < G; ++j) opk[j] = __shfl_sync(kAll, pk, j, G);
   // --- collision (utils.is_collision): grid[AGENTS, pos_i] != i + 1 after the sequential writes
   //     "old cell <- 0, new cell <- j + 1" of every agent j that moved.  The last write to my
   //     cell is not mine iff some mover j entered or left it after my own write.
@@ -408,7 +415,9 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
       if (moved && (nj == (uint32_t)newcell || oj == (uint32_t)newcell)) touch = true;
     }
   }
-  const bool ordered = (__ballot_sync(gmask, touch && agent) & gmask) != 0u;
+  const unsigned touch_b = __ballot_sync(kAll, touch && agent);
+  const unsigned col_b = __ballot_sync(kAll, my_col && agent);
+  const bool collision = (col_b & gmask) != 0u;
   // rotations and the position update do not depend on the other agents
   if (act == 2) d = (d + 3) & 3;
   else if (act == 3) d = (d + 1) & 3;
@@ -416,20 +425,21 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
     x = nx;
     y = ny;
   }
-  if (!ordered) {
+  if (touch_b == 0u) {
     // every cell this step reads or writes belongs to exactly one agent: the turns commute
     if (moved && carry) {
       const uint8_t sid = cells[oldcell];
       cells[oldcell] = 0;
       cells[newcell] = sid;
-    } else if (act == 4) {
+    } else if (act == 4 && agent) {
       if (!carry) carry = cells[oldcell] != 0;
       else if (!is_highway(c, oldcell)) carry = 0;
     }
   } else {
-    // --- agents act one after the other on the shelf grid (scan over agents in env.step)
+    // --- some env of this warp has agents meeting on a cell: agents act one after the other on
+    //     the shelf grid (scan over agents in env.step); for the other envs the order is immaterial
     for (int i = 0; i < c.A; ++i) {
-      if (g == i) {
+      if (g == i && agent) {
         if (moved && carry) {
           const uint8_t sid = cells[oldcell];
           cells[oldcell] = 0;
@@ -439,12 +449,11 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
           else if (!is_highway(c, oldcell)) carry = 0;
         }
       }
-      __syncwarp(gmask);
+      __syncwarp();
     }
   }
   if (agent) reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(x, y, d, carry);
-  __syncwarp(gmask);
-  const bool collision = (__ballot_sync(gmask, my_col && agent) & gmask) != 0u;
+  __syncwarp();
 
   // --- deliveries at the goal cells; a delivered request is replaced by a uniformly drawn
   //     shelf that is not in the queue (env._update_reward_and_request_queue)
@@ -455,7 +464,7 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
   }
   for (int gi = 0; gi < 2; ++gi) {
     const int sid = cells[c.goal[gi]];
-    if (sid != 0 && requested(c, rec, sid - 1)) {
+    if (active && sid != 0 && requested(c, rec, sid - 1)) {
       Key rkey, unused, sub;
       split2(key, key, rkey);
       split2(rkey, unused, sub);
@@ -499,8 +508,8 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
   uint32_t* pstep = reinterpret_cast<uint32_t*>(rec + c.off_step);
   const int step = (int)(*pstep) + 1;
   const bool is_done = collision || step >= c.time_limit;
-  __syncwarp(gmask);
-  if (g == 0) {
+  __syncwarp();
+  if (g == 0 && active) {
     *pstep = (uint32_t)step;
     uint32_t* k = reinterpret_cast<uint32_t*>(rec + c.off_key);
     k[0] = key.k0;
@@ -524,8 +533,8 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
     ep_length[env] = len_info;
   }
   if (agent) reward[(size_t)env * c.A + g] = rew;
-  needs_reset = is_done && auto_reset != 0;
-  replay = collision && !needs_reset;
+  needs_reset = active && is_done && auto_reset != 0;
+  replay = active && collision && !needs_reset;
 }
 
 }  // namespace rware
