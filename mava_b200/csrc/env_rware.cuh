@@ -98,7 +98,7 @@ __device__ __forceinline__ bool requested(const RwareConst& c, const uint8_t* re
 
 // K smallest of the composites (random_bits(sub, size)[i] << 32 | i), i.e. the first K entries of
 // jax.random.permutation-by-stable-sort.  Every lane returns the same out[].
-template <int G, int KMAX>
+template <int G, int KMAX, class P = PrngInline>
 __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsigned gmask,
                                            unsigned long long (&out)[KMAX]) {
   unsigned long long top[KMAX];
@@ -107,7 +107,7 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
   const int half = (size + 1) >> 1;
   for (int p = g; p < half; p += G) {
     uint32_t lo, hi;
-    random_bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
+    P::bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
     unsigned long long v = ((unsigned long long)lo << 32) | (unsigned)p;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) {
@@ -147,7 +147,7 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
 // jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
 // their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
 // lanes cooperate; State.key is what is left of `key`).
-template <int GG>
+template <int GG, class P = PrngInline>
 __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
                                          unsigned gmask) {
   // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
@@ -156,16 +156,16 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
   // other for the scheduler (critical path: 4 splits instead of 7), and the per-agent direction
   // draws run on the agents' own lanes.
   Key k1, pos_key, k2, dir_key, k3, q_key, unused, sub_pos, sub_q, d_hi, d_lo;
-  split2(key, k1, pos_key);
-  split2(k1, k2, dir_key);
-  split2(pos_key, unused, sub_pos);
-  split2(k2, k3, q_key);
-  split2(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
-  split2(q_key, unused, sub_q);
+  P::split(key, k1, pos_key);
+  P::split(k1, k2, dir_key);
+  P::split(pos_key, unused, sub_pos);
+  P::split(k2, k3, q_key);
+  P::split(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
+  P::split(q_key, unused, sub_q);
   const int my_dir =
-      g < c.A ? (int)(random_bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
+      g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
   unsigned long long pick[kMaxAgents];
-  smallest_k<GG, kMaxAgents>(sub_pos, c.HW, c.A, g, gmask, pick);
+  smallest_k<GG, kMaxAgents, P>(sub_pos, c.HW, c.A, g, gmask, pick);
   if (g < c.A) {
     unsigned long long mine = 0ull;
 #pragma unroll
@@ -175,7 +175,7 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(cell / c.W, cell % c.W, my_dir, 0);
   }
   unsigned long long qpick[kMaxQueue];
-  smallest_k<GG, kMaxQueue>(sub_q, c.n, c.Q, g, gmask, qpick);
+  smallest_k<GG, kMaxQueue, P>(sub_q, c.n, c.Q, g, gmask, qpick);
   uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
   for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
   __syncwarp(gmask);
@@ -331,6 +331,79 @@ __device__ __forceinline__ uint8_t build_row(const RwareConst& c, const uint8_t*
   return (uint8_t)(0x1Du | ((stuck || blocked) ? 0u : 0x2u));
 }
 
+// A quarter of build_row + store_row, for callers that put four threads on a row (the agents are on
+// distinct cells: not the replay case).  part 0: the agent's own features -- returns the action
+// mask; part 1: the other agents around it; parts 2, 3: the shelf cells.  Every word / half word
+// goes to the int8 row (`row`, 2-byte aligned) and to a second, 4-byte aligned copy `img`.
+template <int G, int R>
+__device__ __forceinline__ uint8_t build_row_part(const RwareConst& c, const uint8_t* rec, int g,
+                                                  int part, uint8_t* row, uint8_t* img) {
+  using O = ObsDims<R>;
+  const uint32_t* agents = reinterpret_cast<const uint32_t*>(rec + c.off_agents);
+  const uint8_t* cells = rec + c.off_cells;
+  const uint32_t me = agents[g];
+  const int x = me & 0xff, y = (me >> 8) & 0xff, d = (me >> 16) & 0xff, carry = me >> 24;
+  auto put32 = [&](int off, uint32_t v) {
+    *reinterpret_cast<uint32_t*>(img + off) = v;
+    reinterpret_cast<uint16_t*>(row + off)[0] = (uint16_t)v;
+    reinterpret_cast<uint16_t*>(row + off)[1] = (uint16_t)(v >> 16);
+  };
+  if (part == 0) {
+    put32(0, (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)carry << 16) | ((uint32_t)(d == 0) << 24));
+    put32(4, (uint32_t)(d == 1) | ((uint32_t)(d == 2) << 8) | ((uint32_t)(d == 3) << 16) |
+                 ((uint32_t)is_highway(c, x * c.W + y) << 24));
+    // utils.compute_action_mask: only FORWARD can be illegal
+    int nx, ny;
+    forward_cell(c, x, y, d, nx, ny);
+    const bool stuck = nx == x && ny == y;
+    const bool blocked = carry && cells[nx * c.W + ny] != 0;
+    return (uint8_t)(0x1Du | ((stuck || blocked) ? 0u : 0x2u));
+  }
+  if (part == 1) {
+    unsigned long long M[O::MW];
+#pragma unroll
+    for (int i = 0; i < O::MW; ++i) M[i] = 0ull;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (j < c.A && j != g) {
+        const uint32_t aj = agents[j];
+        const int dx = (int)(aj & 0xff) - x + R, dy = (int)((aj >> 8) & 0xff) - y + R;
+        if ((unsigned)dx <= 2u * R && (unsigned)dy <= 2u * R) {
+          int k = dx * O::SIDE + dy;
+          if (k != O::CENTER) {
+            k -= k > O::CENTER;
+            set5<O::MW>(M, 5 * k, 1ull | (2ull << ((aj >> 16) & 3u)));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < O::NAG / 4; ++i) {
+      const uint32_t nib = (uint32_t)(M[i >> 4] >> ((i & 15) * 4)) & 0xFu;
+      put32(8 + 4 * i, (nib * 0x00204081u) & 0x01010101u);
+    }
+    return 0;
+  }
+  const uint32_t* rq = reinterpret_cast<const uint32_t*>(rec + c.off_reqbits);
+  constexpr int HALF = (O::LOC + 1) / 2;
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const int ci = part == 2 ? i : HALF + i;
+    if (ci < O::LOC) {
+      const int cx = x + ci / O::SIDE - R, cy = y + ci % O::SIDE - R;
+      const bool inside = (unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W;
+      const int sid = inside ? (int)cells[cx * c.W + cy] : 0;
+      const int s1 = sid - 1;
+      const uint32_t word = rq[sid ? s1 >> 5 : 0];
+      const uint32_t present = sid != 0;
+      const uint16_t h = (uint16_t)(present | (((word >> (s1 & 31)) & present) << 8));
+      *reinterpret_cast<uint16_t*>(img + 4 * O::SH0 + 2 * ci) = h;
+      *reinterpret_cast<uint16_t*>(row + 4 * O::SH0 + 2 * ci) = h;
+    }
+  }
+  return 0;
+}
+
 // The words of build_row to the int8 row at `row` (rows are FR = 2 (mod 4) bytes long: odd rows
 // start on a half word).
 template <int R>
@@ -365,7 +438,7 @@ __device__ __forceinline__ uint8_t emit_row(const RwareConst& c, const uint8_t* 
 // slots of this step (index env, env * A + g).  Returns through the references whether the env must
 // be regenerated, whether the terminal observation needs the exact grid replay, and the (old cell,
 // new cell, moved) words of all agents.
-template <int G, bool VALIDATED = false>
+template <int G, bool VALIDATED = false, class P = PrngInline>
 __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, int g, unsigned gmask,
                                            bool active, bool agent, int act, int env,
                                            int auto_reset, float* __restrict__ reward,
@@ -462,12 +535,13 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
     const uint32_t* k = reinterpret_cast<const uint32_t*>(rec + c.off_key);
     key = Key{k[0], k[1]};
   }
+#pragma unroll 1
   for (int gi = 0; gi < 2; ++gi) {
     const int sid = cells[c.goal[gi]];
     if (active && sid != 0 && requested(c, rec, sid - 1)) {
       Key rkey, unused, sub;
-      split2(key, key, rkey);
-      split2(rkey, unused, sub);
+      P::split(key, key, rkey);
+      P::split(rkey, unused, sub);
       const int msize = c.n - c.Q;
       unsigned long long best = ~0ull;
       for (int s = g; s < c.n; s += G) {
@@ -480,7 +554,7 @@ __device__ __forceinline__ void step_group(const RwareConst& c, uint8_t* rec, in
         }
         if (!inq) {
           const int p = s - below;  // position in the sorted not-in-queue list
-          const uint32_t b = random_bits_at(sub, (uint32_t)p, (uint32_t)msize);
+          const uint32_t b = P::bits_at(sub, (uint32_t)p, (uint32_t)msize);
           const unsigned long long v =
               ((unsigned long long)b << 32) | ((unsigned long long)p << 16) | (unsigned)s;
           best = v < best ? v : best;

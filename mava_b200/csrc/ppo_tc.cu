@@ -764,16 +764,26 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       // paths: fetched here, in flight during the forward pass
       LossIn li{};
       float g_norm_adv = 0.0f;  // (advantage - mean) / (std + 1e-8) of this row's replica (actor)
-      if (L.q == 0 && prefetch) {
+      // this tile's loss inputs were published by the loader warps during the previous tile (its
+      // BAR_FULL): they are unpacked, and the advantage normalised, while layer 2 is in the tensor
+      // pipe -- not here, where layer 1 is already waiting, nor between the head GEMM and dZ3
+      auto unpack_loss_inputs = [&]() {
         li.valid = row0 + L.r < M;
         li.j = li.valid ? tile * spt + r_j : 0;
-        // this tile's loss inputs were published by the loader warps during the previous tile (its
-        // BAR_FULL): unpack them here, off the path between the head GEMM and dZ3
         const uint32_t w0 = ctrl.lin[it & 1][L.r][0];
         li.mk = w0 & 0xffu;
         li.act = (int)(signed char)(w0 >> 8);
         li.f0[0] = __uint_as_float(ctrl.lin[it & 1][L.r][1]);
         li.f1[0] = __uint_as_float(ctrl.lin[it & 1][L.r][2]);
+      };
+      auto normalise_adv = [&]() {
+        int u = 0;  // replica of this minibatch position (at most 8: no division)
+#pragma unroll
+        for (int k = 1; k < 8; ++k) u += (k < p.num_replicas && li.j >= k * p.mb_size) ? 1 : 0;
+        g_norm_adv = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
+      };
+      if (L.q == 0 && prefetch) {
+        // (below, behind the layer-2 arrive)
       } else if (L.q == 0 && cl) {
         li.valid = row0 + L.r < M;
         li.j = li.valid ? row0 + L.r : 0;
@@ -815,12 +825,7 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
           }
         }
       }
-      if (L.q == 0 && is_actor) {
-        int u = 0;  // replica of this minibatch position (at most 8: no division)
-#pragma unroll
-        for (int k = 1; k < 8; ++k) u += (k < p.num_replicas && li.j >= k * p.mb_size) ? 1 : 0;
-        g_norm_adv = (li.f1[0] - ctrl.adv_mean[u]) * ctrl.adv_isd[u];
-      }
+      if (L.q == 0 && is_actor && !prefetch) normalise_adv();
       MAVA_STAMP(2);
       // ---- forward
       wait_acc(&ctrl.mbar1, phase1);
@@ -829,6 +834,10 @@ __global__ void __launch_bounds__(NT_F, 1) ppo_fused_kernel(const TrainArgs p) {
       MAVA_STAMP(4);
       epi_arrive(rb);  // -> layer 2
       MAVA_STAMP(5);
+      if (L.q == 0 && prefetch) {
+        unpack_loss_inputs();
+        if (is_actor) normalise_adv();
+      }
       wait_acc(&ctrl.mbar, phase);
       hidden_epilogue(L, tmem + COL_ACC, h2t);  // X is dead (not folded): H2 replaces it
       epi_arrive(rb);  // -> head

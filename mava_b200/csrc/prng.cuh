@@ -82,6 +82,50 @@ __host__ __device__ __forceinline__ void random_bits_pair(Key k, uint32_t p, uin
   threefry2x32(k, p, c1, lo, hi);
 }
 
+// How a device function that draws random bits wants the Threefry block emitted: inline
+// (throughput kernels) or as ONE out-of-line copy per kernel (latency-bound kernels, where the
+// instruction footprint of ~110 instructions per block, several blocks per draw, costs more in
+// instruction-cache misses than a call).
+#ifdef __CUDACC__
+struct PrngInline {
+  static __device__ __forceinline__ void split(Key k, Key& first, Key& second) {
+    split2(k, first, second);
+  }
+  static __device__ __forceinline__ uint32_t bits_at(Key k, uint32_t i, uint32_t size) {
+    return random_bits_at(k, i, size);
+  }
+  static __device__ __forceinline__ void bits_pair(Key k, uint32_t p, uint32_t size, uint32_t& lo,
+                                                   uint32_t& hi) {
+    random_bits_pair(k, p, size, lo, hi);
+  }
+};
+struct PrngCall {
+  static __device__ __noinline__ uint2 block(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+    uint32_t o0, o1;
+    threefry2x32(Key{k0, k1}, x0, x1, o0, o1);
+    return make_uint2(o0, o1);
+  }
+  static __device__ __forceinline__ void split(Key k, Key& first, Key& second) {
+    const uint2 a = block(k.k0, k.k1, 0u, 2u), b = block(k.k0, k.k1, 1u, 3u);
+    first = Key{a.x, b.x};
+    second = Key{a.y, b.y};
+  }
+  static __device__ __forceinline__ void bits_pair(Key k, uint32_t p, uint32_t size, uint32_t& lo,
+                                                   uint32_t& hi) {
+    const uint32_t half = (size + 1u) >> 1;
+    const uint2 y = block(k.k0, k.k1, p, (p + half < size) ? p + half : 0u);
+    lo = y.x;
+    hi = y.y;
+  }
+  static __device__ __forceinline__ uint32_t bits_at(Key k, uint32_t i, uint32_t size) {
+    const uint32_t half = (size + 1u) >> 1;
+    uint32_t lo, hi;
+    bits_pair(k, i < half ? i : i - half, size, lo, hi);
+    return i < half ? lo : hi;
+  }
+};
+#endif
+
 // jax.random.uniform(minval=tiny, maxval=1) then gumbel = -log(-log(u)).
 __device__ __forceinline__ float bits_to_gumbel(uint32_t bits) {
   const float tiny = 1.17549435e-38f;
