@@ -238,18 +238,21 @@ int mava_clip_adam_pair_pack(float* params, float* mu, float* nu, int32_t* count
  * NVSwitch) -> clip_by_global_norm -> adam -> apply_updates -> bf16 image refresh -> loss metrics.
  *
  * Every rank of the node owns ONE exchange buffer: [n_grad floats: actor grads | critic grads |
- * 8 loss scalars][flag block].  mava_peer_alloc creates it (cudaMalloc, zeroed) and returns the
- * 64-byte CUDA IPC handle the host layer sends to the other ranks (torch.distributed /
- * MPI / a pipe - not this library's business); mava_peer_open maps a peer's buffer.  The loss kernels
- * write their gradients straight into the rank's own buffer (grad_out = buf), so nothing is copied.
- * Each rank adds the W vectors in rank order: all ranks obtain bit-identical sums, like the
- * reference's psum.  Flag handshakes inside the kernel order "gradients complete" before the reads
- * and "everybody has read" before the kernel ends (the buffer may be overwritten right after it).
- * A handshake that does not complete within 2 s raises the buffer's error word (mava_peer_status)
- * instead of hanging the device.  world == 1 degenerates to clip + Adam on buf[0], which must still
- * be a mava_peer_alloc buffer: the kernel keeps its call counter, its grid-barrier word and the two
- * squared-norm accumulators in the flag block (no device-global scratch: re-entrant across learners
- * and streams). */
+ * 8 loss scalars][flag block][receive area: 2 call parities x 8 source ranks x 128-byte lines].
+ * mava_peer_alloc creates it (cudaMalloc, zeroed) and returns the 64-byte CUDA IPC handle the host
+ * layer sends to the other ranks (torch.distributed / MPI / a pipe - not this library's business);
+ * mava_peer_open maps a peer's buffer.  The loss kernels write their gradients straight into the
+ * rank's own buffer (grad_out = buf), so nothing is copied.  Inside the kernel every rank pushes its
+ * vector into its slot of every peer's receive area as 128-byte lines that carry the call number
+ * (one one-way NVLink traversal, no flag round trip; slots double buffered by call parity, so the
+ * rank may overwrite its gradients right after the call), then adds the W vectors in rank order:
+ * all ranks obtain bit-identical sums, like the reference's psum.  Environment MAVA_PEER_PULL=1
+ * selects the checker protocol instead (flag handshake, peers' vectors read over NVLink, second
+ * handshake).  Lines / flags that do not arrive within 2 s raise the buffer's error word
+ * (mava_peer_status) instead of hanging the device.  All ranks must make the same sequence of calls.
+ * world == 1 degenerates to clip + Adam on buf[0], which must still be a mava_peer_alloc buffer: the
+ * kernel keeps its call counter, its grid-barrier word and the two squared-norm accumulators in the
+ * flag block (no device-global scratch: re-entrant across learners and streams). */
 #define MAVA_PEER_MAX_RANKS 8
 typedef struct mava_peer_group {
   int32_t rank, world;

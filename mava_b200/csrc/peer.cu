@@ -6,18 +6,27 @@
 // and the next minibatch any more.
 //
 // Every rank owns one exchange buffer (cudaMalloc + cudaIpc, mapped by all ranks of the node over
-// NVLink / NVSwitch): its gradient vector followed by a flag block.  One-shot all-reduce: after a
-// flag handshake ("my gradients are complete") every rank READS the vectors of all ranks and adds
-// them in rank order 0..W-1, so all ranks hold bit-identical sums (the replicated parameters stay
-// replicated), 7 x 307 KB per rank and minibatch for the headline networks.  A second handshake at
-// the end of the kernel ("I have read yours") lets a rank overwrite its buffer as soon as the
-// kernel is done: one buffer, no parity games with the host-side schedule.
+// NVLink / NVSwitch): its gradient vector, a flag block and a receive area.  One-shot all-reduce,
+// PUSH protocol (default): every rank writes its vector into its slot of every peer's receive area
+// as 128-byte lines of seven 16-byte data chunks + one chunk that carries the call number -- the
+// eight lanes that own a line store it with one coalesced 128-byte write, which NVLink delivers
+// whole, so a receiver that reads the line back (one coalesced 128-byte read) and finds the call
+// number it expects has the data too: no separate flag, no fence, no round trip -- one one-way
+// NVLink traversal between "my gradients are complete" and "I hold everybody's" (NCCL's LL128 idea).
+// Every rank then adds the vectors in rank order 0..W-1, so all ranks hold bit-identical sums (the
+// replicated parameters stay replicated).  The slots are double buffered by call parity: a rank
+// pushes call k+2 only after it has completed call k+1, for which it needed every peer's push of
+// k+1, which a peer issues after it has consumed call k -- so nothing is overwritten before it is
+// read and there is no "I have read yours" handshake either.
+// PULL protocol (MAVA_PEER_PULL=1, the checker): flag handshake ("my gradients are complete"), every
+// rank READS the vectors of all ranks, second handshake ("I have read yours").
 //
 // The kernel is a cooperative launch of up to 128 small CTAs (all co-resident): the squared global
 // norms are combined through two fp64 accumulators and one grid barrier, both kept in the rank's own
 // flag block, so the kernel is re-entrant across learners and streams (no device-global scratch).
 // Peer handshakes give up after 2 s and raise the buffer's error word instead of hanging the
 // device (a rank that died, a mismatched call sequence).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -38,9 +47,17 @@ constexpr int F_ERR = 2 * kMaxRanks + 1;  // != 0: a handshake timed out (local)
 constexpr int F_GRID = 2 * kMaxRanks + 2;  // arrivals at the kernel's grid barrier, ever growing (local)
 constexpr int F_NORM = 2 * kMaxRanks + 4;  // 2 x 2 doubles: squared norms of call parity 0 / 1 (local)
 constexpr int F_WORDS = 32;
+constexpr int kLineData = 7;  // 16-byte data chunks per 128-byte line of the receive area
 
 __host__ __device__ inline int64_t grad_bytes_padded(int64_t n_grad) {
   return (n_grad * 4 + 255) / 256 * 256;
+}
+// receive area: [parity 0 | 1][source rank 0 .. kMaxRanks) slots of `lines` 128-byte lines
+__host__ __device__ inline int64_t recv_lines(int64_t n_grad) {
+  return ((n_grad + 3) / 4 + kLineData - 1) / kLineData;
+}
+__host__ __device__ inline int64_t recv_offset(int64_t n_grad) {
+  return grad_bytes_padded(n_grad) + 256;  // behind the flag block, 128-byte aligned
 }
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -58,6 +75,19 @@ __device__ __forceinline__ float4 ld_sys_f4(const float* p) {
                : "l"(p)
                : "memory");
   return v;
+}
+__device__ __forceinline__ uint4 ld_sys_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_u4(void* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ float ld_sys_f(const float* p) {
   float v;
@@ -80,12 +110,31 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t seq) {
   return true;
 }
 
+// Phase timing (development aid, -DMAVA_PEER_STAMPS, scripts/exp_peer_stamps.sh): thread 0 of CTA 0
+// accumulates globaltimer deltas of the kernel's phases over the calls.
+#ifdef MAVA_PEER_STAMPS
+__device__ unsigned long long g_peer_ns[8];
+#define MAVA_PSTAMP(k)                                                  \
+  do {                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                          \
+      const unsigned long long now_ = global_ns();                      \
+      g_peer_ns[k] += now_ - pst_;                                      \
+      pst_ = now_;                                                      \
+    }                                                                   \
+  } while (0)
+#else
+#define MAVA_PSTAMP(k) do { } while (0)
+#endif
+
 struct ReduceAdamArgs {
   float *params, *mu, *nu;
   int32_t* counts;
   const float* grad[kMaxRanks];  // this rank's mapping of every rank's gradient vector
   uint32_t* flags[kMaxRanks];    // ... and of every rank's flag block (world > 1)
   uint32_t* local_flags;         // this rank's flag block (world == 1: a block owned by the library)
+  unsigned char* recv[kMaxRanks];  // ... and of every rank's receive area (push protocol)
+  int64_t lines;                 // 128-byte lines per slot
+  int push;                      // 1: push protocol, 0: pull
   int rank, world;
   float* gsum;  // local scratch, n[0] + n[1] floats: the reduced, scaled gradients
   int64_t n[2];
@@ -133,7 +182,7 @@ __device__ __forceinline__ void grid_arrive_wait(uint32_t* counter, uint32_t tar
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const ReduceAdamArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const ReduceAdamArgs a) {
   const int t = threadIdx.x;
   const int64_t tid = (int64_t)blockIdx.x * kThreads + t;
   const int64_t nthreads = (int64_t)gridDim.x * kThreads;
@@ -144,38 +193,16 @@ __global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const Reduce
   const uint32_t calls = my_flags[F_SEQ];  // calls completed on this flag block
   const uint32_t seq = calls + 1u;
   double* norm2 = reinterpret_cast<double*>(my_flags + F_NORM) + 2 * (seq & 1u);
+#ifdef MAVA_PEER_STAMPS
+  unsigned long long pst_ = global_ns();
+  if (blockIdx.x == 0 && t == 0) g_peer_ns[7] += 1;
+#endif
 
-  // ---- handshake 1: every rank's gradients of this call are complete ---------------------------
-  if (a.world > 1) {
-    if (blockIdx.x == 0 && t < a.world && t != a.rank) {
-      __threadfence_system();
-      st_release_sys(a.flags[t] + F_READY + a.rank, seq);
-    }
-    if (t < a.world && t != a.rank) {
-      if (!wait_flag(my_flags + F_READY + t, seq)) my_flags[F_ERR] = 1u;
-    }
-    __syncthreads();
-  }
-
-  // ---- sum over ranks (rank order), scale, squared norms per network ----------------------------
   const int64_t n0 = a.n[0], n01 = a.n[0] + a.n[1], n_all = n01 + 8;
-  const int64_t chunks = n_all >> 2;  // the buffers are padded: n_all floats are always readable
+  const int64_t chunks = (n_all + 3) >> 2;  // the buffers are padded: whole chunks are always readable
   float ss[2] = {0.0f, 0.0f};
-  for (int64_t c = tid; c < chunks; c += nthreads) {
-    float4 s;
-    if (a.world > 1) {
-      // all ranks' chunks in flight at once (an NVLink round trip is ~2 us), added in rank order
-      float4 v[kMaxRanks];
-#pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) v[r] = ld_sys_f4(a.grad[r] + 4 * c);
-      s = v[0];
-#pragma unroll
-      for (int r = 1; r < kMaxRanks; ++r)
-        if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-    } else {
-      s = *reinterpret_cast<const float4*>(a.grad[0] + 4 * c);
-    }
+  // one reduced chunk: scale, keep, squared norms, loss metrics
+  auto take = [&](int64_t c, float4 s) {
     float g[4] = {s.x * a.grad_scale, s.y * a.grad_scale, s.z * a.grad_scale, s.w * a.grad_scale};
     if (4 * c + 4 <= n01) *reinterpret_cast<float4*>(a.gsum + 4 * c) = make_float4(g[0], g[1], g[2], g[3]);
 #pragma unroll
@@ -189,19 +216,106 @@ __global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const Reduce
         a.loss_out[i - n01] = g[j];
       }
     }
-  }
-  for (int64_t i = 4 * chunks + tid; i < n_all; i += nthreads) {  // tail (n_all not a multiple of 4)
-    float s = a.world > 1 ? ld_sys_f(a.grad[0] + i) : a.grad[0][i];
-    for (int r = 1; r < a.world; ++r) s += ld_sys_f(a.grad[r] + i);
-    const float g = s * a.grad_scale;
-    if (i < n01) {
-      a.gsum[i] = g;
-      const int net = i < n0 ? 0 : 1;
-      ss[net] = fmaf(g, g, ss[net]);
-    } else if (i < n01 + 5 && a.loss_out != nullptr) {
-      a.loss_out[i - n01] = g;
+  };
+  if (a.world > 1 && a.push) {
+    // ---- push: my vector into my slot of every peer's receive area, 128-byte lines -------------
+    const int sub = t & 7;                       // chunk of the line this lane owns (7: call number)
+    const int64_t grp = tid >> 3, ngrp = nthreads >> 3;
+    const int64_t slot_bytes = a.lines * 128;
+    const int64_t my_slot = ((int64_t)(seq & 1u) * kMaxRanks + a.rank) * slot_bytes;
+    for (int64_t line = grp; line < a.lines; line += ngrp) {
+      const int64_t c = line * kLineData + sub;
+      uint4 w = make_uint4(seq, seq, seq, seq);
+      if (sub < kLineData) {
+        w = make_uint4(0u, 0u, 0u, 0u);
+        if (c < chunks) w = *reinterpret_cast<const uint4*>(a.grad[a.rank] + 4 * c);
+      }
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < a.world && r != a.rank) st_sys_u4(a.recv[r] + my_slot + line * 128 + sub * 16, w);
+    }
+    MAVA_PSTAMP(0);
+    // ---- receive: every peer's line must carry this call's number; sum in rank order -------------
+    const unsigned char* mine = a.recv[a.rank] + (int64_t)(seq & 1u) * kMaxRanks * slot_bytes;
+    for (int64_t line0 = (tid >> 5) * 4; line0 < a.lines; line0 += (nthreads >> 5) * 4) {
+      const int64_t line = line0 + ((t & 31) >> 3);  // a warp takes four lines at a time
+      const bool live = line < a.lines;
+      const int64_t c = line * kLineData + sub;
+      uint4 v[kMaxRanks];
+      unsigned pending = 0u;  // peers whose line has not arrived yet
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < a.world && r != a.rank) pending |= 1u << r;
+      const unsigned long long t0 = global_ns();
+      for (uint32_t spins = 0;; ++spins) {
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (live && ((pending >> r) & 1u)) v[r] = ld_sys_u4(mine + r * slot_bytes + line * 128 + sub * 16);
+        unsigned still = 0u;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+          if (r < a.world && r != a.rank) {
+            const uint32_t tag = __shfl_sync(0xffffffffu, v[r].x, 7, 8);  // the line's eighth chunk
+            if (live && ((pending >> r) & 1u) && tag != seq) still |= 1u << r;
+          }
+        }
+        pending = still;
+        if (!__any_sync(0xffffffffu, pending != 0u)) break;
+        if ((spins & 255u) == 255u && global_ns() - t0 > 2000000000ull) {
+          my_flags[F_ERR] = 1u;
+          break;
+        }
+      }
+      if (live && sub < kLineData && c < chunks) {
+        float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+          if (r < a.world) {
+            float4 x;
+            if (r == a.rank) {
+              x = *reinterpret_cast<const float4*>(a.grad[a.rank] + 4 * c);
+            } else {
+              x = make_float4(__uint_as_float(v[r].x), __uint_as_float(v[r].y),
+                              __uint_as_float(v[r].z), __uint_as_float(v[r].w));
+            }
+            if (r == 0) s = x;
+            else { s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w; }
+          }
+        }
+        take(c, s);
+      }
+    }
+  } else {
+    // ---- pull, handshake 1: every rank's gradients of this call are complete ---------------------
+    if (a.world > 1) {
+      if (blockIdx.x == 0 && t < a.world && t != a.rank)
+        st_release_sys(a.flags[t] + F_READY + a.rank, seq);
+      if (t < a.world && t != a.rank) {
+        if (!wait_flag(my_flags + F_READY + t, seq)) my_flags[F_ERR] = 1u;
+      }
+      __syncthreads();
+    }
+    MAVA_PSTAMP(0);
+    // ---- sum over ranks (rank order) --------------------------------------------------------------
+    for (int64_t c = tid; c < chunks; c += nthreads) {
+      float4 s;
+      if (a.world > 1) {
+        // all ranks' chunks in flight at once (an NVLink round trip is ~2 us), added in rank order
+        float4 v[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < a.world) v[r] = ld_sys_f4(a.grad[r] + 4 * c);
+        s = v[0];
+#pragma unroll
+        for (int r = 1; r < kMaxRanks; ++r)
+          if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+      } else {
+        s = *reinterpret_cast<const float4*>(a.grad[0] + 4 * c);
+      }
+      take(c, s);
     }
   }
+  MAVA_PSTAMP(1);
   // fp32 partial sums per thread (a handful of elements), combined in fp64
   for (int o = 16; o > 0; o >>= 1) {
     ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
@@ -223,9 +337,10 @@ __global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const Reduce
   }
   // every CTA of this rank has consumed its share of the peers' buffers and posted its norms
   grid_arrive_wait(my_flags + F_GRID, seq * gridDim.x);
+  MAVA_PSTAMP(2);
 
   // ---- handshake 2, first half: tell the peers their buffers have been read ---------------------
-  if (a.world > 1 && blockIdx.x == 0 && t < a.world && t != a.rank)
+  if (a.world > 1 && !a.push && blockIdx.x == 0 && t < a.world && t != a.rank)
     st_release_sys(a.flags[t] + F_DONE + a.rank, seq);
 
   // ---- clip + Adam + apply (+ bf16 image refresh); every thread re-reads what it wrote ----------
@@ -291,9 +406,10 @@ __global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const Reduce
     store_image(a, net, i - (net ? n0i : 0), pn);
   }
 
+  MAVA_PSTAMP(3);
   // ---- handshake 2, second half: nobody reads this rank's buffer any more -----------------------
   if (blockIdx.x == 0) {
-    if (a.world > 1 && t < a.world && t != a.rank) {
+    if (a.world > 1 && !a.push && t < a.world && t != a.rank) {
       if (!wait_flag(my_flags + F_DONE + t, seq)) my_flags[F_ERR] = 1u;
     }
     __syncthreads();
@@ -307,15 +423,27 @@ __global__ void __launch_bounds__(kThreads) reduce_clip_adam_kernel(const Reduce
       my_flags[F_SEQ] = seq;
     }
   }
+  MAVA_PSTAMP(4);
 }
 
 }  // namespace
 
 extern "C" {
 
+#ifdef MAVA_PEER_STAMPS
+int mava_debug_peer_stamps(unsigned long long* out8_host, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8_host, g_peer_ns, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && reset) {
+    const unsigned long long z[8] = {};
+    e = cudaMemcpyToSymbol(g_peer_ns, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
+
 int64_t mava_peer_buffer_bytes(int64_t n_grad) {
   if (n_grad <= 0) return -1;
-  return grad_bytes_padded(n_grad) + F_WORDS * 4;
+  return recv_offset(n_grad) + 2 * kMaxRanks * recv_lines(n_grad) * 128;
 }
 
 int mava_peer_alloc(int64_t bytes, void** buf_out, void* ipc_handle64_host) {
@@ -402,6 +530,14 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
     a.flags[r] = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(group_host->buf[r]) +
                                              grad_bytes_padded(n_grad));
   }
+  static_assert(F_WORDS * 4 <= 256, "flag block fits in front of the receive area");
+  for (int r = 0; r < a.world; ++r)
+    a.recv[r] = static_cast<unsigned char*>(group_host->buf[r]) + recv_offset(n_grad);
+  a.lines = recv_lines(n_grad);
+  {
+    const char* pull = getenv("MAVA_PEER_PULL");  // read per call: the tests compare both protocols
+    a.push = (pull != nullptr && pull[0] == '1') ? 0 : 1;
+  }
   a.local_flags = a.flags[a.rank];
   a.gsum = gsum;
   a.n[0] = n_actor; a.n[1] = n_critic;
@@ -424,7 +560,7 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
     }
   }
   const int64_t chunks = (n_grad + 3) / 4;
-  int ctas = (int)ceil_div64(chunks, kThreads);
+  int ctas = (int)ceil_div64(a.world > 1 && a.push ? a.lines * 8 : chunks, kThreads);
   ctas = ctas < 1 ? 1 : (ctas > kMaxCtas ? kMaxCtas : ctas);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)ctas);

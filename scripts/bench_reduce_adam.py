@@ -68,6 +68,25 @@ def main():
             2.5e-4, 0.5, 0, 1, loss))
         seq, err = grp.status()
         assert err == 0, (seq, err)
+        import ctypes
+        from mava_b200 import _lib as _l
+        raw = ctypes.CDLL(str(_l.LIB_PATH))
+        if hasattr(raw, "mava_debug_peer_stamps"):  # built with -DMAVA_PEER_STAMPS
+            buf = (ctypes.c_ulonglong * 8)()
+            raw.mava_debug_peer_stamps(buf, 1)
+            torch.cuda.synchronize()
+            fn = lambda: native.reduce_clip_adam_pair(
+                params, mu, nu, counts, grp, gsum, na, nc, actor, ai, critic, ci, 1.0 / world, 2.5e-4,
+                2.5e-4, 0.5, 0, 1, loss)
+            dist.barrier()
+            for _ in range(256):
+                fn()
+            torch.cuda.synchronize()
+            raw.mava_debug_peer_stamps(buf, 0)
+            nn = max(int(buf[7]), 1)
+            names = ["ready handshake", "peer reads + sum", "norm + grid barrier", "adam", "done handshake"]
+            print("PEER_STAMPS rank", rank, "calls", nn,
+                  {k: round(buf[i] / nn / 1e3, 2) for i, k in enumerate(names)}, flush=True)
 
         def nccl_path():
             dist.all_reduce(local.grad)

@@ -93,10 +93,15 @@ def test_reduce_clip_adam_world1(lib_built, big_grads):
     grp.release()
 
 
+@pytest.mark.parametrize("pull", [0, 1], ids=["push", "pull"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_reduce_clip_adam_ranks_as_streams(lib_built, world):
+def test_reduce_clip_adam_ranks_as_streams(lib_built, world, pull, monkeypatch):
     from mava_b200 import native
     from mava_b200.peer import PeerGroup
+
+    # both exchange protocols of csrc/peer.cu: lines pushed into the peers' receive areas (default)
+    # and the flag handshake + peer reads it is checked against
+    monkeypatch.setenv("MAVA_PEER_PULL", str(pull))
 
     # world 8: eight cooperative grids must be co-resident on ONE GPU here (register file: 592 CTAs
     # of this kernel), so the eight-rank case runs on half-size vectors (2 agents, 32 features)
@@ -120,7 +125,8 @@ def test_reduce_clip_adam_ranks_as_streams(lib_built, world):
         for r in range(world):
             with torch.cuda.stream(streams[r]):
                 # the rank overwrites its buffer right after the previous call on ITS stream: legal
-                # only because that call ended after every peer had read the buffer
+                # because only the rank itself reads it (push), or because that call ended after
+                # every peer had read it (pull)
                 groups[r].grad.copy_(dgrads[k][r], non_blocking=True)
                 native.reduce_clip_adam_pair(st[r]["p"], st[r]["mu"], st[r]["nu"], st[r]["c"],
                                              groups[r], st[r]["gsum"], na, nc, None, None, None,
