@@ -423,33 +423,51 @@ def run_ours(args) -> None:
     clocks = sampler.stop()
 
     # ---- end to end through the public API: learn(state) + host copies each step ---------------
-    host_params = torch.empty_like(L.params, device="cpu").pin_memory()
-    host_opt = torch.empty(2 * L.params.numel(), dtype=torch.float32).pin_memory()
-    host_key = torch.empty(2, dtype=torch.uint32).pin_memory()
-    host_params.copy_(L.params)
-    host_opt[: L.params.numel()].copy_(L.mu)
-    host_opt[L.params.numel():].copy_(L.nu)
-    host_key.copy_(L.key)
-    pin_loss = torch.empty(4, 1, L.epochs, L.nmb).pin_memory()
-    h2d = (host_params.numel() + host_opt.numel()) * 4 + 8
-    d2h = 10 * 8 + pin_loss.numel() * 4  # finished-episode statistics (device reduction) + losses
-    def e2e_step():
-        # host -> device: the replicated learner inputs (params, optimiser moments, key)
-        L.params.copy_(host_params, non_blocking=True)
-        L.mu.copy_(host_opt[: L.params.numel()], non_blocking=True)
-        L.nu.copy_(host_opt[L.params.numel():], non_blocking=True)
-        L.key.copy_(host_key, non_blocking=True)
-        out = learn(state)
-        # device -> host: what run_experiment consumes (episode statistics + train metrics), then the
-        # parameters back
-        for i, k2 in enumerate(("total_loss", "value_loss", "actor_loss", "entropy")):
-            pin_loss[i].copy_(out.train_metrics[k2], non_blocking=True)
-        host_params.copy_(L.params, non_blocking=True)
-        host_opt[: L.params.numel()].copy_(L.mu, non_blocking=True)
-        host_opt[L.params.numel():].copy_(L.nu, non_blocking=True)
-        host_key.copy_(L.key, non_blocking=True)
-        episode_summary(L)  # 80 bytes, synchronises the stream
-        torch.cuda.synchronize(device)
+    blob = getattr(L, "state_blob", None)  # params | Adam moments | key in one allocation
+    if blob is not None:
+        host_blob = torch.empty_like(blob, device="cpu").pin_memory()
+        host_blob.copy_(blob)
+        h2d = blob.numel() * 4
+        d2h = L.report.numel()  # episode statistics + sort flag + minibatch losses, read by learn()
+
+        def e2e_step():
+            # host -> device: the replicated learner inputs (params, optimiser moments, key)
+            blob.copy_(host_blob, non_blocking=True)
+            out = learn(state)  # ends with the device -> host copy of the report block + a sync
+            assert out.train_metrics["entropy"].shape[-2:] == L.loss_host.shape[:2]
+            # device -> host: the learner state back; what run_experiment logs is already there
+            host_blob.copy_(blob, non_blocking=True)
+            episode_summary(L)  # from the report block of this call: no further copy
+            torch.cuda.synchronize(device)
+    else:
+        host_params = torch.empty_like(L.params, device="cpu").pin_memory()
+        host_opt = torch.empty(2 * L.params.numel(), dtype=torch.float32).pin_memory()
+        host_key = torch.empty(2, dtype=torch.uint32).pin_memory()
+        host_params.copy_(L.params)
+        host_opt[: L.params.numel()].copy_(L.mu)
+        host_opt[L.params.numel():].copy_(L.nu)
+        host_key.copy_(L.key)
+        pin_loss = torch.empty(4, 1, L.epochs, L.nmb).pin_memory()
+        h2d = (host_params.numel() + host_opt.numel()) * 4 + 8
+        d2h = 10 * 8 + pin_loss.numel() * 4  # finished-episode statistics (device reduction) + losses
+
+        def e2e_step():
+            # host -> device: the replicated learner inputs (params, optimiser moments, key)
+            L.params.copy_(host_params, non_blocking=True)
+            L.mu.copy_(host_opt[: L.params.numel()], non_blocking=True)
+            L.nu.copy_(host_opt[L.params.numel():], non_blocking=True)
+            L.key.copy_(host_key, non_blocking=True)
+            out = learn(state)
+            # device -> host: what run_experiment consumes (episode statistics + train metrics), then
+            # the parameters back
+            for i, k2 in enumerate(("total_loss", "value_loss", "actor_loss", "entropy")):
+                pin_loss[i].copy_(out.train_metrics[k2], non_blocking=True)
+            host_params.copy_(L.params, non_blocking=True)
+            host_opt[: L.params.numel()].copy_(L.mu, non_blocking=True)
+            host_opt[L.params.numel():].copy_(L.nu, non_blocking=True)
+            host_key.copy_(L.key, non_blocking=True)
+            episode_summary(L)  # 80 bytes, synchronises the stream
+            torch.cuda.synchronize(device)
 
     for _ in range(3):  # warm-up of the host path (first pinned copies, allocator, metric code)
         e2e_step()

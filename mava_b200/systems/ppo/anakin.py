@@ -85,10 +85,16 @@ class FFLearner:
         dev, T, NE, A = device, self.T, self.NE, self.A
         z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
         # learner state
-        self.params = z(self.na + self.nc)
-        self.mu, self.nu = z(self.na + self.nc), z(self.na + self.nc)
+        # parameters | Adam moments | key live in ONE allocation: a host that keeps the learner state
+        # moves it with one copy each way (bench.py's end-to-end leg)
+        n_par = self.na + self.nc
+        n_pad = (n_par + 3) // 4 * 4  # the optimiser kernel wants 16-byte aligned vectors
+        self.state_blob = z(3 * n_pad + 4)
+        self.params = self.state_blob[:n_par]
+        self.mu = self.state_blob[n_pad:n_pad + n_par]
+        self.nu = self.state_blob[2 * n_pad:2 * n_pad + n_par]
+        self.key = self.state_blob[3 * n_pad:3 * n_pad + 2].view(torch.uint32)
         self.counts = z(2, dtype=torch.int32)
-        self.key = z(2, dtype=torch.uint32)
         self.env_buf = env.native.alloc_state(NE, dev)
         # rollout buffers (slot t holds the observation step t acts on; slot T the bootstrap obs)
         self.view = z(T + 1, NE, A, self.FR, dtype=torch.int8)
@@ -102,7 +108,13 @@ class FFLearner:
         self.ep_len = z(T, NE, dtype=torch.int32)
         self.adv, self.targets = z(T, NE, A), z(T, NE, A)
         # finished-episode statistics of the current learn() call, reduced on the device
-        self.ep_stats = z(10, dtype=torch.float64)
+        # ... in one small block with everything else the host reads after a learn() call (sort
+        # overflow flag, the minibatch losses): one device -> host copy, one synchronisation
+        n_loss = int(s.ppo_epochs) * int(s.num_minibatches) * 5
+        self.report = z(96 + 4 * n_loss, dtype=torch.uint8)
+        self.ep_stats = self.report[:80].view(torch.float64)
+        self._report_host = None
+        self._report_fresh = False
         self._stats_host = None
         # scratch
         self.policy_keys = z(T, 2, dtype=torch.uint32)
@@ -115,8 +127,7 @@ class FFLearner:
         self.perm_buf = z(int(s.ppo_epochs), 2, n_perm, dtype=torch.int32)
         self.key2_r = z(int(s.ppo_epochs), max(1, self.perm_rounds), 2, 2, dtype=torch.uint32)
         self.sort_ws = z(native.sort_workspace_bytes(n_perm), dtype=torch.uint8)
-        self.sort_overflow = z(1, dtype=torch.int32)
-        self._ovf_host = None
+        self.sort_overflow = self.report[80:84].view(torch.int32)
         self.key2 = z(2, 2, dtype=torch.uint32)
         self.bits = z(T * self.E, dtype=torch.uint32)
         self.rows = z(self.U * self.mb, dtype=torch.int32)
@@ -133,7 +144,7 @@ class FFLearner:
             PeerGroup(n_grad, dev, 0, 1, local_bufs=[self.peer.struct.buf[self.rank]])
         self.grad = self.peer.grad
         self.gsum = z(self.na + self.nc)
-        self.loss_buf = z(self.epochs, self.nmb, 5)
+        self.loss_buf = self.report[96:].view(torch.float32).view(self.epochs, self.nmb, 5)
         # precision: the bf16 tensor-core kernels need two hidden layers of width 128
         tc_ok = all(d.h1 == 128 and d.h2 == 128 and d.out_dim <= 16
                     for d in (self.actor_desc, self.critic_desc))
@@ -411,11 +422,14 @@ class FFLearner:
     def check_sort(self) -> None:
         """The permutation sort assumes uniform keys; a bucket overflow is raised by the learn()
         call that produced it (the flag is read after that call's work has drained)."""
-        if self._ovf_host is None:
-            self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self._ovf_host.copy_(self.sort_overflow, non_blocking=True)
+        if self._report_host is None:
+            self._report_host = torch.zeros_like(self.report, device="cpu").pin_memory()
+            self.loss_host = self._report_host[96:].view(torch.float32).view(self.epochs, self.nmb, 5)
+        # the flag travels with the finished-episode statistics and the losses of the call
+        self._report_host.copy_(self.report, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        if int(self._ovf_host[0]) != 0:
+        self._report_fresh = True
+        if int(self._report_host[80:84].view(torch.int32)[0]) != 0:
             raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
                                "parameters of this learn() call are not to be trusted")
         self.peer.check()  # a peer handshake of the fused all-reduce timed out
@@ -435,6 +449,7 @@ class FFLearner:
         dev, T, NE = self.device, self.T, self.NE
         if self.use_graph and self._graph is None:
             self._capture()
+        self._report_fresh = False
         native.episode_stats(None, None, None, 0, True, self.ep_stats)  # re-initialise
         single = num_updates == 1  # the rollout buffers themselves are the metrics: no copies
         if not single:
@@ -485,6 +500,9 @@ def episode_summary(learner) -> Tuple[Dict[str, Dict[str, float]], bool]:
         mnr, mxr = float(a[:, 3].min()), float(a[:, 4].max())
         sl, ql = float(a[:, 5].sum()), float(a[:, 6].sum())
         mnl, mxl = float(a[:, 7].min()), float(a[:, 8].max())
+    elif getattr(learner, "_report_fresh", False):
+        # check_sort() of the learn() call has already brought them over with the overflow flag
+        n, sr, qr, mnr, mxr, sl, ql, mnl, mxl, _ = learner._report_host[:80].view(torch.float64).tolist()
     else:
         learner._stats_host.copy_(learner.ep_stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -154,25 +154,39 @@ def test_bf16_stats_kernels_vs_fp64_autograd(lib_built, T, E, U, nmb, m):
     assert not bad, f"gradient blocks above the measured bf16 bars {BARS}: {bad}"
 
 
-def test_fused_rollout_vs_c_oracle_at_config2_shape(lib_built):
-    """BASELINE.json configs[1] shape: every env transition the fused rollout kernel produces is what
-    the C port of the oracle produces for the same actions (bit-exact, incl. auto-resets)."""
+@pytest.mark.parametrize("system,overrides,NE,T", [
+    ("ff_mappo", ["env/scenario=tiny-4ag", "arch.num_envs=1024", "system.update_batch_size=2",
+                  "system.rollout_length=128"], 2048, 128),                        # BASELINE.json configs[1]
+    ("ff_mappo", ["env/scenario=tiny-4ag", "arch.num_envs=4096", "system.update_batch_size=2",
+                  "system.rollout_length=24"], 8192, 24),                          # full 128-row tiles, 2 waves
+    ("ff_mappo", ["env/scenario=tiny-2ag", "arch.num_envs=1000", "system.update_batch_size=1",
+                  "system.rollout_length=32"], 1000, 32),                          # 2 agents, ragged last CTA
+    # (8 agents: the joint observation of a centralised critic is wider than the bf16 path takes)
+    ("ff_ippo", ["env/scenario=small-4ag", "env.scenario.task_config.num_agents=8",
+                 "arch.num_envs=300", "system.update_batch_size=1", "system.rollout_length=32"],
+     300, 32),
+], ids=["config2", "full-tiles", "2ag-ragged", "8ag"])
+def test_fused_rollout_vs_c_oracle_at_config2_shape(lib_built, system, overrides, NE, T):
+    """Every env transition the fused rollout kernel produces is what the C port of the oracle
+    produces for the same actions (bit-exact, incl. auto-resets) -- at the BASELINE.json configs[1]
+    shape and at the shapes that take the kernel's other paths (rows built by one thread / four
+    threads, CTAs with dead rows / full tiles, every env-lane group width)."""
     from mava_b200 import native, prng
     from mava_b200.config import compose
-    from mava_b200.systems.ppo import ff_mappo
+    from mava_b200.systems.ppo import ff_ippo, ff_mappo
     from mava_b200.utils import make_env
     from oracle import threefry as tf
     from oracle.rware_c import RwareC
 
     torch.cuda.set_device(0)
-    cfg = compose(ff_mappo.CONFIG_NAME, [
-        "env/scenario=tiny-4ag", "arch.num_envs=1024", "system.update_batch_size=2",
-        "system.rollout_length=128", "+arch.use_cuda_graph=False", "logger.use_console=False"])
-    env, _ = make_env.make(cfg, add_global_state=True)
+    mod = {"ff_mappo": ff_mappo, "ff_ippo": ff_ippo}[system]
+    cfg = compose(mod.CONFIG_NAME, overrides + [
+        "+arch.use_cuda_graph=False", "logger.use_console=False"])
+    env, _ = make_env.make(cfg, add_global_state=system == "ff_mappo")
     key, _, ak, ck = prng.split(prng.PRNGKey(21), 4)
-    learn, _, state = ff_mappo.learner_setup(env, (key, ak, ck), cfg)
+    learn, _, state = mod.learner_setup(env, (key, ak, ck), cfg)
     L = learn.learner
-    assert L.fused_rollout and L.NE == 2048 and L.T == 128
+    assert L.fused_rollout and L.NE == NE and L.T == T
 
     oc = RwareC(time_limit=int(cfg.env.kwargs.get("time_limit", 500)),
                 **dict(cfg.env.scenario.task_config))
@@ -197,7 +211,7 @@ def test_fused_rollout_vs_c_oracle_at_config2_shape(lib_built):
         np.testing.assert_array_equal(er[t], ret, err_msg=f"episode_return t={t}")
         np.testing.assert_array_equal(el[t], ln, err_msg=f"episode_length t={t}")
         n_done += int(d.sum())
-    assert n_done > L.NE  # the untrained policy collides: several auto-resets per env
+    assert n_done >= 32  # the untrained policy collides: auto-resets (spare copies) all along
     # sampled actions are legal under the mask the oracle produced for the same step
     legal = (masks[:L.T].astype(np.int32) >> act.astype(np.int32)) & 1
     assert legal.all()
