@@ -1,4 +1,6 @@
 // GAE reverse scan, minibatch row lists and the fused clip-by-global-norm + Adam step.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mlp_tc.cuh"  // layout of the packed bf16 weight images (clip_adam_pair_pack)
 
@@ -46,6 +48,64 @@ gae_kernel(const float* __restrict__ reward, const float* __restrict__ value,
         if (REC) next_nd = nd[u];
       }
     }
+  }
+}
+
+// The same scan for small problems (config 2: 8192 env-agents x 128 steps = 18 MB, where one thread per
+// env-agent leaves most SMs without a warp and every block of kU steps pays a DRAM round trip): a CTA
+// owns 32 env-agents; its four warps bring kTS time steps of reward / value / done into shared
+// memory with every load in flight at once, warp 0 walks them backwards (same arithmetic, same
+// order: bit-identical to gae_kernel), and the four warps write adv / targets back.
+constexpr int kGaeCols = 32, kGaeTS = 128, kGaeThreads = 128;
+template <bool REC>
+__global__ void __launch_bounds__(kGaeThreads)
+gae_tile_kernel(const float* __restrict__ reward, const float* __restrict__ value,
+                const uint8_t* __restrict__ done, const float* __restrict__ last_val,
+                const uint8_t* __restrict__ last_done, float gamma, float gamma_lambda, int T,
+                int num_envs, int A, float* __restrict__ adv, float* __restrict__ targets) {
+  __shared__ float s_r[kGaeTS][kGaeCols], s_v[kGaeTS][kGaeCols];  // in: reward, value; out: adv, targets
+  __shared__ float s_nd[kGaeTS][kGaeCols];
+  const int64_t n = (int64_t)num_envs * A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * kGaeCols + lane;
+  const bool ok = i < n;
+  const int e = ok ? (int)(i / A) : 0;
+  float gae = 0.0f, next_value = 0.0f, next_nd = 1.0f;
+  if (warp == 0 && ok) {
+    next_value = last_val[i];
+    if (REC) next_nd = last_done[e] ? 0.0f : 1.0f;
+  }
+  for (int t1 = T; t1 > 0; t1 -= kGaeTS) {
+    const int t0 = t1 > kGaeTS ? t1 - kGaeTS : 0, nt = t1 - t0;
+    for (int k = warp; k < nt; k += kGaeThreads / 32) {
+      const int t = t0 + k;
+      s_r[k][lane] = ok ? __ldg(reward + (int64_t)t * n + i) : 0.0f;
+      s_v[k][lane] = ok ? __ldg(value + (int64_t)t * n + i) : 0.0f;
+      s_nd[k][lane] = (ok && __ldg(done + (int64_t)t * num_envs + e)) ? 0.0f : 1.0f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 4
+      for (int k = nt - 1; k >= 0; --k) {
+        const float r = s_r[k][lane], v = s_v[k][lane], nd = s_nd[k][lane];
+        const float m = REC ? next_nd : nd;
+        const float delta = r + gamma * next_value * m - v;
+        gae = delta + gamma_lambda * m * gae;
+        s_r[k][lane] = gae;
+        s_v[k][lane] = gae + v;
+        next_value = v;
+        if (REC) next_nd = nd;
+      }
+    }
+    __syncthreads();
+    if (ok) {
+      for (int k = warp; k < nt; k += kGaeThreads / 32) {
+        const int t = t0 + k;
+        adv[(int64_t)t * n + i] = s_r[k][lane];
+        targets[(int64_t)t * n + i] = s_v[k][lane];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -376,6 +436,18 @@ int mava_gae(const float* reward, const float* value, const uint8_t* done, const
   const int blocks = (int)ceil_div64(n, 256);
   // gamma * gae_lambda is folded in double like the reference's Python floats (ff_mappo.py:127)
   const float gl = (float)((double)gamma * (double)gae_lambda);
+  const char* no_tile = getenv("MAVA_GAE_NO_TILE");  // development switch (sweep_gae.py compares)
+  if (n <= (int64_t)1 << 16 && !(no_tile && no_tile[0] == '1')) {
+    // small: spread over the SMs, stage through shared memory
+    const int tb = (int)ceil_div64(n, kGaeCols);
+    if (rec)
+      gae_tile_kernel<true><<<tb, kGaeThreads, 0, as_stream(s)>>>(
+          reward, value, done, last_val, last_done, gamma, gl, T, num_envs, num_agents, adv, targets);
+    else
+      gae_tile_kernel<false><<<tb, kGaeThreads, 0, as_stream(s)>>>(
+          reward, value, done, last_val, last_done, gamma, gl, T, num_envs, num_agents, adv, targets);
+    return launch_status();
+  }
   if (rec)
     gae_kernel<true><<<blocks, 256, 0, as_stream(s)>>>(reward, value, done, last_val, last_done,
                                                        gamma, gl, T, num_envs, num_agents, adv,

@@ -425,10 +425,20 @@ class FFLearner:
         if self._report_host is None:
             self._report_host = torch.zeros_like(self.report, device="cpu").pin_memory()
             self.loss_host = self._report_host[96:].view(torch.float32).view(self.epochs, self.nmb, 5)
-        # the flag travels with the finished-episode statistics and the losses of the call
+        # the flag travels with the finished-episode statistics and the losses of the call; with
+        # several ranks the statistics of all of them are gathered first (the reference reduces over
+        # the pmap output of all devices), so that the host waits once
+        gathered = self.world > 1 and self.allreduce is not None
+        if gathered:
+            if getattr(self, "_stats_all", None) is None:
+                self._stats_all = torch.zeros(self.world, 10, dtype=torch.float64, device=self.device)
+                self._stats_all_host = torch.zeros(self.world, 10, dtype=torch.float64).pin_memory()
+            dist.all_gather_into_tensor(self._stats_all, self.ep_stats)
+            self._stats_all_host.copy_(self._stats_all, non_blocking=True)
         self._report_host.copy_(self.report, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self._report_fresh = True
+        self._gather_fresh = gathered
         if int(self._report_host[80:84].view(torch.int32)[0]) != 0:
             raise RuntimeError("mava_sort_by_key: bucket overflow (non-uniform sort keys); the "
                                "parameters of this learn() call are not to be trusted")
@@ -449,7 +459,7 @@ class FFLearner:
         dev, T, NE = self.device, self.T, self.NE
         if self.use_graph and self._graph is None:
             self._capture()
-        self._report_fresh = False
+        self._report_fresh = self._gather_fresh = False
         native.episode_stats(None, None, None, 0, True, self.ep_stats)  # re-initialise
         single = num_updates == 1  # the rollout buffers themselves are the metrics: no copies
         if not single:
@@ -492,9 +502,10 @@ def episode_summary(learner) -> Tuple[Dict[str, Dict[str, float]], bool]:
             learner._stats_all = torch.zeros(learner.world, 10, dtype=torch.float64,
                                              device=learner.device)
             learner._stats_all_host = torch.zeros(learner.world, 10, dtype=torch.float64).pin_memory()
-        dist.all_gather_into_tensor(learner._stats_all, learner.ep_stats)
-        learner._stats_all_host.copy_(learner._stats_all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if not getattr(learner, "_gather_fresh", False):  # else: check_sort() of the call did it
+            dist.all_gather_into_tensor(learner._stats_all, learner.ep_stats)
+            learner._stats_all_host.copy_(learner._stats_all, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         a = learner._stats_all_host
         n, sr, qr = float(a[:, 0].sum()), float(a[:, 1].sum()), float(a[:, 2].sum())
         mnr, mxr = float(a[:, 3].min()), float(a[:, 4].max())

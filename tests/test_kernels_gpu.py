@@ -42,7 +42,10 @@ def test_split_and_chain_bit_exact(lib_built):
 
 
 @pytest.mark.parametrize("rec", [False, True])
-@pytest.mark.parametrize("T,NE,A", [(128, 33, 4), (5, 7, 2), (37, 129, 3)])
+# (small problems take the staged kernel -- 128-step chunks of 32 env-agents through shared memory --,
+#  more than 2^16 env-agents the one-thread-per-env-agent kernel)
+@pytest.mark.parametrize("T,NE,A", [(128, 33, 4), (5, 7, 2), (37, 129, 3), (300, 50, 3),
+                                    (128, 2048, 4), (16, 40000, 2)])
 def test_gae_matches_oracle(lib_built, rec, T, NE, A):
     from mava_b200 import native
 
