@@ -98,17 +98,16 @@ __device__ __forceinline__ bool requested(const RwareConst& c, const uint8_t* re
 
 // K smallest of the composites (random_bits(sub, size)[i] << 32 | i), i.e. the first K entries of
 // jax.random.permutation-by-stable-sort.  Every lane returns the same out[].
-template <int G, int KMAX, class P = PrngInline>
+// COMPACT: the two insertion passes and the K extraction rounds as rolled loops (a third of the
+// instructions; for kernels whose instruction footprint matters more than this function's speed).
+template <int G, int KMAX, class P = PrngInline, bool COMPACT = false>
 __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsigned gmask,
                                            unsigned long long (&out)[KMAX]) {
   unsigned long long top[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) top[j] = ~0ull;
   const int half = (size + 1) >> 1;
-  for (int p = g; p < half; p += G) {
-    uint32_t lo, hi;
-    P::bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
-    unsigned long long v = ((unsigned long long)lo << 32) | (unsigned)p;
+  auto insert = [&](unsigned long long v) {
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) {
       if (v < top[j]) {
@@ -117,37 +116,48 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
         v = t;
       }
     }
-    if (p + half < size) {
-      v = ((unsigned long long)hi << 32) | (unsigned)(p + half);
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (v < top[j]) {
-          unsigned long long t = top[j];
-          top[j] = v;
-          v = t;
-        }
+  };
+  for (int p = g; p < half; p += G) {
+    uint32_t lo, hi;
+    P::bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
+    if (COMPACT) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int idx = p + h * half;
+        if (idx < size) insert(((unsigned long long)(h ? hi : lo) << 32) | (unsigned)idx);
       }
+    } else {
+      insert(((unsigned long long)lo << 32) | (unsigned)p);
+      if (p + half < size) insert(((unsigned long long)hi << 32) | (unsigned)(p + half));
     }
   }
-#pragma unroll
-  for (int r = 0; r < KMAX; ++r) {
-    out[r] = ~0ull;
+  auto extract = [&](int r) {
+    unsigned long long mn = ~0ull;
     if (r < K) {
-      unsigned long long mn = group_min<G>(top[0], gmask);
+      mn = group_min<G>(top[0], gmask);
       if (top[0] == mn) {
 #pragma unroll
         for (int j = 0; j + 1 < KMAX; ++j) top[j] = top[j + 1];
         top[KMAX - 1] = ~0ull;
       }
-      out[r] = mn;
     }
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j == r) out[j] = mn;
+  };
+  if (COMPACT) {
+#pragma unroll 1
+    for (int r = 0; r < KMAX; ++r) extract(r);
+  } else {
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) extract(r);
   }
 }
 
 // jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
 // their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
 // lanes cooperate; State.key is what is left of `key`).
-template <int GG, class P = PrngInline>
+template <int GG, class P = PrngInline, bool COMPACT = false, int KA = kMaxAgents>
 __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
                                          unsigned gmask) {
   // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
@@ -164,18 +174,18 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
   P::split(q_key, unused, sub_q);
   const int my_dir =
       g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
-  unsigned long long pick[kMaxAgents];
-  smallest_k<GG, kMaxAgents, P>(sub_pos, c.HW, c.A, g, gmask, pick);
+  unsigned long long pick[KA];  // KA >= c.A
+  smallest_k<GG, KA, P, COMPACT>(sub_pos, c.HW, c.A, g, gmask, pick);
   if (g < c.A) {
     unsigned long long mine = 0ull;
 #pragma unroll
-    for (int i = 0; i < kMaxAgents; ++i)
+    for (int i = 0; i < KA; ++i)
       if (i == g) mine = pick[i];
     const int cell = (int)(mine & 0xffffffffull);
     reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(cell / c.W, cell % c.W, my_dir, 0);
   }
   unsigned long long qpick[kMaxQueue];
-  smallest_k<GG, kMaxQueue, P>(sub_q, c.n, c.Q, g, gmask, qpick);
+  smallest_k<GG, kMaxQueue, P, COMPACT>(sub_q, c.n, c.Q, g, gmask, qpick);
   uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
   for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
   __syncwarp(gmask);

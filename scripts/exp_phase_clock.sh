@@ -64,9 +64,9 @@ print("rollout kernel, cycles per phase of a step (CTA 0, steps 16..31):")
 for n_, v in zip(rn, np.diff(ra[:, :10], axis=1).mean(0)):
     print(f"  {n_:22s} {v:8.0f}")
 print(f"  {'regeneration + store':22s} {(ra[:, 12] - ra[:, 9]).mean():8.0f}")
-print("  inside 'reset + rows + X row': reset %.0f, wait for the row's warps %.0f, quarter row %.0f, wait %.0f + expand %.0f" %
+print("  inside 'reset + rows + X row': reset %.0f, wait for the quadrant's env steps %.0f, quarter row %.0f, wait for the other quarters %.0f, expand %.0f" %
       ((ra[:, 13] - ra[:, 7]).mean(), (ra[:, 14] - ra[:, 13]).mean(), (ra[:, 15] - ra[:, 14]).mean(),
-       0.0, (ra[:, 8] - ra[:, 15]).mean()))
+       (ra[:, 11] - ra[:, 15]).mean(), (ra[:, 8] - ra[:, 11]).mean()))
 print("  per step: total", np.diff(ra[:, 0]), " regeneration + store", ra[:, 12] - ra[:, 9])
 print("  step total (start->start):", np.diff(ra[:, 0]).mean())
 PY

@@ -3,7 +3,8 @@
 # step loop emitted in different ways (MAVA_ROLL_GEN x MAVA_ROLL_COLD, see csrc/rollout_tc.cu)
 cd "$(dirname "$0")/.."
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -I include"
-for cfg in ${@:-"0 0" "0 1" "1 0" "1 1" "2 0" "2 1"}; do
+if [ $# -eq 0 ]; then set -- "0 1" "1 0" "1 1" "3 1" "2 1"; fi
+for cfg in "$@"; do
   set -- $cfg
   nvcc $FLAGS -DMAVA_ROLL_GEN=$1 -DMAVA_ROLL_COLD=$2 $MAVA_EXTRA_FLAGS -c mava_b200/csrc/rollout_tc.cu -o mava_b200/build/rollout_tc.o || exit 1
   nvcc -shared -o mava_b200/libmava_b200.so mava_b200/build/*.o -lcudart || exit 1
