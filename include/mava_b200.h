@@ -277,6 +277,31 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
                                int lr_decay_num_updates, int steps_per_update, float* loss_out5,
                                mava_stream_t s);
 
+/* The pair above without three graph nodes per minibatch: mava_ppo_loss_grad_bf16_acc ADDS into
+ * grad_out and into the loss accumulators of its workspace (it clears nothing and does not finalise
+ * the loss metrics); mava_reduce_clip_adam_pair_acc computes the five loss scalars from those
+ * accumulators (loss_workspace = the loss call's workspace, loss_rows = num_replicas * mb_size *
+ * num_agents, hyper = the loss call's), and leaves the rank's gradient vector and the accumulators
+ * ZERO for the next minibatch.  Both start from zeroed buffers (mava_peer_alloc zeroes; zero the
+ * first 256 bytes of the workspace once).  Only with one rank or the push protocol (nobody else reads
+ * the rank's vector): MAVA_E_UNSUPPORTED under MAVA_PEER_PULL=1 with world > 1. */
+int mava_ppo_loss_grad_bf16_acc(const mava_mlp_desc* actor, const float* actor_params,
+                                const void* actor_image, const mava_mlp_desc* critic,
+                                const float* critic_params, const void* critic_image,
+                                const mava_ppo_hyper* hyper, const int8_t* view, const uint8_t* mask,
+                                const int8_t* action, const float* old_logp, const float* old_value,
+                                const float* adv, const float* targets, const int32_t* rows,
+                                int num_replicas, int mb_size, const double* adv_stats,
+                                float* grad_out, void* workspace, mava_stream_t stream);
+int mava_reduce_clip_adam_pair_acc(float* params, float* mu, float* nu, int32_t* counts,
+                                   const mava_peer_group* group_host, float* gsum, int64_t n_actor,
+                                   int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
+                                   const mava_mlp_desc* critic, void* critic_image,
+                                   float grad_scale, float lr_actor, float lr_critic, float max_norm,
+                                   int lr_decay_num_updates, int steps_per_update, float* loss_out5,
+                                   void* loss_workspace, const mava_ppo_hyper* hyper,
+                                   int64_t loss_rows, mava_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core path (tcgen05 + TMEM).  Same regions as mava_ff_act / mava_ppo_loss_grad with
  * bf16 operands and fp32 accumulation (tolerance 2e-2, BASELINE.json).  Requires h1 == h2 == 128.

@@ -129,6 +129,13 @@ SIGNATURES = {
     "mava_reduce_clip_adam_pair": (c_int, [c_void, c_void, c_void, c_void, P(PeerGroup), c_void,
                                            c_i64, c_i64, P(MlpDesc), c_void, P(MlpDesc), c_void,
                                            c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_void, c_void]),
+    "mava_reduce_clip_adam_pair_acc": (c_int, [c_void, c_void, c_void, c_void, P(PeerGroup), c_void,
+                                               c_i64, c_i64, P(MlpDesc), c_void, P(MlpDesc), c_void,
+                                               c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_void,
+                                               c_void, P(PpoHyper), c_i64, c_void]),
+    "mava_ppo_loss_grad_bf16_acc": (c_int, [P(MlpDesc), c_void, c_void, P(MlpDesc), c_void, c_void,
+                                            P(PpoHyper)] + [c_void] * 8 +
+                                    [c_int, c_int, c_void, c_void, c_void, c_void]),
     "mava_clip_adam": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32,
                                c_int, c_int, c_void]),
 }

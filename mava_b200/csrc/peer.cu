@@ -144,7 +144,39 @@ struct ReduceAdamArgs {
   unsigned char* image[2];
   int in_dim[2], k1p[2], out[2];
   float* loss_out;  // [5] or null: mean over ranks of the loss scalars behind the gradients
+  // accumulating pairing with mava_ppo_loss_grad_bf16_acc: the five loss scalars behind the
+  // gradients are computed here from the loss kernel's accumulators, and both the rank's gradient
+  // vector and the accumulators are left zero for the next minibatch
+  double* loss_acc;  // null: the scalars are in the buffer already, nothing is cleared
+  double loss_denom;
+  float ent_coef, vf_coef;
 };
+
+// element i of the rank's own [gradients | 5 loss scalars | pad] vector
+__device__ __forceinline__ float loss_scalar(const ReduceAdamArgs& a, int k) {
+  const double actor_loss = a.loss_acc[0] / a.loss_denom, entropy = a.loss_acc[1] / a.loss_denom,
+               value_loss = a.loss_acc[2] / a.loss_denom;
+  switch (k) {  // as finalize_loss_kernel (mlp_f32.cu)
+    case 0: return (float)(actor_loss - (double)a.ent_coef * entropy);
+    case 1: return (float)actor_loss;
+    case 2: return (float)entropy;
+    case 3: return (float)((double)a.vf_coef * value_loss);
+    case 4: return (float)value_loss;
+    default: return 0.0f;
+  }
+}
+__device__ __forceinline__ float4 own_chunk(const ReduceAdamArgs& a, int64_t c, int64_t n01) {
+  float4 v = *reinterpret_cast<const float4*>(a.grad[a.rank] + 4 * c);
+  if (a.loss_acc != nullptr && 4 * c + 4 > n01) {
+    float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = 4 * c + j;
+      if (i >= n01) f[j] = loss_scalar(a, (int)(i - n01));
+    }
+  }
+  return v;
+}
 
 struct AdamStep {  // per network: what every element of one call shares
   float g_norm, step_lr, bc1, bc2;
@@ -228,7 +260,11 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const Red
       uint4 w = make_uint4(seq, seq, seq, seq);
       if (sub < kLineData) {
         w = make_uint4(0u, 0u, 0u, 0u);
-        if (c < chunks) w = *reinterpret_cast<const uint4*>(a.grad[a.rank] + 4 * c);
+        if (c < chunks) {
+          const float4 f = own_chunk(a, c, n01);
+          w = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z),
+                         __float_as_uint(f.w));
+        }
       }
 #pragma unroll
       for (int r = 0; r < kMaxRanks; ++r)
@@ -273,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const Red
           if (r < a.world) {
             float4 x;
             if (r == a.rank) {
-              x = *reinterpret_cast<const float4*>(a.grad[a.rank] + 4 * c);
+              x = own_chunk(a, c, n01);
             } else {
               x = make_float4(__uint_as_float(v[r].x), __uint_as_float(v[r].y),
                               __uint_as_float(v[r].z), __uint_as_float(v[r].w));
@@ -310,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const Red
         for (int r = 1; r < kMaxRanks; ++r)
           if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
       } else {
-        s = *reinterpret_cast<const float4*>(a.grad[0] + 4 * c);
+        s = own_chunk(a, c, n01);
       }
       take(c, s);
     }
@@ -360,8 +396,11 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const Red
   // Whole 16-byte chunks: the four moments / parameters of a chunk are loaded together (no store
   // sits between the loads of a thread's elements), updated in registers and stored together.
   const int n0i = (int)n0, n01i = (int)n01;
+  float* own = const_cast<float*>(a.grad[a.rank]);
   for (int64_t c = tid; c < chunks; c += nthreads) {
     const int i0 = (int)(4 * c);
+    // every CTA is past the grid barrier: the rank's own vector has been consumed
+    if (a.loss_acc != nullptr) *reinterpret_cast<float4*>(own + i0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (i0 + 4 <= n01i) {
       const float4 g4 = *reinterpret_cast<const float4*>(a.gsum + i0);
       float4 m4 = *reinterpret_cast<const float4*>(a.mu + i0);
@@ -417,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_clip_adam_kernel(const Red
       // every CTA has passed the grid barrier, i.e. has read counts, F_SEQ and the norms of this call
       a.counts[0] = c0[0] + 1;
       a.counts[1] = c0[1] + 1;
+      if (a.loss_acc != nullptr) a.loss_acc[0] = a.loss_acc[1] = a.loss_acc[2] = 0.0;
       double* other = reinterpret_cast<double*>(my_flags + F_NORM) + 2 * ((seq + 1u) & 1u);
       other[0] = 0.0;  // the next call's accumulators (this call's are zeroed by the call after it)
       other[1] = 0.0;
@@ -500,13 +540,14 @@ int mava_peer_status(const void* buf, int64_t n_grad, uint32_t* seq_out_host, ui
   return 0;
 }
 
-int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts,
-                               const mava_peer_group* group_host, float* gsum, int64_t n_actor,
-                               int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
-                               const mava_mlp_desc* critic, void* critic_image, float grad_scale,
-                               float lr_actor, float lr_critic, float max_norm,
-                               int lr_decay_num_updates, int steps_per_update, float* loss_out5,
-                               mava_stream_t s) {
+static int reduce_clip_adam_impl(float* params, float* mu, float* nu, int32_t* counts,
+                                 const mava_peer_group* group_host, float* gsum, int64_t n_actor,
+                                 int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
+                                 const mava_mlp_desc* critic, void* critic_image, float grad_scale,
+                                 float lr_actor, float lr_critic, float max_norm,
+                                 int lr_decay_num_updates, int steps_per_update, float* loss_out5,
+                                 double* loss_acc, double loss_denom, float ent_coef, float vf_coef,
+                                 mava_stream_t s) {
   MAVA_CHECK_PTR(params);
   MAVA_CHECK_PTR(mu);
   MAVA_CHECK_PTR(nu);
@@ -539,6 +580,13 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
     a.push = (pull != nullptr && pull[0] == '1') ? 0 : 1;
   }
   a.local_flags = a.flags[a.rank];
+  // clearing the rank's vector is only legal when nobody else reads it (one rank, or push)
+  if (loss_acc != nullptr && a.world > 1 && !a.push) return MAVA_E_UNSUPPORTED;
+  MAVA_CHECK_ARG(loss_acc == nullptr || loss_denom > 0.0);
+  a.loss_acc = loss_acc;
+  a.loss_denom = loss_denom;
+  a.ent_coef = ent_coef;
+  a.vf_coef = vf_coef;
   a.gsum = gsum;
   a.n[0] = n_actor; a.n[1] = n_critic;
   a.lr[0] = lr_actor; a.lr[1] = lr_critic;
@@ -575,6 +623,38 @@ int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* cou
   cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_clip_adam_kernel, a);
   if (e != cudaSuccess) return (int)e;
   return launch_status();
+}
+
+int mava_reduce_clip_adam_pair(float* params, float* mu, float* nu, int32_t* counts,
+                               const mava_peer_group* group_host, float* gsum, int64_t n_actor,
+                               int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
+                               const mava_mlp_desc* critic, void* critic_image, float grad_scale,
+                               float lr_actor, float lr_critic, float max_norm,
+                               int lr_decay_num_updates, int steps_per_update, float* loss_out5,
+                               mava_stream_t s) {
+  return reduce_clip_adam_impl(params, mu, nu, counts, group_host, gsum, n_actor, n_critic, actor,
+                               actor_image, critic, critic_image, grad_scale, lr_actor, lr_critic,
+                               max_norm, lr_decay_num_updates, steps_per_update, loss_out5, nullptr,
+                               0.0, 0.0f, 0.0f, s);
+}
+
+int mava_reduce_clip_adam_pair_acc(float* params, float* mu, float* nu, int32_t* counts,
+                                   const mava_peer_group* group_host, float* gsum, int64_t n_actor,
+                                   int64_t n_critic, const mava_mlp_desc* actor, void* actor_image,
+                                   const mava_mlp_desc* critic, void* critic_image,
+                                   float grad_scale, float lr_actor, float lr_critic, float max_norm,
+                                   int lr_decay_num_updates, int steps_per_update, float* loss_out5,
+                                   void* loss_workspace, const mava_ppo_hyper* hyper,
+                                   int64_t loss_rows, mava_stream_t s) {
+  MAVA_CHECK_PTR(loss_workspace);
+  MAVA_CHECK_PTR(hyper);
+  MAVA_CHECK_ARG(loss_rows > 0);
+  // the loss accumulators of mava_ppo_loss_grad_bf16_acc: three doubles at byte 128 of its workspace
+  double* acc = reinterpret_cast<double*>(static_cast<unsigned char*>(loss_workspace) + 128);
+  return reduce_clip_adam_impl(params, mu, nu, counts, group_host, gsum, n_actor, n_critic, actor,
+                               actor_image, critic, critic_image, grad_scale, lr_actor, lr_critic,
+                               max_norm, lr_decay_num_updates, steps_per_update, loss_out5, acc,
+                               (double)loss_rows, hyper->ent_coef, hyper->vf_coef, s);
 }
 
 }  // extern "C"

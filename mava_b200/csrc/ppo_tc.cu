@@ -1282,7 +1282,7 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
                                    const float* old_value, const float* adv, const float* targets,
                                    const int32_t* rows, int num_replicas, int mb_size,
                                    float* grad_out, void* workspace, const double* adv_stats,
-                                   mava_stream_t stream) {
+                                   mava_stream_t stream, bool acc = false) {
   TrainArgs a{};
   int rc = make_net(actor, actor_params, &a.actor);
   if (rc) return rc;
@@ -1338,10 +1338,14 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
   const int64_t ta = tile_count(actor, R), tcn = tile_count(critic, R);
   const int sms = sm_count();
 
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(grad_out, 0, (size_t)(na + nc + 8) * sizeof(float), s);
-  if (e != cudaSuccess) return (int)e;
+  // (accumulating variant: the caller's optimiser kernel left grad_out and the loss accumulators
+  //  zero, and finalises the loss metrics itself)
+  if (!acc) {
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(grad_out, 0, (size_t)(na + nc + 8) * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (!adv_stats) {
     rc = launch_adv_stats(adv, rows, mb_size, actor->num_agents, num_replicas, stats, s);
     if (rc) return rc;
@@ -1439,6 +1443,7 @@ static int ppo_loss_grad_bf16_impl(const mava_mlp_desc* actor, const float* acto
     rc = launch_status();
     if (rc) return rc;
   }
+  if (acc) return 0;
   return launch_finalize_loss(loss_acc, (double)R * actor->num_agents, hyper->ent_coef,
                               hyper->vf_coef, grad_out + na + nc, s);
 }
@@ -1482,6 +1487,21 @@ int mava_ppo_loss_grad_bf16_stats(const mava_mlp_desc* actor, const float* actor
                                  critic_image, hyper, view, mask, action, old_logp, old_value, adv,
                                  targets, rows, num_replicas, mb_size, grad_out, workspace, adv_stats,
                                  stream);
+}
+
+int mava_ppo_loss_grad_bf16_acc(const mava_mlp_desc* actor, const float* actor_params,
+                                const void* actor_image, const mava_mlp_desc* critic,
+                                const float* critic_params, const void* critic_image,
+                                const mava_ppo_hyper* hyper, const int8_t* view, const uint8_t* mask,
+                                const int8_t* action, const float* old_logp, const float* old_value,
+                                const float* adv, const float* targets, const int32_t* rows,
+                                int num_replicas, int mb_size, const double* adv_stats,
+                                float* grad_out, void* workspace, mava_stream_t stream) {
+  MAVA_CHECK_PTR(adv_stats);
+  return ppo_loss_grad_bf16_impl(actor, actor_params, actor_image, critic, critic_params,
+                                 critic_image, hyper, view, mask, action, old_logp, old_value, adv,
+                                 targets, rows, num_replicas, mb_size, grad_out, workspace, adv_stats,
+                                 stream, /*acc=*/true);
 }
 
 }  // extern "C"

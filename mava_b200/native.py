@@ -444,6 +444,30 @@ def ppo_loss_grad_bf16_stats(actor: MlpDesc, actor_params, actor_image, critic: 
         _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16_stats")
 
 
+def ppo_loss_grad_bf16_acc(actor: MlpDesc, actor_params, actor_image, critic: MlpDesc,
+                           critic_params, critic_image, hyper: PpoHyper, view, mask, action,
+                           old_logp, old_value, adv, targets, rows, num_replicas: int,
+                           mb_size: int, adv_stats, grad_out, workspace) -> None:
+    """ppo_loss_grad_bf16_stats that ADDS into ``grad_out`` and the loss accumulators of its
+    workspace (both left zero by ``reduce_clip_adam_pair_acc``): no memsets, no finalize launch."""
+    na, nc = mlp_param_count(actor), mlp_param_count(critic)
+    need = ppo_workspace_bytes_bf16(actor, critic, num_replicas * mb_size)
+    _count(2)  # fused fwd+bwd, first-layer wgrad
+    check(_lib.load().mava_ppo_loss_grad_bf16_acc(
+        C.byref(actor), _p(actor_params, torch.float32, na, "actor_params"),
+        _p(actor_image, torch.uint8, mlp_pack_bytes(actor), "actor_image"), C.byref(critic),
+        _p(critic_params, torch.float32, nc, "critic_params"),
+        _p(critic_image, torch.uint8, mlp_pack_bytes(critic), "critic_image"), C.byref(hyper),
+        _p(view, torch.int8, None, "view"), _p(mask, torch.uint8, None, "mask"),
+        _p(action, torch.int8, None, "action"), _p(old_logp, torch.float32, None, "old_logp"),
+        _p(old_value, torch.float32, None, "old_value"), _p(adv, torch.float32, None, "adv"),
+        _p(targets, torch.float32, None, "targets"),
+        _p(rows, torch.int32, num_replicas * mb_size, "rows"), num_replicas, mb_size,
+        _p(adv_stats, torch.float64, 16, "adv_stats"),
+        _p(grad_out, torch.float32, na + nc + 8, "grad_out"),
+        _p(workspace, torch.uint8, need, "workspace"), _stream()), "mava_ppo_loss_grad_bf16_acc")
+
+
 def clip_adam_pair(params, mu, nu, counts, grad, n_actor: int, n_critic: int, grad_scale: float,
                    lr_actor: float, lr_critic: float, max_norm: float,
                    lr_decay_num_updates: int = 0, steps_per_update: int = 1) -> None:
@@ -621,6 +645,29 @@ def rec_ppo_loss_grad(actor: RnnDesc, actor_params, critic: RnnDesc, critic_para
 # ---------------------------------------------------------------------------------------------
 # pmean("device") fused with the optimiser step (csrc/peer.cu)
 # ---------------------------------------------------------------------------------------------
+def reduce_clip_adam_pair_acc(params, mu, nu, counts, group, gsum, n_actor: int, n_critic: int,
+                              actor: Optional[MlpDesc], actor_image, critic: Optional[MlpDesc],
+                              critic_image, grad_scale: float, lr_actor: float, lr_critic: float,
+                              max_norm: float, lr_decay_num_updates: int, steps_per_update: int,
+                              loss_out, loss_workspace, hyper: PpoHyper, loss_rows: int) -> None:
+    """``reduce_clip_adam_pair`` paired with ``ppo_loss_grad_bf16_acc``: the loss metrics come from
+    the loss kernel's accumulators, and the rank's gradient vector and the accumulators are left
+    zero for the next minibatch."""
+    n = n_actor + n_critic
+    _count(1)
+    check(_lib.load().mava_reduce_clip_adam_pair_acc(
+        _p(params, torch.float32, n, "params"), _p(mu, torch.float32, n, "mu"),
+        _p(nu, torch.float32, n, "nu"), _p(counts, torch.int32, 2, "counts"),
+        C.byref(group.struct), _p(gsum, torch.float32, n, "gsum"), n_actor, n_critic,
+        C.byref(actor) if actor is not None else None,
+        _p(actor_image, torch.uint8, None, "actor_image"),
+        C.byref(critic) if critic is not None else None,
+        _p(critic_image, torch.uint8, None, "critic_image"), grad_scale, lr_actor, lr_critic,
+        max_norm, lr_decay_num_updates, steps_per_update,
+        _p(loss_out, torch.float32, 5, "loss_out"), _p(loss_workspace, torch.uint8, 256, "workspace"),
+        C.byref(hyper), int(loss_rows), _stream()), "mava_reduce_clip_adam_pair_acc")
+
+
 def reduce_clip_adam_pair(params, mu, nu, counts, group, gsum, n_actor: int, n_critic: int,
                           actor: Optional[MlpDesc], actor_image, critic: Optional[MlpDesc],
                           critic_image, grad_scale: float, lr_actor: float, lr_critic: float,

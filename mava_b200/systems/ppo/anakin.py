@@ -15,6 +15,7 @@ the same file with a decentralised critic).  The JAX program
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
@@ -165,6 +166,12 @@ class FFLearner:
             ws_bytes = native.ppo_workspace_bytes(self.actor_desc, self.critic_desc,
                                                   self.U * self.mb)
         self.workspace = z(ws_bytes, dtype=torch.uint8)
+        # the loss call adds into the (zeroed) gradient vector and the optimiser kernel clears it
+        # again -- legal when nobody else reads the vector: one rank, or the push exchange
+        # (a learner built with ``rank_world`` has its gradients summed by its caller: plain pair)
+        self.acc = (self.bf16 and self.collective in ("peer", "none") and rank_world is None
+                    and bool(config.arch.get("accumulate_grads", True))
+                    and not (self.world > 1 and os.environ.get("MAVA_PEER_PULL", "0") == "1"))
         n = T * self.E
         self.perm_rounds = int(math.ceil(3 * math.log(max(1, n)) / math.log(2 ** 32 - 1)))
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -312,7 +319,8 @@ class FFLearner:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
         if self.bf16:
-            native.ppo_loss_grad_bf16_stats(
+            loss_grad = native.ppo_loss_grad_bf16_acc if self.acc else native.ppo_loss_grad_bf16_stats
+            loss_grad(
                 self.actor_desc, self.actor_params, self.actor_img, self.critic_desc,
                 self.critic_params, self.critic_img, self.hyper, self.view, self.mask,
                 self.action, self.logp, self.value, self.adv, self.targets,
@@ -341,12 +349,22 @@ class FFLearner:
             e0.record()
         if self.collective == "nccl":
             self.allreduce(self.grad)
-        native.reduce_clip_adam_pair(
-            self.params, self.mu, self.nu, self.counts, group, self.gsum, self.na, self.nc,
-            self.actor_desc if self.bf16 else None, self.actor_img if self.bf16 else None,
-            self.critic_desc if self.bf16 else None, self.critic_img if self.bf16 else None,
-            1.0 / self.world, float(s.actor_lr), float(s.critic_lr), float(s.max_grad_norm),
-            self.lr_decay_updates, steps_per_update, self.loss_buf[ep, m])
+        if self.acc:
+            # paired with ppo_loss_grad_bf16_acc: loss metrics from the accumulators, gradient
+            # vector and accumulators left zero (no memsets, no finalize launch per minibatch)
+            native.reduce_clip_adam_pair_acc(
+                self.params, self.mu, self.nu, self.counts, group, self.gsum, self.na, self.nc,
+                self.actor_desc, self.actor_img, self.critic_desc, self.critic_img,
+                1.0 / self.world, float(s.actor_lr), float(s.critic_lr), float(s.max_grad_norm),
+                self.lr_decay_updates, steps_per_update, self.loss_buf[ep, m], self.workspace,
+                self.hyper, self.U * self.mb * self.A)
+        else:
+            native.reduce_clip_adam_pair(
+                self.params, self.mu, self.nu, self.counts, group, self.gsum, self.na, self.nc,
+                self.actor_desc if self.bf16 else None, self.actor_img if self.bf16 else None,
+                self.critic_desc if self.bf16 else None, self.critic_img if self.bf16 else None,
+                1.0 / self.world, float(s.actor_lr), float(s.critic_lr), float(s.max_grad_norm),
+                self.lr_decay_updates, steps_per_update, self.loss_buf[ep, m])
         if self.time_reduce_apply is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()

@@ -248,3 +248,47 @@ def test_golden_file_on_gpu(lib_built, name):
         np.testing.assert_array_equal(done.cpu().numpy().astype(bool), g[f"{name}/dones"][t])
         np.testing.assert_array_equal(er.cpu().numpy(), g[f"{name}/ep_returns"][t])
         np.testing.assert_array_equal(el.cpu().numpy(), g[f"{name}/ep_lengths"][t])
+
+
+def test_accumulating_pair_matches_plain_pair(lib_built):
+    """mava_ppo_loss_grad_bf16_acc + mava_reduce_clip_adam_pair_acc (no memsets, no finalize launch:
+    the optimiser kernel computes the loss metrics from the accumulators and clears the gradient
+    vector) against the plain pair, from the same seed through one whole update."""
+    from mava_b200 import prng
+    from mava_b200.config import compose
+    from mava_b200.systems.ppo import ff_mappo
+    from mava_b200.utils import make_env
+
+    torch.cuda.set_device(0)
+    learners = []
+    for acc in (True, False):
+        cfg = compose(ff_mappo.CONFIG_NAME, [
+            "env/scenario=tiny-4ag", "arch.num_envs=256", "system.update_batch_size=2",
+            "system.rollout_length=32", "system.ppo_epochs=2", "system.num_minibatches=2",
+            f"+arch.accumulate_grads={acc}", "+arch.use_cuda_graph=False", "logger.use_console=False"])
+        env, _ = make_env.make(cfg, add_global_state=True)
+        key, _, ak, ck = prng.split(prng.PRNGKey(5), 4)
+        learn, _, state = ff_mappo.learner_setup(env, (key, ak, ck), cfg)
+        cfg.system.num_updates_per_eval = 1
+        L = learn.learner
+        assert L.acc == acc and L.bf16
+        p0 = L.params.clone()
+        learn(state)
+        torch.cuda.synchronize()
+        learners.append((L, p0))
+    (a, p0), (b, _) = learners
+    # the first minibatch sees the same parameters and the same rollout: its metrics agree to the
+    # rounding of the double accumulators (the later ones follow parameters that differ by the order
+    # of the gradient atomics)
+    torch.testing.assert_close(a.loss_buf[0, 0], b.loss_buf[0, 0], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(a.loss_buf, b.loss_buf, rtol=2e-3, atol=1e-5)
+    moved = float((a.params - p0).abs().max())
+    diff = (a.params - b.params).abs()
+    assert moved > 1e-4 and float(diff.max()) < 0.05 * moved, (moved, float(diff.max()))
+    assert float((diff < 1e-3 * moved).float().mean()) > 0.99
+    assert torch.equal(a.key, b.key) and torch.equal(a.counts, b.counts)
+    # ... and it leaves its buffers as it needs to find them
+    assert float(a.grad.abs().max()) == 0.0
+    assert float(a.workspace[128:152].view(torch.float64).abs().max()) == 0.0
+    for L, _ in learners:
+        L.release()
