@@ -322,11 +322,16 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
   __syncthreads();
   const int el = threadIdx.x / G, g = threadIdx.x % G;
   const int env = env0 + el;
-  const unsigned gmask = group_mask<G>();
   bool needs_reset = false;
-  if (el < nenv) {
+  // Every lane of a warp runs the step (lanes without an env compute on whatever their record slot
+  // holds and store nothing): the exchanges between an env's lanes are then whole-warp shuffles /
+  // barriers, one instruction each, instead of collectives on a run-time lane mask (a MATCH.ANY +
+  // vote + divergence check in front of each, see env_rware.cuh::step_group)
+  constexpr unsigned kAll = 0xffffffffu;
+  const bool active = el < nenv;
+  {
     uint8_t* rec = srec + el * L.rec_stride;
-    const bool is_agent = g < c.A;
+    const bool is_agent = active && g < c.A;
     // ---- simultaneous moves against the old positions (utils.simulate_agent_movement)
     const int act = is_agent ? action[(size_t)env * c.A + g] : 0;
     const int ox = is_agent ? rec[c.off_ax + g] : -100 - g, oy = is_agent ? rec[c.off_ay + g] : -100;
@@ -345,7 +350,7 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
     // ---- fix_collisions: everybody whose target is shared stays where they were
     bool dup = false;
     for (int j = 0; j < G; ++j) {
-      const int jx = __shfl_sync(gmask, nx, j, G), jy = __shfl_sync(gmask, ny, j, G);
+      const int jx = __shfl_sync(kAll, nx, j, G), jy = __shfl_sync(kAll, ny, j, G);
       dup |= j != g && j < c.A && jx == nx && jy == ny;
     }
     if (dup) { nx = ox; ny = oy; }
@@ -361,24 +366,24 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       const int fx = rec[c.off_fx + f], fy = rec[c.off_fy + f], fl = rec[c.off_flvl + f];
       const bool was = rec[c.off_featen + f];
       const int lv = (is_agent && loading && !was && (abs(nx - fx) + abs(ny - fy) == 1)) ? lvl : 0;
-      const int sum = group_sum<G>(lv, gmask);
+      const int sum = group_sum<G>(lv, kAll);
       const bool now = sum >= fl;
       if (sum != 0) rew += (float)(lv * (now ? 1 : 0) * fl) / (float)(sum * total_food_level);
       eaten_bits |= (uint32_t)(now || was) << f;
       all_eaten &= now || was;
     }
-    __syncwarp(gmask);
+    __syncwarp();
     if (is_agent) {
       rec[c.off_ax + g] = (uint8_t)nx;
       rec[c.off_ay + g] = (uint8_t)ny;
     }
-    if (g == 0)
+    if (g == 0 && active)
       for (int f = 0; f < c.NF; ++f) rec[c.off_featen + f] = (eaten_bits >> f) & 1u;
     // ---- LbfWrapper.aggregate_rewards (sum over agents in index order) / individual rewards
     float team = 0.0f, mean = 0.0f;
-    for (int j = 0; j < c.A; ++j) team += __shfl_sync(gmask, rew, j, G);
+    for (int j = 0; j < c.A; ++j) team += __shfl_sync(kAll, rew, j, G);
     const float my_reward = c.individual_rewards ? rew : team;
-    for (int j = 0; j < c.A; ++j) mean += __shfl_sync(gmask, my_reward, j, G);
+    for (int j = 0; j < c.A; ++j) mean += __shfl_sync(kAll, my_reward, j, G);
     mean = mean / (float)c.A;
     uint32_t* pstep = reinterpret_cast<uint32_t*>(rec + c.off_step);
     const int step = (int)(*pstep) + 1;
@@ -388,8 +393,8 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       const uint32_t* k = reinterpret_cast<const uint32_t*>(rec + c.off_key);
       key = Key{k[0], k[1]};
     }
-    __syncwarp(gmask);
-    if (g == 0) {
+    __syncwarp();
+    if (g == 0 && active) {
       *pstep = (uint32_t)step;
       float* run_ret = reinterpret_cast<float*>(rec + c.off_run_ret);
       int32_t* run_len = reinterpret_cast<int32_t*>(rec + c.off_run_len);
@@ -409,8 +414,8 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       ep_length[env] = len_info;
     }
     if (is_agent) reward[(size_t)env * c.A + g] = my_reward;
-    __syncwarp(gmask);
-    needs_reset = is_done && auto_reset != 0;
+    __syncwarp();
+    needs_reset = active && is_done && auto_reset != 0;
   }
   // ---- AutoResetWrapper (auto_reset_wrapper.py:74-75): finished envs go into a CTA queue and every
   //      warp regenerates one at a time with all 32 lanes (warp-cooperative generator), instead of
