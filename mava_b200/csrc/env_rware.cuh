@@ -157,24 +157,13 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
 // jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
 // their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
 // lanes cooperate; State.key is what is left of `key`).
-template <int GG, class P = PrngInline, bool COMPACT = false, int KA = kMaxAgents>
-__device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
-                                         unsigned gmask) {
-  // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
-  // steps under random actions), and a regeneration is a chain of dependent threefry calls.  All
-  // keys are therefore derived first, in an order that leaves the independent splits next to each
-  // other for the scheduler (critical path: 4 splits instead of 7), and the per-agent direction
-  // draws run on the agents' own lanes.
-  Key k1, pos_key, k2, dir_key, k3, q_key, unused, sub_pos, sub_q, d_hi, d_lo;
-  P::split(key, k1, pos_key);
-  P::split(k1, k2, dir_key);
-  P::split(pos_key, unused, sub_pos);
-  P::split(k2, k3, q_key);
-  P::split(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
-  P::split(q_key, unused, sub_q);
-  const int my_dir =
-      g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
-  unsigned long long pick[KA];  // KA >= c.A
+// Agents on the KA-list's cells, requested shelves from the KQ-list, shelf grid, step, key: the part
+// of generate() behind the key derivation (KA >= c.A, KQ >= c.Q: the top-k lists are as short as
+// the caller can promise).
+template <int GG, class P, bool COMPACT, int KA, int KQ>
+__device__ __forceinline__ void place(const RwareConst& c, uint8_t* rec, Key sub_pos, Key sub_q,
+                                      Key k3, int my_dir, int g, unsigned gmask) {
+  unsigned long long pick[KA];
   smallest_k<GG, KA, P, COMPACT>(sub_pos, c.HW, c.A, g, gmask, pick);
   if (g < c.A) {
     unsigned long long mine = 0ull;
@@ -184,8 +173,8 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     const int cell = (int)(mine & 0xffffffffull);
     reinterpret_cast<uint32_t*>(rec + c.off_agents)[g] = pack_agent(cell / c.W, cell % c.W, my_dir, 0);
   }
-  unsigned long long qpick[kMaxQueue];
-  smallest_k<GG, kMaxQueue, P, COMPACT>(sub_q, c.n, c.Q, g, gmask, qpick);
+  unsigned long long qpick[KQ];
+  smallest_k<GG, KQ, P, COMPACT>(sub_q, c.n, c.Q, g, gmask, qpick);
   uint32_t* cw = reinterpret_cast<uint32_t*>(rec + c.off_cells);
   for (int i = g; i < c.cells_words; i += GG) cw[i] = 0u;
   __syncwarp(gmask);
@@ -195,7 +184,7 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     uint32_t* rq = reinterpret_cast<uint32_t*>(rec + c.off_reqbits);
     for (int i = 0; i < c.req_words; ++i) rq[i] = 0u;
 #pragma unroll
-    for (int i = 0; i < kMaxQueue; ++i) {
+    for (int i = 0; i < KQ; ++i) {
       if (i < c.Q) {
         const int s = (int)(qpick[i] & 0xffffffffull);
         rec[c.off_queue + i] = (uint8_t)s;
@@ -208,6 +197,59 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     k[1] = k3.k1;
   }
   __syncwarp(gmask);
+}
+
+template <int GG, class P = PrngInline, bool COMPACT = false, int KA = kMaxAgents>
+__device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
+                                         unsigned gmask) {
+  // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
+  // steps under random actions: they are most of the step kernel's instructions there), and a
+  // regeneration is a chain of dependent threefry calls.  All keys are derived first (a tree of
+  // depth four, one Threefry block per lane and level), and the per-agent direction draws run on the
+  // agents' own lanes.
+  Key k1, pos_key, k2, dir_key, k3, q_key, unused, sub_pos, sub_q, d_hi, d_lo;
+  if constexpr (GG >= 4) {
+    // The six splits are twelve Threefry blocks in a tree of depth four.  Every lane would compute
+    // all of them for itself; instead lane role r = g & 3 computes ONE block per level (r & 1: the
+    // block with counters (0, 2) or (1, 3) of a split; r >> 1: which of the level's two keys) and
+    // the halves are exchanged with shuffles: four block times instead of twelve.
+    const int r = g & 3;
+    const uint32_t c0 = (uint32_t)(r & 1), c1 = c0 + 2u;
+    auto sh = [&](uint32_t v, int src) { return __shfl_sync(gmask, v, src, GG); };
+    uint2 y = P::block(key.k0, key.k1, c0, c1);                       // split(key)
+    k1 = Key{sh(y.x, 0), sh(y.x, 1)};
+    pos_key = Key{sh(y.y, 0), sh(y.y, 1)};
+    Key ks = (r >> 1) ? pos_key : k1;                                 // split(k1) | split(pos_key)
+    y = P::block(ks.k0, ks.k1, c0, c1);
+    k2 = Key{sh(y.x, 0), sh(y.x, 1)};
+    dir_key = Key{sh(y.y, 0), sh(y.y, 1)};
+    sub_pos = Key{sh(y.y, 2), sh(y.y, 3)};
+    ks = (r >> 1) ? dir_key : k2;                                     // split(k2) | split(dir_key)
+    y = P::block(ks.k0, ks.k1, c0, c1);
+    k3 = Key{sh(y.x, 0), sh(y.x, 1)};
+    q_key = Key{sh(y.y, 0), sh(y.y, 1)};
+    d_lo = Key{sh(y.y, 2), sh(y.y, 3)};  // randint: span 4 -> only the low-bits draw matters
+    y = P::block(q_key.k0, q_key.k1, c0, c1);                         // split(q_key)
+    sub_q = Key{sh(y.y, 0), sh(y.y, 1)};
+  } else {
+    P::split(key, k1, pos_key);
+    P::split(k1, k2, dir_key);
+    P::split(pos_key, unused, sub_pos);
+    P::split(k2, k3, q_key);
+    P::split(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
+    P::split(q_key, unused, sub_q);
+  }
+  const int my_dir =
+      g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
+  // (a kernel that minds its instruction footprint gets one instantiation; the others the short
+  //  lists whenever the configuration allows them)
+  if (COMPACT) {
+    place<GG, P, COMPACT, KA, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+  } else if (c.A <= 4 && c.Q <= 4) {
+    place<GG, P, COMPACT, 4, 4>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+  } else {
+    place<GG, P, COMPACT, kMaxAgents, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+  }
 }
 
 // ---- observation rows --------------------------------------------------------------------------

@@ -88,6 +88,11 @@ __host__ __device__ __forceinline__ void random_bits_pair(Key k, uint32_t p, uin
 // instruction-cache misses than a call).
 #ifdef __CUDACC__
 struct PrngInline {
+  static __device__ __forceinline__ uint2 block(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+    uint32_t o0, o1;
+    threefry2x32(Key{k0, k1}, x0, x1, o0, o1);
+    return make_uint2(o0, o1);
+  }
   static __device__ __forceinline__ void split(Key k, Key& first, Key& second) {
     split2(k, first, second);
   }
