@@ -100,9 +100,12 @@ __device__ __forceinline__ bool requested(const RwareConst& c, const uint8_t* re
 // jax.random.permutation-by-stable-sort.  Every lane returns the same out[].
 // COMPACT: the two insertion passes and the K extraction rounds as rolled loops (a third of the
 // instructions; for kernels whose instruction footprint matters more than this function's speed).
+// pre[0..4): composites of pairs [0, p_start) this lane has computed already (~0 = none); the other
+// pairs are computed here.
 template <int G, int KMAX, class P = PrngInline, bool COMPACT = false>
 __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsigned gmask,
-                                           unsigned long long (&out)[KMAX]) {
+                                           unsigned long long (&out)[KMAX],
+                                           const unsigned long long (&pre)[4], int p_start) {
   unsigned long long top[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) top[j] = ~0ull;
@@ -117,7 +120,11 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
       }
     }
   };
-  for (int p = g; p < half; p += G) {
+  if (p_start > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) insert(pre[i]);  // (~0 never displaces anything)
+  }
+  for (int p = p_start + g; p < half; p += G) {
     uint32_t lo, hi;
     P::bits_pair(sub, (uint32_t)p, (uint32_t)size, lo, hi);
     if (COMPACT) {
@@ -154,17 +161,22 @@ __device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsi
   }
 }
 
-// jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
-// their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
-// lanes cooperate; State.key is what is left of `key`).
+template <int G, int KMAX, class P = PrngInline, bool COMPACT = false>
+__device__ __forceinline__ void smallest_k(Key sub, int size, int K, int g, unsigned gmask,
+                                           unsigned long long (&out)[KMAX]) {
+  const unsigned long long none[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  smallest_k<G, KMAX, P, COMPACT>(sub, size, K, g, gmask, out, none, 0);
+}
+
 // Agents on the KA-list's cells, requested shelves from the KQ-list, shelf grid, step, key: the part
 // of generate() behind the key derivation (KA >= c.A, KQ >= c.Q: the top-k lists are as short as
 // the caller can promise).
 template <int GG, class P, bool COMPACT, int KA, int KQ>
 __device__ __forceinline__ void place(const RwareConst& c, uint8_t* rec, Key sub_pos, Key sub_q,
-                                      Key k3, int my_dir, int g, unsigned gmask) {
+                                      Key k3, int my_dir, int g, unsigned gmask,
+                                      const unsigned long long (&pre)[4], int p_start) {
   unsigned long long pick[KA];
-  smallest_k<GG, KA, P, COMPACT>(sub_pos, c.HW, c.A, g, gmask, pick);
+  smallest_k<GG, KA, P, COMPACT>(sub_pos, c.HW, c.A, g, gmask, pick, pre, p_start);
   if (g < c.A) {
     unsigned long long mine = 0ull;
 #pragma unroll
@@ -199,20 +211,25 @@ __device__ __forceinline__ void place(const RwareConst& c, uint8_t* rec, Key sub
   __syncwarp(gmask);
 }
 
+// jumanji RandomGenerator.__call__: agents on distinct random cells, random directions, shelves on
+// their home cells, Q distinct requested shelves.  Writes the inner-env part of the record (GG
+// lanes cooperate; State.key is what is left of `key`).
 template <int GG, class P = PrngInline, bool COMPACT = false, int KA = kMaxAgents>
 __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key key, int g,
                                          unsigned gmask) {
   // Regenerations are on the hot path of an untrained policy (in tiny-4ag an episode lasts a few
   // steps under random actions: they are most of the step kernel's instructions there), and a
-  // regeneration is a chain of dependent threefry calls.  All keys are derived first (a tree of
-  // depth four, one Threefry block per lane and level), and the per-agent direction draws run on the
-  // agents' own lanes.
+  // regeneration is a chain of dependent Threefry blocks.  The six key splits are twelve blocks in
+  // a tree of depth four: every lane would compute all of them for itself; instead a lane computes
+  // ONE block per level (lanes 0..3: role r = g & 3, r & 1 = the block with counters (0, 2) or (1, 3)
+  // of a split, r >> 1 = which of the level's two keys) and the halves are exchanged with shuffles.
+  // A whole warp has 28 lanes to spare on the last two levels: they draw the first 54 pairs of the
+  // position permutation (its key is known after level two) and the agents' directions, so a
+  // regeneration is five block times (four levels + the request draw) instead of fifteen.
   Key k1, pos_key, k2, dir_key, k3, q_key, unused, sub_pos, sub_q, d_hi, d_lo;
+  unsigned long long pre[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  int p_start = 0, my_dir = 0;
   if constexpr (GG >= 4) {
-    // The six splits are twelve Threefry blocks in a tree of depth four.  Every lane would compute
-    // all of them for itself; instead lane role r = g & 3 computes ONE block per level (r & 1: the
-    // block with counters (0, 2) or (1, 3) of a split; r >> 1: which of the level's two keys) and
-    // the halves are exchanged with shuffles: four block times instead of twelve.
     const int r = g & 3;
     const uint32_t c0 = (uint32_t)(r & 1), c1 = c0 + 2u;
     auto sh = [&](uint32_t v, int src) { return __shfl_sync(gmask, v, src, GG); };
@@ -224,13 +241,45 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     k2 = Key{sh(y.x, 0), sh(y.x, 1)};
     dir_key = Key{sh(y.y, 0), sh(y.y, 1)};
     sub_pos = Key{sh(y.y, 2), sh(y.y, 3)};
-    ks = (r >> 1) ? dir_key : k2;                                     // split(k2) | split(dir_key)
-    y = P::block(ks.k0, ks.k1, c0, c1);
-    k3 = Key{sh(y.x, 0), sh(y.x, 1)};
-    q_key = Key{sh(y.y, 0), sh(y.y, 1)};
-    d_lo = Key{sh(y.y, 2), sh(y.y, 3)};  // randint: span 4 -> only the low-bits draw matters
-    y = P::block(q_key.k0, q_key.k1, c0, c1);                         // split(q_key)
-    sub_q = Key{sh(y.y, 0), sh(y.y, 1)};
+    if constexpr (GG == 32) {
+      const int half = (c.HW + 1) >> 1, dhalf = (c.A + 1) >> 1;
+      auto pair_c1 = [](int p, int hf, int size) { return (uint32_t)(p + hf < size ? p + hf : 0); };
+      auto keep = [&](int slot, uint2 v, int p) {  // both halves of position pair p
+        if (p < half) {
+          pre[slot] = ((unsigned long long)v.x << 32) | (unsigned)p;
+          if (p + half < c.HW) pre[slot + 1] = ((unsigned long long)v.y << 32) | (unsigned)(p + half);
+        }
+      };
+      // level 3: split(k2) | split(dir_key) | position pairs 0..27
+      const int p3 = g - 4;
+      ks = g < 2 ? k2 : (g < 4 ? dir_key : sub_pos);
+      y = P::block(ks.k0, ks.k1, g < 4 ? c0 : (uint32_t)p3, g < 4 ? c1 : pair_c1(p3, half, c.HW));
+      k3 = Key{sh(y.x, 0), sh(y.x, 1)};
+      q_key = Key{sh(y.y, 0), sh(y.y, 1)};
+      d_lo = Key{sh(y.y, 2), sh(y.y, 3)};  // randint: span 4 -> only the low-bits draw matters
+      if (g >= 4) keep(0, y, p3);
+      // level 4: split(q_key) | position pairs 28..53 | direction pairs
+      const int p4 = 26 + g, dp = g - 28;
+      ks = g < 2 ? q_key : (g < 28 ? sub_pos : d_lo);
+      y = P::block(ks.k0, ks.k1, g < 2 ? c0 : (g < 28 ? (uint32_t)p4 : (uint32_t)dp),
+                   g < 2 ? c1 : (g < 28 ? pair_c1(p4, half, c.HW) : pair_c1(dp, dhalf, c.A)));
+      sub_q = Key{sh(y.y, 0), sh(y.y, 1)};
+      if (g >= 2 && g < 28) keep(2, y, p4);
+      p_start = 54;
+      // randint(0, 4) of agent g = element g of random_bits(d_lo, (A,)): pair g mod dhalf
+      const int dpl = g < c.A ? (g < dhalf ? g : g - dhalf) : 0;
+      const uint32_t dx = sh(y.x, 28 + dpl), dy = sh(y.y, 28 + dpl);
+      my_dir = g < c.A ? (int)((g < dhalf ? dx : dy) & 3u) : 0;
+    } else {
+      ks = (r >> 1) ? dir_key : k2;                                   // split(k2) | split(dir_key)
+      y = P::block(ks.k0, ks.k1, c0, c1);
+      k3 = Key{sh(y.x, 0), sh(y.x, 1)};
+      q_key = Key{sh(y.y, 0), sh(y.y, 1)};
+      d_lo = Key{sh(y.y, 2), sh(y.y, 3)};
+      y = P::block(q_key.k0, q_key.k1, c0, c1);                       // split(q_key)
+      sub_q = Key{sh(y.y, 0), sh(y.y, 1)};
+      my_dir = g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
+    }
   } else {
     P::split(key, k1, pos_key);
     P::split(k1, k2, dir_key);
@@ -238,17 +287,17 @@ __device__ __forceinline__ void generate(const RwareConst& c, uint8_t* rec, Key 
     P::split(k2, k3, q_key);
     P::split(dir_key, d_hi, d_lo);  // randint: span 4 -> only the low-bits draw matters
     P::split(q_key, unused, sub_q);
+    my_dir = g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
   }
-  const int my_dir =
-      g < c.A ? (int)(P::bits_at(d_lo, (uint32_t)g, (uint32_t)c.A) & 3u) : 0;
   // (a kernel that minds its instruction footprint gets one instantiation; the others the short
   //  lists whenever the configuration allows them)
   if (COMPACT) {
-    place<GG, P, COMPACT, KA, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+    place<GG, P, COMPACT, KA, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask, pre, p_start);
   } else if (c.A <= 4 && c.Q <= 4) {
-    place<GG, P, COMPACT, 4, 4>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+    place<GG, P, COMPACT, 4, 4>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask, pre, p_start);
   } else {
-    place<GG, P, COMPACT, kMaxAgents, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask);
+    place<GG, P, COMPACT, kMaxAgents, kMaxQueue>(c, rec, sub_pos, sub_q, k3, my_dir, g, gmask, pre,
+                                                 p_start);
   }
 }
 
