@@ -318,14 +318,27 @@ __device__ __forceinline__ uint32_t s8x2_bf16x2(uint32_t h) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// ... and for bytes known to be in [0, 127] (RobotWarehouse observations: coordinates < 128, flags):
+// 0x4300 | b is the bf16 128 + b, minus 128.
+__device__ __forceinline__ uint32_t u7x2_bf16x2(uint32_t h) {
+  uint32_t m = __byte_perm(h, 0x43004300u, 0x7150);  // [b0, 0x43, b1, 0x43]
+  const uint32_t c = 0x43004300u;
+  __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&m),
+                             *reinterpret_cast<const __nv_bfloat162*>(&c));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // Thread (row L.r) expands chunks cg0, cg0 + cg_step, ... of its padded staging row into the bf16
-// tile; rows that are not valid become zero rows.  Four chunks' loads are in flight at a time.
+// tile; rows that are not valid become zero rows.  NS chunks' loads are in flight at a time; NONNEG:
+// every byte is in [0, 127].
+template <int NS = 4, bool NONNEG = false>
 __device__ __forceinline__ void expand_padded_row(const Tile& xt, const Lane& L, uint32_t stage_row,
                                                   bool valid, int nchunks, int cg0, int cg_step) {
-  for (int cgb = cg0; cgb < nchunks; cgb += 4 * cg_step) {
-    uint32_t w[4][2];
+  auto cv = [](uint32_t h) { return NONNEG ? u7x2_bf16x2(h) : s8x2_bf16x2(h); };
+  for (int cgb = cg0; cgb < nchunks; cgb += NS * cg_step) {
+    uint32_t w[NS][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NS; ++i) {
       const int cg = cgb + i * cg_step;
       w[i][0] = w[i][1] = 0u;
       if (valid && cg < nchunks)
@@ -334,11 +347,11 @@ __device__ __forceinline__ void expand_padded_row(const Tile& xt, const Lane& L,
                      : "r"(stage_row + 8u * cg));
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NS; ++i) {
       const int cg = cgb + i * cg_step;
       if (cg < nchunks)
-        st_shared_v4(xt.base + chunk_off(xt, L.r, cg), s8x2_bf16x2(w[i][0]),
-                     s8x2_bf16x2(w[i][0] >> 16), s8x2_bf16x2(w[i][1]), s8x2_bf16x2(w[i][1] >> 16));
+        st_shared_v4(xt.base + chunk_off(xt, L.r, cg), cv(w[i][0]), cv(w[i][0] >> 16), cv(w[i][1]),
+                     cv(w[i][1] >> 16));
     }
   }
 }
