@@ -215,6 +215,18 @@ __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const ui
   const int ox = min(c.fov, px), oy = min(c.fov, py);
   int o = 0;
   bool adj_food = false;
+  // cells a move cannot enter (another agent, food that has not been eaten): one bit per cell,
+  // filled while the observation entries are written, so that the action mask below is four bit
+  // tests instead of 6 x (A + NF) position compares on bytes re-read from shared memory
+  unsigned long long occ[kMaxCellsLbf / 64];
+#pragma unroll
+  for (int i = 0; i < kMaxCellsLbf / 64; ++i) occ[i] = 0ull;
+  auto occupy = [&](int cell) {
+    const unsigned long long bit = 1ull << (cell & 63);
+#pragma unroll
+    for (int i = 0; i < kMaxCellsLbf / 64; ++i)
+      if (i == (cell >> 6)) occ[i] |= bit;
+  };
   for (int f = 0; f < c.NF; ++f) {
     const int fx = rec[c.off_fx + f], fy = rec[c.off_fy + f];
     const bool alive = !rec[c.off_featen + f];
@@ -223,6 +235,7 @@ __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const ui
     row[o++] = vis ? (int8_t)(fy - py + oy) : -1;
     row[o++] = vis ? (int8_t)rec[c.off_flvl + f] : 0;
     adj_food |= alive && (abs(px - fx) + abs(py - fy) == 1);
+    if (alive) occupy(fx * c.S + fy);
   }
   for (int q = 0; q < c.A; ++q) {  // own entry first, then the others in index order
     const int j = q == 0 ? g : (q <= g ? q - 1 : q);
@@ -231,19 +244,23 @@ __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const ui
     row[o++] = vis ? (int8_t)(ax - px + ox) : -1;
     row[o++] = vis ? (int8_t)(ay - py + oy) : -1;
     row[o++] = vis ? (int8_t)rec[c.off_alvl + j] : 0;
+    if (q != 0) occupy(ax * c.S + ay);
   }
-  uint8_t mk = 0;
-  for (int a = 0; a < 6; ++a) {
+  // NOOP is always legal, LOAD next to food; a move into the grid and onto a free cell
+  uint8_t mk = (uint8_t)(1u | (adj_food ? 1u << 5 : 0u));
+#pragma unroll
+  for (int a = 1; a < 5; ++a) {
     int dx, dy;
     move_of(a, dx, dy);
     const int nx = px + dx, ny = py + dy;
-    bool bad = nx < 0 || ny < 0 || nx >= c.S || ny >= c.S;
-    for (int j = 0; j < c.A; ++j)
-      bad |= j != g && rec[c.off_ax + j] == nx && rec[c.off_ay + j] == ny;
-    for (int f = 0; f < c.NF; ++f)
-      bad |= !rec[c.off_featen + f] && rec[c.off_fx + f] == nx && rec[c.off_fy + f] == ny;
-    if (a == 5 && !adj_food) bad = true;
-    mk |= (uint8_t)((bad ? 0u : 1u) << a);
+    const bool inside = nx >= 0 && ny >= 0 && nx < c.S && ny < c.S;
+    const int cell = inside ? nx * c.S + ny : 0;
+    unsigned long long w = occ[0];
+#pragma unroll
+    for (int i = 1; i < kMaxCellsLbf / 64; ++i)
+      if (i == (cell >> 6)) w = occ[i];
+    const bool free_cell = !((w >> (cell & 63)) & 1ull);
+    mk |= (uint8_t)((inside && free_cell ? 1u : 0u) << a);
   }
   return mk;
 }
