@@ -67,17 +67,56 @@ template <int G>
 __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32_t* cellmask,
                                          Key key, int g, unsigned gmask) {
   const int S = c.S, flat = S * S;
-  const Key k_food = split_n(key, 5, 0), k_agents = split_n(key, 5, 1),
-            k_flevel = split_n(key, 5, 2), k_alevel = split_n(key, 5, 3),
-            k_state = split_n(key, 5, 4);
+  Key k_food, k_agents, k_flevel, k_alevel, k_state;
+  uint2 y3 = make_uint2(0u, 0u);  // G == 32: level-3 blocks (food draws, agent-level draws)
+  if constexpr (G == 32) {
+    // Warp-cooperative form (in-step regeneration).  Its ~26 Threefry blocks are a tree of depth
+    // three (+ the agent-position draw); a lane computes ONE block per level and the results travel
+    // by shuffles, instead of every lane computing every block:
+    //   level 1: split(key, 5): blocks p = 0..4 (counters p, p + 5) on lanes 0..4
+    //   level 2: split(k_food, NF): blocks 0..NF-1 on lanes 0..7; split(k_alevel): lanes 8, 9
+    //   level 3: the foods' uniform draws on lanes 0..7; randint's high / low draws for the agent
+    //            levels on lanes 8..11 / 12..15
+    auto blk = [](Key k, uint32_t a, uint32_t b) {
+      uint32_t o0, o1;
+      threefry2x32(k, a, b, o0, o1);
+      return make_uint2(o0, o1);
+    };
+    auto sh = [](uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); };
+    const uint32_t p1 = g < 5 ? (uint32_t)g : 0u;
+    const uint2 y1 = blk(key, p1, p1 + 5u);
+    // flat output f of split(key, 5): f < 5 ? x of block f : y of block f - 5; key j = (2j, 2j + 1)
+    k_food = Key{sh(y1.x, 0), sh(y1.x, 1)};
+    k_agents = Key{sh(y1.x, 2), sh(y1.x, 3)};
+    k_flevel = Key{sh(y1.x, 4), sh(y1.y, 0)};
+    k_alevel = Key{sh(y1.y, 1), sh(y1.y, 2)};
+    k_state = Key{sh(y1.y, 3), sh(y1.y, 4)};
+    const uint32_t NF = (uint32_t)c.NF, A = (uint32_t)c.A, ahalf = (A + 1u) >> 1;
+    const uint32_t a2 = g < 8 ? ((uint32_t)g < NF ? (uint32_t)g : 0u) : (uint32_t)(g & 1);
+    const uint2 y2 = blk(g < 8 ? k_food : k_alevel, a2, g < 8 ? a2 + NF : a2 + 2u);
+    const Key ka_hi{sh(y2.x, 8), sh(y2.x, 9)}, ka_lo{sh(y2.y, 8), sh(y2.y, 9)};  // split(k_alevel)
+    // lane f < NF: the key of food f = flat outputs (2f, 2f + 1) of split(k_food, NF)
+    const uint32_t fl = (uint32_t)g < NF ? (uint32_t)g : 0u, i0 = 2u * fl, i1 = i0 + 1u;
+    const int s0 = (int)(i0 < NF ? i0 : i0 - NF), s1 = (int)(i1 < NF ? i1 : i1 - NF);
+    const uint32_t x0 = sh(y2.x, s0), w0 = sh(y2.y, s0), x1 = sh(y2.x, s1), w1 = sh(y2.y, s1);
+    const Key kf{i0 < NF ? x0 : w0, i1 < NF ? x1 : w1};
+    const uint32_t q3 = (uint32_t)(g & 3);
+    y3 = blk(g < 8 ? kf : (g < 12 ? ka_hi : ka_lo), g < 8 ? 0u : q3,
+             g < 8 ? 0u : (q3 + ahalf < A ? q3 + ahalf : 0u));
+  } else {
+    k_food = split_n(key, 5, 0);
+    k_agents = split_n(key, 5, 1);
+    k_flevel = split_n(key, 5, 2);
+    k_alevel = split_n(key, 5, 3);
+    k_state = split_n(key, 5, 4);
+  }
   // ---- food: inverse CDF over the cells that are not on the border / next to an earlier food
   if constexpr (G == 32) {
-    // warp-cooperative form (in-step regeneration): lane w < 8 owns mask word w; the cumulative
-    // count is a prefix sum over the word popcounts and the hit is the k-th set bit of one word
+    // lane w < 8 owns mask word w; the cumulative count is a prefix sum over the word popcounts
+    // and the hit is the k-th set bit of one word
     uint32_t word = g < kMaxCellsLbf / 32 ? c.interior[g] : 0u;
     for (int f = 0; f < c.NF; ++f) {
-      const Key kf = split_n(k_food, (uint32_t)c.NF, (uint32_t)f);
-      const uint32_t bits = random_bits_at(kf, 0u, 1u);
+      const uint32_t bits = __shfl_sync(0xffffffffu, y3.x, f);  // random_bits(key of food f, (1,))
       const float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
       const int pc = __popc(word);
       int incl = pc;
@@ -154,9 +193,9 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
   unsigned long long top[kMaxAgents];
 #pragma unroll
   for (int j = 0; j < kMaxAgents; ++j) top[j] = ~0ull;
-  for (int i = g; i < flat; i += G) {
+  auto offer = [&](uint32_t bits, int i) {
     if ((cellmask[i >> 5] >> (i & 31)) & 1u) {
-      const uint32_t m = random_bits_at(k_agents, (uint32_t)i, (uint32_t)flat) >> 9;
+      const uint32_t m = bits >> 9;
       unsigned long long v = ((unsigned long long)(0x7FFFFFu - m) << 32) | (unsigned)i;
 #pragma unroll
       for (int j = 0; j < kMaxAgents; ++j) {
@@ -167,6 +206,18 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
         }
       }
     }
+  };
+  if constexpr (G == 32) {
+    // one block per PAIR of cells (i, i + half): both halves of every Threefry block are used
+    const int half = (flat + 1) >> 1;
+    for (int p = g; p < half; p += G) {
+      uint32_t lo, hi;
+      random_bits_pair(k_agents, (uint32_t)p, (uint32_t)flat, lo, hi);
+      offer(lo, p);
+      if (p + half < flat) offer(hi, p + half);
+    }
+  } else {
+    for (int i = g; i < flat; i += G) offer(random_bits_at(k_agents, (uint32_t)i, (uint32_t)flat), i);
   }
   int lv_sorted[3] = {1 << 20, 1 << 20, 1 << 20};
 #pragma unroll
@@ -179,7 +230,21 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
         top[kMaxAgents - 1] = ~0ull;
       }
       const int cell = (int)(mn & 0xffffffffull);
-      const int lvl = randint_1(k_alevel, r, c.A, c.max_level);
+      int lvl;
+      if constexpr (G == 32) {
+        // randint(1, max_level + 1)[r] from the level-3 draws: element r of random_bits(k, (A,)) is
+        // half r / ahalf of the block of pair r mod ahalf
+        const int ahalf = (c.A + 1) >> 1, q = r < ahalf ? r : r - ahalf;
+        const uint32_t hx = __shfl_sync(0xffffffffu, y3.x, 8 + q), hy = __shfl_sync(0xffffffffu, y3.y, 8 + q);
+        const uint32_t lx = __shfl_sync(0xffffffffu, y3.x, 12 + q), ly = __shfl_sync(0xffffffffu, y3.y, 12 + q);
+        const uint32_t hi = r < ahalf ? hx : hy, lo = r < ahalf ? lx : ly;
+        const uint32_t sp = (uint32_t)c.max_level;
+        uint32_t mult = 65536u % sp;
+        mult = (mult * mult) % sp;
+        lvl = 1 + (int)((((hi % sp) * mult) + (lo % sp)) % sp);
+      } else {
+        lvl = randint_1(k_alevel, r, c.A, c.max_level);
+      }
       if (g == 0) {
         rec[c.off_ax + r] = (uint8_t)(cell / S);
         rec[c.off_ay + r] = (uint8_t)(cell % S);
