@@ -207,7 +207,7 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
       }
     }
   };
-  if constexpr (G == 32) {
+  {
     // one block per PAIR of cells (i, i + half): both halves of every Threefry block are used
     const int half = (flat + 1) >> 1;
     for (int p = g; p < half; p += G) {
@@ -216,8 +216,6 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
       offer(lo, p);
       if (p + half < flat) offer(hi, p + half);
     }
-  } else {
-    for (int i = g; i < flat; i += G) offer(random_bits_at(k_agents, (uint32_t)i, (uint32_t)flat), i);
   }
   int lv_sorted[3] = {1 << 20, 1 << 20, 1 << 20};
 #pragma unroll
