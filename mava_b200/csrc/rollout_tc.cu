@@ -1,21 +1,28 @@
 // Fused persistent rollout for ff_ippo / ff_mappo on RobotWarehouse: the whole scan over
 // `rollout_length` env steps of mava/systems/ppo/ff_mappo.py:76-106 in ONE kernel launch.
 //
-// A CTA owns TM / A environments (32 for 4 agents = one 128-row tile of the actor) for the whole
-// rollout.  Their packed records, their current observation rows and the actor's bf16 weight image
-// stay in shared memory from the first step to the last; per step the CTA
-//   1. expands the int8 observation rows to the bf16 X tile,
-//   2. runs the actor MLP on the tcgen05 tensor cores (three MMA chains into TMEM, as act_kernel),
-//   3. finishes each row in the head epilogue: action mask, Gumbel arg-max on the threefry bits of
-//      this step's policy key, log-prob -- the sampled action stays in the register of the thread
-//      that is also lane g of its env,
-//   4. advances the envs (env_rware.cuh: sequential agent turns, collisions, deliveries, episode
-//      metrics, CTA-queued regeneration of finished envs) and builds the next observation rows,
-//   5. streams observation rows, mask, action, log-prob, reward, done and episode metrics of the
-//      step to the rollout buffers (bulk store for the observation block).
-// No state leaves the SM between steps and there is no launch per step: the rollout is latency
-// bound at 2048 envs per GPU, and this removes 2 launches, a weight reload and an HBM round trip
-// of the env records from every step.
+// A CTA owns up to TM / A environments (32 for 4 agents = one 128-row tile of the actor; 16 at 2048
+// envs, so that 128 SMs take part) for the whole rollout.  Their packed records, their current
+// observation rows and the actor's bf16 weight image stay in shared memory from the first step to
+// the last.  640 threads: sixteen foreground warps walk the step loop, four background warps only
+// generate spare records (see RCtrl).  Per step
+//   1. the actor MLP runs on the tcgen05 tensor cores (three MMA chains into TMEM, as act_kernel);
+//      warps whose tile rows are all dead skip their epilogues and their waits,
+//   2. threads 0 .. TM-1 (thread r = lane g of its env = tile row r) finish their row in the head
+//      epilogue -- action mask, Gumbel arg-max on the noise prepared one step ahead by the idle
+//      warps, log-prob -- and advance their env (env_rware.cuh::step_group: whole-warp collectives,
+//      sequential agent turns only where they matter, deliveries, episode metrics); a finished env
+//      copies its spare record in on its own lanes,
+//   3. four threads per row build the next observation row (a quarter each) into the int8
+//      observation block and into a padded int8 image of the X row, and expand every fourth chunk
+//      of the image into the bf16 X tile -- the row never takes a detour through a separate
+//      expansion phase,
+//   4. the idle warps write the step's outputs (staged in shared memory by the env lanes) and the
+//      observation block to the rollout buffers with plain stores.
+// No state leaves the SM between steps and there is no launch per step.  The kernel is latency
+// bound by construction -- a step is a dependent chain MLP -> sample -> env step -> observation row
+// and every env of the job is already in flight -- so everything here is about a shorter chain on
+// the env lanes (DESIGN.md 4.4 has the phase clocks).
 //
 // The critic is not needed to act (ff_mappo.py:83 only records its value), so the values of all
 // T + 1 observation slots are computed afterwards by one batched critic launch
