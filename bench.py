@@ -10,11 +10,12 @@ one full update = 262 144 env-steps per GPU.  N > 1 is launched by torchrun, one
 synchronize, timed with CUDA events, max over ranks.  Prints ONE JSON line on rank 0.
 
 `e2e` is the same metric through the public `learn(state)` call with host buffers: every step copies
-the learner inputs (parameters, Adam moments, key) from pinned host memory, runs `learn`, and copies
-back what the run loop consumes -- the finished-episode statistics (reduced on the device,
-mava_episode_stats), the four loss metrics, and the updated parameters / moments / key.
-`roofline` times the PPO minibatch kernels (fused forward + backward, critic first-layer gradient,
-loss finalize) with CUDA events around each call; `cpu_baseline` / `--impl reference` time the oracle
+the learner inputs (parameters, Adam moments, key: one allocation, one copy) from pinned host memory,
+runs `learn` -- which ends with the device -> host copy of what the run loop consumes (sort-overflow
+flag, finished-episode statistics reduced on the device, minibatch losses: one 256-byte block) and
+its only host wait -- and copies the updated parameters / moments / key back.
+`roofline` times the PPO minibatch kernels (fused forward + backward, critic first-layer gradient)
+with CUDA events around each call (median over the timed launches); `cpu_baseline` / `--impl reference` time the oracle
 port on the host cores (the reference itself cannot run in this image).
 """
 from __future__ import annotations

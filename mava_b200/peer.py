@@ -4,9 +4,12 @@ One process per GPU: every rank allocates ONE exchange buffer through the C ABI
 (``mava_peer_alloc``: cudaMalloc + CUDA IPC handle), the 64-byte handles travel through
 ``torch.distributed.all_gather_object`` (plumbing), and every rank maps the buffers of its peers
 (``mava_peer_open``).  The loss kernels write their gradients straight into the rank's own buffer
-(``group.grad`` is a torch view of it); ``native.reduce_clip_adam_pair`` then reads all ranks'
-buffers over NVLink inside the optimiser kernel.  No NCCL call is left on the update path, so the
-CUDA graph of an update holds no collective and the process group tears down normally.
+(``group.grad`` is a torch view of it); inside the optimiser kernel
+(``native.reduce_clip_adam_pair``) every rank then pushes its vector over NVLink into its slot of
+every peer's receive area -- the tail of the same buffer -- as 128-byte lines tagged with the call
+number, and sums what it received in rank order (``MAVA_PEER_PULL=1``: flag handshake + reads of the
+peers' vectors instead, the checker).  No NCCL call is left on the update path, so the CUDA graph of
+an update holds no collective and the process group tears down normally.
 """
 from __future__ import annotations
 
