@@ -226,3 +226,17 @@ def test_xla_ffi_shim_type_checks_against_the_header():
                 "MavaPpoLossGrad", "MavaReduceClipAdam"):
         assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL(\n    {sym}," in src
     assert "static mava_env_t g_env" not in src  # handles are attributes, not process globals
+
+
+def test_peer_buffer_layout_without_gpu(lib_built):
+    """The exchange buffer of csrc/peer.cu: [gradients, padded to 256 B][flag block, 256 B][receive
+    area: 2 call parities x 8 source ranks x ceil(chunks / 7) lines of 128 B] (include/mava_b200.h)."""
+    from mava_b200 import _lib
+
+    lib = _lib.load()
+    for n in (1, 7, 77454, 1 << 20):
+        chunks = (n + 3) // 4
+        lines = (chunks + 6) // 7
+        want = (n * 4 + 255) // 256 * 256 + 256 + 2 * 8 * lines * 128
+        assert int(lib.mava_peer_buffer_bytes(n)) == want, n
+    assert int(lib.mava_peer_buffer_bytes(0)) < 0
