@@ -272,8 +272,11 @@ __device__ __forceinline__ void generate(const LbfConst& c, uint8_t* rec, uint32
 }
 
 // VectorObserver.make_observation + compute_action_mask for agent g.
+// TA / TNF > 0: the agent / food counts are compile-time constants (the loops unroll fully).
+template <int TA = 0, int TNF = 0>
 __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const uint8_t* rec, int g,
                                                      int8_t* row) {
+  const int A_ = TA ? TA : c.A, NF_ = TNF ? TNF : c.NF;
   const int px = rec[c.off_ax + g], py = rec[c.off_ay + g];
   const int ox = min(c.fov, px), oy = min(c.fov, py);
   int o = 0;
@@ -290,7 +293,8 @@ __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const ui
     for (int i = 0; i < kMaxCellsLbf / 64; ++i)
       if (i == (cell >> 6)) occ[i] |= bit;
   };
-  for (int f = 0; f < c.NF; ++f) {
+#pragma unroll
+  for (int f = 0; f < NF_; ++f) {
     const int fx = rec[c.off_fx + f], fy = rec[c.off_fy + f];
     const bool alive = !rec[c.off_featen + f];
     const bool vis = abs(px - fx) <= c.fov && abs(py - fy) <= c.fov && alive;
@@ -300,7 +304,8 @@ __device__ __forceinline__ uint8_t emit_obs_and_mask(const LbfConst& c, const ui
     adj_food |= alive && (abs(px - fx) + abs(py - fy) == 1);
     if (alive) occupy(fx * c.S + fy);
   }
-  for (int q = 0; q < c.A; ++q) {  // own entry first, then the others in index order
+#pragma unroll
+  for (int q = 0; q < A_; ++q) {  // own entry first, then the others in index order
     const int j = q == 0 ? g : (q <= g ? q - 1 : q);
     const int ax = rec[c.off_ax + j], ay = rec[c.off_ay + j];
     const bool vis = abs(px - ax) <= c.fov && abs(py - ay) <= c.fov;
@@ -380,7 +385,7 @@ __device__ __forceinline__ void store_obs(const LbfConst& c, const uint8_t* sobs
   }
 }
 
-template <int G>
+template <int G, int TA = 0, int TNF = 0>
 __global__ void __launch_bounds__(kThreads)
 lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
                 const int8_t* __restrict__ action, int8_t* __restrict__ view,
@@ -408,12 +413,13 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
   // barriers, one instruction each, instead of collectives on a run-time lane mask (a MATCH.ANY +
   // vote + divergence check in front of each, see env_rware.cuh::step_group)
   constexpr unsigned kAll = 0xffffffffu;
+  const int A_ = TA ? TA : c.A, NF_ = TNF ? TNF : c.NF;  // compile-time in the specialised kernel
   const bool active = el < nenv;
   {
     uint8_t* rec = srec + el * L.rec_stride;
-    const bool is_agent = active && g < c.A;
+    const bool is_agent = active && g < A_;
     // ---- simultaneous moves against the old positions (utils.simulate_agent_movement)
-    const int act = is_agent ? action[(size_t)env * c.A + g] : 0;
+    const int act = is_agent ? action[(size_t)env * A_ + g] : 0;
     const int ox = is_agent ? rec[c.off_ax + g] : -100 - g, oy = is_agent ? rec[c.off_ay + g] : -100;
     int nx = ox, ny = oy;
     if (is_agent) {
@@ -421,9 +427,9 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       move_of(act, dx, dy);
       const int tx = ox + dx, ty = oy + dy;
       bool bad = tx < 0 || ty < 0 || tx >= c.S || ty >= c.S;
-      for (int j = 0; j < c.A; ++j)
+      _Pragma("unroll") for (int j = 0; j < A_; ++j)
         bad |= j != g && rec[c.off_ax + j] == tx && rec[c.off_ay + j] == ty;
-      for (int f = 0; f < c.NF; ++f)
+      _Pragma("unroll") for (int f = 0; f < NF_; ++f)
         bad |= !rec[c.off_featen + f] && rec[c.off_fx + f] == tx && rec[c.off_fy + f] == ty;
       if (!bad) { nx = tx; ny = ty; }
     }
@@ -431,18 +437,18 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
     bool dup = false;
     for (int j = 0; j < G; ++j) {
       const int jx = __shfl_sync(kAll, nx, j, G), jy = __shfl_sync(kAll, ny, j, G);
-      dup |= j != g && j < c.A && jx == nx && jy == ny;
+      dup |= j != g && j < A_ && jx == nx && jy == ny;
     }
     if (dup) { nx = ox; ny = oy; }
     const bool loading = is_agent && act == 5;
     const int lvl = is_agent ? rec[c.off_alvl + g] : 0;
     // ---- eat_food + get_reward (normalised, no penalty)
     int total_food_level = 0;
-    for (int f = 0; f < c.NF; ++f) total_food_level += rec[c.off_flvl + f];
+    _Pragma("unroll") for (int f = 0; f < NF_; ++f) total_food_level += rec[c.off_flvl + f];
     float rew = 0.0f;
     bool all_eaten = true;
     uint32_t eaten_bits = 0;
-    for (int f = 0; f < c.NF; ++f) {
+    _Pragma("unroll") for (int f = 0; f < NF_; ++f) {
       const int fx = rec[c.off_fx + f], fy = rec[c.off_fy + f], fl = rec[c.off_flvl + f];
       const bool was = rec[c.off_featen + f];
       const int lv = (is_agent && loading && !was && (abs(nx - fx) + abs(ny - fy) == 1)) ? lvl : 0;
@@ -458,13 +464,13 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       rec[c.off_ay + g] = (uint8_t)ny;
     }
     if (g == 0 && active)
-      for (int f = 0; f < c.NF; ++f) rec[c.off_featen + f] = (eaten_bits >> f) & 1u;
+      _Pragma("unroll") for (int f = 0; f < NF_; ++f) rec[c.off_featen + f] = (eaten_bits >> f) & 1u;
     // ---- LbfWrapper.aggregate_rewards (sum over agents in index order) / individual rewards
     float team = 0.0f, mean = 0.0f;
-    for (int j = 0; j < c.A; ++j) team += __shfl_sync(kAll, rew, j, G);
+    _Pragma("unroll") for (int j = 0; j < A_; ++j) team += __shfl_sync(kAll, rew, j, G);
     const float my_reward = c.individual_rewards ? rew : team;
-    for (int j = 0; j < c.A; ++j) mean += __shfl_sync(kAll, my_reward, j, G);
-    mean = mean / (float)c.A;
+    _Pragma("unroll") for (int j = 0; j < A_; ++j) mean += __shfl_sync(kAll, my_reward, j, G);
+    mean = mean / (float)A_;
     uint32_t* pstep = reinterpret_cast<uint32_t*>(rec + c.off_step);
     const int step = (int)(*pstep) + 1;
     const bool is_done = all_eaten || step >= c.time_limit;
@@ -493,7 +499,7 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
       ep_return[env] = ret_info;
       ep_length[env] = len_info;
     }
-    if (is_agent) reward[(size_t)env * c.A + g] = my_reward;
+    if (is_agent) reward[(size_t)env * A_ + g] = my_reward;
     __syncwarp();
     needs_reset = active && is_done && auto_reset != 0;
   }
@@ -516,10 +522,10 @@ lbf_step_kernel(const __grid_constant__ LbfConst c, uint8_t* __restrict__ state,
     }
   }
   __syncthreads();
-  if (el < nenv && g < c.A) {
+  if (el < nenv && g < A_) {
     const uint8_t* rec = srec + el * L.rec_stride;
-    int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * c.A + g) * c.FR;
-    mask[(size_t)env * c.A + g] = emit_obs_and_mask(c, rec, g, row);
+    int8_t* row = reinterpret_cast<int8_t*>(sobs) + (el * A_ + g) * c.FR;
+    mask[(size_t)env * A_ + g] = emit_obs_and_mask<TA, TNF>(c, rec, g, row);
   }
   __syncthreads();
   store_obs(c, sobs, view, env0, nenv);
@@ -682,6 +688,12 @@ int lbf_step(const mava_env_s* env, uint8_t* state, const int8_t* action, int8_t
              uint8_t* mask, float* reward, uint8_t* done, float* ep_return, int32_t* ep_length,
              int num_envs, int auto_reset, cudaStream_t s) {
   const LbfConst& c = env->lbf;
+  if (c.A == 2 && c.NF == 2) {  // the benchmark scenarios: agent / food loops unrolled at compile time
+    const size_t smem = smem_bytes(c, kThreads / 2);
+    lbf_step_kernel<2, 2, 2><<<ceil_div(num_envs, kThreads / 2), kThreads, smem, s>>>(
+        c, state, action, view, mask, reward, done, ep_return, ep_length, num_envs, auto_reset);
+    return launch_status();
+  }
   MAVA_LBF_DISPATCH(lbf_step_kernel, c, state, action, view, mask, reward, done, ep_return,
                     ep_length, num_envs, auto_reset);
   return launch_status();
