@@ -81,11 +81,12 @@ struct RCtrl {
   int rcount;
   uint16_t rlist[TM];
   // Speculative regeneration.  What a finished env is regenerated from is its State.key, which only
-  // deliveries change, and a regeneration is a long dependent threefry chain (~5 K cycles) -- so
-  // every env's NEXT initial state is generated ahead of time into a spare record, tagged with the
-  // key it came from, by NBG background warps that take no part in the step loop: the lane-0 agent
-  // of an env posts (env, key) into a ticket queue whenever the env has no spare for its current
-  // key, a background warp generates it and marks it ready.  A finished env whose key still matches
+  // deliveries change, and a regeneration is a dependent chain of Threefry blocks (five block times
+  // with a whole warp, env_rware.cuh::generate) -- so every env's NEXT initial state is generated
+  // ahead of time into a spare record, tagged with the key it came from, by NBG background warps
+  // that take no part in the step loop: one of the threads that build the env's observation rows
+  // posts (env, key) into a ticket queue whenever the env has no spare for its current key, a
+  // background warp generates it and marks it ready.  A finished env whose key still matches
   // copies its spare in on the spot (its own lanes, no CTA barrier); otherwise (a delivery since, or
   // the spare is still being generated) it is regenerated by a whole warp after the step's barrier.
   // Same bits either way.
@@ -128,8 +129,9 @@ __device__ __forceinline__ void fg_wait_mma(uint64_t* bar, uint32_t parity) {
   fence_after_sync();
 }
 
-// The thread that issues, commits and waits for the bulk stores: not in warp 0, which issues the MMAs
-// (a bulk copy issued between two MMA chains delays the next one by ~500 cycles).
+// The thread that issues, commits and waits for the bulk store of the records at the end (not in warp
+// 0, the MMA issuer: a bulk copy issued next to an MMA chain was measured to delay it by ~500
+// cycles, which is why the per-step outputs leave with plain stores).
 constexpr int kStoreThread = TM;
 // Staged block -> HBM by the NT foreground threads: one bulk store when size and address allow
 // it, else a copy.  Returns true when a bulk store was issued (the caller commits / waits).
